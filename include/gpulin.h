@@ -1,0 +1,154 @@
+/* gpulin.h -- C ABI of the B200-native linear bound propagation library (libgpulin.so).
+ *
+ * This is the drop-in boundary for the reference path
+ *      propagationRound (solve.c:437) -> consPropLinear (cons_linear.c:16126) -> propagateCons (:7621)
+ *      -> tightenBounds (:6980) -> tightenVarBoundsEasy / tightenVarBounds (:5380 / :6700)
+ * The reference has no FFI for this path (it is in-process C); the entry points below are what the SCIP
+ * propagator plugin scip_b200/plugin/prop_gpulinear.c (SCIP_DECL_PROPEXEC, type_prop.h:217) binds.
+ * No SCIP, torch or C++ types cross this boundary: plain pointers and sizes only.
+ *
+ * All functions return GPULIN_OK (0) or a negative error code; gpulin_last_error() gives the text.
+ * There is NO CPU fallback: if CUDA is unavailable every call fails with GPULIN_ERR_CUDA.
+ */
+#ifndef GPULIN_H
+#define GPULIN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPULIN_OK            0
+#define GPULIN_ERR_CUDA     -1   /* CUDA runtime / driver failure (SCIP side: SCIP_ERROR) */
+#define GPULIN_ERR_ARG      -2   /* invalid argument */
+#define GPULIN_ERR_NOMEM    -3   /* host or device allocation failed */
+#define GPULIN_ERR_STATE    -4   /* call sequence violated (e.g. propagate before set_bounds) */
+
+/* propagation verdicts (gpulin_result.status) */
+#define GPULIN_FIXPOINT      0   /* no bound changed in the last round */
+#define GPULIN_CUTOFF        1   /* infeasibility proven (SCIP_CUTOFF) */
+#define GPULIN_ROUNDLIMIT    2   /* maxrounds reached while bounds were still moving */
+
+/* variable types (SCIPvarIsIntegral, pub_var.h:1209) */
+#define GPULIN_VAR_CONTINUOUS 0
+#define GPULIN_VAR_INTEGRAL   1
+
+typedef struct gpulin gpulin_t;
+
+/** numerical tolerances; replaces SCIPinfinity/SCIPepsilon/SCIPsumepsilon/SCIPfeastol/SCIPgetHugeValue
+ *  (scip_numerics.c:140-546), numerics/boundstreps (set.c:2404) and constraints/linear/maxeasyactivitydelta
+ *  (cons_linear.c:135) */
+typedef struct gpulin_numerics
+{
+   double infinity;             /* 1e20 */
+   double epsilon;              /* 1e-9 */
+   double sumepsilon;           /* 1e-6 */
+   double feastol;              /* 1e-6 */
+   double boundstreps;          /* 0.05 */
+   double hugeval;              /* 1e15 */
+   double maxeasyactivitydelta; /* 1e6  */
+} gpulin_numerics;
+
+typedef struct gpulin_result
+{
+   int32_t status;        /* GPULIN_FIXPOINT / _CUTOFF / _ROUNDLIMIT */
+   int32_t nrounds;       /* propagation rounds executed (the last one found no change unless cutoff/limit) */
+   int64_t nchanges;      /* accepted bound changes, counted per variable bound and round */
+   int64_t nnz_processed; /* nonzeros swept over all rounds (dirty rows only after the first round) */
+   double  device_ms;     /* device time of the whole call (CUDA events on the library's stream) */
+} gpulin_result;
+
+/** one accepted bound change, in round order (for SCIPinferVarLbProp/UbProp, scip_var.c:7589/7705) */
+typedef struct gpulin_change
+{
+   int32_t var;        /* column index */
+   int32_t round;      /* round in which the change was accepted (0-based) */
+   double  newbound;
+   int32_t is_upper;   /* 0: lower bound raised, 1: upper bound lowered */
+   int32_t reserved;
+} gpulin_change;
+
+/** fills the reference's default tolerances (def.h:172-184) */
+void gpulin_default_numerics(gpulin_numerics* num);
+
+/** text of the last error on the calling thread */
+const char* gpulin_last_error(void);
+
+/** number of CUDA devices visible, or a negative error code */
+int gpulin_device_count(void);
+
+/** builds the device copy (row-binned sliced CSR + column->row-block map) of the linear rows
+ *      lhs[i] <= sum_k vals[k] * x[colidx[k]] <= rhs[i],   k in [rowptr[i], rowptr[i+1])
+ *  replaces the per-constraint SCIP_CONSDATA arrays (cons_linear.c:187-266) read through
+ *  SCIPgetVarsLinear/SCIPgetValsLinear/SCIPgetLhsLinear/SCIPgetRhsLinear (cons_linear.c:18326-18452).
+ *  Rows may be a slice of a larger problem (multi-GPU row partition): ncols is always the global count. */
+int gpulin_create(
+   int                    device,     /* CUDA device ordinal */
+   int64_t                nrows,
+   int64_t                ncols,
+   int64_t                nnz,
+   const int64_t*         rowptr,     /* host, nrows+1 */
+   const int32_t*         colidx,     /* host, nnz */
+   const double*          vals,       /* host, nnz; no zeros (cons_linear.c:5422) */
+   const double*          lhs,        /* host, nrows; <= -infinity: none */
+   const double*          rhs,        /* host, nrows; >= +infinity: none */
+   const uint8_t*         vartype,    /* host, ncols; GPULIN_VAR_* */
+   const gpulin_numerics* num,        /* NULL: defaults */
+   gpulin_t**             out
+   );
+
+void gpulin_destroy(gpulin_t* h);
+
+/** (re)loads all variable bounds from host memory and marks every row for propagation
+ *  (SCIPvarGetLbLocal/UbLocal, pub_var.h:877,889) */
+int gpulin_set_bounds(gpulin_t* h, const double* lb, const double* ub);
+
+/** same, bounds already on the device of this handle */
+int gpulin_set_bounds_device(gpulin_t* h, const double* d_lb, const double* d_ub);
+
+/** overwrites n bounds (tightened or relaxed: branching, backtracking) and marks only the rows of those
+ *  columns -- the counterpart of eventExecLinear's SCIPmarkConsPropagate (cons_linear.c:17229) */
+int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, const double* lb, const double* ub);
+
+/** runs propagation rounds on the device until fixpoint, cutoff or maxrounds (<= 0: unlimited); the round
+ *  loop runs inside one persistent kernel, no host round trip per round (propagateDomains, solve.c:766) */
+int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res);
+
+/** copies the current bounds to host memory */
+int gpulin_get_bounds(gpulin_t* h, double* lb, double* ub);
+
+/** copies the current bounds to device memory of this handle's device */
+int gpulin_get_bounds_device(gpulin_t* h, double* d_lb, double* d_ub);
+
+/** enables (capacity > 0) or disables the round-ordered change log kept for the SCIP plugin */
+int gpulin_set_change_log(gpulin_t* h, int64_t capacity);
+
+/** copies up to maxn log entries of the last gpulin_propagate call; *n gets the number of entries that
+ *  were produced (if *n > capacity the log overflowed and only the first `capacity` are valid) */
+int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n);
+
+/** device time [ms] of each round of the last gpulin_propagate call (up to maxn), *n = rounds recorded */
+int gpulin_get_round_times(gpulin_t* h, double* ms, int32_t maxn, int32_t* n);
+
+/** storage statistics: nonzeros incl. padding in the thread-per-row bin, rows per bin, bytes on device */
+int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
+
+/* ---- multi-GPU (rows partitioned over ranks, bounds replicated) ------------------------
+ * One round = gpulin_round_sweep on every rank, a MAX/MIN all-reduce of the two int64 key vectors
+ * returned by gpulin_exchange_buffers (NCCL, done by the host language), then gpulin_round_apply. */
+
+/** device pointers to the order-preserving int64 keys of the candidate lower / upper bounds (ncols each) */
+int gpulin_exchange_buffers(gpulin_t* h, int64_t** d_lbkeys, int64_t** d_ubkeys, int32_t** d_flags);
+
+/** one sweep over the rows marked for propagation; candidates are merged into the key vectors */
+int gpulin_round_sweep(gpulin_t* h);
+
+/** accepts the (all-reduced) key vectors as the new bounds; *nchanges = changed bounds, *cutoff = verdict */
+int gpulin_round_apply(gpulin_t* h, int64_t* nchanges, int32_t* cutoff);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -224,6 +224,9 @@ static SCIP_DECL_PROPEXEC(propExecDump)
    return SCIP_OKAY;
 }
 
+/** variables in .lpb (creation) order; SCIPgetOrigVars is sorted by variable type instead */
+static SCIP_VAR** g_lpbvars = NULL;
+
 static SCIP_RETCODE buildFromLpb(SCIP* scip, const LPB* p)
 {
    SCIP_VAR** vars;
@@ -262,6 +265,8 @@ static SCIP_RETCODE buildFromLpb(SCIP* scip, const LPB* p)
       }
       free(rowvars);
    }
+   g_lpbvars = (SCIP_VAR**)malloc(sizeof(SCIP_VAR*) * (size_t)(p->ncols + 1));
+   memcpy(g_lpbvars, vars, sizeof(SCIP_VAR*) * (size_t)p->ncols);
    for( i = 0; i < p->ncols; ++i )
       SCIP_CALL( SCIPreleaseVar(scip, &vars[i]) );
    free(vars);
@@ -366,7 +371,7 @@ static SCIP_RETCODE run(int argc, char** argv)
 
    propdata.norigvars = SCIPgetNOrigVars(scip);
    propdata.origvars = (SCIP_VAR**)malloc(sizeof(SCIP_VAR*) * (size_t)(propdata.norigvars + 1));
-   memcpy(propdata.origvars, SCIPgetOrigVars(scip), sizeof(SCIP_VAR*) * (size_t)propdata.norigvars);
+   memcpy(propdata.origvars, g_lpbvars != NULL ? g_lpbvars : SCIPgetOrigVars(scip), sizeof(SCIP_VAR*) * (size_t)propdata.norigvars);
 
    t0 = wallclock();
    SCIP_CALL( SCIPsolve(scip) );
@@ -416,6 +421,7 @@ static SCIP_RETCODE run(int argc, char** argv)
 
    free(propdata.origvars);
    free(g_probidx2orig);
+   free(g_lpbvars);
    SCIP_CALL( SCIPfree(&scip) );
    return SCIP_OKAY;
 }

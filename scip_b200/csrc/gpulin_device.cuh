@@ -1,0 +1,496 @@
+// gpulin_device.cuh -- device-side arithmetic of the linear bound propagation path (sm_100a).
+//
+// Everything here is fp64 + small integer counters; there is no GEMM-shaped work and no tensor-core use.
+// The functions restate the reference's rules (file:line cited per function, relative to
+// /root/reference/src/scip) as straight-line device code.  Compiled with -fmad=false so that every product
+// and sum rounds exactly like the reference's C code (built with -ffp-contract=off).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gpulin {
+
+struct Num
+{
+   double inf;        // SCIPinfinity          def.h:172
+   double eps;        // SCIPepsilon           def.h:173
+   double sumeps;     // SCIPsumepsilon        def.h:174
+   double feastol;    // SCIPfeastol           def.h:175
+   double bstreps;    // numerics/boundstreps  def.h:180
+   double huge;       // SCIPgetHugeValue      def.h:184
+   double maxeasy;    // constraints/linear/maxeasyactivitydelta  cons_linear.c:135
+};
+
+// ---- order-preserving int64 encoding of fp64 bounds: atomicMax/atomicMin on the keys is
+// ---- max/min on the doubles; "+ 0.0" folds -0.0 into +0.0; an involution, so decode == encode
+__device__ __forceinline__ long long d2key(double x)
+{
+   long long u = __double_as_longlong(x + 0.0);
+   return u >= 0 ? u : (u ^ 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double key2d(long long k)
+{
+   return __longlong_as_double(k >= 0 ? k : (k ^ 0x7fffffffffffffffLL));
+}
+
+// ---- tolerance predicates: set.c:6824-6976, 7133-7150, 7254-7372; misc.c:11162 -----------------------------
+__device__ __forceinline__ bool isInf(const Num& n, double v) { return v >= n.inf; }
+__device__ __forceinline__ bool isHuge(const Num& n, double v) { return v >= n.huge; }
+__device__ __forceinline__ bool isLT(const Num& n, double a, double b) { return a - b < -n.eps; }
+__device__ __forceinline__ bool isLE(const Num& n, double a, double b) { return a - b <= n.eps; }
+__device__ __forceinline__ bool isGT(const Num& n, double a, double b) { return a - b > n.eps; }
+__device__ __forceinline__ bool isGE(const Num& n, double a, double b) { return a - b >= -n.eps; }
+__device__ __forceinline__ bool isEQ(const Num& n, double a, double b) { return fabs(a - b) <= n.eps; }
+__device__ __forceinline__ double relDiff(double a, double b)
+{
+   double q = fmax(1.0, fmax(fabs(a), fabs(b)));
+   return (a - b) / q;
+}
+__device__ __forceinline__ bool isFeasLT(const Num& n, double a, double b) { return relDiff(a, b) < -n.feastol; }
+__device__ __forceinline__ bool isFeasGT(const Num& n, double a, double b) { return relDiff(a, b) > n.feastol; }
+
+// set.c:7711-7753
+__device__ __forceinline__ bool isLbBetter(const Num& n, double newlb, double oldlb, double oldub)
+{
+   if( oldlb < 0.0 && newlb >= 0.0 )
+      return true;
+   double m = fmax(fmin(oldub - oldlb, fabs(oldlb)), 1e-3);
+   return newlb - oldlb > n.bstreps * m;
+}
+__device__ __forceinline__ bool isUbBetter(const Num& n, double newub, double oldlb, double oldub)
+{
+   if( oldub > 0.0 && newub <= 0.0 )
+      return true;
+   double m = fmax(fmin(oldub - oldlb, fabs(oldub)), 1e-3);
+   return newub - oldub < -(n.bstreps * m);
+}
+
+// var.c:1957-1974 / 2006-2023
+__device__ __forceinline__ double adjustedLb(const Num& n, bool integral, double lb)
+{
+   if( lb < 0.0 && isInf(n, -lb) )
+      return -n.inf;
+   if( lb > 0.0 && isInf(n, lb) )
+      return n.inf;
+   if( integral )
+      return ceil(lb - n.feastol);
+   if( lb > 0.0 && lb < n.eps )
+      return 0.0;
+   return lb;
+}
+__device__ __forceinline__ double adjustedUb(const Num& n, bool integral, double ub)
+{
+   if( ub > 0.0 && isInf(n, ub) )
+      return n.inf;
+   if( ub < 0.0 && isInf(n, -ub) )
+      return -n.inf;
+   if( integral )
+      return floor(ub + n.feastol);
+   if( ub < 0.0 && ub > -n.eps )
+      return 0.0;
+   return ub;
+}
+
+// ---- double-double accumulation: dbldblarith.h:154-187 (SCIPdbldblSum21) ------------------------------------
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double b)
+{
+   double s = hi + b;
+   double t = s - hi;
+   double e = (hi - (s - t)) + (b - t);
+   lo = e + lo;
+   hi = s;
+}
+// (hi,lo) += (bhi,blo): merges the partial sums of two lanes
+__device__ __forceinline__ void dd_add_dd(double& hi, double& lo, double bhi, double blo)
+{
+   double s = hi + bhi;
+   double t = s - hi;
+   double e = (hi - (s - t)) + (bhi - t);
+   lo = (e + lo) + blo;
+   hi = s;
+}
+
+// ---- per-row activity state --------------------------------------------------------------------------------
+// The eight counters of infinite / huge contributions (cons_linear.c:187-266) are kept as 4-bit fields that
+// saturate at 2: every rule of the path only asks "0, 1 or more" (canTightenBounds :5234, getMinActivity
+// :2373-2392, residual counters :2726-2805).
+enum CntField { MINPOSINF = 0, MINNEGINF = 1, MINPOSHUGE = 2, MINNEGHUGE = 3,
+                MAXPOSINF = 4, MAXNEGINF = 5, MAXPOSHUGE = 6, MAXNEGHUGE = 7 };
+
+__device__ __forceinline__ unsigned cntGet(unsigned cnt, int f) { return (cnt >> (4 * f)) & 0xFu; }
+__device__ __forceinline__ void cntInc(unsigned& cnt, int f)
+{
+   if( cntGet(cnt, f) < 2u )
+      cnt += 1u << (4 * f);
+}
+__device__ __forceinline__ unsigned cntDec(unsigned cnt, int f) { return cnt - (1u << (4 * f)); }
+__device__ __forceinline__ unsigned cntMerge(unsigned a, unsigned b)
+{
+   unsigned x = a + b;                                       // fields 0..4
+   unsigned ge2 = ((x >> 1) | (x >> 2)) & 0x11111111u;       // 1 where field >= 2
+   return (ge2 << 1) | (x & 0x11111111u & ~ge2);
+}
+__device__ __forceinline__ unsigned cntMinSum(unsigned c) { return cntGet(c, 0) + cntGet(c, 1) + cntGet(c, 2) + cntGet(c, 3); }
+__device__ __forceinline__ unsigned cntMaxSum(unsigned c) { return cntGet(c, 4) + cntGet(c, 5) + cntGet(c, 6) + cntGet(c, 7); }
+
+struct RowAcc
+{
+   double   minhi, minlo;   // finite part of the minimal activity (double-double)
+   double   maxhi, maxlo;   // finite part of the maximal activity
+   double   maxdelta;       // max_i |a_i| (ub_i - lb_i), infinity if a variable is unbounded (:1542-1599)
+   unsigned cnt;
+};
+
+__device__ __forceinline__ void accInit(RowAcc& r)
+{
+   r.minhi = r.minlo = r.maxhi = r.maxlo = 0.0;
+   r.maxdelta = 0.0;
+   r.cnt = 0u;
+}
+
+// one bound of one term enters one activity: consdataUpdateActivities with oldbound = 0 (:1773-1948)
+__device__ __forceinline__ void addContributionSlow(const Num& n, double a, double bound, double& hi, double& lo,
+   unsigned& cnt, int fposinf, int fneginf, int fposhuge, int fneghuge)
+{
+   if( isInf(n, fabs(bound)) )
+      cntInc(cnt, bound > 0.0 ? fposinf : fneginf);
+   else
+   {
+      double c = a * bound;
+      if( isHuge(n, fabs(c)) )
+         cntInc(cnt, c > 0.0 ? fposhuge : fneghuge);
+      else
+         dd_add(hi, lo, c);
+   }
+}
+
+// classification + accumulation of one nonzero (a, [l,u]); the common case (finite bounds, no huge product)
+// is branch-free
+__device__ __forceinline__ void accElem(const Num& n, RowAcc& r, double a, double l, double u)
+{
+   const bool pos = a > 0.0;
+   const double bmin = pos ? l : u;
+   const double bmax = pos ? u : l;
+   const double cmin = a * bmin;
+   const double cmax = a * bmax;
+   const bool fast = (fabs(l) < n.inf) && (fabs(u) < n.inf) && (fabs(cmin) < n.huge) && (fabs(cmax) < n.huge);
+   if( fast )
+   {
+      dd_add(r.minhi, r.minlo, cmin);
+      dd_add(r.maxhi, r.maxlo, cmax);
+      r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
+   }
+   else
+   {
+      if( pos )
+      {
+         addContributionSlow(n, a, l, r.minhi, r.minlo, r.cnt, MINPOSINF, MINNEGINF, MINPOSHUGE, MINNEGHUGE);
+         addContributionSlow(n, a, u, r.maxhi, r.maxlo, r.cnt, MAXPOSINF, MAXNEGINF, MAXPOSHUGE, MAXNEGHUGE);
+      }
+      else
+      {
+         // negative coefficient: the infinity counters are switched, the huge counters follow the sign of the
+         // contribution (:1737-1769)
+         addContributionSlow(n, a, l, r.maxhi, r.maxlo, r.cnt, MAXNEGINF, MAXPOSINF, MAXPOSHUGE, MAXNEGHUGE);
+         addContributionSlow(n, a, u, r.minhi, r.minlo, r.cnt, MINNEGINF, MINPOSINF, MINPOSHUGE, MINNEGHUGE);
+      }
+      if( isInf(n, -l) || isInf(n, u) )
+         r.maxdelta = n.inf;
+      else
+         r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
+   }
+}
+
+__device__ __forceinline__ void accMerge(RowAcc& r, const RowAcc& o)
+{
+   dd_add_dd(r.minhi, r.minlo, o.minhi, o.minlo);
+   dd_add_dd(r.maxhi, r.maxlo, o.maxhi, o.maxlo);
+   r.maxdelta = fmax(r.maxdelta, o.maxdelta);
+   r.cnt = cntMerge(r.cnt, o.cnt);
+}
+
+// getMinActivity / getMaxActivity: cons_linear.c:2345-2434 / 2440-2529
+__device__ __forceinline__ void getMinActivity(const Num& n, double hi, double lo, unsigned posinf, unsigned neginf,
+   unsigned poshuge, unsigned neghuge, double delta, bool goodrelax, double& act, bool& tight, bool& settoinf)
+{
+   if( neginf > 0 )
+   {
+      act = -n.inf; settoinf = true; tight = (posinf == 0);
+   }
+   else if( posinf > 0 )
+   {
+      act = n.inf; settoinf = true; tight = true;
+   }
+   else if( neghuge > 0 || (poshuge > 0 && !goodrelax) )
+   {
+      act = -n.inf; settoinf = true; tight = false;
+   }
+   else
+   {
+      dd_add(hi, lo, -delta);
+      if( poshuge > 0 )
+      {
+         dd_add(hi, lo, (double)poshuge * n.huge);
+         tight = false;
+      }
+      else
+         tight = true;
+      act = hi + lo;
+      settoinf = false;
+   }
+}
+__device__ __forceinline__ void getMaxActivity(const Num& n, double hi, double lo, unsigned posinf, unsigned neginf,
+   unsigned poshuge, unsigned neghuge, double delta, bool goodrelax, double& act, bool& tight, bool& settoinf)
+{
+   if( posinf > 0 )
+   {
+      act = n.inf; settoinf = true; tight = (neginf == 0);
+   }
+   else if( neginf > 0 )
+   {
+      act = -n.inf; settoinf = true; tight = true;
+   }
+   else if( poshuge > 0 || (neghuge > 0 && !goodrelax) )
+   {
+      act = n.inf; settoinf = true; tight = false;
+   }
+   else
+   {
+      dd_add(hi, lo, -delta);
+      if( neghuge > 0 )
+      {
+         dd_add(hi, lo, -(double)neghuge * n.huge);
+         tight = false;
+      }
+      else
+         tight = true;
+      act = hi + lo;
+      settoinf = false;
+   }
+}
+
+// ---- what the candidate phase needs to know about its row ------------------------------------------------------
+struct RowInfo
+{
+   RowAcc acc;
+   double lhs, rhs;
+   double minact, maxact;   // finite parts as doubles (easy path: cons_linear.c:5450-5515)
+   double slackR, slackL;   // clamped rhs - minact / maxact - lhs of the easy path
+   bool   easy;             // maxactdelta < maxeasyactivitydelta  (:7086)
+   bool   force;            // single-variable row                 (:7029)
+   bool   rhsfin, lhsfin;
+};
+
+// row gates of tightenBounds (cons_linear.c:7021-7086); returns true if the row's nonzeros must be visited.
+// *cutoff is set when the easy path's side test proves infeasibility (:5450, :5506).
+__device__ __forceinline__ bool rowGates(const Num& n, RowInfo& ri, int len, bool& cutoff)
+{
+   const RowAcc& a = ri.acc;
+   ri.force = (len == 1);
+   ri.rhsfin = !isInf(n, ri.rhs);
+   ri.lhsfin = !isInf(n, -ri.lhs);
+   // canTightenBounds (:5214-5238)
+   if( cntMinSum(a.cnt) > 1u && cntMaxSum(a.cnt) > 1u )
+      return false;
+   // all variables fixed (:7057)
+   if( fabs(a.maxdelta) <= n.feastol )
+      return false;
+   if( !isInf(n, a.maxdelta) )
+   {
+      double minact, maxact;
+      bool t1, t2, s1, s2;
+      getMinActivity(n, a.minhi, a.minlo, cntGet(a.cnt, MINPOSINF), cntGet(a.cnt, MINNEGINF), cntGet(a.cnt, MINPOSHUGE),
+         cntGet(a.cnt, MINNEGHUGE), 0.0, false, minact, t1, s1);
+      getMaxActivity(n, a.maxhi, a.maxlo, cntGet(a.cnt, MAXPOSINF), cntGet(a.cnt, MAXNEGINF), cntGet(a.cnt, MAXPOSHUGE),
+         cntGet(a.cnt, MAXNEGHUGE), 0.0, false, maxact, t2, s2);
+      double slack = (!ri.rhsfin || s1) ? n.inf : (ri.rhs - minact);
+      double surplus = (!ri.lhsfin || s2) ? n.inf : (maxact - ri.lhs);
+      if( isLE(n, a.maxdelta, fmin(slack, surplus)) )
+         return false;
+   }
+   ri.easy = isLT(n, a.maxdelta, n.maxeasy);
+   if( ri.easy )
+   {
+      ri.minact = a.minhi + a.minlo;
+      ri.maxact = a.maxhi + a.maxlo;
+      ri.slackR = 0.0;
+      ri.slackL = 0.0;
+      if( ri.rhsfin )
+      {
+         if( isFeasLT(n, ri.rhs, ri.minact) )
+            cutoff = true;
+         double s = ri.rhs - ri.minact;
+         ri.slackR = (s > n.eps) ? s : 0.0;
+      }
+      if( ri.lhsfin )
+      {
+         if( isFeasLT(n, ri.maxact, ri.lhs) )
+            cutoff = true;
+         double s = ri.maxact - ri.lhs;
+         ri.slackL = (s > n.eps) ? s : 0.0;
+      }
+   }
+   return true;
+}
+
+// row verdict of propagateCons (cons_linear.c:7715-7742), goodrelax = TRUE
+__device__ __forceinline__ bool rowInfeasible(const Num& n, const RowAcc& a, double lhs, double rhs)
+{
+   double minact, maxact;
+   bool t1, t2, s1, s2;
+   getMinActivity(n, a.minhi, a.minlo, cntGet(a.cnt, MINPOSINF), cntGet(a.cnt, MINNEGINF), cntGet(a.cnt, MINPOSHUGE),
+      cntGet(a.cnt, MINNEGHUGE), 0.0, true, minact, t1, s1);
+   getMaxActivity(n, a.maxhi, a.maxlo, cntGet(a.cnt, MAXPOSINF), cntGet(a.cnt, MAXNEGINF), cntGet(a.cnt, MAXPOSHUGE),
+      cntGet(a.cnt, MAXNEGHUGE), 0.0, true, maxact, t2, s2);
+   return isFeasGT(n, minact, rhs) || isFeasLT(n, maxact, lhs);
+}
+
+// ---- commit filter: SCIPinferVarUbCons/LbCons (scip_var.c:7071-7157 / 6965-7051) followed by the last drop of
+// ---- SCIPnodeAddBoundinfer (tree.c:2020-2059), judged against the round-start bounds [l,u]; a surviving value
+// ---- is merged with atomicMin/atomicMax on its int64 key
+struct Sink
+{
+   long long*     nlb;       // candidate lower bounds (keys)
+   long long*     nub;       // candidate upper bounds (keys)
+   unsigned char* changed;   // per-column "a key moved this round" flag
+};
+
+__device__ __forceinline__ void inferUb(const Num& n, const Sink& s, int j, bool integral, double newub, double l,
+   double u, bool force, bool& cutoff)
+{
+   newub = adjustedUb(n, integral, newub);
+   if( isInf(n, -newub) || isFeasLT(n, newub, l) )
+   {
+      cutoff = true;
+      return;
+   }
+   newub = fmax(newub, l);
+   if( force ? isGE(n, newub, u) : !isUbBetter(n, newub, l, u) )
+      return;
+   if( !isLT(n, newub, u) )
+      return;
+   const long long key = d2key(newub);
+   if( atomicMin(&s.nub[j], key) > key )
+      s.changed[j] = 1;
+}
+__device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool integral, double newlb, double l,
+   double u, bool force, bool& cutoff)
+{
+   newlb = adjustedLb(n, integral, newlb);
+   if( isInf(n, newlb) || isFeasGT(n, newlb, u) )
+   {
+      cutoff = true;
+      return;
+   }
+   newlb = fmin(newlb, u);
+   if( force ? isLE(n, newlb, l) : !isLbBetter(n, newlb, l, u) )
+      return;
+   if( !isGT(n, newlb, l) )
+      return;
+   const long long key = d2key(newlb);
+   if( atomicMax(&s.nlb[j], key) < key )
+      s.changed[j] = 1;
+}
+
+// tightenVarUb / tightenVarLb: cons_linear.c:5242-5307 / 5311-5376
+__device__ __forceinline__ void tightenVarUb(const Num& n, const Sink& s, int j, bool integral, double newub, double l,
+   double u, bool force, bool& cutoff)
+{
+   newub = adjustedUb(n, integral, newub);
+   if( force || isUbBetter(n, newub, l, u) )
+      inferUb(n, s, j, integral, newub, l, u, force, cutoff);
+}
+__device__ __forceinline__ void tightenVarLb(const Num& n, const Sink& s, int j, bool integral, double newlb, double l,
+   double u, bool force, bool& cutoff)
+{
+   newlb = adjustedLb(n, integral, newlb);
+   if( force || isLbBetter(n, newlb, l, u) )
+      inferLb(n, s, j, integral, newlb, l, u, force, cutoff);
+}
+
+// candidate bounds of one nonzero: tightenVarBoundsEasy (cons_linear.c:5380-5653) or tightenVarBounds (:6700-6974)
+__device__ __forceinline__ void candidates(const Num& n, const Sink& s, const RowInfo& ri, double a, int j, bool integral,
+   double l, double u, bool& cutoff)
+{
+   const bool pos = a > 0.0;
+   if( ri.easy )
+   {
+      const double alpha = pos ? a * (u - l) : a * (l - u);
+      if( ri.rhsfin && ((alpha - ri.slackR > n.sumeps) || (ri.force && alpha - ri.slackR > n.eps)) )
+      {
+         if( pos )
+            tightenVarUb(n, s, j, integral, l + (ri.slackR / a), l, u, ri.force, cutoff);
+         else
+            tightenVarLb(n, s, j, integral, u + ri.slackR / a, l, u, ri.force, cutoff);
+      }
+      if( ri.lhsfin && ((alpha - ri.slackL > n.sumeps) || (ri.force && alpha - ri.slackL > n.eps)) )
+      {
+         if( pos )
+            tightenVarLb(n, s, j, integral, u - (ri.slackL / a), l, u, ri.force, cutoff);
+         else
+            tightenVarUb(n, s, j, integral, l - (ri.slackL / a), l, u, ri.force, cutoff);
+      }
+      return;
+   }
+
+   // general case via residual activities: consdataGetActivityResiduals (cons_linear.c:2661-2806), goodrelax = FALSE
+   const RowAcc& r = ri.acc;
+   const double minactbound = pos ? l : -u;
+   const double maxactbound = pos ? u : -l;
+   const double absval = fabs(a);
+   double minres, maxres;
+   bool mintight, maxtight, minsettoinf, maxsettoinf;
+   {
+      unsigned c = r.cnt;
+      double delta = 0.0;
+      if( isInf(n, minactbound) ) c = cntDec(c, MINPOSINF);
+      else if( isInf(n, -minactbound) ) c = cntDec(c, MINNEGINF);
+      else if( isHuge(n, minactbound * absval) ) c = cntDec(c, MINPOSHUGE);
+      else if( isHuge(n, -minactbound * absval) ) c = cntDec(c, MINNEGHUGE);
+      else delta = absval * minactbound;
+      getMinActivity(n, r.minhi, r.minlo, cntGet(c, MINPOSINF), cntGet(c, MINNEGINF), cntGet(c, MINPOSHUGE),
+         cntGet(c, MINNEGHUGE), delta, false, minres, mintight, minsettoinf);
+   }
+   {
+      unsigned c = r.cnt;
+      double delta = 0.0;
+      if( isInf(n, -maxactbound) ) c = cntDec(c, MAXNEGINF);
+      else if( isInf(n, maxactbound) ) c = cntDec(c, MAXPOSINF);
+      else if( isHuge(n, absval * maxactbound) ) c = cntDec(c, MAXPOSHUGE);
+      else if( isHuge(n, -absval * maxactbound) ) c = cntDec(c, MAXNEGHUGE);
+      else delta = absval * maxactbound;
+      getMaxActivity(n, r.maxhi, r.maxlo, cntGet(c, MAXPOSINF), cntGet(c, MAXNEGINF), cntGet(c, MAXPOSHUGE),
+         cntGet(c, MAXNEGHUGE), delta, false, maxres, maxtight, maxsettoinf);
+   }
+   if( !minsettoinf && ri.rhsfin && mintight && (isLT(n, fabs(ri.rhs), 1.0) || !isEQ(n, minres / ri.rhs, 1.0)) )
+   {
+      const double nb = (ri.rhs - minres) / a;
+      if( pos )
+      {
+         if( !isInf(n, nb) && ((ri.force && isLT(n, nb, u)) || (integral && isFeasLT(n, nb, u)) || isUbBetter(n, nb, l, u)) )
+            inferUb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+      }
+      else
+      {
+         if( !isInf(n, -nb) && ((ri.force && isGT(n, nb, l)) || (integral && isFeasGT(n, nb, l)) || isLbBetter(n, nb, l, u)) )
+            inferLb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+      }
+   }
+   if( !maxsettoinf && ri.lhsfin && maxtight && (isLT(n, fabs(ri.lhs), 1.0) || !isEQ(n, maxres / ri.lhs, 1.0)) )
+   {
+      const double nb = (ri.lhs - maxres) / a;
+      if( pos )
+      {
+         if( !isInf(n, -nb) && ((ri.force && isGT(n, nb, l)) || (integral && isFeasGT(n, nb, l)) || isLbBetter(n, nb, l, u)) )
+            inferLb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+      }
+      else
+      {
+         if( !isInf(n, nb) && ((ri.force && isLT(n, nb, u)) || (integral && isFeasLT(n, nb, u)) || isUbBetter(n, nb, l, u)) )
+            inferUb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+      }
+   }
+}
+
+} // namespace gpulin
