@@ -128,24 +128,51 @@ int gpulin_set_change_log(gpulin_t* h, int64_t capacity);
  *  were produced (if *n > capacity the log overflowed and only the first `capacity` are valid) */
 int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n);
 
-/** device time [ms] of each round of the last gpulin_propagate call (up to maxn), *n = rounds recorded */
-int gpulin_get_round_times(gpulin_t* h, double* ms, int32_t maxn, int32_t* n);
+/** per-round statistics of the last gpulin_propagate call (up to maxn rounds; any output array may be NULL):
+ *  device time [ms] (%globaltimer stamps taken by the kernels), nonzeros swept, bound changes accepted */
+int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n);
 
-/** storage statistics: nonzeros incl. padding in the thread-per-row bin, rows per bin, bytes on device */
+/** storage statistics: [0] nnz, [1] stored nonzeros incl. SELL padding, [2..4] rows in the thread-per-row /
+ *  warp-per-row / block-per-row bins, [5] bytes on device, [6] row classes, [7] sweep blocks, [8] longest row,
+ *  [9] shared-memory staging capacity of the long-row kernel [nonzeros] */
 int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 
-/* ---- multi-GPU (rows partitioned over ranks, bounds replicated) ------------------------
- * One round = gpulin_round_sweep on every rank, a MAX/MIN all-reduce of the two int64 key vectors
- * returned by gpulin_exchange_buffers (NCCL, done by the host language), then gpulin_round_apply. */
+/** algorithmic bytes of one full round: nnz*12 + nrows*20 + ncols*17 */
+int gpulin_algorithmic_bytes(gpulin_t* h, int64_t* bytes);
 
-/** device pointers to the order-preserving int64 keys of the candidate lower / upper bounds (ncols each) */
-int gpulin_exchange_buffers(gpulin_t* h, int64_t** d_lbkeys, int64_t** d_ubkeys, int32_t** d_flags);
+/** all following work of this handle is enqueued on the given cudaStream_t (default: a private stream) */
+int gpulin_set_stream(gpulin_t* h, void* stream);
 
-/** one sweep over the rows marked for propagation; candidates are merged into the key vectors */
+/** blocks until all work enqueued by this handle is done */
+int gpulin_sync(gpulin_t* h);
+
+/* ---- single rounds: multi-GPU (rows partitioned over ranks, bounds replicated) and profiling ----
+ * One sharded round = gpulin_round_sweep on every rank, ONE ncclMin all-reduce (int64) over the buffer returned by
+ * gpulin_exchange_buffer (done by the host language on the handle's stream), then gpulin_round_apply(dense=1).
+ * All calls are asynchronous on the handle's stream except gpulin_round_apply with non-NULL outputs. */
+
+/** device pointer to the candidate keys: 2*ncols order-preserving int64 keys, [2j] = ~key(lb_j), [2j+1] = key(ub_j)
+ *  (both tighten by MIN), followed by 2 spare keys that carry the cutoff verdict (negative = cutoff) */
+int gpulin_exchange_buffer(gpulin_t* h, int64_t** d_keys, int64_t* nkeys);
+
+/** copies the key vector to / from host memory (nkeys int64 each) -- for hosts that merge the ranks' candidates
+ *  without device-side collectives (tests; an MPI based host) */
+int gpulin_get_keys(gpulin_t* h, int64_t* keys);
+int gpulin_set_keys(gpulin_t* h, const int64_t* keys);
+
+/** marks every row for propagation */
+int gpulin_mark_all(gpulin_t* h);
+
+/** resets round counter, verdict and statistics (what gpulin_propagate does at its start) */
+int gpulin_round_begin(gpulin_t* h);
+
+/** one sweep over the rows marked for propagation; candidates are merged into the key vector */
 int gpulin_round_sweep(gpulin_t* h);
 
-/** accepts the (all-reduced) key vectors as the new bounds; *nchanges = changed bounds, *cutoff = verdict */
-int gpulin_round_apply(gpulin_t* h, int64_t* nchanges, int32_t* cutoff);
+/** accepts the key vector as the new bounds and marks the rows of changed columns.  dense = 0: only columns
+ *  flagged by this handle's own sweep are examined; dense = 1: all columns (keys may have been moved by other
+ *  ranks).  If nchanges or cutoff is non-NULL the call synchronises and returns the round's change count / verdict */
+int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int32_t* cutoff);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,887 @@
+// gpulin.cu -- host side of libgpulin.so: the C ABI of include/gpulin.h over the kernels of gpulin_kernels.cuh.
+//
+// Builds the device copy of the linear rows (row-binned SELL-32 + CSR, and the column -> row map), keeps the bound
+// vectors resident, and drives the propagation rounds either from a CUDA graph with a device-side WHILE node
+// (default: no host round trip per round) or from the host (GPULIN_LOOP=host; used for profiling single rounds).
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include "../../include/gpulin.h"
+#include "gpulin_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+using namespace gpl;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(g_err, sizeof(g_err), fmt, ap);
+   va_end(ap);
+   return code;
+}
+
+#define CU(call)                                                                                                  \
+   do                                                                                                             \
+   {                                                                                                              \
+      cudaError_t e_ = (call);                                                                                    \
+      if( e_ != cudaSuccess )                                                                                     \
+         return fail(GPULIN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+   } while( 0 )
+
+struct gpulin
+{
+   int         device = 0;
+   int64_t     nrows = 0, ncols = 0, nnz = 0;
+   int64_t     nstored = 0;      // nonzeros incl. SELL padding
+   int         nshort = 0, nmedium = 0, nlong = 0;
+   int         maxlen = 0;
+   DevProblem  p{};
+   ClassTable  ct{};
+   int         nsweepblocks = 0;
+   int         nlongblocks = 0;
+   int         longsmemcap = 0;  // doubles of dynamic shared memory of the long-row kernel
+   int         napplyblocks = 0;
+   int         nsm = 148;
+   std::vector<int> perm;        // permuted row -> caller's row
+   // device allocations
+   void*       d_all[24] = {nullptr};
+   int         nalloc = 0;
+   size_t      devbytes = 0;
+   double*     d_tmplb = nullptr;   // staging for set/get_bounds
+   double*     d_tmpub = nullptr;
+   ChangeRec*  d_log = nullptr;
+   int64_t     logcap = 0;
+   Ctrl*       h_ctrl = nullptr;    // pinned mirror
+   int*        h_params = nullptr;  // pinned {maxrounds, logcap}
+   int*        d_updidx = nullptr;  // staging of gpulin_update_bounds
+   double*     d_updlb = nullptr;
+   double*     d_updub = nullptr;
+   int64_t     updcap = 0;
+   cudaStream_t stream = nullptr;
+   bool        ownstream = true;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   cudaGraph_t graph = nullptr;
+   cudaGraphExec_t gexec = nullptr;
+   cudaGraphConditionalHandle handle = 0;
+   bool        hostloop = false;
+   bool        havebounds = false;
+   // results of the last propagate call
+   gpulin_result last{};
+   int         lastrounds = 0;
+};
+
+template <typename T>
+static int devAlloc(gpulin* h, T** out, size_t count)
+{
+   void* ptr = nullptr;
+   size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+   cudaError_t e = cudaMalloc(&ptr, bytes);
+   if( e != cudaSuccess )
+      return fail(GPULIN_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+   h->d_all[h->nalloc++] = ptr;
+   h->devbytes += bytes;
+   *out = (T*)ptr;
+   return GPULIN_OK;
+}
+
+#define OK(call)                 \
+   do                            \
+   {                             \
+      int rc_ = (call);          \
+      if( rc_ != GPULIN_OK )     \
+         return rc_;             \
+   } while( 0 )
+
+extern "C" void gpulin_default_numerics(gpulin_numerics* num)
+{
+   num->infinity = 1e20;
+   num->epsilon = 1e-9;
+   num->sumepsilon = 1e-6;
+   num->feastol = 1e-6;
+   num->boundstreps = 0.05;
+   num->hugeval = 1e15;
+   num->maxeasyactivitydelta = 1e6;
+}
+
+extern "C" const char* gpulin_last_error(void)
+{
+   return g_err;
+}
+
+extern "C" int gpulin_device_count(void)
+{
+   int n = 0;
+   cudaError_t e = cudaGetDeviceCount(&n);
+   if( e != cudaSuccess )
+      return fail(GPULIN_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+   return n;
+}
+
+static int classOfLen(int len)
+{
+   if( len <= 4 ) return CK_T4;
+   if( len <= 8 ) return CK_T8;
+   if( len <= 16 ) return CK_T16;
+   if( len <= 32 ) return CK_T32;
+   if( len <= 64 ) return CK_W2;
+   if( len <= 128 ) return CK_W4;
+   if( len <= 256 ) return CK_W8;
+   if( len <= 512 ) return CK_W16;
+   return CK_W32;
+}
+
+static void destroyGraph(gpulin* h)
+{
+   if( h->gexec != nullptr )
+      cudaGraphExecDestroy(h->gexec);
+   if( h->graph != nullptr )
+      cudaGraphDestroy(h->graph);
+   h->gexec = nullptr;
+   h->graph = nullptr;
+}
+
+// one propagation round on h->stream
+template <bool DENSE, bool GRAPH>
+static void launchRoundKernels(gpulin* h, bool sweep, bool apply)
+{
+   if( sweep )
+   {
+      if( h->nsweepblocks > 0 )
+         sweep_rows_kernel<<<h->nsweepblocks, SWEEP_THREADS, 0, h->stream>>>(h->p, h->ct);
+      if( h->nlong > 0 )
+         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, (size_t)h->longsmemcap * sizeof(double), h->stream>>>(
+            h->p, h->nshort + h->nmedium, h->nlong, h->longsmemcap);
+   }
+   if( apply )
+      apply_kernel<DENSE, GRAPH><<<h->napplyblocks, 256, 0, h->stream>>>(h->p, h->handle);
+}
+
+// graph:  begin_kernel -> WHILE(cont) { sweep kernels; apply kernel (sets cont) }
+static int buildGraph(gpulin* h)
+{
+   destroyGraph(h);
+   CU(cudaGraphCreate(&h->graph, 0));
+   CU(cudaGraphConditionalHandleCreate(&h->handle, h->graph, 1, cudaGraphCondAssignDefault));
+
+   cudaGraphNode_t beginNode;
+   {
+      cudaKernelNodeParams kp;
+      memset(&kp, 0, sizeof(kp));
+      void* args[1] = {(void*)&h->p.ctrl};
+      kp.func = (void*)begin_kernel;
+      kp.gridDim = dim3(1);
+      kp.blockDim = dim3(1);
+      kp.kernelParams = args;
+      CU(cudaGraphAddKernelNode(&beginNode, h->graph, nullptr, 0, &kp));
+   }
+   cudaGraphNodeParams cp = {};
+   cp.type = cudaGraphNodeTypeConditional;
+   cp.conditional.handle = h->handle;
+   cp.conditional.type = cudaGraphCondTypeWhile;
+   cp.conditional.size = 1;
+   cudaGraphNode_t whileNode;
+   CU(cudaGraphAddNode(&whileNode, h->graph, &beginNode, 1, &cp));
+   cudaGraph_t body = cp.conditional.phGraph_out[0];
+
+   CU(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+   launchRoundKernels<false, true>(h, true, true);
+   cudaGraph_t captured = nullptr;
+   CU(cudaStreamEndCapture(h->stream, &captured));
+   CU(cudaGraphInstantiate(&h->gexec, h->graph, 0));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* rowptr,
+   const int32_t* colidx, const double* vals, const double* lhs, const double* rhs, const uint8_t* vartype,
+   const gpulin_numerics* num, gpulin_t** out)
+{
+   if( out == nullptr )
+      return fail(GPULIN_ERR_ARG, "out is NULL");
+   *out = nullptr;
+   if( nrows < 0 || ncols < 0 || nnz < 0 || (nrows > 0 && rowptr == nullptr) || (nnz > 0 && (colidx == nullptr || vals == nullptr))
+      || (nrows > 0 && (lhs == nullptr || rhs == nullptr)) || (ncols > 0 && vartype == nullptr) )
+      return fail(GPULIN_ERR_ARG, "invalid problem arrays");
+   if( nrows >= (1LL << 31) - 64 || ncols >= (1LL << 31) - 64 )
+      return fail(GPULIN_ERR_ARG, "more than 2^31 rows or columns are not supported");
+   if( nrows > 0 && (rowptr[0] != 0 || rowptr[nrows] != nnz) )
+      return fail(GPULIN_ERR_ARG, "rowptr does not span [0,nnz]");
+   for( int64_t r = 0; r < nrows; ++r )
+   {
+      if( rowptr[r + 1] < rowptr[r] )
+         return fail(GPULIN_ERR_ARG, "rowptr is not monotone at row %lld", (long long)r);
+      if( rowptr[r + 1] - rowptr[r] >= (1LL << 31) )
+         return fail(GPULIN_ERR_ARG, "row %lld is too long", (long long)r);
+   }
+   for( int64_t k = 0; k < nnz; ++k )
+   {
+      if( colidx[k] < 0 || colidx[k] >= ncols )
+         return fail(GPULIN_ERR_ARG, "column index %d out of range at position %lld", colidx[k], (long long)k);
+      if( vals[k] == 0.0 || vals[k] != vals[k] )
+         return fail(GPULIN_ERR_ARG, "zero or NaN coefficient at position %lld (cons_linear.c:5422)", (long long)k);
+   }
+
+   {
+      int ndev = 0;
+      cudaError_t e = cudaGetDeviceCount(&ndev);
+      if( e != cudaSuccess || ndev <= 0 )
+         return fail(GPULIN_ERR_CUDA, "no CUDA device available (%s); libgpulin has no CPU fallback",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+      if( device < 0 || device >= ndev )
+         return fail(GPULIN_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+   }
+   CU(cudaSetDevice(device));
+
+   gpulin* h = new gpulin();
+   h->device = device;
+   h->nrows = nrows;
+   h->ncols = ncols;
+   h->nnz = nnz;
+   {
+      int nsm = 0;
+      if( cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && nsm > 0 )
+         h->nsm = nsm;
+   }
+   const char* loopenv = getenv("GPULIN_LOOP");
+   h->hostloop = (loopenv != nullptr && strcmp(loopenv, "host") == 0);
+
+   // ---- bin the rows: stable sort by (class group, length) ------------------------------------------------
+   std::vector<int> len((size_t)nrows);
+   for( int64_t r = 0; r < nrows; ++r )
+   {
+      len[(size_t)r] = (int)(rowptr[r + 1] - rowptr[r]);
+      h->maxlen = std::max(h->maxlen, len[(size_t)r]);
+   }
+   std::vector<int>& perm = h->perm;
+   perm.resize((size_t)nrows);
+   std::iota(perm.begin(), perm.end(), 0);
+   auto group = [&](int r) { return len[(size_t)r] <= SHORT_MAXLEN ? 0 : (len[(size_t)r] <= MEDIUM_MAXLEN ? 1 : 2); };
+   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+      const int ga = group(a), gb = group(b);
+      if( ga != gb )
+         return ga < gb;
+      if( ga == 0 )
+         return len[(size_t)a] < len[(size_t)b];   // short: ascending, minimal SELL padding
+      return len[(size_t)a] > len[(size_t)b];      // medium / long: heaviest first
+   });
+   for( int64_t i = 0; i < nrows; ++i )
+   {
+      const int g = group(perm[(size_t)i]);
+      if( g == 0 ) ++h->nshort;
+      else if( g == 1 ) ++h->nmedium;
+      else ++h->nlong;
+   }
+
+   // ---- SELL-32 slices of the short rows, CSR of the rest ------------------------------------------------------
+   const int nslices = (h->nshort + 31) / 32;
+   std::vector<long long> sell_off((size_t)nslices + 1, 0);
+   std::vector<long long> rowbeg((size_t)nrows + 1, 0);
+   std::vector<int> plen((size_t)nrows);
+   for( int64_t i = 0; i < nrows; ++i )
+      plen[(size_t)i] = len[(size_t)perm[(size_t)i]];
+   for( int s = 0; s < nslices; ++s )
+   {
+      const int last = std::min(h->nshort, 32 * s + 32) - 1;
+      sell_off[(size_t)s + 1] = sell_off[(size_t)s] + 32LL * plen[(size_t)last];
+   }
+   long long off = sell_off[(size_t)nslices];
+   for( int64_t i = h->nshort; i < nrows; ++i )
+   {
+      off = (off + 1) & ~1LL;     // even start: 16-byte aligned coefficients
+      rowbeg[(size_t)i] = off;
+      off += plen[(size_t)i];
+   }
+   h->nstored = off;
+   if( h->nstored >= (1LL << 40) )
+   {
+      delete h;
+      return fail(GPULIN_ERR_ARG, "matrix too large");
+   }
+   std::vector<double> pvals((size_t)h->nstored + 2, 0.0);
+   std::vector<int> pcols((size_t)h->nstored + 2, 0);
+   for( int64_t i = 0; i < nrows; ++i )
+   {
+      const int64_t r = perm[(size_t)i];
+      const int64_t b = rowptr[r];
+      if( i < h->nshort )
+      {
+         const long long base = sell_off[(size_t)(i >> 5)] + (i & 31);
+         for( int k = 0; k < plen[(size_t)i]; ++k )
+         {
+            const int j = colidx[b + k];
+            pvals[(size_t)(base + 32LL * k)] = vals[b + k];
+            pcols[(size_t)(base + 32LL * k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
+         }
+      }
+      else
+      {
+         const long long base = rowbeg[(size_t)i];
+         for( int k = 0; k < plen[(size_t)i]; ++k )
+         {
+            const int j = colidx[b + k];
+            pvals[(size_t)(base + k)] = vals[b + k];
+            pcols[(size_t)(base + k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
+         }
+      }
+   }
+   std::vector<double2> sides((size_t)nrows + 1);
+   for( int64_t i = 0; i < nrows; ++i )
+      sides[(size_t)i] = make_double2(lhs[perm[(size_t)i]], rhs[perm[(size_t)i]]);
+
+   // ---- column -> (permuted) rows --------------------------------------------------------------------------------
+   std::vector<long long> colbeg((size_t)ncols + 2, 0);
+   for( int64_t k = 0; k < nnz; ++k )
+      ++colbeg[(size_t)colidx[k] + 1];
+   for( int64_t j = 0; j < ncols; ++j )
+      colbeg[(size_t)j + 1] += colbeg[(size_t)j];
+   std::vector<int> colrows((size_t)nnz + 1);
+   {
+      std::vector<long long> fill(colbeg.begin(), colbeg.begin() + (size_t)ncols + 1);
+      for( int64_t i = 0; i < nrows; ++i )
+      {
+         const int64_t r = perm[(size_t)i];
+         for( int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k )
+            colrows[(size_t)fill[(size_t)colidx[k]]++] = (int)i;
+      }
+   }
+
+   // ---- class table of the fused short/medium sweep kernel -------------------------------------------------------
+   ClassTable& ct = h->ct;
+   memset(&ct, 0, sizeof(ct));
+   {
+      // short rows: a class is a run of whole slices whose width falls into the same template instance
+      int i = 0;
+      int blocks = 0;
+      while( i < h->nshort )
+      {
+         const int s0 = i >> 5;
+         const int lastOfSlice = std::min(h->nshort, 32 * s0 + 32) - 1;
+         const int kind = classOfLen(plen[(size_t)lastOfSlice]);
+         int e = lastOfSlice + 1;
+         while( e < h->nshort )
+         {
+            const int l2 = std::min(h->nshort, e + 32) - 1;
+            if( classOfLen(plen[(size_t)l2]) != kind )
+               break;
+            e = l2 + 1;
+         }
+         ct.kind[ct.n] = kind;
+         ct.row0[ct.n] = i;
+         ct.nrows[ct.n] = e - i;
+         ct.block0[ct.n] = blocks;
+         blocks += (e - i + SWEEP_THREADS - 1) / SWEEP_THREADS;
+         ++ct.n;
+         i = e;
+      }
+      // medium rows: descending length
+      i = h->nshort;
+      const int mend = h->nshort + h->nmedium;
+      while( i < mend )
+      {
+         const int kind = classOfLen(plen[(size_t)i]);
+         int e = i + 1;
+         while( e < mend && classOfLen(plen[(size_t)e]) == kind )
+            ++e;
+         ct.kind[ct.n] = kind;
+         ct.row0[ct.n] = i;
+         ct.nrows[ct.n] = e - i;
+         ct.block0[ct.n] = blocks;
+         blocks += (e - i + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32);
+         ++ct.n;
+         i = e;
+      }
+      ct.block0[ct.n] = blocks;
+      h->nsweepblocks = blocks;
+   }
+
+   // ---- upload ---------------------------------------------------------------------------------------------------
+   DevProblem& p = h->p;
+   long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
+   unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned char* d_colflag; long long* d_colbeg; int* d_colrows;
+   Ctrl* d_ctrl;
+   int rc = GPULIN_OK;
+#define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
+#define TRYCU(x) do { if( rc == GPULIN_OK ) { cudaError_t e_ = (x); if( e_ != cudaSuccess ) rc = fail(GPULIN_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while( 0 )
+   TRY(devAlloc(h, &d_sell_off, (size_t)nslices + 1));
+   TRY(devAlloc(h, &d_rowlen, (size_t)nrows + 1));
+   TRY(devAlloc(h, &d_rowbeg, (size_t)nrows + 1));
+   TRY(devAlloc(h, &d_vals, (size_t)h->nstored + 2));
+   TRY(devAlloc(h, &d_cols, (size_t)h->nstored + 2));
+   TRY(devAlloc(h, &d_sides, (size_t)nrows + 1));
+   TRY(devAlloc(h, &d_dirty, (size_t)nrows + 64));
+   TRY(devAlloc(h, &d_bnd, (size_t)ncols + 1));
+   TRY(devAlloc(h, &d_cand, 2 * (size_t)ncols + 2));
+   TRY(devAlloc(h, &d_colflag, (size_t)ncols + 64));
+   TRY(devAlloc(h, &d_colbeg, (size_t)ncols + 2));
+   TRY(devAlloc(h, &d_colrows, (size_t)nnz + 1));
+   TRY(devAlloc(h, &d_ctrl, 1));
+   TRY(devAlloc(h, &h->d_tmplb, (size_t)ncols + 1));
+   TRY(devAlloc(h, &h->d_tmpub, (size_t)ncols + 1));
+   TRYCU(cudaMemcpy(d_sell_off, sell_off.data(), sizeof(long long) * ((size_t)nslices + 1), cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_rowlen, plen.data(), sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_rowbeg, rowbeg.data(), sizeof(long long) * ((size_t)nrows + 1), cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_vals, pvals.data(), sizeof(double) * (size_t)h->nstored, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_cols, pcols.data(), sizeof(int) * (size_t)h->nstored, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_sides, sides.data(), sizeof(double2) * (size_t)nrows, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_colbeg, colbeg.data(), sizeof(long long) * ((size_t)ncols + 1), cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_colrows, colrows.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemset(d_dirty, 0, (size_t)nrows + 64));
+   TRYCU(cudaMemset(d_colflag, 0, (size_t)ncols + 64));
+   TRYCU(cudaMemset(d_ctrl, 0, sizeof(Ctrl)));
+   TRYCU(cudaMemset(d_cand, 0, sizeof(long long) * (2 * (size_t)ncols + 2)));
+   TRYCU(cudaMallocHost((void**)&h->h_ctrl, sizeof(Ctrl)));
+   TRYCU(cudaMallocHost((void**)&h->h_params, 4 * sizeof(int)));
+   if( rc == GPULIN_OK )
+      memset(h->h_ctrl, 0, sizeof(Ctrl));
+   TRYCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+   TRYCU(cudaEventCreate(&h->ev0));
+   TRYCU(cudaEventCreate(&h->ev1));
+   if( rc != GPULIN_OK )
+   {
+      gpulin_destroy(h);
+      return rc;
+   }
+
+   p.nrows = (int)nrows;
+   p.ncols = (int)ncols;
+   p.sell_off = d_sell_off;
+   p.rowlen = d_rowlen;
+   p.rowbeg = d_rowbeg;
+   p.vals = d_vals;
+   p.cols = d_cols;
+   p.sides = d_sides;
+   p.dirty = d_dirty;
+   p.bnd = d_bnd;
+   p.cand = d_cand;
+   p.colflag = d_colflag;
+   p.colbeg = d_colbeg;
+   p.colrows = d_colrows;
+   p.ctrl = d_ctrl;
+   p.log = nullptr;
+   gpulin_numerics defnum;
+   gpulin_default_numerics(&defnum);
+   if( num == nullptr )
+      num = &defnum;
+   p.num.inf = num->infinity;
+   p.num.eps = num->epsilon;
+   p.num.sumeps = num->sumepsilon;
+   p.num.feastol = num->feastol;
+   p.num.bstreps = num->boundstreps;
+   p.num.huge = num->hugeval;
+   p.num.maxeasy = num->maxeasyactivitydelta;
+
+   // ---- launch geometry ------------------------------------------------------------------------------------------
+   h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols + 255) / 256, (int64_t)h->nsm * 8));
+   if( h->nlong > 0 )
+   {
+      int maxsmem = 0;
+      cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+      // keep two blocks per SM resident: half of the opt-in limit minus the static part
+      int cap = (maxsmem / 2 - 4096) / (int)sizeof(double);
+      cap = std::max(cap, 0);
+      // longest row is first in the long bin
+      const int longest = plen[(size_t)(h->nshort + h->nmedium)];
+      h->longsmemcap = std::min(cap, longest);
+      if( cudaFuncSetAttribute(sweep_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int)(h->longsmemcap * sizeof(double))) != cudaSuccess )
+      {
+         cudaGetLastError();
+         h->longsmemcap = std::min(h->longsmemcap, (48 * 1024 - 4096) / (int)sizeof(double));
+      }
+      h->nlongblocks = std::min(h->nlong, h->nsm * 2);
+   }
+
+   if( !h->hostloop )
+   {
+      rc = buildGraph(h);
+      if( rc != GPULIN_OK )
+      {
+         gpulin_destroy(h);
+         return rc;
+      }
+   }
+   *out = h;
+   return GPULIN_OK;
+}
+
+extern "C" void gpulin_destroy(gpulin_t* h)
+{
+   if( h == nullptr )
+      return;
+   cudaSetDevice(h->device);
+   if( h->stream != nullptr )
+      cudaStreamSynchronize(h->stream);
+   destroyGraph(h);
+   for( int i = 0; i < h->nalloc; ++i )
+      cudaFree(h->d_all[i]);
+   if( h->d_log != nullptr )
+      cudaFree(h->d_log);
+   if( h->h_ctrl != nullptr )
+      cudaFreeHost(h->h_ctrl);
+   if( h->h_params != nullptr )
+      cudaFreeHost(h->h_params);
+   cudaFree(h->d_updidx);
+   cudaFree(h->d_updlb);
+   cudaFree(h->d_updub);
+   if( h->ev0 != nullptr )
+      cudaEventDestroy(h->ev0);
+   if( h->ev1 != nullptr )
+      cudaEventDestroy(h->ev1);
+   if( h->stream != nullptr && h->ownstream )
+      cudaStreamDestroy(h->stream);
+   delete h;
+}
+
+static int gridFor(const gpulin* h, int64_t n)
+{
+   return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)h->nsm * 8));
+}
+
+extern "C" int gpulin_set_stream(gpulin_t* h, void* stream)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   CU(cudaSetDevice(h->device));
+   CU(cudaStreamSynchronize(h->stream));
+   if( h->ownstream && h->stream != nullptr )
+      cudaStreamDestroy(h->stream);
+   h->stream = (cudaStream_t)stream;
+   h->ownstream = false;
+   if( !h->hostloop )
+      OK(buildGraph(h));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_set_bounds_device(gpulin_t* h, const double* d_lb, const double* d_ub)
+{
+   if( h == nullptr || d_lb == nullptr || d_ub == nullptr )
+      return fail(GPULIN_ERR_ARG, "NULL argument");
+   CU(cudaSetDevice(h->device));
+   set_bounds_kernel<<<gridFor(h, std::max(h->ncols, h->nrows)), 256, 0, h->stream>>>(h->p, d_lb, d_ub);
+   CU(cudaGetLastError());
+   h->havebounds = true;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_set_bounds(gpulin_t* h, const double* lb, const double* ub)
+{
+   if( h == nullptr || lb == nullptr || ub == nullptr )
+      return fail(GPULIN_ERR_ARG, "NULL argument");
+   CU(cudaSetDevice(h->device));
+   CU(cudaMemcpyAsync(h->d_tmplb, lb, sizeof(double) * (size_t)h->ncols, cudaMemcpyHostToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->d_tmpub, ub, sizeof(double) * (size_t)h->ncols, cudaMemcpyHostToDevice, h->stream));
+   return gpulin_set_bounds_device(h, h->d_tmplb, h->d_tmpub);
+}
+
+extern "C" int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, const double* lb, const double* ub)
+{
+   if( h == nullptr || n < 0 || (n > 0 && (idx == nullptr || lb == nullptr || ub == nullptr)) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( !h->havebounds )
+      return fail(GPULIN_ERR_STATE, "gpulin_update_bounds before gpulin_set_bounds");
+   if( n == 0 )
+      return GPULIN_OK;
+   for( int64_t i = 0; i < n; ++i )
+   {
+      if( idx[i] < 0 || idx[i] >= h->ncols )
+         return fail(GPULIN_ERR_ARG, "column index %d out of range", idx[i]);
+   }
+   CU(cudaSetDevice(h->device));
+   if( n > h->updcap )
+   {
+      CU(cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_updidx);
+      cudaFree(h->d_updlb);
+      cudaFree(h->d_updub);
+      h->d_updidx = nullptr;
+      h->d_updlb = nullptr;
+      h->d_updub = nullptr;
+      h->updcap = 0;
+      const int64_t cap = std::max<int64_t>(n, 1024);
+      if( cudaMalloc((void**)&h->d_updidx, sizeof(int) * (size_t)cap) != cudaSuccess
+         || cudaMalloc((void**)&h->d_updlb, sizeof(double) * (size_t)cap) != cudaSuccess
+         || cudaMalloc((void**)&h->d_updub, sizeof(double) * (size_t)cap) != cudaSuccess )
+         return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the bound-update staging failed");
+      h->updcap = cap;
+   }
+   CU(cudaMemcpyAsync(h->d_updidx, idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->d_updlb, lb, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->d_updub, ub, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+   update_bounds_kernel<<<gridFor(h, n), 256, 0, h->stream>>>(h->p, n, h->d_updidx, h->d_updlb, h->d_updub);
+   CU(cudaGetLastError());
+   return GPULIN_OK;
+}
+
+static int fetchCtrl(gpulin* h)
+{
+   CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   if( !h->havebounds )
+      return fail(GPULIN_ERR_STATE, "gpulin_propagate before gpulin_set_bounds");
+   CU(cudaSetDevice(h->device));
+   h->h_params[0] = maxrounds;
+   h->h_params[1] = (int)h->logcap;
+   CU(cudaMemcpyAsync(&h->p.ctrl->maxrounds, h->h_params, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   CU(cudaEventRecord(h->ev0, h->stream));
+   if( !h->hostloop )
+   {
+      CU(cudaGraphLaunch(h->gexec, h->stream));
+   }
+   else
+   {
+      begin_kernel<<<1, 1, 0, h->stream>>>(h->p.ctrl);
+      for( ;; )
+      {
+         launchRoundKernels<false, false>(h, true, true);
+         CU(cudaGetLastError());
+         int cont = 0;
+         CU(cudaMemcpyAsync(&h->h_ctrl->cont, &h->p.ctrl->cont, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+         CU(cudaStreamSynchronize(h->stream));
+         cont = h->h_ctrl->cont;
+         if( !cont )
+            break;
+      }
+   }
+   CU(cudaEventRecord(h->ev1, h->stream));
+   OK(fetchCtrl(h));
+   CU(cudaEventSynchronize(h->ev1));
+   float ms = 0.0f;
+   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+   const Ctrl* c = h->h_ctrl;
+   h->last.status = c->status;
+   h->last.nrounds = c->round;
+   h->last.nchanges = (int64_t)c->total_nchg;
+   h->last.nnz_processed = (int64_t)c->total_nnz;
+   h->last.device_ms = (double)ms;
+   h->lastrounds = c->round;
+   if( res != nullptr )
+      *res = h->last;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_bounds_device(gpulin_t* h, double* d_lb, double* d_ub)
+{
+   if( h == nullptr || d_lb == nullptr || d_ub == nullptr )
+      return fail(GPULIN_ERR_ARG, "NULL argument");
+   CU(cudaSetDevice(h->device));
+   get_bounds_kernel<<<gridFor(h, h->ncols), 256, 0, h->stream>>>(h->p, d_lb, d_ub);
+   CU(cudaGetLastError());
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_bounds(gpulin_t* h, double* lb, double* ub)
+{
+   if( h == nullptr || lb == nullptr || ub == nullptr )
+      return fail(GPULIN_ERR_ARG, "NULL argument");
+   OK(gpulin_get_bounds_device(h, h->d_tmplb, h->d_tmpub));
+   CU(cudaMemcpyAsync(lb, h->d_tmplb, sizeof(double) * (size_t)h->ncols, cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaMemcpyAsync(ub, h->d_tmpub, sizeof(double) * (size_t)h->ncols, cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_set_change_log(gpulin_t* h, int64_t capacity)
+{
+   if( h == nullptr || capacity < 0 || capacity >= (1LL << 31) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   CU(cudaSetDevice(h->device));
+   CU(cudaStreamSynchronize(h->stream));
+   if( h->d_log != nullptr )
+   {
+      cudaFree(h->d_log);
+      h->d_log = nullptr;
+   }
+   h->logcap = 0;
+   h->p.log = nullptr;
+   if( capacity > 0 )
+   {
+      cudaError_t e = cudaMalloc((void**)&h->d_log, sizeof(ChangeRec) * (size_t)capacity);
+      if( e != cudaSuccess )
+         return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the change log failed: %s", cudaGetErrorString(e));
+      h->logcap = capacity;
+      h->p.log = h->d_log;
+   }
+   // kernel parameters are baked into the graph
+   if( !h->hostloop )
+      OK(buildGraph(h));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n)
+{
+   if( h == nullptr || n == nullptr || maxn < 0 || (maxn > 0 && out == nullptr) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   CU(cudaSetDevice(h->device));
+   const int64_t produced = (int64_t)h->h_ctrl->logcount;
+   *n = produced;
+   const int64_t m = std::min(std::min(produced, h->logcap), maxn);
+   if( m > 0 )
+   {
+      static_assert(sizeof(gpulin_change) == sizeof(ChangeRec), "change record layout");
+      CU(cudaMemcpyAsync(out, h->d_log, sizeof(ChangeRec) * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+   }
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n)
+{
+   if( h == nullptr || n == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   const Ctrl* c = h->h_ctrl;
+   const int m = std::min(std::min(h->lastrounds, (int)MAX_HIST), (int)maxn);
+   unsigned long long prev = c->t_start;
+   for( int i = 0; i < m; ++i )
+   {
+      if( ms != nullptr )
+         ms[i] = 1e-6 * (double)(c->hist_time[i] - prev);
+      if( nnz != nullptr )
+         nnz[i] = (int64_t)c->hist_nnz[i];
+      if( nchg != nullptr )
+         nchg[i] = (int64_t)c->hist_nchg[i];
+      prev = c->hist_time[i];
+   }
+   *n = m;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats)
+{
+   if( h == nullptr || stats == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   const int64_t v[10] = {h->nnz, h->nstored, h->nshort, h->nmedium, h->nlong, (int64_t)h->devbytes, h->ct.n,
+      h->nsweepblocks, h->maxlen, h->longsmemcap};
+   for( int i = 0; i < nstats && i < 10; ++i )
+      stats[i] = v[i];
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_algorithmic_bytes(gpulin_t* h, int64_t* bytes)
+{
+   if( h == nullptr || bytes == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   *bytes = h->nnz * 12 + h->nrows * 20 + h->ncols * 17;
+   return GPULIN_OK;
+}
+
+// ---- single steps (multi-GPU rounds, profiling) -----------------------------------------------------------------
+
+extern "C" int gpulin_exchange_buffer(gpulin_t* h, int64_t** d_keys, int64_t* nkeys)
+{
+   if( h == nullptr || d_keys == nullptr || nkeys == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   *d_keys = (int64_t*)h->p.cand;
+   *nkeys = 2 * h->ncols + 2;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_keys(gpulin_t* h, int64_t* keys)
+{
+   if( h == nullptr || keys == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   CU(cudaSetDevice(h->device));
+   CU(cudaMemcpyAsync(keys, h->p.cand, sizeof(long long) * (2 * (size_t)h->ncols + 2), cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_set_keys(gpulin_t* h, const int64_t* keys)
+{
+   if( h == nullptr || keys == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   CU(cudaSetDevice(h->device));
+   CU(cudaMemcpyAsync(h->p.cand, keys, sizeof(long long) * (2 * (size_t)h->ncols + 2), cudaMemcpyHostToDevice, h->stream));
+   CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_mark_all(gpulin_t* h)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   CU(cudaSetDevice(h->device));
+   mark_all_kernel<<<gridFor(h, h->nrows), 256, 0, h->stream>>>(h->p);
+   CU(cudaGetLastError());
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_round_begin(gpulin_t* h)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   if( !h->havebounds )
+      return fail(GPULIN_ERR_STATE, "gpulin_round_begin before gpulin_set_bounds");
+   CU(cudaSetDevice(h->device));
+   h->h_params[0] = 0;
+   h->h_params[1] = (int)h->logcap;
+   CU(cudaMemcpyAsync(&h->p.ctrl->maxrounds, h->h_params, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   begin_kernel<<<1, 1, 0, h->stream>>>(h->p.ctrl);
+   CU(cudaGetLastError());
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_round_sweep(gpulin_t* h)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   if( !h->havebounds )
+      return fail(GPULIN_ERR_STATE, "gpulin_round_sweep before gpulin_set_bounds");
+   CU(cudaSetDevice(h->device));
+   launchRoundKernels<false, false>(h, true, false);
+   publish_cutoff_kernel<<<1, 1, 0, h->stream>>>(h->p);
+   CU(cudaGetLastError());
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int32_t* cutoff)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   CU(cudaSetDevice(h->device));
+   absorb_cutoff_kernel<<<1, 1, 0, h->stream>>>(h->p);
+   if( dense )
+      launchRoundKernels<true, false>(h, false, true);
+   else
+      launchRoundKernels<false, false>(h, false, true);
+   CU(cudaGetLastError());
+   if( nchanges != nullptr || cutoff != nullptr )
+   {
+      OK(fetchCtrl(h));
+      const Ctrl* c = h->h_ctrl;
+      const int r = c->round - 1;
+      if( nchanges != nullptr )
+         *nchanges = (r >= 0 && r < MAX_HIST) ? (int64_t)c->hist_nchg[r] : -1;
+      if( cutoff != nullptr )
+         *cutoff = c->cutoff;
+      h->lastrounds = c->round;
+      h->last.status = c->status;
+      h->last.nrounds = c->round;
+      h->last.nchanges = (int64_t)c->total_nchg;
+      h->last.nnz_processed = (int64_t)c->total_nnz;
+   }
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_sync(gpulin_t* h)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   CU(cudaSetDevice(h->device));
+   CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}

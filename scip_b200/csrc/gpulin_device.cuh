@@ -9,7 +9,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-namespace gpulin {
+namespace gpl {
 
 struct Num
 {
@@ -348,12 +348,14 @@ __device__ __forceinline__ bool rowInfeasible(const Num& n, const RowAcc& a, dou
 
 // ---- commit filter: SCIPinferVarUbCons/LbCons (scip_var.c:7071-7157 / 6965-7051) followed by the last drop of
 // ---- SCIPnodeAddBoundinfer (tree.c:2020-2059), judged against the round-start bounds [l,u]; a surviving value
-// ---- is merged with atomicMin/atomicMax on its int64 key
+// ---- is merged with atomicMin on its int64 key.  Candidate layout per column j (one 16-byte pair):
+// ----    cand[2j]   = ~d2key(lb)   (bitwise NOT reverses the order: a larger lower bound is a smaller key)
+// ----    cand[2j+1] =  d2key(ub)
+// ---- so both sides tighten by MIN -- one ncclMin all-reduce over the whole vector merges the ranks' candidates.
 struct Sink
 {
-   long long*     nlb;       // candidate lower bounds (keys)
-   long long*     nub;       // candidate upper bounds (keys)
-   unsigned char* changed;   // per-column "a key moved this round" flag
+   long long*     cand;      // 2*ncols candidate keys
+   unsigned char* colflag;   // per-column "a key moved this round" flag, consumed by the apply kernel
 };
 
 __device__ __forceinline__ void inferUb(const Num& n, const Sink& s, int j, bool integral, double newub, double l,
@@ -371,8 +373,8 @@ __device__ __forceinline__ void inferUb(const Num& n, const Sink& s, int j, bool
    if( !isLT(n, newub, u) )
       return;
    const long long key = d2key(newub);
-   if( atomicMin(&s.nub[j], key) > key )
-      s.changed[j] = 1;
+   if( atomicMin(&s.cand[2 * (size_t)j + 1], key) > key )
+      s.colflag[j] = 1;
 }
 __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool integral, double newlb, double l,
    double u, bool force, bool& cutoff)
@@ -388,9 +390,9 @@ __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool
       return;
    if( !isGT(n, newlb, l) )
       return;
-   const long long key = d2key(newlb);
-   if( atomicMax(&s.nlb[j], key) < key )
-      s.changed[j] = 1;
+   const long long key = ~d2key(newlb);
+   if( atomicMin(&s.cand[2 * (size_t)j], key) > key )
+      s.colflag[j] = 1;
 }
 
 // tightenVarUb / tightenVarLb: cons_linear.c:5242-5307 / 5311-5376
@@ -493,4 +495,4 @@ __device__ __forceinline__ void candidates(const Num& n, const Sink& s, const Ro
    }
 }
 
-} // namespace gpulin
+} // namespace gpl

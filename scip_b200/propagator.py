@@ -1,0 +1,276 @@
+"""ctypes binding of libgpulin.so (include/gpulin.h) -- the harness side of the C ABI.
+
+The product is the CUDA library plus the SCIP plugin ``plugin/prop_gpulinear.c``; this module only lets tests,
+``bench.py`` and the multi-GPU driver call the same C entry points from Python.  Nothing here computes bounds:
+if the library or a CUDA device is missing every call raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+FIXPOINT, CUTOFF, ROUNDLIMIT = 0, 1, 2
+STATUS_NAMES = {0: "fixpoint", 1: "cutoff", 2: "roundlimit"}
+
+
+class GpulinError(RuntimeError):
+    pass
+
+
+class Numerics(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in
+                ("infinity", "epsilon", "sumepsilon", "feastol", "boundstreps", "hugeval", "maxeasyactivitydelta")]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int32), ("nrounds", ctypes.c_int32), ("nchanges", ctypes.c_int64),
+                ("nnz_processed", ctypes.c_int64), ("device_ms", ctypes.c_double)]
+
+
+CHANGE_DTYPE = np.dtype([("var", np.int32), ("round", np.int32), ("newbound", np.float64), ("is_upper", np.int32),
+                         ("reserved", np.int32)])
+
+_lib = None
+
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    "gpulin_default_numerics": (None, [ctypes.POINTER(Numerics)]),
+    "gpulin_last_error": (ctypes.c_char_p, []),
+    "gpulin_device_count": (ctypes.c_int, []),
+    "gpulin_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P, _P, _P, _P, _P,
+                                     _P, ctypes.POINTER(Numerics), ctypes.POINTER(_P)]),
+    "gpulin_destroy": (None, [_P]),
+    "gpulin_set_bounds": (ctypes.c_int, [_P, _P, _P]),
+    "gpulin_set_bounds_device": (ctypes.c_int, [_P, _P, _P]),
+    "gpulin_update_bounds": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P]),
+    "gpulin_propagate": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(Result)]),
+    "gpulin_get_bounds": (ctypes.c_int, [_P, _P, _P]),
+    "gpulin_get_bounds_device": (ctypes.c_int, [_P, _P, _P]),
+    "gpulin_set_change_log": (ctypes.c_int, [_P, ctypes.c_int64]),
+    "gpulin_get_changes": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_get_round_stats": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+    "gpulin_get_layout": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
+    "gpulin_algorithmic_bytes": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_set_stream": (ctypes.c_int, [_P, _P]),
+    "gpulin_sync": (ctypes.c_int, [_P]),
+    "gpulin_exchange_buffer": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_get_keys": (ctypes.c_int, [_P, _P]),
+    "gpulin_set_keys": (ctypes.c_int, [_P, _P]),
+    "gpulin_mark_all": (ctypes.c_int, [_P]),
+    "gpulin_round_begin": (ctypes.c_int, [_P]),
+    "gpulin_round_sweep": (ctypes.c_int, [_P]),
+    "gpulin_round_apply": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                          ctypes.POINTER(ctypes.c_int32)]),
+}
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def exported_symbols():
+    """names declared in include/gpulin.h (kept in one place for the symbol test)"""
+    return sorted(_SIGNATURES)
+
+
+def load_library():
+    """dlopen libgpulin.so (never builds implicitly on a GPU box: the in-tree library must be there)"""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise GpulinError(f"{path} is missing: run `python -m scip_b200.build` (no CPU fallback exists)")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise GpulinError(f"libgpulin error {rc}: {load_library().gpulin_last_error().decode()}")
+
+
+def default_numerics(**kw) -> Numerics:
+    num = Numerics()
+    load_library().gpulin_default_numerics(ctypes.byref(num))
+    for k, v in kw.items():
+        setattr(num, k, float(v))
+    return num
+
+
+class LinearPropagator:
+    """device-resident copy of the linear rows of one problem + its bound vectors (one gpulin_t handle)
+
+    ``prob``: dict with rowptr[int64], colidx[int32], vals[f64], lhs/rhs[f64 per row], vartype[u8 per column] and
+    optionally lb/ub.  ``rows=(begin,end)`` keeps only that row block (multi-GPU row partition)."""
+
+    def __init__(self, prob, device: int = 0, rows=None, **numerics):
+        lib = load_library()
+        rowptr = np.ascontiguousarray(prob["rowptr"], dtype=np.int64)
+        colidx = np.ascontiguousarray(prob["colidx"], dtype=np.int32)
+        vals = np.ascontiguousarray(prob["vals"], dtype=np.float64)
+        lhs = np.ascontiguousarray(prob["lhs"], dtype=np.float64)
+        rhs = np.ascontiguousarray(prob["rhs"], dtype=np.float64)
+        vartype = np.ascontiguousarray(prob["vartype"], dtype=np.uint8)
+        if rows is not None:
+            b, e = int(rows[0]), int(rows[1])
+            k0, k1 = int(rowptr[b]), int(rowptr[e])
+            rowptr = np.ascontiguousarray(rowptr[b:e + 1] - k0)
+            colidx = np.ascontiguousarray(colidx[k0:k1])
+            vals = np.ascontiguousarray(vals[k0:k1])
+            lhs = np.ascontiguousarray(lhs[b:e])
+            rhs = np.ascontiguousarray(rhs[b:e])
+        self.nrows, self.ncols, self.nnz = len(lhs), len(vartype), len(vals)
+        self.numerics = default_numerics(**numerics)
+        self._h = _P()
+        _check(lib.gpulin_create(int(device), self.nrows, self.ncols, self.nnz, rowptr.ctypes.data, colidx.ctypes.data,
+                                 vals.ctypes.data, lhs.ctypes.data, rhs.ctypes.data, vartype.ctypes.data,
+                                 ctypes.byref(self.numerics), ctypes.byref(self._h)))
+        self._lib = lib
+        self.device = int(device)
+        if "lb" in prob and "ub" in prob:
+            self.set_bounds(prob["lb"], prob["ub"])
+
+    # -- lifetime ----------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.gpulin_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- bounds ------------------------------------------------------------------------------------------------
+    def set_bounds(self, lb, ub):
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        assert lb.shape == (self.ncols,) and ub.shape == (self.ncols,)
+        _check(self._lib.gpulin_set_bounds(self._h, lb.ctypes.data, ub.ctypes.data))
+        # the host arrays may be pageable and temporary: the copy must be done before they go away
+        _check(self._lib.gpulin_sync(self._h))
+
+    def set_bounds_ptr(self, lb_ptr: int, ub_ptr: int, on_device: bool):
+        """raw pointers: pinned host memory (asynchronous copy) or device memory"""
+        fn = self._lib.gpulin_set_bounds_device if on_device else self._lib.gpulin_set_bounds
+        _check(fn(self._h, lb_ptr, ub_ptr))
+
+    def get_bounds_ptr(self, lb_ptr: int, ub_ptr: int, on_device: bool):
+        fn = self._lib.gpulin_get_bounds_device if on_device else self._lib.gpulin_get_bounds
+        _check(fn(self._h, lb_ptr, ub_ptr))
+
+    def update_bounds(self, idx, lb, ub):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        _check(self._lib.gpulin_update_bounds(self._h, len(idx), idx.ctypes.data, lb.ctypes.data, ub.ctypes.data))
+        _check(self._lib.gpulin_sync(self._h))
+
+    def get_bounds(self):
+        lb = np.empty(self.ncols, dtype=np.float64)
+        ub = np.empty(self.ncols, dtype=np.float64)
+        _check(self._lib.gpulin_get_bounds(self._h, lb.ctypes.data, ub.ctypes.data))
+        return lb, ub
+
+    # -- propagation -------------------------------------------------------------------------------------------
+    def propagate(self, maxrounds: int = 0) -> dict:
+        res = Result()
+        _check(self._lib.gpulin_propagate(self._h, int(maxrounds), ctypes.byref(res)))
+        return dict(status=res.status, nrounds=res.nrounds, nchanges=res.nchanges, nnz_processed=res.nnz_processed,
+                    device_ms=res.device_ms)
+
+    def round_stats(self, maxn: int = 1024):
+        ms = np.zeros(maxn, dtype=np.float64)
+        nnz = np.zeros(maxn, dtype=np.int64)
+        nchg = np.zeros(maxn, dtype=np.int64)
+        n = ctypes.c_int32(0)
+        _check(self._lib.gpulin_get_round_stats(self._h, ms.ctypes.data, nnz.ctypes.data, nchg.ctypes.data, maxn,
+                                                ctypes.byref(n)))
+        return ms[:n.value], nnz[:n.value], nchg[:n.value]
+
+    def set_change_log(self, capacity: int):
+        _check(self._lib.gpulin_set_change_log(self._h, int(capacity)))
+
+    def changes(self, maxn: int):
+        out = np.zeros(maxn, dtype=CHANGE_DTYPE)
+        n = ctypes.c_int64(0)
+        _check(self._lib.gpulin_get_changes(self._h, out.ctypes.data, maxn, ctypes.byref(n)))
+        return out[:min(n.value, maxn)], n.value
+
+    def layout(self) -> dict:
+        st = np.zeros(10, dtype=np.int64)
+        _check(self._lib.gpulin_get_layout(self._h, st.ctypes.data, 10))
+        keys = ("nnz", "stored_nnz", "rows_thread", "rows_warp", "rows_block", "device_bytes", "classes",
+                "sweep_blocks", "maxlen", "long_smem_cap")
+        return dict(zip(keys, (int(x) for x in st)))
+
+    def algorithmic_bytes(self) -> int:
+        b = ctypes.c_int64(0)
+        _check(self._lib.gpulin_algorithmic_bytes(self._h, ctypes.byref(b)))
+        return b.value
+
+    # -- single rounds (multi-GPU, profiling) ------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        _check(self._lib.gpulin_set_stream(self._h, cuda_stream))
+
+    def sync(self):
+        _check(self._lib.gpulin_sync(self._h))
+
+    def exchange_buffer(self):
+        ptr = _P()
+        n = ctypes.c_int64(0)
+        _check(self._lib.gpulin_exchange_buffer(self._h, ctypes.byref(ptr), ctypes.byref(n)))
+        return ptr.value, n.value
+
+    def get_keys(self):
+        keys = np.empty(2 * self.ncols + 2, dtype=np.int64)
+        _check(self._lib.gpulin_get_keys(self._h, keys.ctypes.data))
+        return keys
+
+    def set_keys(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.int64)
+        assert keys.shape == (2 * self.ncols + 2,)
+        _check(self._lib.gpulin_set_keys(self._h, keys.ctypes.data))
+
+    def mark_all(self):
+        _check(self._lib.gpulin_mark_all(self._h))
+
+    def round_begin(self):
+        _check(self._lib.gpulin_round_begin(self._h))
+
+    def round_sweep(self):
+        _check(self._lib.gpulin_round_sweep(self._h))
+
+    def round_apply(self, dense: bool = False, fetch: bool = True):
+        if not fetch:
+            _check(self._lib.gpulin_round_apply(self._h, int(dense), None, None))
+            return None
+        nchg = ctypes.c_int64(0)
+        cutoff = ctypes.c_int32(0)
+        _check(self._lib.gpulin_round_apply(self._h, int(dense), ctypes.byref(nchg), ctypes.byref(cutoff)))
+        return nchg.value, cutoff.value
+
+
+def propagate(prob, lb=None, ub=None, maxrounds: int = 0, device: int = 0, **numerics) -> dict:
+    """one-shot: build, propagate to the fixpoint, read back; returns dict(status, lb, ub, nrounds, nchanges, ...)"""
+    with LinearPropagator(prob, device=device, **numerics) as lp:
+        lp.set_bounds(prob["lb"] if lb is None else lb, prob["ub"] if ub is None else ub)
+        res = lp.propagate(maxrounds)
+        res["lb"], res["ub"] = lp.get_bounds()
+    return res

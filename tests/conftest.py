@@ -1,0 +1,57 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        return sorted(json.load(f))
+
+
+def load_golden(name, bs):
+    """(problem dict from <name>.lpb, reference result from <name>.bs<bs>.lpr)"""
+    import oracle
+    from scip_b200.lpb import read_lpb
+    prob = read_lpb(os.path.join(GOLDEN, name + ".lpb"))
+    ref = oracle.read_lpr(os.path.join(GOLDEN, f"{name}.bs{bs}.lpr"))
+    return prob, ref
+
+
+def rel_diff(a, b):
+    return np.abs(a - b) / np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+
+
+def assert_bounds_match(got_lb, got_ub, want_lb, want_ub, vartype, tol=1e-9, what=""):
+    """the parity bar of BASELINE.json: integer-variable bounds exact (value-equal, -0.0 == 0.0), continuous bounds
+    within 1e-9 relative"""
+    integral = np.asarray(vartype) != 0
+    bad_int = np.flatnonzero(((got_lb != want_lb) | (got_ub != want_ub)) & integral)
+    assert bad_int.size == 0, (f"{what}: {bad_int.size} integer bound mismatches, first var {bad_int[0]}: "
+                               f"got [{got_lb[bad_int[0]]!r},{got_ub[bad_int[0]]!r}] "
+                               f"want [{want_lb[bad_int[0]]!r},{want_ub[bad_int[0]]!r}]")
+    cont = ~integral
+    if cont.any():
+        d = max(rel_diff(got_lb[cont], want_lb[cont]).max(), rel_diff(got_ub[cont], want_ub[cont]).max())
+        assert d <= tol, f"{what}: continuous bounds differ by {d:.3e} relative (> {tol})"
+
+
+@pytest.fixture(scope="session")
+def gpulin():
+    """the ctypes binding, with the in-tree library built if it is stale (nvcc only; no GPU needed to build)"""
+    from scip_b200 import build, propagator
+    build.build_library()
+    propagator.load_library()
+    return propagator

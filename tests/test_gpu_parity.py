@@ -1,0 +1,250 @@
+"""GPU: the CUDA path, called through the C ABI, against (a) the fixtures of the UNMODIFIED reference and (b) the CPU
+oracle on the same seeded inputs.  Bar (BASELINE.json): integer bounds and verdicts exact, continuous bounds within
+1e-9 relative."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_bounds_match, golden_names, load_golden
+from scip_b200 import synth
+
+pytestmark = pytest.mark.gpu
+NAMES = golden_names()
+INF = 1e20
+
+
+def gpu_vs_oracle(gpulin, prob, maxrounds=0, what="", **numerics):
+    want = oracle.propagate(prob, maxrounds=maxrounds, **numerics)
+    got = gpulin.propagate(prob, maxrounds=maxrounds, **numerics)
+    assert got["status"] == want["status"], f"{what}: verdict {got['status']} != {want['status']}"
+    if want["status"] != oracle.STATUS_CUTOFF:
+        assert got["nrounds"] == want["nrounds"], what
+        assert got["nchanges"] == want["nchanges"], what
+        assert_bounds_match(got["lb"], got["ub"], want["lb"], want["ub"], prob["vartype"], what=what)
+    return got, want
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_fixpoint_exact_protocol(gpulin, name):
+    """CUDA fixpoint == the reference's own cons_linear fixpoint (numerics/boundstreps = 1e-9 on both sides)"""
+    prob, ref = load_golden(name, "1e-9")
+    got = gpulin.propagate(prob, maxrounds=1000, boundstreps=1e-9)
+    assert (got["status"] == gpulin.CUTOFF) == ref["infeasible"]
+    if not ref["infeasible"]:
+        assert got["status"] == gpulin.FIXPOINT
+        assert_bounds_match(got["lb"], got["ub"], ref["lb"], ref["ub"], prob["vartype"], what=name)
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("bs", [1e-9, 0.05])
+def test_oracle_parity_on_golden_inputs(gpulin, name, bs):
+    prob, _ = load_golden(name, "1e-9")
+    gpu_vs_oracle(gpulin, prob, maxrounds=1000, what=f"{name} bs={bs}", boundstreps=bs)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_setcover_100k(gpulin, seed):
+    prob = synth.setcover(100_000, 100_000, 1_000_000, seed=seed)
+    got, _ = gpu_vs_oracle(gpulin, prob, what=f"setcover seed {seed}")
+    assert got["nchanges"] > 0
+
+
+def test_setcover_infeasible(gpulin):
+    prob = synth.setcover(50_000, 50_000, 500_000, seed=5, infeasible=True)
+    got, want = gpu_vs_oracle(gpulin, prob, what="setcover infeasible")
+    assert got["status"] == gpulin.CUTOFF
+
+
+@pytest.mark.parametrize("seed,bs", [(21, 1e-9), (22, 0.05), (23, 1e-9)])
+def test_mixed_knapsack_all_row_bins(gpulin, seed, bs):
+    # normal rows 50..350 (warp-per-row), 1 % dense rows 1500..6000 (block-per-row), equalities, general integers
+    prob = synth.mixed_knapsack(4000, 40_000, 1_000_000, seed=seed, dense_range=(1500, 6000), eq_frac=0.2)
+    with gpulin.LinearPropagator(prob) as lp:
+        lay = lp.layout()
+    assert lay["rows_warp"] > 0 and lay["rows_block"] > 0
+    got, _ = gpu_vs_oracle(gpulin, prob, maxrounds=200, what=f"mixedknap seed {seed}", boundstreps=bs)
+    assert got["nchanges"] > 0
+
+
+def test_mixed_knapsack_infeasible(gpulin):
+    prob = synth.mixed_knapsack(2000, 20_000, 400_000, seed=31, dense_range=(1500, 3000), infeasible=True)
+    got, _ = gpu_vs_oracle(gpulin, prob, what="mixedknap infeasible")
+    assert got["status"] == gpulin.CUTOFF
+
+
+def test_very_long_row_beyond_shared_memory_staging(gpulin):
+    # one row with 60k nonzeros: longer than the shared-memory alpha staging of the block-per-row kernel
+    rng = np.random.default_rng(7)
+    ncols = 80_000
+    cols = rng.permutation(ncols)[:60_000].astype(np.int32)
+    vals = rng.integers(1, 10, size=cols.size).astype(np.float64)
+    rowptr = np.array([0, cols.size, cols.size + 3], dtype=np.int64)
+    colidx = np.concatenate([cols, np.array([0, 1, 2], dtype=np.int32)])
+    vals = np.concatenate([vals, np.array([1.0, 1.0, 1.0])])
+    ub = np.full(ncols, 5.0)
+    prob = dict(rowptr=rowptr, colidx=colidx, vals=vals, lhs=np.array([-INF, 2.0]), rhs=np.array([30.0, INF]),
+                lb=np.zeros(ncols), ub=ub, vartype=(rng.random(ncols) < 0.5).astype(np.uint8))
+    got, _ = gpu_vs_oracle(gpulin, prob, what="long row")
+    assert got["nchanges"] > 10_000
+
+
+def tiny(rows, lhs, rhs, lb, ub, vartype):
+    rowptr = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64)
+    colidx = np.array([c for r in rows for c, _ in r], dtype=np.int32)
+    vals = np.array([v for r in rows for _, v in r], dtype=np.float64)
+    return dict(rowptr=rowptr, colidx=colidx, vals=vals, lhs=np.array(lhs, dtype=np.float64),
+                rhs=np.array(rhs, dtype=np.float64), lb=np.array(lb, dtype=np.float64),
+                ub=np.array(ub, dtype=np.float64), vartype=np.array(vartype, dtype=np.uint8))
+
+
+def test_edge_cases(gpulin):
+    cases = {
+        # singleton row: force = TRUE (cons_linear.c:7029), tightens below the relative threshold
+        "singleton": tiny([[(0, 2.0)]], [-INF], [7.0], [0.0], [100.0], [1]),
+        # infinite bounds: one unbounded variable -> residual path (tightenVarBounds)
+        "one_infinite": tiny([[(0, 1.0), (1, 1.0), (2, -1.0)]], [-INF], [10.0], [-INF, 0.0, 0.0], [INF, 4.0, 3.0], [0, 0, 0]),
+        "two_infinite": tiny([[(0, 1.0), (1, 1.0)]], [-INF], [10.0], [-INF, -INF], [INF, INF], [0, 0]),
+        # huge contributions (>= 1e15) are counted, not summed
+        "huge": tiny([[(0, 1e10), (1, 1.0)]], [-INF], [5.0], [0.0, 0.0], [1e6, 10.0], [0, 0]),
+        # empty row and a row that is infeasible on its own
+        "empty_row": tiny([[], [(0, 1.0)]], [-1.0, -INF], [1.0, 3.0], [0.0], [9.0], [1]),
+        "empty_row_infeasible": tiny([[], [(0, 1.0)]], [1.0, -INF], [INF, 3.0], [0.0], [9.0], [1]),
+        "row_infeasible": tiny([[(0, 1.0), (1, 1.0)]], [5.0], [INF], [0.0, 0.0], [1.0, 1.0], [1, 1]),
+        # equality with a continuous variable and negative zero bounds
+        "negzero": tiny([[(0, 1.0), (1, 2.0)]], [4.0], [4.0], [-0.0, -0.0], [10.0, 10.0], [0, 1]),
+        # integrality rounding: 3 x <= 10 -> x <= 3
+        "rounding": tiny([[(0, 3.0)], [(0, 1.0), (1, 1.0)]], [-INF, 5.5], [10.0, INF], [0.0, 0.0], [100.0, 2.7], [1, 0]),
+        # bounds that cross within one round by more than feastol -> cutoff in the apply step
+        "crossing": tiny([[(0, 1.0), (1, 1.0)], [(0, 1.0), (1, -1.0)]], [-INF, 9.0], [5.0, INF], [0.0, 0.0], [10.0, 10.0], [0, 0]),
+        # fixed variables only: maxactdelta == 0 -> row skipped
+        "all_fixed": tiny([[(0, 1.0), (1, 1.0)]], [-INF], [5.0], [1.0, 2.0], [1.0, 2.0], [1, 1]),
+    }
+    for name, prob in cases.items():
+        for bs in (0.05, 1e-9):
+            gpu_vs_oracle(gpulin, prob, maxrounds=100, what=f"{name} bs={bs}", boundstreps=bs)
+
+
+def test_no_rows_and_no_columns(gpulin):
+    prob = tiny([], [], [], [0.0, 1.0], [2.0, 3.0], [0, 1])
+    got = gpulin.propagate(prob)
+    assert got["status"] == gpulin.FIXPOINT and got["nchanges"] == 0
+    assert np.array_equal(got["lb"], prob["lb"]) and np.array_equal(got["ub"], prob["ub"])
+
+
+def test_round_limit_and_resume(gpulin):
+    prob, _ = load_golden("egout", "1e-9")          # needs 17 Jacobi rounds
+    want = oracle.propagate(prob, boundstreps=1e-9)
+    with gpulin.LinearPropagator(prob, boundstreps=1e-9) as lp:
+        r1 = lp.propagate(5)
+        assert r1["status"] == gpulin.ROUNDLIMIT and r1["nrounds"] == 5
+        lb5, ub5 = lp.get_bounds()
+        w5 = oracle.propagate(prob, boundstreps=1e-9, maxrounds=5)
+        assert_bounds_match(lb5, ub5, w5["lb"], w5["ub"], prob["vartype"], what="egout after 5 rounds")
+        r2 = lp.propagate(0)                          # continues from the device-resident state
+        assert r2["status"] == gpulin.FIXPOINT and r1["nrounds"] + r2["nrounds"] == want["nrounds"]
+        lb, ub = lp.get_bounds()
+        assert_bounds_match(lb, ub, want["lb"], want["ub"], prob["vartype"], what="egout resumed")
+        r3 = lp.propagate(0)                          # idempotent: nothing is marked any more
+        assert r3["nchanges"] == 0 and r3["nnz_processed"] == 0
+
+
+def test_host_loop_equals_graph_loop(gpulin, monkeypatch):
+    prob = synth.setcover(20_000, 20_000, 200_000, seed=9)
+    a = gpulin.propagate(prob)
+    monkeypatch.setenv("GPULIN_LOOP", "host")
+    b = gpulin.propagate(prob)
+    assert a["status"] == b["status"] and a["nrounds"] == b["nrounds"] and a["nchanges"] == b["nchanges"]
+    assert np.array_equal(a["lb"], b["lb"]) and np.array_equal(a["ub"], b["ub"])
+
+
+def test_update_bounds_marks_only_affected_rows(gpulin):
+    prob = synth.setcover(20_000, 20_000, 200_000, seed=10)
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.propagate()
+        lb, ub = lp.get_bounds()
+        free = np.flatnonzero(lb < ub)[:50]
+        # probing-style change: fix 50 free binaries to 1 (SCIPchgVarLbProbing, scip_probing.c:302)
+        lp.update_bounds(free, np.ones(50), np.ones(50))
+        res = lp.propagate()
+        assert 0 < res["nnz_processed"] < lp.nnz // 10     # incremental: only rows of touched columns are swept
+        glb, gub = lp.get_bounds()
+    lb2, ub2 = lb.copy(), ub.copy()
+    lb2[free] = 1.0
+    want = oracle.propagate(prob, lb=lb2, ub=ub2)
+    assert res["status"] == want["status"]
+    if want["status"] != oracle.STATUS_CUTOFF:
+        assert_bounds_match(glb, gub, want["lb"], want["ub"], prob["vartype"], what="after update_bounds")
+
+
+def test_change_log_replays_to_the_fixpoint(gpulin):
+    prob, _ = load_golden("dcmulti", "1e-9")
+    with gpulin.LinearPropagator(prob, boundstreps=1e-9) as lp:
+        lp.set_change_log(10_000)
+        res = lp.propagate()
+        log, n = lp.changes(10_000)
+        lb, ub = lp.get_bounds()
+    assert n == res["nchanges"] == len(log)
+    assert np.all(np.diff(log["round"]) >= 0)            # round ordered
+    rl, ru = prob["lb"] + 0.0, prob["ub"] + 0.0
+    for rec in log:
+        if rec["is_upper"]:
+            assert rec["newbound"] < ru[rec["var"]]
+            ru[rec["var"]] = rec["newbound"]
+        else:
+            assert rec["newbound"] > rl[rec["var"]]
+            rl[rec["var"]] = rec["newbound"]
+    assert np.array_equal(rl, lb) and np.array_equal(ru, ub)
+
+
+def test_single_round_api_matches_oracle_sweep(gpulin):
+    prob = synth.mixed_knapsack(1500, 15_000, 300_000, seed=41, dense_range=(1200, 2500))
+    c, wl, wu = oracle.sweep(prob, prob["lb"], prob["ub"], boundstreps=1e-9)
+    with gpulin.LinearPropagator(prob, boundstreps=1e-9) as lp:
+        lp.round_begin()
+        lp.round_sweep()
+        nchg, cutoff = lp.round_apply(dense=True)
+        lb, ub = lp.get_bounds()
+    assert cutoff == c
+    assert nchg == int((wl != prob["lb"]).sum() + (wu != prob["ub"]).sum())
+    assert_bounds_match(lb, ub, wl, wu, prob["vartype"], what="single round")
+
+
+@pytest.mark.parametrize("nparts", [2, 4])
+def test_row_partition_with_min_merge_equals_single_device(gpulin, nparts):
+    """the multi-GPU protocol on one device: row blocks in separate handles, candidate keys merged by elementwise
+    MIN (what ncclMin does), dense apply"""
+    prob = synth.mixed_knapsack(1200, 12_000, 240_000, seed=43, dense_range=(1100, 2000))
+    want = oracle.propagate(prob)
+    nrows = len(prob["lhs"])
+    cuts = np.searchsorted(prob["rowptr"], np.linspace(0, prob["rowptr"][-1], nparts + 1)).clip(0, nrows)
+    cuts[0], cuts[-1] = 0, nrows
+    parts = [gpulin.LinearPropagator(prob, rows=(cuts[i], cuts[i + 1])) for i in range(nparts)]
+    try:
+        for lp in parts:
+            lp.set_bounds(prob["lb"], prob["ub"])
+            lp.round_begin()
+        rounds = 0
+        while True:
+            rounds += 1
+            bufs = []
+            for lp in parts:
+                lp.round_sweep()
+                bufs.append(lp.get_keys())
+            merged = np.minimum.reduce(bufs)
+            out = []
+            for lp in parts:
+                lp.set_keys(merged)
+                out.append(lp.round_apply(dense=True))
+            assert len(set(out)) == 1
+            nchg, cutoff = out[0]
+            if cutoff or nchg == 0 or rounds > 500:
+                break
+        assert (want["status"] == oracle.STATUS_CUTOFF) == bool(cutoff)
+        if not cutoff:
+            assert rounds == want["nrounds"]
+            for lp in parts:
+                lb, ub = lp.get_bounds()
+                assert_bounds_match(lb, ub, want["lb"], want["ub"], prob["vartype"], what="row partition")
+    finally:
+        for lp in parts:
+            lp.close()
