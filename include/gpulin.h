@@ -133,8 +133,7 @@ int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n
 int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n);
 
 /** storage statistics: [0] nnz, [1] stored nonzeros incl. SELL padding, [2..4] rows in the thread-per-row /
- *  warp-per-row / block-per-row bins, [5] bytes on device, [6] row classes, [7] sweep blocks, [8] longest row,
- *  [9] shared-memory staging capacity of the long-row kernel [nonzeros] */
+ *  warp-per-row / block-per-row bins, [5] bytes on device, [6..8] persistent blocks of the three sweep kernels, [9] longest row */
 int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 
 /** algorithmic bytes of one full round: nnz*12 + nrows*20 + ncols*17 */

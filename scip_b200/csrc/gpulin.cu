@@ -37,6 +37,14 @@ static int fail(int code, const char* fmt, ...)
          return fail(GPULIN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
    } while( 0 )
 
+#define OK(call)                 \
+   do                            \
+   {                             \
+      int rc_ = (call);          \
+      if( rc_ != GPULIN_OK )     \
+         return rc_;             \
+   } while( 0 )
+
 struct gpulin
 {
    int         device = 0;
@@ -45,10 +53,10 @@ struct gpulin
    int         nshort = 0, nmedium = 0, nlong = 0;
    int         maxlen = 0;
    DevProblem  p{};
-   ClassTable  ct{};
-   int         nsweepblocks = 0;
+   int         shortvariant = 8;
+   int         nshortblocks = 0;
+   int         nmediumblocks = 0;
    int         nlongblocks = 0;
-   int         longsmemcap = 0;  // doubles of dynamic shared memory of the long-row kernel
    int         napplyblocks = 0;
    int         nsm = 148;
    std::vector<int> perm;        // permuted row -> caller's row
@@ -68,6 +76,8 @@ struct gpulin
    int64_t     updcap = 0;
    cudaStream_t stream = nullptr;
    bool        ownstream = true;
+   cudaStream_t aux[2] = {nullptr, nullptr};     // the medium / long sweeps run beside the short sweep
+   cudaEvent_t evfork = nullptr, evjoin[2] = {nullptr, nullptr};
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    cudaGraph_t graph = nullptr;
    cudaGraphExec_t gexec = nullptr;
@@ -92,14 +102,6 @@ static int devAlloc(gpulin* h, T** out, size_t count)
    *out = (T*)ptr;
    return GPULIN_OK;
 }
-
-#define OK(call)                 \
-   do                            \
-   {                             \
-      int rc_ = (call);          \
-      if( rc_ != GPULIN_OK )     \
-         return rc_;             \
-   } while( 0 )
 
 extern "C" void gpulin_default_numerics(gpulin_numerics* num)
 {
@@ -126,19 +128,6 @@ extern "C" int gpulin_device_count(void)
    return n;
 }
 
-static int classOfLen(int len)
-{
-   if( len <= 4 ) return CK_T4;
-   if( len <= 8 ) return CK_T8;
-   if( len <= 16 ) return CK_T16;
-   if( len <= 32 ) return CK_T32;
-   if( len <= 64 ) return CK_W2;
-   if( len <= 128 ) return CK_W4;
-   if( len <= 256 ) return CK_W8;
-   if( len <= 512 ) return CK_W16;
-   return CK_W32;
-}
-
 static void destroyGraph(gpulin* h)
 {
    if( h->gexec != nullptr )
@@ -149,20 +138,92 @@ static void destroyGraph(gpulin* h)
    h->graph = nullptr;
 }
 
-// one propagation round on h->stream
+// chunk sizes of the software-pipelined sweeps (elements per thread in flight)
+constexpr int MEDIUM_U = 4;
+constexpr int MEDIUM_MINB = 3;
+
+// variants of the thread-per-row sweep; GPULIN_SHORT_VARIANT selects (experiments; the default is set in gpulin{})
+typedef void (*ShortKernel)(const DevProblem);
+struct ShortVariant
+{
+   ShortKernel kernel;
+   int         threads;
+   int         smem;     // dynamic shared memory per block
+   const char* name;
+};
+#define ASYNC_SMEM(CH, D2, T) (((D2) + 1) * (CH) * (T) * 28 + ((D2) + 1) * (T) * 16)
+#define REGV(CH, PF, MB) {sweep_short_kernel<CH, PF, MB>, SWEEP_THREADS, 0, "reg<" #CH "," #PF "," #MB ">"}
+#define ASYV(CH, D1, D2, T) {sweep_short_async_kernel<CH, D1, D2, T>, T, ASYNC_SMEM(CH, D2, T), "async<" #CH "," #D1 "," #D2 "," #T ">"}
+static const ShortVariant g_shortVariants[] = {
+   REGV(4, true, 3),     // 0
+   REGV(4, false, 4),    // 1
+   REGV(8, false, 2),    // 2
+   REGV(8, true, 2),     // 3
+   REGV(2, true, 4),     // 4
+   REGV(4, true, 2),     // 5
+   REGV(4, false, 3),    // 6
+   REGV(8, false, 3),    // 7
+   ASYV(4, 1, 2, 128),   // 8
+   ASYV(4, 2, 4, 128),   // 9
+   ASYV(4, 1, 3, 128),   // 10
+   ASYV(8, 1, 2, 128),   // 11
+   ASYV(2, 2, 4, 128),   // 12
+   ASYV(2, 1, 2, 256),   // 13
+   ASYV(4, 1, 2, 256),   // 14
+   ASYV(4, 2, 3, 128),   // 15
+   ASYV(8, 2, 3, 128),   // 16
+   ASYV(2, 3, 6, 128),   // 17
+};
+constexpr int NSHORTVARIANTS = sizeof(g_shortVariants) / sizeof(g_shortVariants[0]);
+
+// one propagation round on h->stream; the three row bins are independent and run concurrently (fork / join)
 template <bool DENSE, bool GRAPH>
-static void launchRoundKernels(gpulin* h, bool sweep, bool apply)
+static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
 {
    if( sweep )
    {
-      if( h->nsweepblocks > 0 )
-         sweep_rows_kernel<<<h->nsweepblocks, SWEEP_THREADS, 0, h->stream>>>(h->p, h->ct);
-      if( h->nlong > 0 )
-         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, (size_t)h->longsmemcap * sizeof(double), h->stream>>>(
-            h->p, h->nshort + h->nmedium, h->nlong, h->longsmemcap);
+      const bool fork = (h->nmediumblocks > 0 || h->nlongblocks > 0) && h->nshortblocks > 0;
+      if( fork )
+         CU(cudaEventRecord(h->evfork, h->stream));
+      if( h->nshortblocks > 0 )
+      {
+         const ShortVariant& sv = g_shortVariants[h->shortvariant];
+         sv.kernel<<<h->nshortblocks, sv.threads, sv.smem, h->stream>>>(h->p);
+      }
+      if( h->nmediumblocks > 0 )
+      {
+         cudaStream_t st = fork ? h->aux[0] : h->stream;
+         if( fork )
+            CU(cudaStreamWaitEvent(st, h->evfork, 0));
+         sweep_medium_kernel<MEDIUM_U, MEDIUM_MINB><<<h->nmediumblocks, SWEEP_THREADS, 0, st>>>(h->p);
+         if( fork )
+         {
+            CU(cudaEventRecord(h->evjoin[0], st));
+            CU(cudaStreamWaitEvent(h->stream, h->evjoin[0], 0));
+         }
+      }
+      if( h->nlongblocks > 0 )
+      {
+         const bool f2 = h->nshortblocks > 0 || h->nmediumblocks > 0;
+         cudaStream_t st = f2 ? h->aux[1] : h->stream;
+         if( f2 )
+         {
+            if( !fork )
+               CU(cudaEventRecord(h->evfork, h->stream));
+            CU(cudaStreamWaitEvent(st, h->evfork, 0));
+         }
+         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, 0, st>>>(h->p);
+         if( f2 )
+         {
+            CU(cudaEventRecord(h->evjoin[1], st));
+            CU(cudaStreamWaitEvent(h->stream, h->evjoin[1], 0));
+         }
+      }
    }
    if( apply )
       apply_kernel<DENSE, GRAPH><<<h->napplyblocks, 256, 0, h->stream>>>(h->p, h->handle);
+   CU(cudaGetLastError());
+   return GPULIN_OK;
 }
 
 // graph:  begin_kernel -> WHILE(cont) { sweep kernels; apply kernel (sets cont) }
@@ -193,9 +254,10 @@ static int buildGraph(gpulin* h)
    cudaGraph_t body = cp.conditional.phGraph_out[0];
 
    CU(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-   launchRoundKernels<false, true>(h, true, true);
+   const int lrc = launchRoundKernels<false, true>(h, true, true);
    cudaGraph_t captured = nullptr;
    CU(cudaStreamEndCapture(h->stream, &captured));
+   OK(lrc);
    CU(cudaGraphInstantiate(&h->gexec, h->graph, 0));
    return GPULIN_OK;
 }
@@ -353,55 +415,6 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       }
    }
 
-   // ---- class table of the fused short/medium sweep kernel -------------------------------------------------------
-   ClassTable& ct = h->ct;
-   memset(&ct, 0, sizeof(ct));
-   {
-      // short rows: a class is a run of whole slices whose width falls into the same template instance
-      int i = 0;
-      int blocks = 0;
-      while( i < h->nshort )
-      {
-         const int s0 = i >> 5;
-         const int lastOfSlice = std::min(h->nshort, 32 * s0 + 32) - 1;
-         const int kind = classOfLen(plen[(size_t)lastOfSlice]);
-         int e = lastOfSlice + 1;
-         while( e < h->nshort )
-         {
-            const int l2 = std::min(h->nshort, e + 32) - 1;
-            if( classOfLen(plen[(size_t)l2]) != kind )
-               break;
-            e = l2 + 1;
-         }
-         ct.kind[ct.n] = kind;
-         ct.row0[ct.n] = i;
-         ct.nrows[ct.n] = e - i;
-         ct.block0[ct.n] = blocks;
-         blocks += (e - i + SWEEP_THREADS - 1) / SWEEP_THREADS;
-         ++ct.n;
-         i = e;
-      }
-      // medium rows: descending length
-      i = h->nshort;
-      const int mend = h->nshort + h->nmedium;
-      while( i < mend )
-      {
-         const int kind = classOfLen(plen[(size_t)i]);
-         int e = i + 1;
-         while( e < mend && classOfLen(plen[(size_t)e]) == kind )
-            ++e;
-         ct.kind[ct.n] = kind;
-         ct.row0[ct.n] = i;
-         ct.nrows[ct.n] = e - i;
-         ct.block0[ct.n] = blocks;
-         blocks += (e - i + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32);
-         ++ct.n;
-         i = e;
-      }
-      ct.block0[ct.n] = blocks;
-      h->nsweepblocks = blocks;
-   }
-
    // ---- upload ---------------------------------------------------------------------------------------------------
    DevProblem& p = h->p;
    long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
@@ -442,6 +455,11 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    if( rc == GPULIN_OK )
       memset(h->h_ctrl, 0, sizeof(Ctrl));
    TRYCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+   TRYCU(cudaStreamCreateWithFlags(&h->aux[0], cudaStreamNonBlocking));
+   TRYCU(cudaStreamCreateWithFlags(&h->aux[1], cudaStreamNonBlocking));
+   TRYCU(cudaEventCreateWithFlags(&h->evfork, cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evjoin[0], cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evjoin[1], cudaEventDisableTiming));
    TRYCU(cudaEventCreate(&h->ev0));
    TRYCU(cudaEventCreate(&h->ev1));
    if( rc != GPULIN_OK )
@@ -452,6 +470,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    p.nrows = (int)nrows;
    p.ncols = (int)ncols;
+   p.nshort = h->nshort;
+   p.nmedium = h->nmedium;
    p.sell_off = d_sell_off;
    p.rowlen = d_rowlen;
    p.rowbeg = d_rowbeg;
@@ -477,26 +497,54 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.num.bstreps = num->boundstreps;
    p.num.huge = num->hugeval;
    p.num.maxeasy = num->maxeasyactivitydelta;
+   {
+      DevProblem* d_self = nullptr;
+      int rcs = devAlloc(h, &d_self, 1);
+      if( rcs != GPULIN_OK )
+      {
+         gpulin_destroy(h);
+         return rcs;
+      }
+      p.self = d_self;
+      if( cudaMemcpy(d_self, &p, sizeof(DevProblem), cudaMemcpyHostToDevice) != cudaSuccess )
+      {
+         gpulin_destroy(h);
+         return fail(GPULIN_ERR_CUDA, "cudaMemcpy of the problem descriptor failed");
+      }
+   }
 
    // ---- launch geometry ------------------------------------------------------------------------------------------
+   // persistent grids: as many blocks as stay resident, never more than there is work
    h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols + 255) / 256, (int64_t)h->nsm * 8));
-   if( h->nlong > 0 )
    {
-      int maxsmem = 0;
-      cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-      // keep two blocks per SM resident: half of the opt-in limit minus the static part
-      int cap = (maxsmem / 2 - 4096) / (int)sizeof(double);
-      cap = std::max(cap, 0);
-      // longest row is first in the long bin
-      const int longest = plen[(size_t)(h->nshort + h->nmedium)];
-      h->longsmemcap = std::min(cap, longest);
-      if( cudaFuncSetAttribute(sweep_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int)(h->longsmemcap * sizeof(double))) != cudaSuccess )
+      int occ = 0;
+      const char* ve = getenv("GPULIN_SHORT_VARIANT");
+      if( ve != nullptr && atoi(ve) >= 0 && atoi(ve) < NSHORTVARIANTS )
+         h->shortvariant = atoi(ve);
+      const ShortVariant& sv = g_shortVariants[h->shortvariant];
+      if( sv.smem > 0 && cudaFuncSetAttribute(sv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sv.smem) != cudaSuccess )
       {
-         cudaGetLastError();
-         h->longsmemcap = std::min(h->longsmemcap, (48 * 1024 - 4096) / (int)sizeof(double));
+         gpulin_destroy(h);
+         return fail(GPULIN_ERR_CUDA, "cannot reserve %d bytes of shared memory for %s", sv.smem, sv.name);
       }
-      h->nlongblocks = std::min(h->nlong, h->nsm * 2);
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv.kernel, sv.threads, sv.smem) != cudaSuccess || occ < 1 )
+         occ = 1;
+      const char* oe = getenv("GPULIN_SHORT_OCC");      // experiment: blocks per SM of the persistent grid
+      if( oe != nullptr && atoi(oe) > 0 )
+         occ = atoi(oe);
+      const int wpb = sv.threads / 32;
+      const int64_t need = ((int64_t)nslices + wpb - 1) / wpb;
+      h->nshortblocks = (int)std::min<int64_t>(need, (int64_t)h->nsm * occ);
+      if( getenv("GPULIN_VERBOSE") != nullptr )
+         fprintf(stderr, "gpulin: short sweep %s, %d blocks x %d threads (%d per SM), %d B smem\n", sv.name, h->nshortblocks,
+            sv.threads, occ, sv.smem);
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_medium_kernel<MEDIUM_U, MEDIUM_MINB>, SWEEP_THREADS, 0) != cudaSuccess || occ < 1 )
+         occ = 2;
+      const int64_t needm = ((int64_t)h->nmedium + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32);
+      h->nmediumblocks = (int)std::min<int64_t>(needm, (int64_t)h->nsm * occ);
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_long_kernel, LONG_THREADS, 0) != cudaSuccess || occ < 1 )
+         occ = 1;
+      h->nlongblocks = (int)std::min<int64_t>(h->nlong, (int64_t)h->nsm * occ);
    }
 
    if( !h->hostloop )
@@ -531,6 +579,15 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    cudaFree(h->d_updidx);
    cudaFree(h->d_updlb);
    cudaFree(h->d_updub);
+   for( int i = 0; i < 2; ++i )
+   {
+      if( h->aux[i] != nullptr )
+         cudaStreamDestroy(h->aux[i]);
+      if( h->evjoin[i] != nullptr )
+         cudaEventDestroy(h->evjoin[i]);
+   }
+   if( h->evfork != nullptr )
+      cudaEventDestroy(h->evfork);
    if( h->ev0 != nullptr )
       cudaEventDestroy(h->ev0);
    if( h->ev1 != nullptr )
@@ -647,8 +704,7 @@ extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
       begin_kernel<<<1, 1, 0, h->stream>>>(h->p.ctrl);
       for( ;; )
       {
-         launchRoundKernels<false, false>(h, true, true);
-         CU(cudaGetLastError());
+         OK((launchRoundKernels<false, false>(h, true, true)));
          int cont = 0;
          CU(cudaMemcpyAsync(&h->h_ctrl->cont, &h->p.ctrl->cont, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
          CU(cudaStreamSynchronize(h->stream));
@@ -716,6 +772,7 @@ extern "C" int gpulin_set_change_log(gpulin_t* h, int64_t capacity)
       h->logcap = capacity;
       h->p.log = h->d_log;
    }
+   CU(cudaMemcpy(const_cast<DevProblem*>(h->p.self), &h->p, sizeof(DevProblem), cudaMemcpyHostToDevice));
    // kernel parameters are baked into the graph
    if( !h->hostloop )
       OK(buildGraph(h));
@@ -764,8 +821,8 @@ extern "C" int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats)
 {
    if( h == nullptr || stats == nullptr )
       return fail(GPULIN_ERR_ARG, "invalid argument");
-   const int64_t v[10] = {h->nnz, h->nstored, h->nshort, h->nmedium, h->nlong, (int64_t)h->devbytes, h->ct.n,
-      h->nsweepblocks, h->maxlen, h->longsmemcap};
+   const int64_t v[10] = {h->nnz, h->nstored, h->nshort, h->nmedium, h->nlong, (int64_t)h->devbytes, h->nshortblocks,
+      h->nmediumblocks, h->nlongblocks, h->maxlen};
    for( int i = 0; i < nstats && i < 10; ++i )
       stats[i] = v[i];
    return GPULIN_OK;
@@ -842,7 +899,7 @@ extern "C" int gpulin_round_sweep(gpulin_t* h)
    if( !h->havebounds )
       return fail(GPULIN_ERR_STATE, "gpulin_round_sweep before gpulin_set_bounds");
    CU(cudaSetDevice(h->device));
-   launchRoundKernels<false, false>(h, true, false);
+   OK((launchRoundKernels<false, false>(h, true, false)));
    publish_cutoff_kernel<<<1, 1, 0, h->stream>>>(h->p);
    CU(cudaGetLastError());
    return GPULIN_OK;
@@ -855,10 +912,9 @@ extern "C" int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int
    CU(cudaSetDevice(h->device));
    absorb_cutoff_kernel<<<1, 1, 0, h->stream>>>(h->p);
    if( dense )
-      launchRoundKernels<true, false>(h, false, true);
+      OK((launchRoundKernels<true, false>(h, false, true)));
    else
-      launchRoundKernels<false, false>(h, false, true);
-   CU(cudaGetLastError());
+      OK((launchRoundKernels<false, false>(h, false, true)));
    if( nchanges != nullptr || cutoff != nullptr )
    {
       OK(fetchCtrl(h));

@@ -165,6 +165,27 @@ __device__ __forceinline__ void addContributionSlow(const Num& n, double a, doub
    }
 }
 
+// the rare part of accElem: an infinite bound or a huge product
+__device__ __noinline__ void accElemSlow(const Num& n, RowAcc& r, double a, double l, double u)
+{
+   if( a > 0.0 )
+   {
+      addContributionSlow(n, a, l, r.minhi, r.minlo, r.cnt, MINPOSINF, MINNEGINF, MINPOSHUGE, MINNEGHUGE);
+      addContributionSlow(n, a, u, r.maxhi, r.maxlo, r.cnt, MAXPOSINF, MAXNEGINF, MAXPOSHUGE, MAXNEGHUGE);
+   }
+   else
+   {
+      // negative coefficient: the infinity counters are switched, the huge counters follow the sign of the
+      // contribution (:1737-1769)
+      addContributionSlow(n, a, l, r.maxhi, r.maxlo, r.cnt, MAXNEGINF, MAXPOSINF, MAXPOSHUGE, MAXNEGHUGE);
+      addContributionSlow(n, a, u, r.minhi, r.minlo, r.cnt, MINNEGINF, MINPOSINF, MINPOSHUGE, MINNEGHUGE);
+   }
+   if( isInf(n, -l) || isInf(n, u) )
+      r.maxdelta = n.inf;
+   else
+      r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
+}
+
 // classification + accumulation of one nonzero (a, [l,u]); the common case (finite bounds, no huge product)
 // is branch-free
 __device__ __forceinline__ void accElem(const Num& n, RowAcc& r, double a, double l, double u)
@@ -182,24 +203,7 @@ __device__ __forceinline__ void accElem(const Num& n, RowAcc& r, double a, doubl
       r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
    }
    else
-   {
-      if( pos )
-      {
-         addContributionSlow(n, a, l, r.minhi, r.minlo, r.cnt, MINPOSINF, MINNEGINF, MINPOSHUGE, MINNEGHUGE);
-         addContributionSlow(n, a, u, r.maxhi, r.maxlo, r.cnt, MAXPOSINF, MAXNEGINF, MAXPOSHUGE, MAXNEGHUGE);
-      }
-      else
-      {
-         // negative coefficient: the infinity counters are switched, the huge counters follow the sign of the
-         // contribution (:1737-1769)
-         addContributionSlow(n, a, l, r.maxhi, r.maxlo, r.cnt, MAXNEGINF, MAXPOSINF, MAXPOSHUGE, MAXNEGHUGE);
-         addContributionSlow(n, a, u, r.minhi, r.minlo, r.cnt, MINNEGINF, MINPOSINF, MINPOSHUGE, MINNEGHUGE);
-      }
-      if( isInf(n, -l) || isInf(n, u) )
-         r.maxdelta = n.inf;
-      else
-         r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
-   }
+      accElemSlow(n, r, a, l, u);
 }
 
 __device__ __forceinline__ void accMerge(RowAcc& r, const RowAcc& o)
@@ -372,9 +376,10 @@ __device__ __forceinline__ void inferUb(const Num& n, const Sink& s, int j, bool
       return;
    if( !isLT(n, newub, u) )
       return;
-   const long long key = d2key(newub);
-   if( atomicMin(&s.cand[2 * (size_t)j + 1], key) > key )
-      s.colflag[j] = 1;
+   // every value that gets here is below the round-start bound, so the column changes this round whichever
+   // candidate wins: no need to wait for the atomic's result
+   atomicMin(&s.cand[2 * (size_t)j + 1], d2key(newub));
+   s.colflag[j] = 1;
 }
 __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool integral, double newlb, double l,
    double u, bool force, bool& cutoff)
@@ -390,9 +395,8 @@ __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool
       return;
    if( !isGT(n, newlb, l) )
       return;
-   const long long key = ~d2key(newlb);
-   if( atomicMin(&s.cand[2 * (size_t)j], key) > key )
-      s.colflag[j] = 1;
+   atomicMin(&s.cand[2 * (size_t)j], ~d2key(newlb));
+   s.colflag[j] = 1;
 }
 
 // tightenVarUb / tightenVarLb: cons_linear.c:5242-5307 / 5311-5376
