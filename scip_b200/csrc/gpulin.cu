@@ -53,11 +53,12 @@ struct gpulin
    int         nshort = 0, nmedium = 0, nlong = 0;
    int         maxlen = 0;
    DevProblem  p{};
-   int         shortvariant = 8;
+   int         shortvariant = 1;
    int         nshortblocks = 0;
    int         nmediumblocks = 0;
    int         nlongblocks = 0;
    int         napplyblocks = 0;
+   int         nexactblocks = 0;
    int         nsm = 148;
    std::vector<int> perm;        // permuted row -> caller's row
    // device allocations
@@ -151,9 +152,7 @@ struct ShortVariant
    int         smem;     // dynamic shared memory per block
    const char* name;
 };
-#define ASYNC_SMEM(CH, D2, T) (((D2) + 1) * (CH) * (T) * 28 + ((D2) + 1) * (T) * 16)
 #define REGV(CH, PF, MB) {sweep_short_kernel<CH, PF, MB>, SWEEP_THREADS, 0, "reg<" #CH "," #PF "," #MB ">"}
-#define ASYV(CH, D1, D2, T) {sweep_short_async_kernel<CH, D1, D2, T>, T, ASYNC_SMEM(CH, D2, T), "async<" #CH "," #D1 "," #D2 "," #T ">"}
 static const ShortVariant g_shortVariants[] = {
    REGV(4, true, 3),     // 0
    REGV(4, false, 4),    // 1
@@ -163,16 +162,14 @@ static const ShortVariant g_shortVariants[] = {
    REGV(4, true, 2),     // 5
    REGV(4, false, 3),    // 6
    REGV(8, false, 3),    // 7
-   ASYV(4, 1, 2, 128),   // 8
-   ASYV(4, 2, 4, 128),   // 9
-   ASYV(4, 1, 3, 128),   // 10
-   ASYV(8, 1, 2, 128),   // 11
-   ASYV(2, 2, 4, 128),   // 12
-   ASYV(2, 1, 2, 256),   // 13
-   ASYV(4, 1, 2, 256),   // 14
-   ASYV(4, 2, 3, 128),   // 15
-   ASYV(8, 2, 3, 128),   // 16
-   ASYV(2, 3, 6, 128),   // 17
+   REGV(4, true, 4),     // 8
+   REGV(8, true, 3),     // 9
+   REGV(8, false, 4),    // 10
+   REGV(4, false, 5),    // 11
+   REGV(4, false, 6),    // 12
+   REGV(2, false, 6),    // 13
+   REGV(2, true, 6),     // 14
+   REGV(16, false, 2),   // 15
 };
 constexpr int NSHORTVARIANTS = sizeof(g_shortVariants) / sizeof(g_shortVariants[0]);
 
@@ -220,8 +217,10 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
          }
       }
    }
+   if( sweep )
+      exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
    if( apply )
-      apply_kernel<DENSE, GRAPH><<<h->napplyblocks, 256, 0, h->stream>>>(h->p, h->handle);
+      apply_kernel<DENSE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
    CU(cudaGetLastError());
    return GPULIN_OK;
 }
@@ -418,7 +417,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    // ---- upload ---------------------------------------------------------------------------------------------------
    DevProblem& p = h->p;
    long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
-   unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned char* d_colflag; long long* d_colbeg; int* d_colrows;
+   int* d_xlist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned char* d_colflag; long long* d_colbeg; int* d_colrows;
    Ctrl* d_ctrl;
    int rc = GPULIN_OK;
 #define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
@@ -430,6 +429,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &d_cols, (size_t)h->nstored + 2));
    TRY(devAlloc(h, &d_sides, (size_t)nrows + 1));
    TRY(devAlloc(h, &d_dirty, (size_t)nrows + 64));
+   TRY(devAlloc(h, &d_xlist, (size_t)nrows + 1));
    TRY(devAlloc(h, &d_bnd, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)ncols + 2));
    TRY(devAlloc(h, &d_colflag, (size_t)ncols + 64));
@@ -439,7 +439,27 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &h->d_tmplb, (size_t)ncols + 1));
    TRY(devAlloc(h, &h->d_tmpub, (size_t)ncols + 1));
    TRYCU(cudaMemcpy(d_sell_off, sell_off.data(), sizeof(long long) * ((size_t)nslices + 1), cudaMemcpyHostToDevice));
-   TRYCU(cudaMemcpy(d_rowlen, plen.data(), sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice));
+   {
+      // rows with a coefficient below hugeval / infinity always take the exact rules (see ROWLEN_EXACT)
+      gpulin_numerics dn;
+      gpulin_default_numerics(&dn);
+      const gpulin_numerics* nn = (num != nullptr) ? num : &dn;
+      const double tiny = nn->hugeval / nn->infinity;
+      std::vector<int> flagged(plen);
+      for( int64_t i = 0; i < nrows; ++i )
+      {
+         const int64_t r = perm[(size_t)i];
+         for( int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k )
+         {
+            if( std::fabs(vals[k]) < tiny )
+            {
+               flagged[(size_t)i] |= ROWLEN_EXACT;
+               break;
+            }
+         }
+      }
+      TRYCU(cudaMemcpy(d_rowlen, flagged.data(), sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice));
+   }
    TRYCU(cudaMemcpy(d_rowbeg, rowbeg.data(), sizeof(long long) * ((size_t)nrows + 1), cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_vals, pvals.data(), sizeof(double) * (size_t)h->nstored, cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_cols, pcols.data(), sizeof(int) * (size_t)h->nstored, cudaMemcpyHostToDevice));
@@ -479,6 +499,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.cols = d_cols;
    p.sides = d_sides;
    p.dirty = d_dirty;
+   p.xlist = d_xlist;
    p.bnd = d_bnd;
    p.cand = d_cand;
    p.colflag = d_colflag;
@@ -497,25 +518,11 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.num.bstreps = num->boundstreps;
    p.num.huge = num->hugeval;
    p.num.maxeasy = num->maxeasyactivitydelta;
-   {
-      DevProblem* d_self = nullptr;
-      int rcs = devAlloc(h, &d_self, 1);
-      if( rcs != GPULIN_OK )
-      {
-         gpulin_destroy(h);
-         return rcs;
-      }
-      p.self = d_self;
-      if( cudaMemcpy(d_self, &p, sizeof(DevProblem), cudaMemcpyHostToDevice) != cudaSuccess )
-      {
-         gpulin_destroy(h);
-         return fail(GPULIN_ERR_CUDA, "cudaMemcpy of the problem descriptor failed");
-      }
-   }
 
    // ---- launch geometry ------------------------------------------------------------------------------------------
    // persistent grids: as many blocks as stay resident, never more than there is work
-   h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols + 255) / 256, (int64_t)h->nsm * 8));
+   // flag scan: 16 columns per thread
+   h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols / 16 + APPLY_THREADS) / APPLY_THREADS, (int64_t)h->nsm * 4));
    {
       int occ = 0;
       const char* ve = getenv("GPULIN_SHORT_VARIANT");
@@ -545,6 +552,9 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_long_kernel, LONG_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nlongblocks = (int)std::min<int64_t>(h->nlong, (int64_t)h->nsm * occ);
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_rows_kernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
+         occ = 1;
+      h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
    }
 
    if( !h->hostloop )
@@ -772,7 +782,6 @@ extern "C" int gpulin_set_change_log(gpulin_t* h, int64_t capacity)
       h->logcap = capacity;
       h->p.log = h->d_log;
    }
-   CU(cudaMemcpy(const_cast<DevProblem*>(h->p.self), &h->p, sizeof(DevProblem), cudaMemcpyHostToDevice));
    // kernel parameters are baked into the graph
    if( !h->hostloop )
       OK(buildGraph(h));

@@ -37,12 +37,13 @@ struct Ctrl
    int                status;       // GPULIN_FIXPOINT / _CUTOFF / _ROUNDLIMIT
    int                cutoff;       // set by any kernel that proves infeasibility
    unsigned int       ticket;       // apply kernel: blocks finished
-   int                pad0;
+   unsigned int       pad0;
    unsigned long long logcount;     // entries produced
    unsigned long long round_nchg;   // accepted bound changes of the running round
    unsigned long long total_nchg;
    unsigned long long total_nnz;
    unsigned long long t_start;      // %globaltimer at the start of the call
+   unsigned int       nexact[4];    // rows the filter sweeps handed to the exact kernel in the running round, per bin
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
    unsigned long long hist_time[MAX_HIST];   // %globaltimer at the end of each round
    unsigned long long hist_nnz[MAX_HIST];
@@ -72,6 +73,7 @@ struct DevProblem
    const int*          cols;       // column index | (integral << 31)
    const double2*      sides;      // (lhs, rhs) per row
    unsigned char*      dirty;      // per row: marked for propagation
+   int*                xlist;      // rows handed to exact_rows_kernel; one region per bin: [0,nshort) [nshort,+nmedium) [..,nrows)
    // columns
    const double2*      bnd;        // (lb, ub) at round start
    long long*          cand;       // 2*ncols (+2) candidate keys, see Sink
@@ -81,8 +83,6 @@ struct DevProblem
    const int*          colrows;
    Ctrl*               ctrl;
    ChangeRec*          log;
-   const DevProblem*   self;       // copy of this struct in device memory: what the out-of-line (rare path) functions
-                                   // read, so that the kernel parameter never needs an address
    Num                 num;
 };
 
@@ -174,81 +174,82 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
    }
 }
 
-// ---- hot-path row state: the finite parts only.  An element with an infinite bound or a huge product (rare) just
-// ---- raises `slow`; such a row is redone by the *Slow functions below with the full classification.
-struct FastAcc
+// ---- hot path: an interval filter in plain fp64 ----------------------------------------------------------------
+// The sweep accumulates, per row, the activities minact/maxact as ordinary double sums together with
+//    maxdelta ~ max_k |a_k| (ub_k - lb_k)      and      cabs = max_k max(|a_k lb_k|, |a_k ub_k|),
+// 9 fp64 instructions per nonzero.  With n = row length and u = 2^-52 every one of these differs from the value the
+// exact rules would use (double-double sums, gpulin_device.cuh) by at most E = (n^2 + 8) u cabs.  A row is CLEARLY
+// QUIET if, for every perturbation within E, the reference's gates say "no bound can be tightened"
+// (tightenBounds :7057, :7081) and its verdict says "feasible" (propagateCons :7728).  Such a row is finished --
+// with exactly the result of the full rules.  Every other row (it may tighten something, it may be infeasible, it
+// holds an infinite bound or a huge product, or it is too close to call) is redone by rowExact*: double-double
+// activities with the inf/huge counters, gates, candidates, verdict, as restated from the reference.
+// Once the bounds have settled almost all rows are clearly quiet, so the matrix is streamed once per round and the
+// exact pass touches (from L2) only rows that have work.
+constexpr int ROWLEN_EXACT = 0x40000000;   // flag in rowlen[]: the row has a coefficient so small that an infinite
+                                           // bound could hide behind a non-huge product -> always the exact rules
+
+struct LeanAcc
 {
-   double minhi, minlo, maxhi, maxlo, maxdelta;
+   double minact, maxact, maxdelta, cabs;
 };
 
-__device__ __forceinline__ void fastInit(FastAcc& r)
+__device__ __forceinline__ void leanInit(LeanAcc& r)
 {
-   r.minhi = r.minlo = r.maxhi = r.maxlo = r.maxdelta = 0.0;
+   r.minact = r.maxact = r.maxdelta = r.cabs = 0.0;
 }
 
-// returns false if the element needs the full classification (the sums are garbage then and get discarded)
-__device__ __forceinline__ bool fastElem(const Num& n, FastAcc& r, double a, double l, double u)
+__device__ __forceinline__ void leanElem(LeanAcc& r, double a, double l, double u)
 {
-   const bool pos = a > 0.0;
-   const double cmin = a * (pos ? l : u);
-   const double cmax = a * (pos ? u : l);
-   dd_add(r.minhi, r.minlo, cmin);
-   dd_add(r.maxhi, r.maxlo, cmax);
-   r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
-   return (fabs(l) < n.inf) && (fabs(u) < n.inf) && (fabs(cmin) < n.huge) && (fabs(cmax) < n.huge);
+   const double al = a * l;
+   const double au = a * u;
+   const double cmin = fmin(al, au);
+   const double cmax = fmax(al, au);
+   r.minact += cmin;
+   r.maxact += cmax;
+   r.maxdelta = fmax(r.maxdelta, cmax - cmin);
+   r.cabs = fmax(r.cabs, fmax(fabs(al), fabs(au)));
 }
 
-__device__ __forceinline__ void fastWarpReduce(FastAcc& r, int lane)
+__device__ __forceinline__ void leanWarpReduce(LeanAcc& r)
 {
 #pragma unroll
    for( int m = 16; m >= 1; m >>= 1 )
    {
-      FastAcc o;
-      o.minhi = __shfl_xor_sync(0xffffffffu, r.minhi, m);
-      o.minlo = __shfl_xor_sync(0xffffffffu, r.minlo, m);
-      o.maxhi = __shfl_xor_sync(0xffffffffu, r.maxhi, m);
-      o.maxlo = __shfl_xor_sync(0xffffffffu, r.maxlo, m);
-      o.maxdelta = __shfl_xor_sync(0xffffffffu, r.maxdelta, m);
-      const bool upper = (lane & m) != 0;
-      FastAcc x = upper ? o : r;
-      const FastAcc y = upper ? r : o;
-      dd_add_dd(x.minhi, x.minlo, y.minhi, y.minlo);
-      dd_add_dd(x.maxhi, x.maxlo, y.maxhi, y.maxlo);
-      x.maxdelta = fmax(x.maxdelta, y.maxdelta);
-      r = x;
+      r.minact += __shfl_xor_sync(0xffffffffu, r.minact, m);
+      r.maxact += __shfl_xor_sync(0xffffffffu, r.maxact, m);
+      r.maxdelta = fmax(r.maxdelta, __shfl_xor_sync(0xffffffffu, r.maxdelta, m));
+      r.cabs = fmax(r.cabs, __shfl_xor_sync(0xffffffffu, r.cabs, m));
    }
 }
 
-// ---- exact, division-free early exit for the common row: all contributions finite, the row can neither tighten a
-// ---- bound (tightenBounds gates :7057, :7081) nor be infeasible (propagateCons :7728).  Whatever this test cannot
-// ---- decide goes to rowTighten, which restates the reference's rules in full.
-__device__ __forceinline__ bool rowIsQuiet(const Num& n, const FastAcc& a, double lhs, double rhs)
+__device__ __forceinline__ bool rowClearlyQuiet(const Num& n, const LeanAcc& r, int len, double lhs, double rhs)
 {
-   const double minact = a.minhi + a.minlo;
-   const double maxact = a.maxhi + a.maxlo;
-   // FeasGT(minact,rhs) needs (minact-rhs)/max(1,|minact|,|rhs|) > feastol, impossible if minact-rhs <= feastol/2
-   if( minact - rhs > 0.5 * n.feastol || lhs - maxact > 0.5 * n.feastol )
+   // an infinite bound (|b| >= 1e20, with |a| >= hugeval/infinity by the ROWLEN_EXACT flag) or a huge product shows
+   // up in cabs; NaN compares false
+   if( !(r.cabs < n.huge) )
       return false;
-   if( fabs(a.maxdelta) <= n.feastol )
-      return true;
-   const double slack = isInf(n, rhs) ? n.inf : rhs - minact;
-   const double surplus = isInf(n, -lhs) ? n.inf : maxact - lhs;
-   return isLE(n, a.maxdelta, fmin(slack, surplus));
+   const double E = (double)(len * len + 8) * 2.3e-16 * r.cabs;
+   // verdict: FeasGT(minact,rhs) needs (minact-rhs)/max(1,|minact|,|rhs|) > feastol, impossible if minact-rhs <= feastol/4
+   if( (r.minact - rhs) + E > 0.25 * n.feastol || (lhs - r.maxact) + E > 0.25 * n.feastol )
+      return false;
+   const double md = r.maxdelta + E;
+   if( md <= 0.5 * n.feastol )
+      return true;                // all variables fixed (:7057)
+   const double slack = isInf(n, rhs) ? n.inf : rhs - r.minact;
+   const double surplus = isInf(n, -lhs) ? n.inf : r.maxact - lhs;
+   const double m = fmin(slack, surplus);
+   // the gate maxdelta <= min(slack, surplus) + eps (:7081) with every rounding in its disfavour
+   return md + 2.0 * E + 4.5e-16 * fabs(m) - m <= 0.5 * n.eps;
 }
 
-// gates, candidate pass and verdict of one row whose activities are known (elements first, first+step, ... of the
-// calling thread); everything by value: the caller's state stays in registers
-__device__ __noinline__ void rowTighten(const DevProblem* dp, double minhi, double minlo, double maxhi, double maxlo,
-   double maxdelta, unsigned cnt, double lhs, double rhs, long long base, int stride, int first, int step, int len)
+// gates, candidate pass and verdict of one row whose exact activities are known (elements first, first+step, ... of
+// the calling thread)
+__device__ __forceinline__ void rowTighten(const DevProblem& p, const RowAcc& acc, double lhs, double rhs, long long base,
+   int stride, int first, int step, int len)
 {
-   const DevProblem& p = *dp;
    RowInfo ri;
-   ri.acc.minhi = minhi;
-   ri.acc.minlo = minlo;
-   ri.acc.maxhi = maxhi;
-   ri.acc.maxlo = maxlo;
-   ri.acc.maxdelta = maxdelta;
-   ri.acc.cnt = cnt;
+   ri.acc = acc;
    ri.lhs = lhs;
    ri.rhs = rhs;
    bool cutoff = false;
@@ -258,35 +259,63 @@ __device__ __noinline__ void rowTighten(const DevProblem* dp, double minhi, doub
       p.ctrl->cutoff = 1;
 }
 
-// a row with infinite bounds / huge products, thread-per-row: full classification, sequentially
-__device__ __noinline__ void rowSlowThread(const DevProblem* dp, double lhs, double rhs, long long base, int len)
+// exact activities of the elements first, first+step, ... < len (four independent loads in flight)
+__device__ __forceinline__ void accumulateExact(const DevProblem& p, RowAcc& acc, long long base, int stride, int first,
+   int step, int len)
 {
-   const DevProblem& p = *dp;
-   RowAcc acc;
-   accInit(acc);
-   for( int k = 0; k < len; ++k )
+   for( int k0 = first; k0 < len; k0 += 4 * step )
    {
-      const double a = p.vals[base + 32LL * k];
-      const double2 b = p.bnd[p.cols[base + 32LL * k] & 0x7fffffff];
-      accElem(p.num, acc, a, b.x, b.y);
+      double a[4];
+      int cj[4];
+      double2 b[4];
+#pragma unroll
+      for( int q = 0; q < 4; ++q )
+      {
+         const int k = k0 + q * step;
+         if( k < len )
+         {
+            a[q] = p.vals[base + (long long)stride * k];
+            cj[q] = p.cols[base + (long long)stride * k];
+         }
+      }
+#pragma unroll
+      for( int q = 0; q < 4; ++q )
+      {
+         if( k0 + q * step < len )
+            b[q] = p.bnd[cj[q] & 0x7fffffff];
+      }
+#pragma unroll
+      for( int q = 0; q < 4; ++q )
+      {
+         if( k0 + q * step < len )
+            accElem(p.num, acc, a[q], b[q].x, b[q].y);
+      }
    }
-   rowTighten(dp, acc.minhi, acc.minlo, acc.maxhi, acc.maxlo, acc.maxdelta, acc.cnt, lhs, rhs, base, 32, 0, 1, len);
 }
 
-// the same for a warp-per-row row (called by all 32 lanes)
-__device__ __noinline__ void rowSlowWarp(const DevProblem* dp, double lhs, double rhs, long long beg, int len, int lane)
+constexpr unsigned char ROW_CLEAN = 0;
+constexpr unsigned char ROW_MARKED = 1;
+
+// butterfly over the W lanes of a sub-warp group (all 32 lanes of the warp execute it)
+template <int W>
+__device__ __forceinline__ void accGroupReduce(RowAcc& r, int lane)
 {
-   const DevProblem& p = *dp;
-   RowAcc acc;
-   accInit(acc);
-   for( int idx = lane; idx < len; idx += 32 )
+#pragma unroll
+   for( int m = W / 2; m >= 1; m >>= 1 )
    {
-      const double a = p.vals[beg + idx];
-      const double2 b = p.bnd[p.cols[beg + idx] & 0x7fffffff];
-      accElem(p.num, acc, a, b.x, b.y);
+      RowAcc o;
+      o.minhi = __shfl_xor_sync(0xffffffffu, r.minhi, m);
+      o.minlo = __shfl_xor_sync(0xffffffffu, r.minlo, m);
+      o.maxhi = __shfl_xor_sync(0xffffffffu, r.maxhi, m);
+      o.maxlo = __shfl_xor_sync(0xffffffffu, r.maxlo, m);
+      o.maxdelta = __shfl_xor_sync(0xffffffffu, r.maxdelta, m);
+      o.cnt = __shfl_xor_sync(0xffffffffu, r.cnt, m);
+      const bool upper = (lane & m) != 0;
+      RowAcc a = upper ? o : r;
+      const RowAcc b = upper ? r : o;
+      accMerge(a, b);
+      r = a;
    }
-   accWarpReduce(acc, lane);
-   rowTighten(dp, acc.minhi, acc.minlo, acc.maxhi, acc.maxlo, acc.maxdelta, acc.cnt, lhs, rhs, beg, 1, lane, 32, len);
 }
 
 __device__ __forceinline__ void addRoundNnz(const DevProblem& p, unsigned long long nnzdone, int slot)
@@ -296,8 +325,7 @@ __device__ __forceinline__ void addRoundNnz(const DevProblem& p, unsigned long l
 }
 
 // ---- thread-per-row on SELL-32 slices: element k of the row of lane t sits at slice_off + 32 k + t -------------
-// ---- persistent warps: warp w sweeps slices w, w + W, w + 2W, ...; the coefficients of chunk c+1 are in flight
-// ---- while the bounds of chunk c are gathered
+// ---- persistent warps: warp w sweeps slices w, w + W, w + 2W, ...
 template <int CH>
 __device__ __forceinline__ void loadChunk(const DevProblem& p, long long base, int c, int len, double (&a)[CH], int (&cj)[CH])
 {
@@ -318,17 +346,18 @@ __device__ __forceinline__ void sweepSlice(const DevProblem& p, int slice, int l
    const Num& n = p.num;
    const int row = slice * 32 + lane;
    int len = 0;
+   bool exact = false;
    if( act )
    {
-      p.dirty[row] = 0;
       len = p.rowlen[row];
+      exact = (len & ROWLEN_EXACT) != 0;
+      len &= ~ROWLEN_EXACT;
    }
    const long long base = p.sell_off[slice] + lane;
    const int maxlen = __reduce_max_sync(0xffffffffu, len);
 
-   FastAcc acc;
-   fastInit(acc);
-   bool fast = true;
+   LeanAcc acc;
+   leanInit(acc);
    if( PF )
    {
       // the coefficients of chunk c+1 are in flight while the bounds of chunk c are gathered
@@ -358,7 +387,7 @@ __device__ __forceinline__ void sweepSlice(const DevProblem& p, int slice, int l
          for( int k = 0; k < CH; ++k )
          {
             if( c + k < len )
-               fast &= fastElem(n, acc, a[k], b[k].x, b[k].y);
+               leanElem(acc, a[k], b[k].x, b[k].y);
          }
       }
    }
@@ -380,18 +409,28 @@ __device__ __forceinline__ void sweepSlice(const DevProblem& p, int slice, int l
          for( int k = 0; k < CH; ++k )
          {
             if( c + k < len )
-               fast &= fastElem(n, acc, a[k], b[k].x, b[k].y);
+               leanElem(acc, a[k], b[k].x, b[k].y);
          }
       }
    }
+   bool handoff = false;
    if( act )
    {
       const double2 sd = p.sides[row];
-      if( !fast )
-         rowSlowThread(p.self, sd.x, sd.y, base, len);
-      else if( !rowIsQuiet(n, acc, sd.x, sd.y) )
-         rowTighten(p.self, acc.minhi, acc.minlo, acc.maxhi, acc.maxlo, acc.maxdelta, 0u, sd.x, sd.y, base, 32, 0, 1, len);
+      handoff = exact || !rowClearlyQuiet(n, acc, len, sd.x, sd.y);
+      p.dirty[row] = ROW_CLEAN;
       nnzdone += (unsigned)len;
+   }
+   // rows that need the exact rules go to the work list of exact_rows_kernel (one atomic per warp)
+   const unsigned hm = __ballot_sync(0xffffffffu, handoff);
+   if( hm != 0u )
+   {
+      unsigned pos = 0u;
+      if( lane == 0 )
+         pos = atomicAdd(&p.ctrl->nexact[0], (unsigned)__popc(hm));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if( handoff )
+         p.xlist[pos + __popc(hm & ((1u << lane) - 1u))] = row;
    }
 }
 
@@ -411,7 +450,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) sweep_short_kernel(const 
       for( int i = 0; i < 4; ++i )
       {
          const int row = (s0 + i * nw) * 32 + lane;
-         if( s0 + i * nw < nslices && row < p.nshort && p.dirty[row] != 0 )
+         if( s0 + i * nw < nslices && row < p.nshort && p.dirty[row] == ROW_MARKED )
             fm |= 1u << i;
       }
 #pragma unroll 1
@@ -421,251 +460,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) sweep_short_kernel(const 
          if( __any_sync(0xffffffffu, act) )
             sweepSlice<CH, PF>(p, s0 + i * nw, lane, act, nnzdone);
       }
-   }
-   nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
-   if( lane == 0 )
-      addRoundNnz(p, (unsigned long long)nnzdone, gw);
-}
-
-// ---- thread-per-row on SELL-32 slices with a thread-private asynchronous pipeline (cp.async into shared memory) ----
-// Latency is hidden by depth, not by occupancy: while chunk t is accumulated, the bounds of chunks t+1 .. t+D2-D1 are
-// being gathered (16-byte cp.async.cg each) and the coefficients / column indices of the chunks up to t+D2 are
-// streaming in.  Every thread copies and reads back only its own slots, so the pipeline needs no barrier at all:
-// cp.async.wait_group orders a thread's own copies.  One warp walks slices w, w+W, ... in batches of 16 whose row
-// lengths / flags / slice offsets are fetched up front.
-__device__ __forceinline__ unsigned smemAddr(const void* ptr)
-{
-   return (unsigned)__cvta_generic_to_shared(ptr);
-}
-__device__ __forceinline__ void cpAsync4(unsigned dst, const void* src)
-{
-   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cpAsync8(unsigned dst, const void* src)
-{
-   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cpAsync16(unsigned dst, const void* src)
-{
-   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cpAsyncCommit()
-{
-   asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cpAsyncWait()
-{
-   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-constexpr int ASYNC_BATCH = 16;   // slices per metadata batch
-
-// position in the flat chunk sequence of a batch: slice i of the batch, first element c of the chunk
-struct ChunkCursor
-{
-   int i;
-   int c;
-   int nslice;   // present slices passed so far (ring index of the row sides)
-};
-
-template <int CH, int D1, int D2, int THREADS>
-__global__ void __launch_bounds__(THREADS) sweep_short_async_kernel(const DevProblem p)
-{
-   constexpr int NST = D2 + 1;
-   extern __shared__ __align__(16) unsigned char smem_raw[];
-   // [NST][CH][THREADS] of: double2 bounds | double coefficient | int column ; then [NST][THREADS] double2 sides
-   double2* s_b = reinterpret_cast<double2*>(smem_raw);
-   double* s_a = reinterpret_cast<double*>(s_b + NST * CH * THREADS);
-   int* s_cj = reinterpret_cast<int*>(s_a + NST * CH * THREADS);
-   double2* s_sd = reinterpret_cast<double2*>(s_cj + NST * CH * THREADS);
-
-   const Num& n = p.num;
-   const int tid = threadIdx.x;
-   const int lane = tid & 31;
-   const int gw = (blockIdx.x * THREADS + tid) >> 5;
-   const int nw = (gridDim.x * THREADS) >> 5;
-   const int nslices = (p.nshort + 31) >> 5;
-   unsigned nnzdone = 0;
-
-   for( int s0 = gw; s0 < nslices; s0 += ASYNC_BATCH * nw )
-   {
-      // ---- batch metadata: per lane the lengths of its rows (8 bits each), warp-uniform chunk extents, slice offsets
-      unsigned lenpk[ASYNC_BATCH / 4];
-      unsigned mlpk[ASYNC_BATCH / 4];
-      unsigned actmask = 0u;      // per lane: my row of slice i is marked
-      unsigned present = 0u;      // warp-uniform: slice i has a marked row
-      long long soff = 0;         // lane i: element offset of slice i
-#pragma unroll
-      for( int q = 0; q < ASYNC_BATCH / 4; ++q )
-      {
-         lenpk[q] = 0u;
-         mlpk[q] = 0u;
-      }
-      {
-         int len[ASYNC_BATCH];
-#pragma unroll
-         for( int i = 0; i < ASYNC_BATCH; ++i )
-         {
-            const int slice = s0 + i * nw;
-            const int row = slice * 32 + lane;
-            len[i] = -1;
-            if( slice < nslices && row < p.nshort && p.dirty[row] != 0 )
-               len[i] = p.rowlen[row];
-         }
-         if( lane < ASYNC_BATCH && s0 + lane * nw < nslices )
-            soff = p.sell_off[s0 + lane * nw];
-#pragma unroll
-         for( int i = 0; i < ASYNC_BATCH; ++i )
-         {
-            const bool act = len[i] >= 0;
-            if( __any_sync(0xffffffffu, act) )
-            {
-               present |= 1u << i;
-               if( act )
-               {
-                  actmask |= 1u << i;
-                  p.dirty[(s0 + i * nw) * 32 + lane] = 0;
-                  lenpk[i >> 2] |= (unsigned)len[i] << (8 * (i & 3));
-                  nnzdone += (unsigned)len[i];
-               }
-               const int ml = __reduce_max_sync(0xffffffffu, act ? len[i] : 0);
-               mlpk[i >> 2] |= (unsigned)(ml > 0 ? ml : 1) << (8 * (i & 3));
-            }
-         }
-      }
-      if( present == 0u )
-         continue;
-
-      // total chunks of the batch
-      int total = 0;
-#pragma unroll
-      for( int i = 0; i < ASYNC_BATCH; ++i )
-      {
-         const int ml = (int)((mlpk[i >> 2] >> (8 * (i & 3))) & 0xffu);
-         total += (ml + CH - 1) / CH;
-      }
-
-      auto lenOf = [&](int i) -> int {
-         unsigned w = lenpk[0];
-#pragma unroll
-         for( int q = 1; q < ASYNC_BATCH / 4; ++q )
-            w = ((i >> 2) == q) ? lenpk[q] : w;
-         return (int)((w >> (8 * (i & 3))) & 0xffu);
-      };
-      auto mlOf = [&](int i) -> int {
-         unsigned w = mlpk[0];
-#pragma unroll
-         for( int q = 1; q < ASYNC_BATCH / 4; ++q )
-            w = ((i >> 2) == q) ? mlpk[q] : w;
-         return (int)((w >> (8 * (i & 3))) & 0xffu);
-      };
-      auto advance = [&](ChunkCursor& cur) {
-         cur.c += CH;
-         if( cur.c >= mlOf(cur.i) )
-         {
-            cur.c = 0;
-            ++cur.nslice;
-            // next present slice (warp-uniform)
-            const unsigned rest = present & ~((2u << cur.i) - 1u);
-            cur.i = rest != 0u ? (__ffs(rest) - 1) : ASYNC_BATCH;
-         }
-      };
-
-      ChunkCursor c1, c2, c3;
-      c1.i = __ffs(present) - 1;
-      c1.c = 0;
-      c1.nslice = 0;
-      c2 = c1;
-      c3 = c1;
-
-      FastAcc acc;
-      fastInit(acc);
-      bool fast = true;
-
-      for( int t = 0; t < total + D2; ++t )
-      {
-         // ---- S1: coefficients + column indices of chunk t (and the sides of its row at the first chunk)
-         if( t < total )
-         {
-            const int i = c1.i;
-            const bool act = ((actmask >> i) & 1u) != 0u;
-            const int len = act ? lenOf(i) : 0;
-            const long long base = __shfl_sync(0xffffffffu, soff, i) + lane;
-            const int st = t % NST;
-#pragma unroll
-            for( int k = 0; k < CH; ++k )
-            {
-               if( c1.c + k < len )
-               {
-                  cpAsync8(smemAddr(&s_a[(st * CH + k) * THREADS + tid]), p.vals + base + 32LL * (c1.c + k));
-                  cpAsync4(smemAddr(&s_cj[(st * CH + k) * THREADS + tid]), p.cols + base + 32LL * (c1.c + k));
-               }
-            }
-            if( c1.c == 0 && act )
-               cpAsync16(smemAddr(&s_sd[(c1.nslice % NST) * THREADS + tid]), p.sides + ((s0 + i * nw) * 32 + lane));
-            advance(c1);
-         }
-         cpAsyncCommit();
-
-         // ---- S2: gather the bounds of chunk t - D1
-         if( t >= D1 && t - D1 < total )
-         {
-            cpAsyncWait<2 * D1>();
-            const int i = c2.i;
-            const bool act = ((actmask >> i) & 1u) != 0u;
-            const int len = act ? lenOf(i) : 0;
-            const int st = (t - D1) % NST;
-#pragma unroll
-            for( int k = 0; k < CH; ++k )
-            {
-               if( c2.c + k < len )
-               {
-                  const int cj = s_cj[(st * CH + k) * THREADS + tid];
-                  cpAsync16(smemAddr(&s_b[(st * CH + k) * THREADS + tid]), p.bnd + (cj & 0x7fffffff));
-               }
-            }
-            advance(c2);
-         }
-         cpAsyncCommit();
-
-         // ---- S3: accumulate chunk t - D2; at the last chunk of a slice finish its rows
-         if( t >= D2 )
-         {
-            cpAsyncWait<2 * (D2 - D1)>();
-            const int i = c3.i;
-            const bool act = ((actmask >> i) & 1u) != 0u;
-            const int len = act ? lenOf(i) : 0;
-            const int st = (t - D2) % NST;
-#pragma unroll
-            for( int k = 0; k < CH; ++k )
-            {
-               if( c3.c + k < len )
-               {
-                  const double a = s_a[(st * CH + k) * THREADS + tid];
-                  const double2 b = s_b[(st * CH + k) * THREADS + tid];
-                  fast &= fastElem(n, acc, a, b.x, b.y);
-               }
-            }
-            if( c3.c + CH >= mlOf(i) )
-            {
-               const long long base = __shfl_sync(0xffffffffu, soff, i) + lane;
-               if( act )
-               {
-                  const double2 sd = s_sd[(c3.nslice % NST) * THREADS + tid];
-                  if( !fast )
-                     rowSlowThread(p.self, sd.x, sd.y, base, len);
-                  else if( !rowIsQuiet(n, acc, sd.x, sd.y) )
-                     rowTighten(p.self, acc.minhi, acc.minlo, acc.maxhi, acc.maxlo, acc.maxdelta, 0u, sd.x, sd.y, base, 32,
-                        0, 1, len);
-               }
-               fastInit(acc);
-               fast = true;
-            }
-            advance(c3);
-         }
-      }
-      cpAsyncWait<0>();
    }
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
    if( lane == 0 )
@@ -692,15 +486,14 @@ template <int U>
 __device__ __forceinline__ void sweepWarpRow(const DevProblem& p, int row, int lane, unsigned long long& nnzdone)
 {
    const Num& n = p.num;
-   if( lane == 0 )
-      p.dirty[row] = 0;
-   const int len = p.rowlen[row];
+   int len = p.rowlen[row];
+   const bool exact = (len & ROWLEN_EXACT) != 0;
+   len &= ~ROWLEN_EXACT;
    const long long beg = p.rowbeg[row];
    const double2 sd = p.sides[row];
 
-   FastAcc acc;
-   fastInit(acc);
-   bool fast = true;
+   LeanAcc acc;
+   leanInit(acc);
    double an[U];
    int cjn[U];
    loadChunkW<U>(p, beg, 0, lane, len, an, cjn);
@@ -727,19 +520,18 @@ __device__ __forceinline__ void sweepWarpRow(const DevProblem& p, int row, int l
       for( int k = 0; k < U; ++k )
       {
          if( c + k * 32 + lane < len )
-            fast &= fastElem(n, acc, a[k], b[k].x, b[k].y);
+            leanElem(acc, a[k], b[k].x, b[k].y);
       }
    }
-   if( __any_sync(0xffffffffu, !fast) )
-      rowSlowWarp(p.self, sd.x, sd.y, beg, len, lane);
-   else
-   {
-      fastWarpReduce(acc, lane);
-      if( !rowIsQuiet(n, acc, sd.x, sd.y) )   // warp-uniform: every lane holds the same row state
-         rowTighten(p.self, acc.minhi, acc.minlo, acc.maxhi, acc.maxlo, acc.maxdelta, 0u, sd.x, sd.y, beg, 1, lane, 32, len);
-   }
+   leanWarpReduce(acc);
+   const bool handoff = exact || !rowClearlyQuiet(n, acc, len, sd.x, sd.y);   // warp-uniform: all lanes hold the same sums
    if( lane == 0 )
+   {
+      p.dirty[row] = ROW_CLEAN;
       nnzdone += (unsigned long long)len;
+      if( handoff )
+         p.xlist[p.nshort + atomicAdd(&p.ctrl->nexact[1], 1u)] = row;
+   }
 }
 
 template <int U, int MINB>
@@ -755,7 +547,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) sweep_medium_kernel(const
    {
       // lane i looks at the flag of the i-th next row of this warp
       const int mine = r0 + lane * nw;
-      const bool f = (mine < nrows) && p.dirty[row0 + mine] != 0;
+      const bool f = (mine < nrows) && p.dirty[row0 + mine] == ROW_MARKED;
       unsigned mask = __ballot_sync(0xffffffffu, f);
       while( mask != 0u )
       {
@@ -769,10 +561,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) sweep_medium_kernel(const
 }
 
 // ---- block-per-row for rows longer than MEDIUM_MAXLEN -----------------------------------------------------------
-// full classification in the loop (these rows are few); the reduction over the warps goes through shared memory
 __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProblem p)
 {
-   __shared__ RowAcc s_acc[LONG_THREADS / 32];
+   __shared__ LeanAcc s_lean[LONG_THREADS / 32];
 
    const int lane = threadIdx.x & 31;
    const int warp = threadIdx.x >> 5;
@@ -783,17 +574,17 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
    for( int r = blockIdx.x; r < nrows; r += gridDim.x )
    {
       const int row = row0 + r;
-      __syncthreads();                  // previous row done with s_acc and its dirty flag
-      if( !p.dirty[row] )               // block-uniform: nobody clears the flag before the barrier below
+      __syncthreads();                  // previous row done with the shared state and its flag
+      if( p.dirty[row] != ROW_MARKED )  // block-uniform: nobody rewrites the flag before the barriers below
          continue;
-      __syncthreads();
-      if( threadIdx.x == 0 )
-         p.dirty[row] = 0;
-      const int len = p.rowlen[row];
+      int len = p.rowlen[row];
+      const bool exact = (len & ROWLEN_EXACT) != 0;
+      len &= ~ROWLEN_EXACT;
       const long long beg = p.rowbeg[row];
+      const double2 sd = p.sides[row];
 
-      RowAcc acc;
-      accInit(acc);
+      LeanAcc la;
+      leanInit(la);
       for( int i0 = 0; i0 < len; i0 += 4 * LONG_THREADS )
       {
          double a[4];
@@ -819,23 +610,167 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
          for( int k = 0; k < 4; ++k )
          {
             if( i0 + k * LONG_THREADS + threadIdx.x < len )
-               accElem(n, acc, a[k], b[k].x, b[k].y);
+               leanElem(la, a[k], b[k].x, b[k].y);
          }
       }
+      leanWarpReduce(la);
+      if( lane == 0 )
+         s_lean[warp] = la;
+      __syncthreads();
+      if( threadIdx.x == 0 )
+      {
+         la = s_lean[0];
+#pragma unroll 1
+         for( int w = 1; w < LONG_THREADS / 32; ++w )
+         {
+            la.minact += s_lean[w].minact;
+            la.maxact += s_lean[w].maxact;
+            la.maxdelta = fmax(la.maxdelta, s_lean[w].maxdelta);
+            la.cabs = fmax(la.cabs, s_lean[w].cabs);
+         }
+         const bool handoff = exact || !rowClearlyQuiet(n, la, len, sd.x, sd.y);
+         p.dirty[row] = ROW_CLEAN;
+         addRoundNnz(p, (unsigned long long)len, row);
+         if( handoff )
+            p.xlist[p.nshort + p.nmedium + atomicAdd(&p.ctrl->nexact[2], 1u)] = row;
+      }
+   }
+}
+
+// ---- the exact rules for every row the filter sweeps could not finish ---------------------------------------------
+// one launch over the three work lists: short rows by groups of 8 lanes (the whole row in registers: activities by a
+// butterfly over the group, candidates straight from the registers), medium rows by warps, long rows by blocks
+constexpr int EXACT_THREADS = 256;
+constexpr int EXACT_G = 8;                           // lanes per short row
+constexpr int EXACT_Q = SHORT_MAXLEN / EXACT_G;      // elements per lane
+
+__global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProblem p)
+{
+   __shared__ RowAcc s_acc[EXACT_THREADS / 32];
+
+   const unsigned n0 = p.ctrl->nexact[0];
+   const unsigned n1 = p.ctrl->nexact[1];
+   const unsigned n2 = p.ctrl->nexact[2];
+   if( (n0 | n1 | n2) == 0u )
+      return;
+   const Num& n = p.num;
+   const int lane = threadIdx.x & 31;
+   const int warp = threadIdx.x >> 5;
+   const int gtid = blockIdx.x * EXACT_THREADS + threadIdx.x;
+   const int nthreads = gridDim.x * EXACT_THREADS;
+
+   // ---- short rows: EXACT_G lanes per row
+   {
+      const int gl = lane & (EXACT_G - 1);
+      const int ngroups = nthreads / EXACT_G;
+      const unsigned rounds = (n0 + ngroups - 1) / ngroups;      // warp-uniform trip count
+      for( unsigned it = 0; it < rounds; ++it )
+      {
+         const unsigned item = it * ngroups + gtid / EXACT_G;
+         const bool valid = item < n0;
+         int len = 0;
+         long long base = 0;
+         double2 sd = make_double2(0.0, 0.0);
+         if( valid )
+         {
+            const int row = p.xlist[item];
+            len = p.rowlen[row] & ~ROWLEN_EXACT;
+            base = p.sell_off[row >> 5] + (row & 31);
+            sd = p.sides[row];
+         }
+         double a[EXACT_Q];
+         int cj[EXACT_Q];
+         double2 b[EXACT_Q];
+#pragma unroll
+         for( int q = 0; q < EXACT_Q; ++q )
+         {
+            const int k = gl + EXACT_G * q;
+            if( k < len )
+            {
+               a[q] = p.vals[base + 32LL * k];
+               cj[q] = p.cols[base + 32LL * k];
+            }
+         }
+#pragma unroll
+         for( int q = 0; q < EXACT_Q; ++q )
+         {
+            if( gl + EXACT_G * q < len )
+               b[q] = p.bnd[cj[q] & 0x7fffffff];
+         }
+         RowInfo ri;
+         accInit(ri.acc);
+#pragma unroll
+         for( int q = 0; q < EXACT_Q; ++q )
+         {
+            if( gl + EXACT_G * q < len )
+               accElem(n, ri.acc, a[q], b[q].x, b[q].y);
+         }
+         accGroupReduce<EXACT_G>(ri.acc, lane);
+         if( valid )
+         {
+            ri.lhs = sd.x;
+            ri.rhs = sd.y;
+            bool cutoff = false;
+            if( rowGates(n, ri, len, cutoff) )      // uniform over the group
+            {
+               const double thr = slackThreshold(n, ri.force);
+               Sink sk;
+               sk.cand = p.cand;
+               sk.colflag = p.colflag;
+#pragma unroll
+               for( int q = 0; q < EXACT_Q; ++q )
+               {
+                  if( gl + EXACT_G * q < len )
+                  {
+                     if( !ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr) )
+                        candidates(n, sk, ri, a[q], cj[q] & 0x7fffffff, cj[q] < 0, b[q].x, b[q].y, cutoff);
+                  }
+               }
+            }
+            if( cutoff || (gl == 0 && rowInfeasible(n, ri.acc, ri.lhs, ri.rhs)) )
+               p.ctrl->cutoff = 1;
+         }
+      }
+   }
+
+   // ---- medium rows: one warp per row
+   {
+      const int gw = gtid >> 5;
+      const int nw = nthreads >> 5;
+      for( unsigned item = gw; item < n1; item += nw )
+      {
+         const int row = p.xlist[p.nshort + item];
+         const int len = p.rowlen[row] & ~ROWLEN_EXACT;
+         const long long beg = p.rowbeg[row];
+         const double2 sd = p.sides[row];
+         RowAcc acc;
+         accInit(acc);
+         accumulateExact(p, acc, beg, 1, lane, 32, len);
+         accWarpReduce(acc, lane);
+         rowTighten(p, acc, sd.x, sd.y, beg, 1, lane, 32, len);
+      }
+   }
+
+   // ---- long rows: one block per row
+   for( unsigned item = blockIdx.x; item < n2; item += gridDim.x )
+   {
+      const int row = p.xlist[p.nshort + p.nmedium + item];
+      const int len = p.rowlen[row] & ~ROWLEN_EXACT;
+      const long long beg = p.rowbeg[row];
+      const double2 sd = p.sides[row];
+      RowAcc acc;
+      accInit(acc);
+      accumulateExact(p, acc, beg, 1, threadIdx.x, EXACT_THREADS, len);
       accWarpReduce(acc, lane);
+      __syncthreads();                  // the previous row's s_acc has been read by everybody
       if( lane == 0 )
          s_acc[warp] = acc;
       __syncthreads();
       acc = s_acc[0];
 #pragma unroll 1
-      for( int w = 1; w < LONG_THREADS / 32; ++w )
+      for( int w = 1; w < EXACT_THREADS / 32; ++w )
          accMerge(acc, s_acc[w]);
-
-      const double2 sd = p.sides[row];
-      rowTighten(p.self, acc.minhi, acc.minlo, acc.maxhi, acc.maxlo, acc.maxdelta, acc.cnt, sd.x, sd.y, beg, 1,
-         threadIdx.x, LONG_THREADS, len);
-      if( threadIdx.x == 0 )
-         addRoundNnz(p, (unsigned long long)len, row);
+      rowTighten(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, EXACT_THREADS, len);
    }
 }
 
@@ -865,9 +800,25 @@ __device__ __forceinline__ int applyColumn(const DevProblem& p, int j, double2& 
 
 __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j)
 {
+   // row ids are fetched eight at a time before any flag is stored: the byte stores may alias anything as far as the
+   // compiler knows, and a load-store-load-store chain would cost one memory round trip per row
    const long long e = p.colbeg[j + 1];
-   for( long long q = p.colbeg[j]; q < e; ++q )
-      p.dirty[p.colrows[q]] = 1;
+   for( long long q = p.colbeg[j]; q < e; q += 8 )
+   {
+      int r[8];
+#pragma unroll
+      for( int t = 0; t < 8; ++t )
+      {
+         if( q + t < e )
+            r[t] = p.colrows[q + t];
+      }
+#pragma unroll
+      for( int t = 0; t < 8; ++t )
+      {
+         if( q + t < e )
+            p.dirty[r[t]] = ROW_MARKED;
+      }
+   }
 }
 
 // loop control (propagateDomains, solve.c:766-787), run by one thread after the last column was applied
@@ -892,6 +843,7 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
    c->total_nnz += nnz;
    c->round_nchg = 0;
    c->ticket = 0;
+   c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
    c->round = r + 1;
    int cont = 0;
    if( c->cutoff )
@@ -907,11 +859,48 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
       cudaGraphSetConditional(handle, (unsigned)cont);
 }
 
-// DENSE = false: only columns whose flag was raised by the sweep of this round are looked at (single GPU);
+// one column whose candidate keys may have moved: accept, log, mark its rows; returns the number of changed bounds
+__device__ __forceinline__ int applyAndMark(const DevProblem& p, int j, int round, int logcap)
+{
+   bool lbchg;
+   bool ubchg;
+   double2 nb;
+   const int nc = applyColumn(p, j, nb, lbchg, ubchg);
+   if( nc > 0 )
+   {
+      markColumnRows(p, j);
+      if( logcap > 0 )
+      {
+         unsigned long long pos = atomicAdd(&p.ctrl->logcount, (unsigned long long)nc);
+         if( lbchg )
+         {
+            if( pos < (unsigned long long)logcap )
+            {
+               ChangeRec rec;
+               rec.var = j; rec.round = round; rec.newbound = nb.x; rec.is_upper = 0; rec.reserved = 0;
+               p.log[pos] = rec;
+            }
+            ++pos;
+         }
+         if( ubchg && pos < (unsigned long long)logcap )
+         {
+            ChangeRec rec;
+            rec.var = j; rec.round = round; rec.newbound = nb.y; rec.is_upper = 1; rec.reserved = 0;
+            p.log[pos] = rec;
+         }
+      }
+   }
+   return nc;
+}
+
+// DENSE = false: only columns whose flag was raised by the sweep of this round are looked at (single GPU); the flags
+//                are scanned 16 per thread;
 // DENSE = true : every column compares its (all-reduced) candidate keys with its bounds (rows sharded over ranks:
 //                a key may have been moved by another rank)
+constexpr int APPLY_THREADS = 256;
+
 template <bool DENSE, bool GRAPH>
-__global__ void __launch_bounds__(256) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
+__global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
 {
    __shared__ int s_nchg;
    if( threadIdx.x == 0 )
@@ -923,67 +912,34 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevProblem p, cudaGrap
    const int round = c->round;
    const int logcap = c->logcap;
    int mychg = 0;
-   // warp-uniform trip count so that the log slots of a warp can be claimed with one atomic
-   const int stride = gridDim.x * blockDim.x;
-   const int niter = (p.ncols + stride - 1) / stride;
-   for( int it = 0; it < niter; ++it )
+   const int stride = gridDim.x * APPLY_THREADS;
+   const int gtid = blockIdx.x * APPLY_THREADS + threadIdx.x;
+   if( DENSE )
    {
-      const int j = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-      bool lbchg = false;
-      bool ubchg = false;
-      double2 nb = make_double2(0.0, 0.0);
-      int nc = 0;
-      if( j < p.ncols )
+      for( int j = gtid; j < p.ncols; j += stride )
       {
-         bool look;
-         if( DENSE )
-            look = true;
-         else
-            look = p.colflag[j] != 0;
-         if( look )
-         {
-            p.colflag[j] = 0;
-            nc = applyColumn(p, j, nb, lbchg, ubchg);
-            if( nc > 0 )
-               markColumnRows(p, j);
-         }
+         p.colflag[j] = 0;
+         mychg += applyAndMark(p, j, round, logcap);
       }
-      mychg += nc;
-      if( logcap > 0 )
+   }
+   else
+   {
+      const int nvec = (p.ncols + 15) >> 4;     // colflag is allocated and zeroed beyond ncols
+      for( int v = gtid; v < nvec; v += stride )
       {
-         const unsigned any = __ballot_sync(0xffffffffu, nc > 0);
-         if( any != 0u )
-         {
-            // exclusive prefix of nc over the warp
-            int incl = nc;
+         const uint4 f = reinterpret_cast<const uint4*>(p.colflag)[v];
+         if( (f.x | f.y | f.z | f.w) == 0u )
+            continue;
+         reinterpret_cast<uint4*>(p.colflag)[v] = make_uint4(0u, 0u, 0u, 0u);
+         const unsigned w[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-            for( int d = 1; d < 32; d <<= 1 )
+         for( int q = 0; q < 4; ++q )
+         {
+#pragma unroll
+            for( int t = 0; t < 4; ++t )
             {
-               const int t = __shfl_up_sync(0xffffffffu, incl, d);
-               if( lane >= d )
-                  incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            unsigned long long base = 0;
-            if( lane == 0 )
-               base = atomicAdd(&c->logcount, (unsigned long long)total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            unsigned long long pos = base + (unsigned long long)(incl - nc);
-            if( lbchg )
-            {
-               if( pos < (unsigned long long)logcap )
-               {
-                  ChangeRec rec;
-                  rec.var = j; rec.round = round; rec.newbound = nb.x; rec.is_upper = 0; rec.reserved = 0;
-                  p.log[pos] = rec;
-               }
-               ++pos;
-            }
-            if( ubchg && pos < (unsigned long long)logcap )
-            {
-               ChangeRec rec;
-               rec.var = j; rec.round = round; rec.newbound = nb.y; rec.is_upper = 1; rec.reserved = 0;
-               p.log[pos] = rec;
+               if( (w[q] >> (8 * t)) & 0xffu )
+                  mychg += applyAndMark(p, 16 * v + 4 * q + t, round, logcap);
             }
          }
       }
@@ -1019,7 +975,7 @@ __global__ void set_bounds_kernel(const DevProblem p, const double* lb, const do
       p.colflag[j] = 0;
    }
    for( int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nrows; r += stride )
-      p.dirty[r] = 1;
+      p.dirty[r] = ROW_MARKED;
 }
 
 __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const int* idx, const double* lb, const double* ub)
@@ -1052,7 +1008,7 @@ __global__ void mark_all_kernel(const DevProblem p)
 {
    const int stride = gridDim.x * blockDim.x;
    for( int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nrows; r += stride )
-      p.dirty[r] = 1;
+      p.dirty[r] = ROW_MARKED;
 }
 
 // start of a gpulin_propagate call: reset the loop state
@@ -1063,6 +1019,7 @@ __global__ void begin_kernel(Ctrl* c)
    c->status = 0;
    c->cutoff = 0;
    c->ticket = 0;
+   c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
    c->logcount = 0;
    c->round_nchg = 0;
    for( int i = 0; i < NNZ_SLOTS; ++i )
