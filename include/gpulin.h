@@ -139,6 +139,10 @@ int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 /** algorithmic bytes of one full round: nnz*12 + nrows*20 + ncols*17 */
 int gpulin_algorithmic_bytes(gpulin_t* h, int64_t* bytes);
 
+/** measurement aid: runs ONE full round (every row marked for propagation) on the current bounds and returns the
+ *  CUDA-event time [ms] of its three stages: filter sweep kernel(s), exact kernel, apply kernel */
+int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact_ms, double* apply_ms);
+
 /** all following work of this handle is enqueued on the given cudaStream_t (default: a private stream) */
 int gpulin_set_stream(gpulin_t* h, void* stream);
 

@@ -80,6 +80,7 @@ struct gpulin
    cudaStream_t aux[2] = {nullptr, nullptr};     // the medium / long sweeps run beside the short sweep
    cudaEvent_t evfork = nullptr, evjoin[2] = {nullptr, nullptr};
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   cudaEvent_t evprof[4] = {nullptr, nullptr, nullptr, nullptr};
    cudaGraph_t graph = nullptr;
    cudaGraphExec_t gexec = nullptr;
    cudaGraphConditionalHandle handle = 0;
@@ -217,7 +218,7 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
          }
       }
    }
-   if( sweep )
+   if( sweep && h->nexactblocks > 0 )
       exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
    if( apply )
       apply_kernel<DENSE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
@@ -596,6 +597,11 @@ extern "C" void gpulin_destroy(gpulin_t* h)
       if( h->evjoin[i] != nullptr )
          cudaEventDestroy(h->evjoin[i]);
    }
+   for( int i = 0; i < 4; ++i )
+   {
+      if( h->evprof[i] != nullptr )
+         cudaEventDestroy(h->evprof[i]);
+   }
    if( h->evfork != nullptr )
       cudaEventDestroy(h->evfork);
    if( h->ev0 != nullptr )
@@ -616,6 +622,8 @@ extern "C" int gpulin_set_stream(gpulin_t* h, void* stream)
 {
    if( h == nullptr )
       return fail(GPULIN_ERR_ARG, "handle is NULL");
+   if( stream == nullptr && !h->hostloop )
+      return fail(GPULIN_ERR_ARG, "the legacy default stream cannot be captured into the round graph: pass a created stream");
    CU(cudaSetDevice(h->device));
    CU(cudaStreamSynchronize(h->stream));
    if( h->ownstream && h->stream != nullptr )
@@ -939,6 +947,42 @@ extern "C" int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int
       h->last.nchanges = (int64_t)c->total_nchg;
       h->last.nnz_processed = (int64_t)c->total_nnz;
    }
+   return GPULIN_OK;
+}
+
+// one full round (every row marked) with CUDA events between its kernels: filter sweep(s) | exact kernel | apply
+extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact_ms, double* apply_ms)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   if( !h->havebounds )
+      return fail(GPULIN_ERR_STATE, "gpulin_profile_round before gpulin_set_bounds");
+   CU(cudaSetDevice(h->device));
+   if( h->evprof[0] == nullptr )
+   {
+      for( int i = 0; i < 4; ++i )
+         CU(cudaEventCreate(&h->evprof[i]));
+   }
+   OK(gpulin_round_begin(h));
+   OK(gpulin_mark_all(h));
+   CU(cudaEventRecord(h->evprof[0], h->stream));
+   const int keepexact = h->nexactblocks;
+   h->nexactblocks = 0;                               // launchRoundKernels skips the exact kernel ...
+   OK((launchRoundKernels<false, false>(h, true, false)));
+   h->nexactblocks = keepexact;
+   CU(cudaEventRecord(h->evprof[1], h->stream));
+   exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);   // ... which is timed on its own
+   CU(cudaEventRecord(h->evprof[2], h->stream));
+   OK((launchRoundKernels<false, false>(h, false, true)));
+   CU(cudaEventRecord(h->evprof[3], h->stream));
+   CU(cudaEventSynchronize(h->evprof[3]));
+   float t[3] = {0.f, 0.f, 0.f};
+   for( int i = 0; i < 3; ++i )
+      CU(cudaEventElapsedTime(&t[i], h->evprof[i], h->evprof[i + 1]));
+   if( sweep_ms != nullptr ) *sweep_ms = t[0];
+   if( exact_ms != nullptr ) *exact_ms = t[1];
+   if( apply_ms != nullptr ) *apply_ms = t[2];
+   OK(fetchCtrl(h));
    return GPULIN_OK;
 }
 

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "gpulin_get_round_stats": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_get_layout": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
     "gpulin_algorithmic_bytes": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_profile_round": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_double)]),
     "gpulin_set_stream": (ctypes.c_int, [_P, _P]),
     "gpulin_sync": (ctypes.c_int, [_P]),
     "gpulin_exchange_buffer": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)]),
@@ -224,6 +226,12 @@ class LinearPropagator:
         b = ctypes.c_int64(0)
         _check(self._lib.gpulin_algorithmic_bytes(self._h, ctypes.byref(b)))
         return b.value
+
+    def profile_round(self):
+        """one full round on the current bounds; CUDA-event ms of (filter sweep, exact kernel, apply kernel)"""
+        a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+        _check(self._lib.gpulin_profile_round(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
 
     # -- single rounds (multi-GPU, profiling) ------------------------------------------------------------------
     def set_stream(self, cuda_stream: int):
