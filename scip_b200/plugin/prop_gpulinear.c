@@ -1,0 +1,590 @@
+/* prop_gpulinear.c -- B200 linear bound propagation as an ordinary SCIP propagator plugin.
+ *
+ * Drop-in for the path  propagationRound (solve.c:437) -> consPropLinear (cons_linear.c:16126) -> propagateCons (:7621)
+ * -> tightenBounds (:6980).  As a propagator with non-negative priority it is called by SCIPpropExec (prop.c:646) before
+ * the constraint handlers (solve.c:524).  What it does per call (SCIP_DECL_PROPEXEC, type_prop.h:217):
+ *
+ *   1. (re)build the device copy of the linear rows when the set of linear constraints changed: rows through
+ *      SCIPgetVarsLinear / SCIPgetValsLinear / SCIPgetLhsLinear / SCIPgetRhsLinear (cons_linear.h:263-307), columns =
+ *      SCIPvarGetProbindex (pub_var.h:592); tolerances from SCIPinfinity/SCIPepsilon/SCIPsumepsilon/SCIPfeastol/
+ *      SCIPgetHugeValue and numerics/boundstreps, constraints/linear/maxeasyactivitydelta;
+ *   2. send the local bounds of all variables (SCIPvarGetLbLocal/UbLocal) through gpulin_set_bounds;
+ *   3. gpulin_propagate: all rounds to the fixpoint on the GPU (no host round trip per round);
+ *   4. replay the round-ordered change log with SCIPinferVarLbProp / SCIPinferVarUbProp (scip_var.c:7589/7705,
+ *      force = TRUE: the relative threshold numerics/boundstreps was already applied on the device per inference);
+ *      the replay order makes every change explainable by bounds that SCIP already knows (SCIP_DECL_PROPRESPROP);
+ *   5. *result = SCIP_CUTOFF / SCIP_REDUCEDDOM / SCIP_DIDNOTFIND (type_result.h:42-51).
+ *
+ * There is no CPU fallback: a CUDA failure is returned as SCIP_ERROR.  The propagator is not copied to sub-SCIPs
+ * (PROPCOPY = NULL): copies do not get a GPU.
+ */
+#include <assert.h>
+#include <string.h>
+
+#include "prop_gpulinear.h"
+#include "gpulin.h"
+
+#include "scip/cons_linear.h"
+#include "scip/pub_cons.h"
+#include "scip/pub_message.h"
+#include "scip/pub_prop.h"
+#include "scip/pub_var.h"
+#include "scip/scip_conflict.h"
+#include "scip/scip_cons.h"
+#include "scip/scip_general.h"
+#include "scip/scip_mem.h"
+#include "scip/scip_message.h"
+#include "scip/scip_numerics.h"
+#include "scip/scip_param.h"
+#include "scip/scip_prob.h"
+#include "scip/scip_prop.h"
+#include "scip/scip_probing.h"
+#include "scip/scip_tree.h"
+#include "scip/scip_var.h"
+
+#define PROP_NAME              "gpulinear"
+#define PROP_DESC              "activity-based bound propagation of all linear constraints on a B200 GPU (libgpulin)"
+#define PROP_PRIORITY          10000000   /* >= 0: before the constraint handlers (solve.c:524) */
+#define PROP_FREQ              1
+#define PROP_DELAY             FALSE
+#define PROP_TIMING            SCIP_PROPTIMING_BEFORELP
+
+#define DEFAULT_MAXROUNDS      -1         /* rounds per call on the device (-1: to the fixpoint) */
+#define DEFAULT_DEVICE         0
+#define DEFAULT_LOGCAPFAC      8          /* change log capacity = factor * number of variables */
+
+struct SCIP_PropData
+{
+   gpulin_t*             gpu;                /**< device copy of the linear rows, or NULL */
+   SCIP_VAR**            vars;               /**< column -> variable (by probindex at build time) */
+   SCIP_CONS**           rowcons;            /**< row -> linear constraint */
+   SCIP_Real*            lb;                 /**< host bound buffers */
+   SCIP_Real*            ub;
+   gpulin_change*        changes;            /**< change log buffer */
+   int64_t*              rowptr;             /**< host CSR (kept for PROPRESPROP) */
+   int32_t*              colidx;
+   SCIP_Real*            vals;
+   SCIP_Real*            lhs;
+   SCIP_Real*            rhs;
+   int64_t*              colptr;             /**< column -> rows (for PROPRESPROP) */
+   int32_t*              colrows;
+   int32_t*              colpos;             /**< position of the entry in its row */
+   int                   ncols;
+   int                   nrows;
+   int64_t               nnz;
+   int64_t               logcap;
+   int                   nlinconss;          /**< active linear constraints when the device copy was built */
+   int                   nskipped;           /**< rows not sent to the device (modifiable, local, non-active variables) */
+   int                   maxrounds;          /**< parameter */
+   int                   device;             /**< parameter */
+   SCIP_Longint          ncalls;
+   SCIP_Longint          nrounds;
+   SCIP_Longint          nchanges;
+   SCIP_Real             devicems;
+};
+
+/** frees the device copy and all host arrays */
+static
+void freeDeviceCopy(
+   SCIP*                 scip,
+   SCIP_PROPDATA*        propdata
+   )
+{
+   if( propdata->gpu != NULL )
+   {
+      gpulin_destroy(propdata->gpu);
+      propdata->gpu = NULL;
+   }
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->vars, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->lb, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->ub, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->colptr, propdata->ncols + 1);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->rowcons, propdata->nrows);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->lhs, propdata->nrows);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->rhs, propdata->nrows);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->rowptr, propdata->nrows + 1);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->colidx, propdata->nnz);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->vals, propdata->nnz);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->colrows, propdata->nnz);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->colpos, propdata->nnz);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->changes, propdata->logcap);
+   propdata->ncols = 0;
+   propdata->nrows = 0;
+   propdata->nnz = 0;
+   propdata->logcap = 0;
+   propdata->nlinconss = -1;
+}
+
+/** can this linear constraint be propagated on the device?  (cf. tightenBounds :7010: modifiable rows are skipped) */
+static
+SCIP_Bool rowIsUsable(
+   SCIP*                 scip,
+   SCIP_CONS*            cons
+   )
+{
+   SCIP_VAR** vars;
+   int nvars;
+   int v;
+
+   if( SCIPconsIsModifiable(cons) || SCIPconsIsLocal(cons) || !SCIPconsIsPropagationEnabled(cons) )
+      return FALSE;
+   vars = SCIPgetVarsLinear(scip, cons);
+   nvars = SCIPgetNVarsLinear(scip, cons);
+   for( v = 0; v < nvars; ++v )
+   {
+      if( SCIPvarGetProbindex(vars[v]) < 0 )
+         return FALSE;
+   }
+   return TRUE;
+}
+
+/** builds the device copy of all usable linear rows */
+static
+SCIP_RETCODE buildDeviceCopy(
+   SCIP*                 scip,
+   SCIP_PROPDATA*        propdata
+   )
+{
+   SCIP_CONSHDLR* conshdlr;
+   SCIP_CONS** conss;
+   SCIP_VAR** probvars;
+   gpulin_numerics num;
+   uint8_t* vartype;
+   int64_t* fill;
+   int64_t k;
+   int nconss;
+   int ncols;
+   int nrows;
+   int c;
+   int j;
+   int rc;
+
+   freeDeviceCopy(scip, propdata);
+
+   conshdlr = SCIPfindConshdlr(scip, "linear");
+   if( conshdlr == NULL )
+      return SCIP_OKAY;
+   conss = SCIPconshdlrGetConss(conshdlr);
+   nconss = SCIPconshdlrGetNActiveConss(conshdlr);
+   propdata->nlinconss = nconss;
+   propdata->nskipped = 0;
+
+   probvars = SCIPgetVars(scip);
+   ncols = SCIPgetNVars(scip);
+   nrows = 0;
+   k = 0;
+   for( c = 0; c < nconss; ++c )
+   {
+      if( rowIsUsable(scip, conss[c]) )
+      {
+         ++nrows;
+         k += SCIPgetNVarsLinear(scip, conss[c]);
+      }
+      else
+         ++propdata->nskipped;
+   }
+   if( nrows == 0 || ncols == 0 )
+      return SCIP_OKAY;
+
+   propdata->ncols = ncols;
+   propdata->nrows = nrows;
+   propdata->nnz = k;
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->vars, ncols) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lb, ncols) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->ub, ncols) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colptr, ncols + 1) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowcons, nrows) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lhs, nrows) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rhs, nrows) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowptr, nrows + 1) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colidx, propdata->nnz) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->vals, propdata->nnz) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colrows, propdata->nnz) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colpos, propdata->nnz) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &vartype, ncols) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &fill, ncols + 1) );
+
+   for( j = 0; j < ncols; ++j )
+   {
+      assert(SCIPvarGetProbindex(probvars[j]) == j);
+      propdata->vars[j] = probvars[j];
+      vartype[j] = SCIPvarIsIntegral(probvars[j]) ? GPULIN_VAR_INTEGRAL : GPULIN_VAR_CONTINUOUS;
+      propdata->colptr[j] = 0;
+   }
+   propdata->colptr[ncols] = 0;
+
+   /* rows */
+   nrows = 0;
+   k = 0;
+   for( c = 0; c < nconss; ++c )
+   {
+      SCIP_VAR** vars;
+      SCIP_Real* vals;
+      int nvars;
+      int v;
+
+      if( !rowIsUsable(scip, conss[c]) )
+         continue;
+      vars = SCIPgetVarsLinear(scip, conss[c]);
+      vals = SCIPgetValsLinear(scip, conss[c]);
+      nvars = SCIPgetNVarsLinear(scip, conss[c]);
+      propdata->rowcons[nrows] = conss[c];
+      propdata->rowptr[nrows] = k;
+      propdata->lhs[nrows] = SCIPgetLhsLinear(scip, conss[c]);
+      propdata->rhs[nrows] = SCIPgetRhsLinear(scip, conss[c]);
+      for( v = 0; v < nvars; ++v )
+      {
+         propdata->colidx[k] = SCIPvarGetProbindex(vars[v]);
+         propdata->vals[k] = vals[v];
+         ++propdata->colptr[propdata->colidx[k] + 1];
+         ++k;
+      }
+      ++nrows;
+   }
+   propdata->rowptr[nrows] = k;
+
+   /* column -> rows, for PROPRESPROP */
+   for( j = 0; j < ncols; ++j )
+      propdata->colptr[j + 1] += propdata->colptr[j];
+   for( j = 0; j <= ncols; ++j )
+      fill[j] = propdata->colptr[j];
+   for( c = 0; c < nrows; ++c )
+   {
+      for( k = propdata->rowptr[c]; k < propdata->rowptr[c + 1]; ++k )
+      {
+         int64_t q = fill[propdata->colidx[k]]++;
+         propdata->colrows[q] = c;
+         propdata->colpos[q] = (int32_t)(k - propdata->rowptr[c]);
+      }
+   }
+
+   /* tolerances of this SCIP instance */
+   num.infinity = SCIPinfinity(scip);
+   num.epsilon = SCIPepsilon(scip);
+   num.sumepsilon = SCIPsumepsilon(scip);
+   num.feastol = SCIPfeastol(scip);
+   num.hugeval = SCIPgetHugeValue(scip);
+   SCIP_CALL( SCIPgetRealParam(scip, "numerics/boundstreps", &num.boundstreps) );
+   SCIP_CALL( SCIPgetRealParam(scip, "constraints/linear/maxeasyactivitydelta", &num.maxeasyactivitydelta) );
+
+   rc = gpulin_create(propdata->device, nrows, ncols, propdata->nnz, propdata->rowptr, propdata->colidx, propdata->vals,
+      propdata->lhs, propdata->rhs, vartype, &num, &propdata->gpu);
+   SCIPfreeBufferArray(scip, &fill);
+   SCIPfreeBufferArray(scip, &vartype);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("prop_gpulinear: gpulin_create failed (%d): %s\n", rc, gpulin_last_error());
+      propdata->gpu = NULL;
+      return SCIP_ERROR;
+   }
+
+   propdata->logcap = (int64_t)DEFAULT_LOGCAPFAC * ncols + 1024;
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->changes, propdata->logcap) );
+   rc = gpulin_set_change_log(propdata->gpu, propdata->logcap);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("prop_gpulinear: gpulin_set_change_log failed (%d): %s\n", rc, gpulin_last_error());
+      return SCIP_ERROR;
+   }
+
+   SCIPverbMessage(scip, SCIP_VERBLEVEL_FULL, NULL,
+      "prop_gpulinear: device copy of %d linear rows (%d skipped), %d columns, %lld nonzeros\n", nrows, propdata->nskipped,
+      ncols, (long long)propdata->nnz);
+
+   return SCIP_OKAY;
+}
+
+/*
+ * Callback methods of propagator
+ */
+
+/** destructor of propagator to free user data (called when SCIP is exiting) */
+static
+SCIP_DECL_PROPFREE(propFreeGpulinear)
+{
+   SCIP_PROPDATA* propdata;
+
+   propdata = SCIPpropGetData(prop);
+   assert(propdata != NULL);
+   freeDeviceCopy(scip, propdata);
+   SCIPfreeBlockMemory(scip, &propdata);
+   SCIPpropSetData(prop, NULL);
+
+   return SCIP_OKAY;
+}
+
+/** solving process deinitialization method: the transformed problem goes away, and with it the device copy */
+static
+SCIP_DECL_PROPEXITSOL(propExitsolGpulinear)
+{
+   SCIP_PROPDATA* propdata;
+
+   (void)restart;
+   propdata = SCIPpropGetData(prop);
+   assert(propdata != NULL);
+   if( propdata->ncalls > 0 )
+   {
+      SCIPverbMessage(scip, SCIP_VERBLEVEL_FULL, NULL,
+         "prop_gpulinear: %lld calls, %lld device rounds, %lld bound changes, %.3f ms on the device\n",
+         (long long)propdata->ncalls, (long long)propdata->nrounds, (long long)propdata->nchanges, propdata->devicems);
+   }
+   freeDeviceCopy(scip, propdata);
+
+   return SCIP_OKAY;
+}
+
+/** execution method of propagator */
+static
+SCIP_DECL_PROPEXEC(propExecGpulinear)
+{
+   SCIP_PROPDATA* propdata;
+   SCIP_CONSHDLR* conshdlr;
+   gpulin_result res;
+   int64_t nlog;
+   int64_t e;
+   int ntightened;
+   int rc;
+   int j;
+
+   (void)proptiming;
+   *result = SCIP_DIDNOTRUN;
+
+   propdata = SCIPpropGetData(prop);
+   assert(propdata != NULL);
+
+   conshdlr = SCIPfindConshdlr(scip, "linear");
+   if( conshdlr == NULL || SCIPconshdlrGetNActiveConss(conshdlr) == 0 )
+      return SCIP_OKAY;
+
+   /* staleness: rebuild when the number of active linear constraints or of variables changed */
+   if( propdata->gpu == NULL || propdata->nlinconss != SCIPconshdlrGetNActiveConss(conshdlr)
+      || propdata->ncols != SCIPgetNVars(scip) )
+   {
+      SCIP_CALL( buildDeviceCopy(scip, propdata) );
+      if( propdata->gpu == NULL )
+         return SCIP_OKAY;
+   }
+
+   *result = SCIP_DIDNOTFIND;
+
+   /* bounds of the current node */
+   for( j = 0; j < propdata->ncols; ++j )
+   {
+      propdata->lb[j] = SCIPvarGetLbLocal(propdata->vars[j]);
+      propdata->ub[j] = SCIPvarGetUbLocal(propdata->vars[j]);
+   }
+   rc = gpulin_set_bounds(propdata->gpu, propdata->lb, propdata->ub);
+   if( rc == GPULIN_OK )
+      rc = gpulin_propagate(propdata->gpu, propdata->maxrounds < 0 ? 0 : propdata->maxrounds, &res);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("prop_gpulinear: device propagation failed (%d): %s\n", rc, gpulin_last_error());
+      return SCIP_ERROR;
+   }
+   ++propdata->ncalls;
+   propdata->nrounds += res.nrounds;
+   propdata->nchanges += res.nchanges;
+   propdata->devicems += res.device_ms;
+
+   if( res.status == GPULIN_CUTOFF )
+   {
+      *result = SCIP_CUTOFF;
+      return SCIP_OKAY;
+   }
+   if( res.nchanges == 0 )
+      return SCIP_OKAY;
+
+   ntightened = 0;
+   rc = gpulin_get_changes(propdata->gpu, propdata->changes, propdata->logcap, &nlog);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("prop_gpulinear: gpulin_get_changes failed (%d): %s\n", rc, gpulin_last_error());
+      return SCIP_ERROR;
+   }
+   if( nlog <= propdata->logcap )
+   {
+      /* replay in round order: every change is implied by one row and the bounds SCIP knows at that point */
+      for( e = 0; e < nlog; ++e )
+      {
+         const gpulin_change* chg = &propdata->changes[e];
+         SCIP_Bool infeasible;
+         SCIP_Bool tightened;
+
+         if( chg->is_upper )
+            SCIP_CALL( SCIPinferVarUbProp(scip, propdata->vars[chg->var], chg->newbound, prop, 1, TRUE, &infeasible, &tightened) );
+         else
+            SCIP_CALL( SCIPinferVarLbProp(scip, propdata->vars[chg->var], chg->newbound, prop, 0, TRUE, &infeasible, &tightened) );
+         if( infeasible )
+         {
+            *result = SCIP_CUTOFF;
+            return SCIP_OKAY;
+         }
+         if( tightened )
+            ++ntightened;
+      }
+   }
+   else
+   {
+      /* the log overflowed: hand over the final bounds (no valid replay order: PROPRESPROP may fail for them) */
+      rc = gpulin_get_bounds(propdata->gpu, propdata->lb, propdata->ub);
+      if( rc != GPULIN_OK )
+      {
+         SCIPerrorMessage("prop_gpulinear: gpulin_get_bounds failed (%d): %s\n", rc, gpulin_last_error());
+         return SCIP_ERROR;
+      }
+      for( j = 0; j < propdata->ncols; ++j )
+      {
+         SCIP_Bool infeasible;
+         SCIP_Bool tightened;
+
+         if( propdata->lb[j] > SCIPvarGetLbLocal(propdata->vars[j]) )
+         {
+            SCIP_CALL( SCIPinferVarLbProp(scip, propdata->vars[j], propdata->lb[j], prop, 0, TRUE, &infeasible, &tightened) );
+            if( infeasible )
+            {
+               *result = SCIP_CUTOFF;
+               return SCIP_OKAY;
+            }
+            ntightened += tightened ? 1 : 0;
+         }
+         if( propdata->ub[j] < SCIPvarGetUbLocal(propdata->vars[j]) )
+         {
+            SCIP_CALL( SCIPinferVarUbProp(scip, propdata->vars[j], propdata->ub[j], prop, 1, TRUE, &infeasible, &tightened) );
+            if( infeasible )
+            {
+               *result = SCIP_CUTOFF;
+               return SCIP_OKAY;
+            }
+            ntightened += tightened ? 1 : 0;
+         }
+      }
+   }
+   if( ntightened > 0 )
+      *result = SCIP_REDUCEDDOM;
+
+   return SCIP_OKAY;
+}
+
+/** propagation conflict resolving method of propagator: finds a row of the column of infervar whose residual activity
+ *  at bdchgidx implies the inferred bound and reports the bounds of its other variables -- the simple variant of
+ *  cons_linear's resolvePropagation (cons_linear.c:4951-4971 via addConflictBounds :4690) */
+static
+SCIP_DECL_PROPRESPROP(propRespropGpulinear)
+{
+   SCIP_PROPDATA* propdata;
+   int64_t q;
+   int j;
+
+   (void)inferinfo;
+   *result = SCIP_DIDNOTFIND;
+   propdata = SCIPpropGetData(prop);
+   assert(propdata != NULL);
+   if( propdata->gpu == NULL )
+      return SCIP_OKAY;
+   j = SCIPvarGetProbindex(infervar);
+   if( j < 0 || j >= propdata->ncols || propdata->vars[j] != infervar )
+      return SCIP_OKAY;
+
+   for( q = propdata->colptr[j]; q < propdata->colptr[j + 1]; ++q )
+   {
+      const int r = propdata->colrows[q];
+      const int64_t beg = propdata->rowptr[r];
+      const int64_t end = propdata->rowptr[r + 1];
+      const SCIP_Real a = propdata->vals[beg + propdata->colpos[q]];
+      /* an upper bound of x (a > 0) or a lower bound (a < 0) comes from  rhs - minresidual ; the other two cases from
+       * lhs - maxresidual */
+      const SCIP_Bool userhs = (boundtype == SCIP_BOUNDTYPE_UPPER) == (a > 0.0);
+      const SCIP_Real side = userhs ? propdata->rhs[r] : propdata->lhs[r];
+      SCIP_Real resact = 0.0;
+      SCIP_Bool finite = TRUE;
+      SCIP_Real implied;
+      int64_t k;
+
+      if( SCIPisInfinity(scip, userhs ? side : -side) )
+         continue;
+      for( k = beg; k < end && finite; ++k )
+      {
+         SCIP_VAR* var = propdata->vars[propdata->colidx[k]];
+         SCIP_Real bnd;
+         if( k == beg + propdata->colpos[q] )
+            continue;
+         /* minimal residual activity: lb for positive, ub for negative coefficients; maximal: the other way round */
+         if( (propdata->vals[k] > 0.0) == userhs )
+            bnd = SCIPgetVarLbAtIndex(scip, var, bdchgidx, FALSE);
+         else
+            bnd = SCIPgetVarUbAtIndex(scip, var, bdchgidx, FALSE);
+         if( SCIPisInfinity(scip, REALABS(bnd)) )
+            finite = FALSE;
+         else
+            resact += propdata->vals[k] * bnd;
+      }
+      if( !finite )
+         continue;
+      implied = (side - resact) / a;
+      if( boundtype == SCIP_BOUNDTYPE_UPPER )
+      {
+         if( SCIPvarIsIntegral(infervar) )
+            implied = SCIPfeasFloor(scip, implied);
+         if( !SCIPisFeasLE(scip, implied, relaxedbd) )
+            continue;
+      }
+      else
+      {
+         if( SCIPvarIsIntegral(infervar) )
+            implied = SCIPfeasCeil(scip, implied);
+         if( !SCIPisFeasGE(scip, implied, relaxedbd) )
+            continue;
+      }
+      /* this row explains the bound: report the bounds of all its other variables */
+      for( k = beg; k < end; ++k )
+      {
+         SCIP_VAR* var = propdata->vars[propdata->colidx[k]];
+         if( k == beg + propdata->colpos[q] )
+            continue;
+         if( (propdata->vals[k] > 0.0) == userhs )
+            SCIP_CALL( SCIPaddConflictLb(scip, var, bdchgidx) );
+         else
+            SCIP_CALL( SCIPaddConflictUb(scip, var, bdchgidx) );
+      }
+      *result = SCIP_SUCCESS;
+      return SCIP_OKAY;
+   }
+
+   return SCIP_OKAY;
+}
+
+/*
+ * propagator specific interface methods
+ */
+
+/** creates the gpulinear propagator and includes it in SCIP */
+SCIP_RETCODE SCIPincludePropGpulinear(
+   SCIP*                 scip                /**< SCIP data structure */
+   )
+{
+   SCIP_PROPDATA* propdata;
+   SCIP_PROP* prop;
+
+   SCIP_CALL( SCIPallocBlockMemory(scip, &propdata) );
+   memset(propdata, 0, sizeof(*propdata));
+   propdata->nlinconss = -1;
+
+   prop = NULL;
+   SCIP_CALL( SCIPincludePropBasic(scip, &prop, PROP_NAME, PROP_DESC, PROP_PRIORITY, PROP_FREQ, PROP_DELAY, PROP_TIMING,
+         propExecGpulinear, propdata) );
+   assert(prop != NULL);
+
+   /* PROPCOPY stays NULL: sub-SCIPs and concurrent copies do not get a GPU propagator */
+   SCIP_CALL( SCIPsetPropFree(scip, prop, propFreeGpulinear) );
+   SCIP_CALL( SCIPsetPropExitsol(scip, prop, propExitsolGpulinear) );
+   SCIP_CALL( SCIPsetPropResprop(scip, prop, propRespropGpulinear) );
+
+   SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/maxdevicerounds",
+         "maximal number of propagation rounds per call on the device (-1: to the fixpoint)",
+         &propdata->maxrounds, FALSE, DEFAULT_MAXROUNDS, -1, INT_MAX, NULL, NULL) );
+   SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/device",
+         "CUDA device ordinal",
+         &propdata->device, TRUE, DEFAULT_DEVICE, 0, 1023, NULL, NULL) );
+
+   return SCIP_OKAY;
+}

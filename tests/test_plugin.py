@@ -1,0 +1,68 @@
+"""prop_gpulinear as a SCIP plugin: the unmodified reference (oracle/_ref/lib/libscip.so) is the host application, the
+propagator replaces cons_linear's bound tightening (constraints/linear/tightenboundsfreq = -1)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, ROOT, assert_bounds_match, golden_names, load_golden
+
+DRIVER = os.path.join(ROOT, "scip_b200", "plugin", "_build", "gpulinear_driver")
+needs_driver = pytest.mark.skipif(not (os.path.exists(DRIVER) and oracle.have_reference()),
+                                  reason="plugin driver / oracle/_ref not built (python -c 'import __graft_entry__ as g; g.build()')")
+
+
+def run_driver(*args, check=True):
+    res = subprocess.run([DRIVER, *args], capture_output=True, text=True, timeout=1200)
+    if check:
+        assert res.returncode == 0, res.stderr[-2000:]
+        return json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    return res
+
+
+@needs_driver
+def test_driver_cpu_mode_reproduces_the_golden_fixture(tmp_path):
+    out = str(tmp_path / "o.lpr")
+    run_driver("--lpb", os.path.join(GOLDEN, "dcmulti.lpb"), "--cpu", "--boundstreps", "1e-9", "--out", out)
+    got = oracle.read_lpr(out)
+    _, ref = load_golden("dcmulti", "1e-9")
+    assert np.array_equal(got["lb"], ref["lb"]) and np.array_equal(got["ub"], ref["ub"])
+
+
+@needs_driver
+def test_plugin_fails_loudly_without_a_gpu(gpulin):
+    if gpulin.load_library().gpulin_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    res = run_driver("--lpb", os.path.join(GOLDEN, "bell5.lpb"), check=False)
+    assert res.returncode != 0 and "no CPU fallback" in res.stderr
+
+
+@needs_driver
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_names())
+def test_plugin_reaches_the_reference_fixpoint(tmp_path, name):
+    """SCIP + prop_gpulinear (cons_linear tightening off) == SCIP's own cons_linear propagation, root node"""
+    prob, ref = load_golden(name, "1e-9")
+    out = str(tmp_path / "o.lpr")
+    info = run_driver("--lpb", os.path.join(GOLDEN, name + ".lpb"), "--boundstreps", "1e-9", "--out", out)
+    got = oracle.read_lpr(out)
+    assert got["infeasible"] == ref["infeasible"], name
+    assert info["gpu_prop_calls"] >= 1
+    if not ref["infeasible"]:
+        assert_bounds_match(got["lb"] + 0.0, got["ub"] + 0.0, ref["lb"] + 0.0, ref["ub"] + 0.0, prob["vartype"], what=name)
+        if info["gpu_domreds"] > 0:
+            assert info["linear_domreds"] == 0          # the replaced path really was off
+
+
+@needs_driver
+@pytest.mark.gpu
+def test_plugin_in_tree_search_with_conflict_analysis():
+    """thousands of EXEC calls with local bounds, backtracking and PROPRESPROP: enigma is solved by propagation +
+    branching (the reference build has no LP solver); both runs must prove the same status"""
+    cpu = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--cpu", "--solve")
+    gpu = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve")
+    assert gpu["scip_status"] == cpu["scip_status"]
+    assert gpu["gpu_prop_calls"] > 100 and gpu["linear_domreds"] == 0
