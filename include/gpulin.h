@@ -78,7 +78,7 @@ const char* gpulin_last_error(void);
 /** number of CUDA devices visible, or a negative error code */
 int gpulin_device_count(void);
 
-/** builds the device copy (row-binned sliced CSR + column->row-block map) of the linear rows
+/** builds the device copy (tiled CSR stream + column->row map) of the linear rows
  *      lhs[i] <= sum_k vals[k] * x[colidx[k]] <= rhs[i],   k in [rowptr[i], rowptr[i+1])
  *  replaces the per-constraint SCIP_CONSDATA arrays (cons_linear.c:187-266) read through
  *  SCIPgetVarsLinear/SCIPgetValsLinear/SCIPgetLhsLinear/SCIPgetRhsLinear (cons_linear.c:18326-18452).
@@ -132,8 +132,9 @@ int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n
  *  device time [ms] (%globaltimer stamps taken by the kernels), nonzeros swept, bound changes accepted */
 int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n);
 
-/** storage statistics: [0] nnz, [1] stored nonzeros incl. SELL padding, [2..4] rows in the thread-per-row /
- *  warp-per-row / block-per-row bins, [5] bytes on device, [6..8] persistent blocks of the three sweep kernels, [9] longest row */
+/** storage statistics: [0] nnz, [1] stored nonzeros incl. padding, [2] rows in the CSR stream, [3] tiles of the stream,
+ *  [4] rows swept block-per-row, [5] bytes on device, [6..8] persistent blocks of the stream sweep / long-row sweep /
+ *  exact kernel, [9] longest row */
 int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 
 /** algorithmic bytes of one full round: nnz*12 + nrows*20 + ncols*17 */

@@ -50,12 +50,11 @@ struct gpulin
    int         device = 0;
    int64_t     nrows = 0, ncols = 0, nnz = 0;
    int64_t     nstored = 0;      // nonzeros incl. SELL padding
-   int         nshort = 0, nmedium = 0, nlong = 0;
+   int         nstream = 0, nlong = 0, ntiles = 0;
+   int64_t     nstreamelems = 0;
    int         maxlen = 0;
    DevProblem  p{};
-   int         shortvariant = 1;
-   int         nshortblocks = 0;
-   int         nmediumblocks = 0;
+   int         nstreamblocks = 0;
    int         nlongblocks = 0;
    int         napplyblocks = 0;
    int         nexactblocks = 0;
@@ -140,86 +139,29 @@ static void destroyGraph(gpulin* h)
    h->graph = nullptr;
 }
 
-// chunk sizes of the software-pipelined sweeps (elements per thread in flight)
-constexpr int MEDIUM_U = 4;
-constexpr int MEDIUM_MINB = 3;
-
-// variants of the thread-per-row sweep; GPULIN_SHORT_VARIANT selects (experiments; the default is set in gpulin{})
-typedef void (*ShortKernel)(const DevProblem);
-struct ShortVariant
-{
-   ShortKernel kernel;
-   int         threads;
-   int         smem;     // dynamic shared memory per block
-   const char* name;
-};
-#define REGV(CH, PF, MB) {sweep_short_kernel<CH, PF, MB>, SWEEP_THREADS, 0, "reg<" #CH "," #PF "," #MB ">"}
-static const ShortVariant g_shortVariants[] = {
-   REGV(4, true, 3),     // 0
-   REGV(4, false, 4),    // 1
-   REGV(8, false, 2),    // 2
-   REGV(8, true, 2),     // 3
-   REGV(2, true, 4),     // 4
-   REGV(4, true, 2),     // 5
-   REGV(4, false, 3),    // 6
-   REGV(8, false, 3),    // 7
-   REGV(4, true, 4),     // 8
-   REGV(8, true, 3),     // 9
-   REGV(8, false, 4),    // 10
-   REGV(4, false, 5),    // 11
-   REGV(4, false, 6),    // 12
-   REGV(2, false, 6),    // 13
-   REGV(2, true, 6),     // 14
-   REGV(16, false, 2),   // 15
-};
-constexpr int NSHORTVARIANTS = sizeof(g_shortVariants) / sizeof(g_shortVariants[0]);
-
-// one propagation round on h->stream; the three row bins are independent and run concurrently (fork / join)
+// one propagation round on h->stream; the stream sweep and the long-row sweep are independent and run concurrently
 template <bool DENSE, bool GRAPH>
 static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
 {
    if( sweep )
    {
-      const bool fork = (h->nmediumblocks > 0 || h->nlongblocks > 0) && h->nshortblocks > 0;
+      const bool fork = h->nstreamblocks > 0 && h->nlongblocks > 0;
       if( fork )
+      {
          CU(cudaEventRecord(h->evfork, h->stream));
-      if( h->nshortblocks > 0 )
-      {
-         const ShortVariant& sv = g_shortVariants[h->shortvariant];
-         sv.kernel<<<h->nshortblocks, sv.threads, sv.smem, h->stream>>>(h->p);
+         CU(cudaStreamWaitEvent(h->aux[0], h->evfork, 0));
+         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, 0, h->aux[0]>>>(h->p);
+         CU(cudaEventRecord(h->evjoin[0], h->aux[0]));
       }
-      if( h->nmediumblocks > 0 )
-      {
-         cudaStream_t st = fork ? h->aux[0] : h->stream;
-         if( fork )
-            CU(cudaStreamWaitEvent(st, h->evfork, 0));
-         sweep_medium_kernel<MEDIUM_U, MEDIUM_MINB><<<h->nmediumblocks, SWEEP_THREADS, 0, st>>>(h->p);
-         if( fork )
-         {
-            CU(cudaEventRecord(h->evjoin[0], st));
-            CU(cudaStreamWaitEvent(h->stream, h->evjoin[0], 0));
-         }
-      }
-      if( h->nlongblocks > 0 )
-      {
-         const bool f2 = h->nshortblocks > 0 || h->nmediumblocks > 0;
-         cudaStream_t st = f2 ? h->aux[1] : h->stream;
-         if( f2 )
-         {
-            if( !fork )
-               CU(cudaEventRecord(h->evfork, h->stream));
-            CU(cudaStreamWaitEvent(st, h->evfork, 0));
-         }
-         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, 0, st>>>(h->p);
-         if( f2 )
-         {
-            CU(cudaEventRecord(h->evjoin[1], st));
-            CU(cudaStreamWaitEvent(h->stream, h->evjoin[1], 0));
-         }
-      }
+      else if( h->nlongblocks > 0 )
+         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, 0, h->stream>>>(h->p);
+      if( h->nstreamblocks > 0 )
+         sweep_stream_kernel<<<h->nstreamblocks, SWEEP_THREADS, 0, h->stream>>>(h->p);
+      if( fork )
+         CU(cudaStreamWaitEvent(h->stream, h->evjoin[0], 0));
+      if( h->nexactblocks > 0 )
+         exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
    }
-   if( sweep && h->nexactblocks > 0 )
-      exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
    if( apply )
       apply_kernel<DENSE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
    CU(cudaGetLastError());
@@ -315,7 +257,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    const char* loopenv = getenv("GPULIN_LOOP");
    h->hostloop = (loopenv != nullptr && strcmp(loopenv, "host") == 0);
 
-   // ---- bin the rows: stable sort by (class group, length) ------------------------------------------------
+   // ---- bin the rows: rows of 1..STREAM_MAXLEN nonzeros keep the caller's order and form the CSR stream, the others
+   // ---- (longer, or empty) follow, longest first, and are swept block-per-row
    std::vector<int> len((size_t)nrows);
    for( int64_t r = 0; r < nrows; ++r )
    {
@@ -323,80 +266,81 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       h->maxlen = std::max(h->maxlen, len[(size_t)r]);
    }
    std::vector<int>& perm = h->perm;
-   perm.resize((size_t)nrows);
-   std::iota(perm.begin(), perm.end(), 0);
-   auto group = [&](int r) { return len[(size_t)r] <= SHORT_MAXLEN ? 0 : (len[(size_t)r] <= MEDIUM_MAXLEN ? 1 : 2); };
-   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
-      const int ga = group(a), gb = group(b);
-      if( ga != gb )
-         return ga < gb;
-      if( ga == 0 )
-         return len[(size_t)a] < len[(size_t)b];   // short: ascending, minimal SELL padding
-      return len[(size_t)a] > len[(size_t)b];      // medium / long: heaviest first
-   });
-   for( int64_t i = 0; i < nrows; ++i )
+   perm.clear();
+   perm.reserve((size_t)nrows);
+   std::vector<int> longrows;
+   for( int64_t r = 0; r < nrows; ++r )
    {
-      const int g = group(perm[(size_t)i]);
-      if( g == 0 ) ++h->nshort;
-      else if( g == 1 ) ++h->nmedium;
-      else ++h->nlong;
+      if( len[(size_t)r] >= 1 && len[(size_t)r] <= STREAM_MAXLEN )
+         perm.push_back((int)r);
+      else
+         longrows.push_back((int)r);
    }
+   h->nstream = (int)perm.size();
+   h->nlong = (int)longrows.size();
+   std::stable_sort(longrows.begin(), longrows.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
+   perm.insert(perm.end(), longrows.begin(), longrows.end());
 
-   // ---- SELL-32 slices of the short rows, CSR of the rest ------------------------------------------------------
-   const int nslices = (h->nshort + 31) / 32;
-   std::vector<long long> sell_off((size_t)nslices + 1, 0);
    std::vector<long long> rowbeg((size_t)nrows + 1, 0);
    std::vector<int> plen((size_t)nrows);
+   long long off = 0;
    for( int64_t i = 0; i < nrows; ++i )
+   {
       plen[(size_t)i] = len[(size_t)perm[(size_t)i]];
-   for( int s = 0; s < nslices; ++s )
-   {
-      const int last = std::min(h->nshort, 32 * s + 32) - 1;
-      sell_off[(size_t)s + 1] = sell_off[(size_t)s] + 32LL * plen[(size_t)last];
-   }
-   long long off = sell_off[(size_t)nslices];
-   for( int64_t i = h->nshort; i < nrows; ++i )
-   {
-      off = (off + 1) & ~1LL;     // even start: 16-byte aligned coefficients
+      if( i == h->nstream )
+      {
+         h->nstreamelems = off;
+         off = (off + TILE - 1) / TILE * TILE;      // the stream is padded with zero coefficients to a whole tile
+      }
+      if( i >= h->nstream )
+         off = (off + 3) & ~3LL;                    // long rows start 16-byte aligned
       rowbeg[(size_t)i] = off;
       off += plen[(size_t)i];
    }
+   if( h->nstream == nrows )
+   {
+      h->nstreamelems = off;
+      off = (off + TILE - 1) / TILE * TILE;
+   }
+   h->ntiles = (int)((h->nstreamelems + TILE - 1) / TILE);
    h->nstored = off;
-   if( h->nstored >= (1LL << 40) )
+   if( h->nstored >= (1LL << 40) || (h->nstreamelems + TILE - 1) / TILE >= (1LL << 31) - 64 )
    {
       delete h;
       return fail(GPULIN_ERR_ARG, "matrix too large");
    }
-   std::vector<double> pvals((size_t)h->nstored + 2, 0.0);
-   std::vector<int> pcols((size_t)h->nstored + 2, 0);
+   std::vector<double> pvals((size_t)h->nstored + 8, 0.0);
+   std::vector<int> pcols((size_t)h->nstored + 8, 0);
    for( int64_t i = 0; i < nrows; ++i )
    {
       const int64_t r = perm[(size_t)i];
       const int64_t b = rowptr[r];
-      if( i < h->nshort )
+      const long long base = rowbeg[(size_t)i];
+      for( int k = 0; k < plen[(size_t)i]; ++k )
       {
-         const long long base = sell_off[(size_t)(i >> 5)] + (i & 31);
-         for( int k = 0; k < plen[(size_t)i]; ++k )
-         {
-            const int j = colidx[b + k];
-            pvals[(size_t)(base + 32LL * k)] = vals[b + k];
-            pcols[(size_t)(base + 32LL * k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
-         }
-      }
-      else
-      {
-         const long long base = rowbeg[(size_t)i];
-         for( int k = 0; k < plen[(size_t)i]; ++k )
-         {
-            const int j = colidx[b + k];
-            pvals[(size_t)(base + k)] = vals[b + k];
-            pcols[(size_t)(base + k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
-         }
+         const int j = colidx[b + k];
+         pvals[(size_t)(base + k)] = vals[b + k];
+         pcols[(size_t)(base + k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
       }
    }
    std::vector<double2> sides((size_t)nrows + 1);
    for( int64_t i = 0; i < nrows; ++i )
       sides[(size_t)i] = make_double2(lhs[perm[(size_t)i]], rhs[perm[(size_t)i]]);
+
+   // ---- tiles of the stream: row-end bit per nonzero, first unfinished row per tile ----------------------------------
+   std::vector<unsigned char> endmask((size_t)h->ntiles * 32 + 32, 0);
+   std::vector<int> tile_row0((size_t)h->ntiles + 2, h->nstream);
+   {
+      int t = 0;
+      for( int i = 0; i < h->nstream; ++i )
+      {
+         const long long last = rowbeg[(size_t)i] + plen[(size_t)i] - 1;
+         endmask[(size_t)(last >> 3)] |= (unsigned char)(1u << (last & 7));
+         // row i is the first unfinished row of every tile that starts at or before its last nonzero
+         while( t < h->ntiles && (long long)t * TILE <= last )
+            tile_row0[(size_t)t++] = i;
+      }
+   }
 
    // ---- column -> (permuted) rows --------------------------------------------------------------------------------
    std::vector<long long> colbeg((size_t)ncols + 2, 0);
@@ -417,20 +361,23 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    // ---- upload ---------------------------------------------------------------------------------------------------
    DevProblem& p = h->p;
-   long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
+   int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
+   int* d_tile_row0; unsigned char* d_endmask; unsigned char* d_tileflag;
    int* d_xlist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned char* d_colflag; long long* d_colbeg; int* d_colrows;
    Ctrl* d_ctrl;
    int rc = GPULIN_OK;
 #define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
 #define TRYCU(x) do { if( rc == GPULIN_OK ) { cudaError_t e_ = (x); if( e_ != cudaSuccess ) rc = fail(GPULIN_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while( 0 )
-   TRY(devAlloc(h, &d_sell_off, (size_t)nslices + 1));
+   TRY(devAlloc(h, &d_tile_row0, (size_t)h->ntiles + 2));
+   TRY(devAlloc(h, &d_endmask, (size_t)h->ntiles * 32 + 32));
+   TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
    TRY(devAlloc(h, &d_rowlen, (size_t)nrows + 1));
    TRY(devAlloc(h, &d_rowbeg, (size_t)nrows + 1));
-   TRY(devAlloc(h, &d_vals, (size_t)h->nstored + 2));
-   TRY(devAlloc(h, &d_cols, (size_t)h->nstored + 2));
+   TRY(devAlloc(h, &d_vals, (size_t)h->nstored + 8));
+   TRY(devAlloc(h, &d_cols, (size_t)h->nstored + 8));
    TRY(devAlloc(h, &d_sides, (size_t)nrows + 1));
    TRY(devAlloc(h, &d_dirty, (size_t)nrows + 64));
-   TRY(devAlloc(h, &d_xlist, (size_t)nrows + 1));
+   TRY(devAlloc(h, &d_xlist, 2 * (size_t)h->nstream + (size_t)h->nlong + 1));
    TRY(devAlloc(h, &d_bnd, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)ncols + 2));
    TRY(devAlloc(h, &d_colflag, (size_t)ncols + 64));
@@ -439,7 +386,9 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &d_ctrl, 1));
    TRY(devAlloc(h, &h->d_tmplb, (size_t)ncols + 1));
    TRY(devAlloc(h, &h->d_tmpub, (size_t)ncols + 1));
-   TRYCU(cudaMemcpy(d_sell_off, sell_off.data(), sizeof(long long) * ((size_t)nslices + 1), cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_tile_row0, tile_row0.data(), sizeof(int) * ((size_t)h->ntiles + 1), cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_endmask, endmask.data(), (size_t)h->ntiles * 32, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemset(d_tileflag, 0, (size_t)h->ntiles + 64));
    {
       // rows with a coefficient below hugeval / infinity always take the exact rules (see ROWLEN_EXACT)
       gpulin_numerics dn;
@@ -462,8 +411,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       TRYCU(cudaMemcpy(d_rowlen, flagged.data(), sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice));
    }
    TRYCU(cudaMemcpy(d_rowbeg, rowbeg.data(), sizeof(long long) * ((size_t)nrows + 1), cudaMemcpyHostToDevice));
-   TRYCU(cudaMemcpy(d_vals, pvals.data(), sizeof(double) * (size_t)h->nstored, cudaMemcpyHostToDevice));
-   TRYCU(cudaMemcpy(d_cols, pcols.data(), sizeof(int) * (size_t)h->nstored, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_vals, pvals.data(), sizeof(double) * ((size_t)h->nstored + 8), cudaMemcpyHostToDevice));
+   TRYCU(cudaMemcpy(d_cols, pcols.data(), sizeof(int) * ((size_t)h->nstored + 8), cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_sides, sides.data(), sizeof(double2) * (size_t)nrows, cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_colbeg, colbeg.data(), sizeof(long long) * ((size_t)ncols + 1), cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_colrows, colrows.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
@@ -491,9 +440,11 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    p.nrows = (int)nrows;
    p.ncols = (int)ncols;
-   p.nshort = h->nshort;
-   p.nmedium = h->nmedium;
-   p.sell_off = d_sell_off;
+   p.nstream = h->nstream;
+   p.ntiles = h->ntiles;
+   p.tile_row0 = d_tile_row0;
+   p.endmask = d_endmask;
+   p.tileflag = d_tileflag;
    p.rowlen = d_rowlen;
    p.rowbeg = d_rowbeg;
    p.vals = d_vals;
@@ -526,30 +477,18 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols / 16 + APPLY_THREADS) / APPLY_THREADS, (int64_t)h->nsm * 4));
    {
       int occ = 0;
-      const char* ve = getenv("GPULIN_SHORT_VARIANT");
-      if( ve != nullptr && atoi(ve) >= 0 && atoi(ve) < NSHORTVARIANTS )
-         h->shortvariant = atoi(ve);
-      const ShortVariant& sv = g_shortVariants[h->shortvariant];
-      if( sv.smem > 0 && cudaFuncSetAttribute(sv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sv.smem) != cudaSuccess )
-      {
-         gpulin_destroy(h);
-         return fail(GPULIN_ERR_CUDA, "cannot reserve %d bytes of shared memory for %s", sv.smem, sv.name);
-      }
-      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv.kernel, sv.threads, sv.smem) != cudaSuccess || occ < 1 )
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_stream_kernel, SWEEP_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
-      const char* oe = getenv("GPULIN_SHORT_OCC");      // experiment: blocks per SM of the persistent grid
+      const char* oe = getenv("GPULIN_STREAM_OCC");      // experiment: blocks per SM of the persistent grid
       if( oe != nullptr && atoi(oe) > 0 )
          occ = atoi(oe);
-      const int wpb = sv.threads / 32;
-      const int64_t need = ((int64_t)nslices + wpb - 1) / wpb;
-      h->nshortblocks = (int)std::min<int64_t>(need, (int64_t)h->nsm * occ);
+      const int wpb = SWEEP_THREADS / 32;
+      // at least two tiles per warp, never more blocks than stay resident
+      const int64_t need = ((int64_t)h->ntiles + 2 * wpb - 1) / (2 * wpb);
+      h->nstreamblocks = (int)std::min<int64_t>(need, (int64_t)h->nsm * occ);
       if( getenv("GPULIN_VERBOSE") != nullptr )
-         fprintf(stderr, "gpulin: short sweep %s, %d blocks x %d threads (%d per SM), %d B smem\n", sv.name, h->nshortblocks,
-            sv.threads, occ, sv.smem);
-      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_medium_kernel<MEDIUM_U, MEDIUM_MINB>, SWEEP_THREADS, 0) != cudaSuccess || occ < 1 )
-         occ = 2;
-      const int64_t needm = ((int64_t)h->nmedium + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32);
-      h->nmediumblocks = (int)std::min<int64_t>(needm, (int64_t)h->nsm * occ);
+         fprintf(stderr, "gpulin: stream sweep %d tiles, %d blocks x %d threads (%d per SM); %d long rows\n", h->ntiles,
+            h->nstreamblocks, SWEEP_THREADS, occ, h->nlong);
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_long_kernel, LONG_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nlongblocks = (int)std::min<int64_t>(h->nlong, (int64_t)h->nsm * occ);
@@ -838,8 +777,8 @@ extern "C" int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats)
 {
    if( h == nullptr || stats == nullptr )
       return fail(GPULIN_ERR_ARG, "invalid argument");
-   const int64_t v[10] = {h->nnz, h->nstored, h->nshort, h->nmedium, h->nlong, (int64_t)h->devbytes, h->nshortblocks,
-      h->nmediumblocks, h->nlongblocks, h->maxlen};
+   const int64_t v[10] = {h->nnz, h->nstored, h->nstream, h->ntiles, h->nlong, (int64_t)h->devbytes, h->nstreamblocks,
+      h->nlongblocks, h->nexactblocks, h->maxlen};
    for( int i = 0; i < nstats && i < 10; ++i )
       stats[i] = v[i];
    return GPULIN_OK;

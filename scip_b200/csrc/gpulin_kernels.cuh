@@ -1,31 +1,37 @@
 // gpulin_kernels.cuh -- the propagation round of the linear bound propagation path as sm_100a kernels.
 //
 // One round (= one sweep of the reference's consPropLinear over its marked rows, cons_linear.c:16126-16195, run as a
-// synchronous Jacobi step) is two launches:
+// synchronous Jacobi step) is three launches:
 //
-//   sweep_rows_kernel / sweep_long_kernel     for every row marked for propagation: min/max activity with
-//        inf/huge counters (double-double), row gates, per-nonzero candidate bounds, atomicMin on int64 keys,
-//        row verdict.  Rows are binned by length: thread-per-row on SELL-32 slices (len <= 32), warp-per-row
-//        (33..1024), block-per-row with shared-memory staging (> 1024).  The matrix is streamed ONCE per round:
-//        between the activity pass and the candidate pass only alpha_k = |a_k| (ub_k - lb_k) stays in registers /
-//        shared memory; a nonzero is re-read only if its alpha passes the slack test (tightenVarBoundsEasy
-//        :5474/:5566), which is rare.
-//   apply_kernel                              for every column whose key moved: accept the new bounds, detect
-//        crossing bounds, log the change, mark the rows of the column (CSC) for the next round -- the counterpart
-//        of eventExecLinear's SCIPmarkConsPropagate (:17229); the last block to finish runs the loop control
-//        (propagateDomains, solve.c:766) and sets the CUDA-graph WHILE condition.
+//   sweep_stream_kernel (+ sweep_long_kernel for rows > STREAM_MAXLEN)      THE HOT KERNEL: an interval filter.
+//        All rows of 1..STREAM_MAXLEN nonzeros lie concatenated in one CSR stream that is cut into tiles of 256
+//        nonzeros.  A warp owns a contiguous range of tiles; per tile every lane reads 8 consecutive coefficients and
+//        column indices with 16-byte vector loads, gathers the 8 bound pairs (8 independent 16-byte loads in flight per
+//        lane), and the per-row sums minact/maxact/maxdelta/cabs come out of a segmented scan over the tile (row ends
+//        are a precomputed bit per nonzero; rows may span tiles and warp ranges).  9 fp64 instructions per nonzero,
+//        the matrix is streamed once.  A row that is CLEARLY QUIET (see rowClearlyQuiet) is finished; every other
+//        marked row goes to a work list.
+//   exact_rows_kernel      the reference's rules in full for the rows on the work lists: double-double activities with
+//        inf/huge counters, gates of tightenBounds, candidate bounds per nonzero (tightenVarBoundsEasy /
+//        tightenVarBounds), commit filter, atomicMin on the int64 keys, row verdict.
+//   apply_kernel           for every column whose key moved: accept the new bounds, detect crossing bounds, log the
+//        change, mark the rows of the column (CSC) for the next round -- the counterpart of eventExecLinear's
+//        SCIPmarkConsPropagate (:17229); the last block to finish runs the loop control (propagateDomains,
+//        solve.c:766) and sets the CUDA-graph WHILE condition.
 #pragma once
 
 #include "gpulin_device.cuh"
 
 namespace gpl {
 
-constexpr int SWEEP_THREADS = 256;
+constexpr int SWEEP_THREADS = 128;
 constexpr int LONG_THREADS = 512;
-constexpr int MAX_HIST = 1024;       // rounds with recorded per-round statistics
-constexpr int SHORT_MAXLEN = 32;     // thread-per-row up to this length
-constexpr int MEDIUM_MAXLEN = 1024;  // warp-per-row up to this length
-constexpr int NNZ_SLOTS = 64;        // spread counters of the nonzeros swept in a round
+constexpr int MAX_HIST = 1024;        // rounds with recorded per-round statistics
+constexpr int TILE = 256;             // nonzeros per tile of the CSR stream = 32 lanes x TPL
+constexpr int TPL = 8;                // nonzeros per lane and tile
+constexpr int STREAM_MAXLEN = 4096;   // longer rows (and empty rows) are swept block-per-row
+constexpr int SHORT_MAXLEN = 32;      // exact kernel: rows up to this length are handled by groups of 8 lanes
+constexpr int NNZ_SLOTS = 64;         // spread counters of the nonzeros swept in a round
 
 // loop control + statistics, lives in device memory
 struct Ctrl
@@ -43,7 +49,7 @@ struct Ctrl
    unsigned long long total_nchg;
    unsigned long long total_nnz;
    unsigned long long t_start;      // %globaltimer at the start of the call
-   unsigned int       nexact[4];    // rows the filter sweeps handed to the exact kernel in the running round, per bin
+   unsigned int       nexact[4];    // rows the filter sweeps handed to the exact kernel in the running round, per list
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
    unsigned long long hist_time[MAX_HIST];   // %globaltimer at the end of each round
    unsigned long long hist_nnz[MAX_HIST];
@@ -63,17 +69,21 @@ struct DevProblem
 {
    int                 nrows;
    int                 ncols;
-   int                 nshort;     // rows [0,nshort) are short (SELL-32), then medium, then long (CSR)
-   int                 nmedium;
-   // rows in permuted order
-   const long long*    sell_off;   // per slice of 32 short rows: element offset of the slice
-   const int*          rowlen;     // per row
-   const long long*    rowbeg;     // per row: element offset of its first nonzero (CSR part; unused for short rows)
+   int                 nstream;    // rows [0,nstream) form the CSR stream (caller's order), rows [nstream,nrows) are long / empty
+   int                 ntiles;     // tiles of the stream (its storage is padded with zero coefficients to a whole tile)
+   // rows (permuted numbering)
+   const long long*    rowbeg;     // element offset of the first nonzero
+   const int*          rowlen;     // length | ROWLEN_EXACT
+   const double2*      sides;      // (lhs, rhs)
+   unsigned char*      dirty;      // marked for propagation
    const double*       vals;
    const int*          cols;       // column index | (integral << 31)
-   const double2*      sides;      // (lhs, rhs) per row
-   unsigned char*      dirty;      // per row: marked for propagation
-   int*                xlist;      // rows handed to exact_rows_kernel; one region per bin: [0,nshort) [nshort,+nmedium) [..,nrows)
+   // tiles
+   const int*          tile_row0;  // first row that ends at or behind the first nonzero of the tile
+   const unsigned char* endmask;   // per tile and lane: bit i = nonzero 8*lane+i is the last of its row
+   unsigned char*      tileflag;   // a marked row starts in this tile
+   int*                xlist;      // rows handed to exact_rows_kernel: lists [0,nstream) short, [nstream,2 nstream) medium,
+                                   // [2 nstream, 2 nstream + nlong) long
    // columns
    const double2*      bnd;        // (lb, ub) at round start
    long long*          cand;       // 2*ncols (+2) candidate keys, see Sink
@@ -93,7 +103,15 @@ __device__ __forceinline__ unsigned long long globaltimer()
    return t;
 }
 
-// streaming loads of the matrix: read once per round, evict-first
+// streaming loads of the matrix: read once per round, evict-first, 16 bytes per request
+__device__ __forceinline__ double2 ldStream2(const double* p)
+{
+   return __ldcs(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ int4 ldStream4(const int* p)
+{
+   return __ldcs(reinterpret_cast<const int4*>(p));
+}
 __device__ __forceinline__ double ldStream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int ldStream(const int* p) { return __ldcs(p); }
 
@@ -191,24 +209,61 @@ constexpr int ROWLEN_EXACT = 0x40000000;   // flag in rowlen[]: the row has a co
 
 struct LeanAcc
 {
-   double minact, maxact, maxdelta, cabs;
+   double minact;     // plain fp64 sums
+   double maxact;
+   float  maxdelta;   // max_k (cmax_k - cmin_k), rounded UP to fp32 (exact for integers below 2^24)
+   int    cabshi;     // high word of max_k max(|a_k lb_k|, |a_k ub_k|): an upper bound is (cabshi + 1) << 32
 };
 
 __device__ __forceinline__ void leanInit(LeanAcc& r)
 {
-   r.minact = r.maxact = r.maxdelta = r.cabs = 0.0;
+   r.minact = r.maxact = 0.0;
+   r.maxdelta = 0.0f;
+   r.cabshi = 0;
 }
 
+// 17 instructions per nonzero: the sign of the coefficient comes from its high word, the two maxima are a float and
+// an integer maximum (non-negative IEEE doubles are ordered like their bit patterns); fp64 min/max would cost ~8
+// instructions each on this architecture
 __device__ __forceinline__ void leanElem(LeanAcc& r, double a, double l, double u)
 {
    const double al = a * l;
    const double au = a * u;
-   const double cmin = fmin(al, au);
-   const double cmax = fmax(al, au);
+   const bool pos = __double2hiint(a) >= 0;
+   const double cmin = pos ? al : au;      // = min(al, au) for lb <= ub
+   const double cmax = pos ? au : al;
    r.minact += cmin;
    r.maxact += cmax;
-   r.maxdelta = fmax(r.maxdelta, cmax - cmin);
-   r.cabs = fmax(r.cabs, fmax(fabs(al), fabs(au)));
+   r.maxdelta = fmaxf(r.maxdelta, __double2float_ru(cmax - cmin));
+   r.cabshi = max(r.cabshi, max(__double2hiint(al) & 0x7fffffff, __double2hiint(au) & 0x7fffffff));
+}
+
+__device__ __forceinline__ void leanAdd(LeanAcc& r, const LeanAcc& o)
+{
+   r.minact += o.minact;
+   r.maxact += o.maxact;
+   r.maxdelta = fmaxf(r.maxdelta, o.maxdelta);
+   r.cabshi = max(r.cabshi, o.cabshi);
+}
+
+__device__ __forceinline__ LeanAcc leanShflUp(const LeanAcc& s, int d)
+{
+   LeanAcc o;
+   o.minact = __shfl_up_sync(0xffffffffu, s.minact, d);
+   o.maxact = __shfl_up_sync(0xffffffffu, s.maxact, d);
+   o.maxdelta = __shfl_up_sync(0xffffffffu, s.maxdelta, d);
+   o.cabshi = __shfl_up_sync(0xffffffffu, s.cabshi, d);
+   return o;
+}
+
+__device__ __forceinline__ LeanAcc leanShfl(const LeanAcc& s, int src)
+{
+   LeanAcc o;
+   o.minact = __shfl_sync(0xffffffffu, s.minact, src);
+   o.maxact = __shfl_sync(0xffffffffu, s.maxact, src);
+   o.maxdelta = __shfl_sync(0xffffffffu, s.maxdelta, src);
+   o.cabshi = __shfl_sync(0xffffffffu, s.cabshi, src);
+   return o;
 }
 
 __device__ __forceinline__ void leanWarpReduce(LeanAcc& r)
@@ -218,22 +273,25 @@ __device__ __forceinline__ void leanWarpReduce(LeanAcc& r)
    {
       r.minact += __shfl_xor_sync(0xffffffffu, r.minact, m);
       r.maxact += __shfl_xor_sync(0xffffffffu, r.maxact, m);
-      r.maxdelta = fmax(r.maxdelta, __shfl_xor_sync(0xffffffffu, r.maxdelta, m));
-      r.cabs = fmax(r.cabs, __shfl_xor_sync(0xffffffffu, r.cabs, m));
+      r.maxdelta = fmaxf(r.maxdelta, __shfl_xor_sync(0xffffffffu, r.maxdelta, m));
+      r.cabshi = max(r.cabshi, __shfl_xor_sync(0xffffffffu, r.cabshi, m));
    }
 }
 
 __device__ __forceinline__ bool rowClearlyQuiet(const Num& n, const LeanAcc& r, int len, double lhs, double rhs)
 {
-   // an infinite bound (|b| >= 1e20, with |a| >= hugeval/infinity by the ROWLEN_EXACT flag) or a huge product shows
-   // up in cabs; NaN compares false
-   if( !(r.cabs < n.huge) )
+   // upper bound of the largest |product|; an infinite bound (|b| >= 1e20, with |a| >= hugeval/infinity by the
+   // ROWLEN_EXACT flag), a huge product or a NaN shows up here
+   if( r.cabshi >= 0x7fe00000 )
       return false;
-   const double E = (double)(len * len + 8) * 2.3e-16 * r.cabs;
+   const double cabs = __hiloint2double(r.cabshi + 1, 0);
+   if( !(cabs < n.huge) )
+      return false;
+   const double E = (double)(len * len + 8) * 2.3e-16 * cabs;
    // verdict: FeasGT(minact,rhs) needs (minact-rhs)/max(1,|minact|,|rhs|) > feastol, impossible if minact-rhs <= feastol/4
    if( (r.minact - rhs) + E > 0.25 * n.feastol || (lhs - r.maxact) + E > 0.25 * n.feastol )
       return false;
-   const double md = r.maxdelta + E;
+   const double md = (double)r.maxdelta + E;
    if( md <= 0.5 * n.feastol )
       return true;                // all variables fixed (:7057)
    const double slack = isInf(n, rhs) ? n.inf : rhs - r.minact;
@@ -324,141 +382,285 @@ __device__ __forceinline__ void addRoundNnz(const DevProblem& p, unsigned long l
       atomicAdd(&p.ctrl->round_nnz[slot & (NNZ_SLOTS - 1)], nnzdone);
 }
 
-// ---- thread-per-row on SELL-32 slices: element k of the row of lane t sits at slice_off + 32 k + t -------------
-// ---- persistent warps: warp w sweeps slices w, w + W, w + 2W, ...
-template <int CH>
-__device__ __forceinline__ void loadChunk(const DevProblem& p, long long base, int c, int len, double (&a)[CH], int (&cj)[CH])
+// ---- the filter sweep over the CSR stream --------------------------------------------------------------------------
+
+// a marked row whose sums are complete: is it finished, or does it need the exact rules?  (returns 0: not marked /
+// finished, 1: hand over as a short row, 2: hand over as a medium row)
+__device__ __forceinline__ int finishRow(const DevProblem& p, int row, const LeanAcc& tot, unsigned char flag, int lenword,
+   const double2& sd, unsigned& nnzdone)
 {
-#pragma unroll
-   for( int k = 0; k < CH; ++k )
-   {
-      if( c + k < len )
-      {
-         a[k] = ldStream(p.vals + base + 32LL * (c + k));
-         cj[k] = ldStream(p.cols + base + 32LL * (c + k));
-      }
-   }
+   if( flag != ROW_MARKED )
+      return 0;
+   p.dirty[row] = ROW_CLEAN;
+   const bool exact = (lenword & ROWLEN_EXACT) != 0;
+   const int len = lenword & ~ROWLEN_EXACT;
+   nnzdone += (unsigned)len;
+   if( exact || !rowClearlyQuiet(p.num, tot, len, sd.x, sd.y) )
+      return len <= SHORT_MAXLEN ? 1 : 2;
+   return 0;
 }
 
-template <int CH, bool PF>
-__device__ __forceinline__ void sweepSlice(const DevProblem& p, int slice, int lane, bool act, unsigned& nnzdone)
+// appends `row` of every lane with want == true to a work list (one atomic per warp)
+__device__ __forceinline__ void pushRow(const DevProblem& p, bool want, int row, int lane, int list, int listoff)
 {
-   const Num& n = p.num;
-   const int row = slice * 32 + lane;
-   int len = 0;
-   bool exact = false;
-   if( act )
-   {
-      len = p.rowlen[row];
-      exact = (len & ROWLEN_EXACT) != 0;
-      len &= ~ROWLEN_EXACT;
-   }
-   const long long base = p.sell_off[slice] + lane;
-   const int maxlen = __reduce_max_sync(0xffffffffu, len);
-
-   LeanAcc acc;
-   leanInit(acc);
-   if( PF )
-   {
-      // the coefficients of chunk c+1 are in flight while the bounds of chunk c are gathered
-      double an[CH];
-      int cjn[CH];
-      loadChunk<CH>(p, base, 0, len, an, cjn);
-      for( int c = 0; c < maxlen; c += CH )
-      {
-         double a[CH];
-         int cj[CH];
-         double2 b[CH];
-#pragma unroll
-         for( int k = 0; k < CH; ++k )
-         {
-            a[k] = an[k];
-            cj[k] = cjn[k];
-         }
-         if( c + CH < maxlen )
-            loadChunk<CH>(p, base, c + CH, len, an, cjn);
-#pragma unroll
-         for( int k = 0; k < CH; ++k )
-         {
-            if( c + k < len )
-               b[k] = p.bnd[cj[k] & 0x7fffffff];
-         }
-#pragma unroll
-         for( int k = 0; k < CH; ++k )
-         {
-            if( c + k < len )
-               leanElem(acc, a[k], b[k].x, b[k].y);
-         }
-      }
-   }
-   else
-   {
-      for( int c = 0; c < maxlen; c += CH )
-      {
-         double a[CH];
-         int cj[CH];
-         double2 b[CH];
-         loadChunk<CH>(p, base, c, len, a, cj);
-#pragma unroll
-         for( int k = 0; k < CH; ++k )
-         {
-            if( c + k < len )
-               b[k] = p.bnd[cj[k] & 0x7fffffff];
-         }
-#pragma unroll
-         for( int k = 0; k < CH; ++k )
-         {
-            if( c + k < len )
-               leanElem(acc, a[k], b[k].x, b[k].y);
-         }
-      }
-   }
-   bool handoff = false;
-   if( act )
-   {
-      const double2 sd = p.sides[row];
-      handoff = exact || !rowClearlyQuiet(n, acc, len, sd.x, sd.y);
-      p.dirty[row] = ROW_CLEAN;
-      nnzdone += (unsigned)len;
-   }
-   // rows that need the exact rules go to the work list of exact_rows_kernel (one atomic per warp)
-   const unsigned hm = __ballot_sync(0xffffffffu, handoff);
-   if( hm != 0u )
-   {
-      unsigned pos = 0u;
-      if( lane == 0 )
-         pos = atomicAdd(&p.ctrl->nexact[0], (unsigned)__popc(hm));
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      if( handoff )
-         p.xlist[pos + __popc(hm & ((1u << lane) - 1u))] = row;
-   }
+   const unsigned m = __ballot_sync(0xffffffffu, want);
+   if( m == 0u )
+      return;
+   unsigned pos = 0u;
+   if( lane == 0 )
+      pos = atomicAdd(&p.ctrl->nexact[list], (unsigned)__popc(m));
+   pos = __shfl_sync(0xffffffffu, pos, 0);
+   if( want )
+      p.xlist[listoff + pos + __popc(m & ((1u << lane) - 1u))] = row;
 }
 
-template <int CH, bool PF, int MINB>
-__global__ void __launch_bounds__(SWEEP_THREADS, MINB) sweep_short_kernel(const DevProblem p)
+// 32-byte streaming loads (LDG.256): one full sector per lane and request
+__device__ __forceinline__ void ldStream256(const double* ptr, double& a, double& b, double& c, double& d)
 {
+   asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(ptr));
+}
+__device__ __forceinline__ void ldStream256(const int* ptr, int (&v)[TPL])
+{
+   asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                : "l"(ptr));
+}
+
+struct TileRegs
+{
+   double   a[TPL];
+   int      cj[TPL];
+   unsigned em;
+   int      row0;
+};
+
+__device__ __forceinline__ void loadTile(const DevProblem& p, int t, int lane, TileRegs& r)
+{
+   const long long e0 = (long long)t * TILE + lane * TPL;
+   ldStream256(p.vals + e0, r.a[0], r.a[1], r.a[2], r.a[3]);
+   ldStream256(p.vals + e0 + 4, r.a[4], r.a[5], r.a[6], r.a[7]);
+   ldStream256(p.cols + e0, r.cj);
+   r.em = p.endmask[(size_t)t * 32 + lane];
+   r.row0 = p.tile_row0[t];
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const DevProblem p)
+{
+   static_assert(TPL == 8 && TILE == 256, "the tile layout is wired into the vector loads");
+   // per warp: the sums of the rows that end in the current tile, in row order (at most one row per nonzero)
+   __shared__ LeanAcc s_tot[SWEEP_THREADS / 32][TILE];
+
    const int lane = threadIdx.x & 31;
+   LeanAcc* tot = s_tot[threadIdx.x >> 5];
    const int gw = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
    const int nw = (gridDim.x * SWEEP_THREADS) >> 5;
-   const int nslices = (p.nshort + 31) >> 5;
+   // contiguous tile range of this warp
+   const int per = (p.ntiles + nw - 1) / nw;
+   const int t0 = gw * per;
+   const int t1 = min(p.ntiles, t0 + per);
+   if( t0 >= t1 )
+      return;
+
    unsigned nnzdone = 0;
-   for( int s0 = gw; s0 < nslices; s0 += 4 * nw )
+   LeanAcc carry;                 // sums of the row that is open at the start of the tile (warp-uniform)
+   leanInit(carry);
+   bool opendirty = false;        // ... and it is marked: the tiles it runs through must be processed
+
+   // look-back: a marked row that started in the range of the previous warp and ends in this one is ours to finish
    {
-      // the flags of the next four slices of this warp, one load latency
-      unsigned fm = 0u;
-#pragma unroll
-      for( int i = 0; i < 4; ++i )
+      const int r = p.tile_row0[t0];
+      if( r < p.nstream )
       {
-         const int row = (s0 + i * nw) * 32 + lane;
-         if( s0 + i * nw < nslices && row < p.nshort && p.dirty[row] == ROW_MARKED )
-            fm |= 1u << i;
+         const long long beg = p.rowbeg[r];
+         const long long first = (long long)t0 * TILE;
+         if( beg < first && p.dirty[r] == ROW_MARKED )
+         {
+            LeanAcc part;
+            leanInit(part);
+            for( long long e = beg + lane; e < first; e += 32 )
+            {
+               const double2 b = p.bnd[p.cols[e] & 0x7fffffff];
+               leanElem(part, p.vals[e], b.x, b.y);
+            }
+            leanWarpReduce(part);
+            carry = part;
+            opendirty = true;
+         }
       }
-#pragma unroll 1
-      for( int i = 0; i < 4; ++i )
+   }
+
+   TileRegs cur;
+   bool have = false;             // `cur` already holds the tile that is processed next (prefetched)
+   for( int tb = t0; tb < t1; tb += 32 )
+   {
+      // flags of the next 32 tiles of the range: one load
+      const int mine = tb + lane;
+      const unsigned flags = __ballot_sync(0xffffffffu, mine < t1 && p.tileflag[mine] != 0);
+      if( mine < t1 )
+         p.tileflag[mine] = 0;
+      for( int i = 0; i < 32 && tb + i < t1; ++i )
       {
-         const bool act = ((fm >> i) & 1u) != 0u;
-         if( __any_sync(0xffffffffu, act) )
-            sweepSlice<CH, PF>(p, s0 + i * nw, lane, act, nnzdone);
+         const int t = tb + i;
+         if( !(((flags >> i) & 1u) != 0u || opendirty) )
+         {
+            leanInit(carry);
+            continue;
+         }
+         if( !have )
+            loadTile(p, t, lane, cur);
+         have = false;
+
+         // ---- bounds of this tile: 8 independent 16-byte gathers per lane
+         double2 b[TPL];
+#pragma unroll
+         for( int k = 0; k < TPL; ++k )
+            b[k] = p.bnd[cur.cj[k] & 0x7fffffff];
+         double a[TPL];
+#pragma unroll
+         for( int k = 0; k < TPL; ++k )
+            a[k] = cur.a[k];
+         const unsigned em = cur.em;
+         const int row0 = cur.row0;
+
+         // ---- the next tile streams in while this one is worked on
+         const bool nextflag = i + 1 < 32 && t + 1 < t1 && ((flags >> (i + 1)) & 1u) != 0u;
+         if( nextflag )
+         {
+            loadTile(p, t + 1, lane, cur);
+            have = true;
+         }
+
+         // the rows that end in this tile are row0, row0+1, ..., row0+nrows-1; this lane ends rows slot0, slot0+1, ...
+         const int nends = __popc(em);
+         int incl = nends;
+#pragma unroll
+         for( int d = 1; d < 32; d <<= 1 )
+         {
+            const int s = __shfl_up_sync(0xffffffffu, incl, d);
+            if( lane >= d )
+               incl += s;
+         }
+         const int slot0 = incl - nends;
+         const int nrows = __shfl_sync(0xffffffffu, incl, 31);
+
+         // flag, length and sides of row0 + lane: in flight beside the gathers (lane-per-row, coalesced)
+         unsigned char rflag = ROW_CLEAN;
+         int rlen = 0;
+         double2 rsd = make_double2(0.0, 0.0);
+         if( lane < nrows )
+         {
+            rflag = p.dirty[row0 + lane];
+            rlen = p.rowlen[row0 + lane];
+            rsd = p.sides[row0 + lane];
+         }
+
+         // ---- lane-local pass: `head` = sums up to the first row end (to be completed with the lanes before), rows
+         // ---- that begin and end inside the lane go straight to their slot, `run` = sums behind the last end
+         LeanAcc run;
+         LeanAcc head;
+         leanInit(run);
+         leanInit(head);
+         if( !__any_sync(0xffffffffu, nends > 1) )
+         {
+            // common case, branch free: at most one row ends in this lane, at element `ep`
+            const int ep = em != 0u ? __ffs(em) - 1 : TPL;
+#pragma unroll
+            for( int k = 0; k < TPL; ++k )
+            {
+               LeanAcc x;
+               leanInit(x);
+               leanElem(x, a[k], b[k].x, b[k].y);
+               if( k <= ep )
+                  leanAdd(head, x);
+               else
+                  leanAdd(run, x);
+            }
+            if( em == 0u )
+            {
+               run = head;
+               leanInit(head);
+            }
+         }
+         else
+         {
+            int ends = 0;
+#pragma unroll
+            for( int k = 0; k < TPL; ++k )
+            {
+               leanElem(run, a[k], b[k].x, b[k].y);
+               if( (em >> k) & 1u )
+               {
+                  if( ends == 0 )
+                     head = run;
+                  else
+                     tot[slot0 + ends] = run;
+                  ++ends;
+                  leanInit(run);
+               }
+            }
+         }
+
+         // ---- segmented scan of the tails over the lanes; the open row of the previous tile enters at lane 0
+         LeanAcc s = run;
+         bool f = (em != 0u);
+         if( lane == 0 && !f )
+            leanAdd(s, carry);
+#pragma unroll
+         for( int d = 1; d < 32; d <<= 1 )
+         {
+            const LeanAcc o = leanShflUp(s, d);
+            const bool of = __shfl_up_sync(0xffffffffu, f, d);
+            if( lane >= d && !f )
+            {
+               leanAdd(s, o);
+               f = of;
+            }
+         }
+         // exclusive: what the lanes before contribute to the row that ends first in this lane
+         LeanAcc pre = leanShflUp(s, 1);
+         if( lane == 0 )
+            pre = carry;
+         if( em != 0u )
+         {
+            leanAdd(head, pre);
+            tot[slot0] = head;
+         }
+         // the row that is open behind the last end of the tile
+         carry = leanShfl(s, 31);
+         __syncwarp();
+
+         // ---- one lane per finished row: clearly quiet, or over to the exact kernel
+         for( int r0 = 0; r0 < nrows; r0 += 32 )
+         {
+            const int rr = r0 + lane;
+            int verdict = 0;
+            if( rr < nrows )
+            {
+               if( r0 > 0 )
+               {
+                  rflag = p.dirty[row0 + rr];
+                  rlen = p.rowlen[row0 + rr];
+                  rsd = p.sides[row0 + rr];
+               }
+               verdict = finishRow(p, row0 + rr, tot[rr], rflag, rlen, rsd, nnzdone);
+            }
+            if( __any_sync(0xffffffffu, verdict != 0) )
+            {
+               pushRow(p, verdict == 1, row0 + rr, lane, 0, 0);
+               pushRow(p, verdict == 2, row0 + rr, lane, 1, p.nstream);
+            }
+         }
+         __syncwarp();
+
+         // does a marked row run on into the next tile?  (only matters if that tile is not flagged itself)
+         opendirty = false;
+         if( !nextflag && t + 1 < t1 )
+         {
+            const int ropen = row0 + nrows;
+            const bool lastIsEnd = ((__shfl_sync(0xffffffffu, em, 31) >> (TPL - 1)) & 1u) != 0u;
+            if( !lastIsEnd && ropen < p.nstream )
+               opendirty = p.dirty[ropen] == ROW_MARKED;
+         }
       }
    }
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
@@ -466,101 +668,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) sweep_short_kernel(const 
       addRoundNnz(p, (unsigned long long)nnzdone, gw);
 }
 
-// ---- warp-per-row on CSR (rows of 33..1024 nonzeros): lane t reads elements t, t+32, ... ----------------------
-template <int U>
-__device__ __forceinline__ void loadChunkW(const DevProblem& p, long long beg, int c, int lane, int len, double (&a)[U], int (&cj)[U])
-{
-#pragma unroll
-   for( int k = 0; k < U; ++k )
-   {
-      const int idx = c + k * 32 + lane;
-      if( idx < len )
-      {
-         a[k] = ldStream(p.vals + beg + idx);
-         cj[k] = ldStream(p.cols + beg + idx);
-      }
-   }
-}
-
-template <int U>
-__device__ __forceinline__ void sweepWarpRow(const DevProblem& p, int row, int lane, unsigned long long& nnzdone)
-{
-   const Num& n = p.num;
-   int len = p.rowlen[row];
-   const bool exact = (len & ROWLEN_EXACT) != 0;
-   len &= ~ROWLEN_EXACT;
-   const long long beg = p.rowbeg[row];
-   const double2 sd = p.sides[row];
-
-   LeanAcc acc;
-   leanInit(acc);
-   double an[U];
-   int cjn[U];
-   loadChunkW<U>(p, beg, 0, lane, len, an, cjn);
-   for( int c = 0; c < len; c += 32 * U )
-   {
-      double a[U];
-      int cj[U];
-      double2 b[U];
-#pragma unroll
-      for( int k = 0; k < U; ++k )
-      {
-         a[k] = an[k];
-         cj[k] = cjn[k];
-      }
-      if( c + 32 * U < len )
-         loadChunkW<U>(p, beg, c + 32 * U, lane, len, an, cjn);
-#pragma unroll
-      for( int k = 0; k < U; ++k )
-      {
-         if( c + k * 32 + lane < len )
-            b[k] = p.bnd[cj[k] & 0x7fffffff];
-      }
-#pragma unroll
-      for( int k = 0; k < U; ++k )
-      {
-         if( c + k * 32 + lane < len )
-            leanElem(acc, a[k], b[k].x, b[k].y);
-      }
-   }
-   leanWarpReduce(acc);
-   const bool handoff = exact || !rowClearlyQuiet(n, acc, len, sd.x, sd.y);   // warp-uniform: all lanes hold the same sums
-   if( lane == 0 )
-   {
-      p.dirty[row] = ROW_CLEAN;
-      nnzdone += (unsigned long long)len;
-      if( handoff )
-         p.xlist[p.nshort + atomicAdd(&p.ctrl->nexact[1], 1u)] = row;
-   }
-}
-
-template <int U, int MINB>
-__global__ void __launch_bounds__(SWEEP_THREADS, MINB) sweep_medium_kernel(const DevProblem p)
-{
-   const int lane = threadIdx.x & 31;
-   const int gw = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
-   const int nw = (gridDim.x * SWEEP_THREADS) >> 5;
-   const int row0 = p.nshort;
-   const int nrows = p.nmedium;
-   unsigned long long nnzdone = 0;
-   for( int r0 = gw; r0 < nrows; r0 += 32 * nw )
-   {
-      // lane i looks at the flag of the i-th next row of this warp
-      const int mine = r0 + lane * nw;
-      const bool f = (mine < nrows) && p.dirty[row0 + mine] == ROW_MARKED;
-      unsigned mask = __ballot_sync(0xffffffffu, f);
-      while( mask != 0u )
-      {
-         const int i = __ffs(mask) - 1;
-         mask &= mask - 1u;
-         sweepWarpRow<U>(p, row0 + r0 + i * nw, lane, nnzdone);
-      }
-   }
-   if( lane == 0 )
-      addRoundNnz(p, nnzdone, gw);
-}
-
-// ---- block-per-row for rows longer than MEDIUM_MAXLEN -----------------------------------------------------------
+// ---- block-per-row for rows longer than STREAM_MAXLEN (and empty rows) ---------------------------------------------
 __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProblem p)
 {
    __shared__ LeanAcc s_lean[LONG_THREADS / 32];
@@ -568,14 +676,14 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
    const int lane = threadIdx.x & 31;
    const int warp = threadIdx.x >> 5;
    const Num& n = p.num;
-   const int row0 = p.nshort + p.nmedium;
+   const int row0 = p.nstream;
    const int nrows = p.nrows - row0;
 
    for( int r = blockIdx.x; r < nrows; r += gridDim.x )
    {
       const int row = row0 + r;
       __syncthreads();                  // previous row done with the shared state and its flag
-      if( p.dirty[row] != ROW_MARKED )  // block-uniform: nobody rewrites the flag before the barriers below
+      if( p.dirty[row] != ROW_MARKED )  // block-uniform: nobody rewrites the flag before the barrier below
          continue;
       int len = p.rowlen[row];
       const bool exact = (len & ROWLEN_EXACT) != 0;
@@ -622,17 +730,12 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
          la = s_lean[0];
 #pragma unroll 1
          for( int w = 1; w < LONG_THREADS / 32; ++w )
-         {
-            la.minact += s_lean[w].minact;
-            la.maxact += s_lean[w].maxact;
-            la.maxdelta = fmax(la.maxdelta, s_lean[w].maxdelta);
-            la.cabs = fmax(la.cabs, s_lean[w].cabs);
-         }
+            leanAdd(la, s_lean[w]);
          const bool handoff = exact || !rowClearlyQuiet(n, la, len, sd.x, sd.y);
          p.dirty[row] = ROW_CLEAN;
          addRoundNnz(p, (unsigned long long)len, row);
          if( handoff )
-            p.xlist[p.nshort + p.nmedium + atomicAdd(&p.ctrl->nexact[2], 1u)] = row;
+            p.xlist[2 * p.nstream + atomicAdd(&p.ctrl->nexact[2], 1u)] = row;
       }
    }
 }
@@ -675,7 +778,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
          {
             const int row = p.xlist[item];
             len = p.rowlen[row] & ~ROWLEN_EXACT;
-            base = p.sell_off[row >> 5] + (row & 31);
+            base = p.rowbeg[row];
             sd = p.sides[row];
          }
          double a[EXACT_Q];
@@ -687,8 +790,8 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
             const int k = gl + EXACT_G * q;
             if( k < len )
             {
-               a[q] = p.vals[base + 32LL * k];
-               cj[q] = p.cols[base + 32LL * k];
+               a[q] = p.vals[base + k];
+               cj[q] = p.cols[base + k];
             }
          }
 #pragma unroll
@@ -739,7 +842,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
       const int nw = nthreads >> 5;
       for( unsigned item = gw; item < n1; item += nw )
       {
-         const int row = p.xlist[p.nshort + item];
+         const int row = p.xlist[p.nstream + item];
          const int len = p.rowlen[row] & ~ROWLEN_EXACT;
          const long long beg = p.rowbeg[row];
          const double2 sd = p.sides[row];
@@ -754,7 +857,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
    // ---- long rows: one block per row
    for( unsigned item = blockIdx.x; item < n2; item += gridDim.x )
    {
-      const int row = p.xlist[p.nshort + p.nmedium + item];
+      const int row = p.xlist[2 * p.nstream + item];
       const int len = p.rowlen[row] & ~ROWLEN_EXACT;
       const long long beg = p.rowbeg[row];
       const double2 sd = p.sides[row];
@@ -812,11 +915,22 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j)
          if( q + t < e )
             r[t] = p.colrows[q + t];
       }
+      long long rb[8];
+#pragma unroll
+      for( int t = 0; t < 8; ++t )
+      {
+         if( q + t < e && r[t] < p.nstream )
+            rb[t] = p.rowbeg[r[t]];
+      }
 #pragma unroll
       for( int t = 0; t < 8; ++t )
       {
          if( q + t < e )
+         {
             p.dirty[r[t]] = ROW_MARKED;
+            if( r[t] < p.nstream )
+               p.tileflag[rb[t] >> 8] = 1;
+         }
       }
    }
 }
@@ -976,6 +1090,8 @@ __global__ void set_bounds_kernel(const DevProblem p, const double* lb, const do
    }
    for( int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nrows; r += stride )
       p.dirty[r] = ROW_MARKED;
+   for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.ntiles; t += stride )
+      p.tileflag[t] = 1;
 }
 
 __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const int* idx, const double* lb, const double* ub)
@@ -1009,6 +1125,8 @@ __global__ void mark_all_kernel(const DevProblem p)
    const int stride = gridDim.x * blockDim.x;
    for( int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nrows; r += stride )
       p.dirty[r] = ROW_MARKED;
+   for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.ntiles; t += stride )
+      p.tileflag[t] = 1;
 }
 
 // start of a gpulin_propagate call: reset the loop state

@@ -61,7 +61,7 @@ def test_mixed_knapsack_all_row_bins(gpulin, seed, bs):
     prob = synth.mixed_knapsack(4000, 40_000, 1_000_000, seed=seed, dense_range=(1500, 6000), eq_frac=0.2)
     with gpulin.LinearPropagator(prob) as lp:
         lay = lp.layout()
-    assert lay["rows_warp"] > 0 and lay["rows_block"] > 0
+    assert lay["rows_stream"] > 0 and lay["rows_block"] > 0
     got, _ = gpu_vs_oracle(gpulin, prob, maxrounds=200, what=f"mixedknap seed {seed}", boundstreps=bs)
     assert got["nchanges"] > 0
 
