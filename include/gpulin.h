@@ -132,9 +132,9 @@ int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n
  *  device time [ms] (%globaltimer stamps taken by the kernels), nonzeros swept, bound changes accepted */
 int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n);
 
-/** storage statistics: [0] nnz, [1] stored nonzeros incl. padding, [2] rows in the CSR stream, [3] tiles of the stream,
- *  [4] rows swept block-per-row, [5] bytes on device, [6..8] persistent blocks of the stream sweep / long-row sweep /
- *  exact kernel, [9] longest row */
+/** storage statistics: [0] nnz, [1] stored nonzeros incl. padding, [2] rows swept thread-per-row (SELL-32 slices),
+ *  [3] rows in the tiled CSR stream, [4] rows swept block-per-row, [5] bytes on device, [6] tiles of the stream,
+ *  [7..8] persistent blocks of the thread-per-row / tile sweep, [9] longest row */
 int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 
 /** algorithmic bytes of one full round: nnz*12 + nrows*20 + ncols*17 */

@@ -50,10 +50,12 @@ struct gpulin
    int         device = 0;
    int64_t     nrows = 0, ncols = 0, nnz = 0;
    int64_t     nstored = 0;      // nonzeros incl. SELL padding
-   int         nstream = 0, nlong = 0, ntiles = 0;
+   int         nsell = 0, nstream = 0, nlong = 0, ntiles = 0;
    int64_t     nstreamelems = 0;
    int         maxlen = 0;
    DevProblem  p{};
+   int         sellvariant = 3;
+   int         nsellblocks = 0;
    int         nstreamblocks = 0;
    int         nlongblocks = 0;
    int         napplyblocks = 0;
@@ -139,26 +141,56 @@ static void destroyGraph(gpulin* h)
    h->graph = nullptr;
 }
 
-// one propagation round on h->stream; the stream sweep and the long-row sweep are independent and run concurrently
+// instances of the thread-per-row sweep: {nonzeros per thread and chunk, minimal resident blocks per SM};
+// GPULIN_SELL_VARIANT selects one for experiments
+typedef void (*SellKernel)(const DevProblem);
+static const SellKernel g_sellKernels[] = {
+   sweep_sell_kernel<4, 2>,   // 0
+   sweep_sell_kernel<4, 3>,   // 1
+   sweep_sell_kernel<2, 3>,   // 2
+   sweep_sell_kernel<2, 4>,   // 3
+   sweep_sell_kernel<8, 2>,   // 4
+   sweep_sell_kernel<8, 1>,   // 5
+};
+constexpr int NSELLVARIANTS = sizeof(g_sellKernels) / sizeof(g_sellKernels[0]);
+
+// one propagation round on h->stream
 template <bool DENSE, bool GRAPH>
 static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
 {
    if( sweep )
    {
-      const bool fork = h->nstreamblocks > 0 && h->nlongblocks > 0;
-      if( fork )
-      {
+      // the three bins are independent: the smaller ones run on side streams beside the largest
+      const int nkinds = (h->nsellblocks > 0) + (h->nstreamblocks > 0) + (h->nlongblocks > 0);
+      int side = 0;
+      if( nkinds > 1 )
          CU(cudaEventRecord(h->evfork, h->stream));
-         CU(cudaStreamWaitEvent(h->aux[0], h->evfork, 0));
-         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, 0, h->aux[0]>>>(h->p);
-         CU(cudaEventRecord(h->evjoin[0], h->aux[0]));
+      if( h->nlongblocks > 0 )
+      {
+         cudaStream_t st = nkinds > 1 ? h->aux[side] : h->stream;
+         if( nkinds > 1 )
+            CU(cudaStreamWaitEvent(st, h->evfork, 0));
+         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, 0, st>>>(h->p);
+         if( nkinds > 1 )
+         {
+            CU(cudaEventRecord(h->evjoin[side], st));
+            ++side;
+         }
       }
-      else if( h->nlongblocks > 0 )
-         sweep_long_kernel<<<h->nlongblocks, LONG_THREADS, 0, h->stream>>>(h->p);
-      if( h->nstreamblocks > 0 )
+      if( h->nstreamblocks > 0 && h->nsellblocks > 0 )
+      {
+         cudaStream_t st = h->aux[side];
+         CU(cudaStreamWaitEvent(st, h->evfork, 0));
+         sweep_stream_kernel<<<h->nstreamblocks, SWEEP_THREADS, 0, st>>>(h->p);
+         CU(cudaEventRecord(h->evjoin[side], st));
+         ++side;
+      }
+      else if( h->nstreamblocks > 0 )
          sweep_stream_kernel<<<h->nstreamblocks, SWEEP_THREADS, 0, h->stream>>>(h->p);
-      if( fork )
-         CU(cudaStreamWaitEvent(h->stream, h->evjoin[0], 0));
+      if( h->nsellblocks > 0 )
+         g_sellKernels[h->sellvariant]<<<h->nsellblocks, SELL_THREADS, 0, h->stream>>>(h->p);
+      for( int i = 0; i < side; ++i )
+         CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
       if( h->nexactblocks > 0 )
          exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
    }
@@ -257,8 +289,10 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    const char* loopenv = getenv("GPULIN_LOOP");
    h->hostloop = (loopenv != nullptr && strcmp(loopenv, "host") == 0);
 
-   // ---- bin the rows: rows of 1..STREAM_MAXLEN nonzeros keep the caller's order and form the CSR stream, the others
-   // ---- (longer, or empty) follow, longest first, and are swept block-per-row
+   // ---- bin the rows ------------------------------------------------------------------------------------------------
+   //   1..32 nonzeros       SELL-32 slices, sorted by length (stable: neighbours stay neighbours)   thread-per-row sweep
+   //   33..STREAM_MAXLEN    one CSR stream in the caller's order, cut into tiles of 256 nonzeros     tile sweep
+   //   longer, or empty     CSR, longest first                                                      block-per-row sweep
    std::vector<int> len((size_t)nrows);
    for( int64_t r = 0; r < nrows; ++r )
    {
@@ -268,43 +302,59 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    std::vector<int>& perm = h->perm;
    perm.clear();
    perm.reserve((size_t)nrows);
+   std::vector<int> streamrows;
    std::vector<int> longrows;
    for( int64_t r = 0; r < nrows; ++r )
    {
-      if( len[(size_t)r] >= 1 && len[(size_t)r] <= STREAM_MAXLEN )
+      const int l = len[(size_t)r];
+      if( l >= 1 && l <= SHORT_MAXLEN )
          perm.push_back((int)r);
+      else if( l > SHORT_MAXLEN && l <= STREAM_MAXLEN )
+         streamrows.push_back((int)r);
       else
          longrows.push_back((int)r);
    }
-   h->nstream = (int)perm.size();
-   h->nlong = (int)longrows.size();
+   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return len[(size_t)a] < len[(size_t)b]; });
    std::stable_sort(longrows.begin(), longrows.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
+   h->nsell = (int)perm.size();
+   h->nstream = (int)streamrows.size();
+   h->nlong = (int)longrows.size();
+   perm.insert(perm.end(), streamrows.begin(), streamrows.end());
    perm.insert(perm.end(), longrows.begin(), longrows.end());
+   const int nsx = h->nsell + h->nstream;
 
-   std::vector<long long> rowbeg((size_t)nrows + 1, 0);
    std::vector<int> plen((size_t)nrows);
-   long long off = 0;
    for( int64_t i = 0; i < nrows; ++i )
-   {
       plen[(size_t)i] = len[(size_t)perm[(size_t)i]];
-      if( i == h->nstream )
-      {
-         h->nstreamelems = off;
-         off = (off + TILE - 1) / TILE * TILE;      // the stream is padded with zero coefficients to a whole tile
-      }
-      if( i >= h->nstream )
-         off = (off + 3) & ~3LL;                    // long rows start 16-byte aligned
+
+   // SELL slices
+   const int nslices = (h->nsell + 31) / 32;
+   std::vector<long long> sell_off((size_t)nslices + 1, 0);
+   for( int sl = 0; sl < nslices; ++sl )
+   {
+      const int last = std::min(h->nsell, 32 * sl + 32) - 1;
+      sell_off[(size_t)sl + 1] = sell_off[(size_t)sl] + 32LL * plen[(size_t)last];
+   }
+   // stream and long rows
+   std::vector<long long> rowbeg((size_t)nrows + 1, 0);
+   long long off = (sell_off[(size_t)nslices] + TILE - 1) / TILE * TILE;
+   const long long streambase = off;
+   for( int64_t i = h->nsell; i < nsx; ++i )
+   {
       rowbeg[(size_t)i] = off;
       off += plen[(size_t)i];
    }
-   if( h->nstream == nrows )
-   {
-      h->nstreamelems = off;
-      off = (off + TILE - 1) / TILE * TILE;
-   }
+   h->nstreamelems = off - streambase;
    h->ntiles = (int)((h->nstreamelems + TILE - 1) / TILE);
+   off = streambase + (long long)h->ntiles * TILE;      // the stream is padded with zero coefficients to a whole tile
+   for( int64_t i = nsx; i < nrows; ++i )
+   {
+      off = (off + 3) & ~3LL;                           // long rows start 16-byte aligned
+      rowbeg[(size_t)i] = off;
+      off += plen[(size_t)i];
+   }
    h->nstored = off;
-   if( h->nstored >= (1LL << 40) || (h->nstreamelems + TILE - 1) / TILE >= (1LL << 31) - 64 )
+   if( h->nstored >= (1LL << 40) || h->nstreamelems / TILE >= (1LL << 31) - 64 )
    {
       delete h;
       return fail(GPULIN_ERR_ARG, "matrix too large");
@@ -315,12 +365,13 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    {
       const int64_t r = perm[(size_t)i];
       const int64_t b = rowptr[r];
-      const long long base = rowbeg[(size_t)i];
+      const long long base = i < h->nsell ? sell_off[(size_t)(i >> 5)] + (i & 31) : rowbeg[(size_t)i];
+      const long long stride = i < h->nsell ? 32 : 1;
       for( int k = 0; k < plen[(size_t)i]; ++k )
       {
          const int j = colidx[b + k];
-         pvals[(size_t)(base + k)] = vals[b + k];
-         pcols[(size_t)(base + k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
+         pvals[(size_t)(base + stride * k)] = vals[b + k];
+         pcols[(size_t)(base + stride * k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
       }
    }
    std::vector<double2> sides((size_t)nrows + 1);
@@ -329,12 +380,12 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    // ---- tiles of the stream: row-end bit per nonzero, first unfinished row per tile ----------------------------------
    std::vector<unsigned char> endmask((size_t)h->ntiles * 32 + 32, 0);
-   std::vector<int> tile_row0((size_t)h->ntiles + 2, h->nstream);
+   std::vector<int> tile_row0((size_t)h->ntiles + 2, nsx);
    {
       int t = 0;
-      for( int i = 0; i < h->nstream; ++i )
+      for( int i = h->nsell; i < nsx; ++i )
       {
-         const long long last = rowbeg[(size_t)i] + plen[(size_t)i] - 1;
+         const long long last = rowbeg[(size_t)i] - streambase + plen[(size_t)i] - 1;
          endmask[(size_t)(last >> 3)] |= (unsigned char)(1u << (last & 7));
          // row i is the first unfinished row of every tile that starts at or before its last nonzero
          while( t < h->ntiles && (long long)t * TILE <= last )
@@ -361,13 +412,14 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    // ---- upload ---------------------------------------------------------------------------------------------------
    DevProblem& p = h->p;
-   int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
+   long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
    int* d_tile_row0; unsigned char* d_endmask; unsigned char* d_tileflag;
-   int* d_xlist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned char* d_colflag; long long* d_colbeg; int* d_colrows;
+   int* d_xlist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned* d_colbits; int* d_chglist; long long* d_colbeg; int* d_colrows;
    Ctrl* d_ctrl;
    int rc = GPULIN_OK;
 #define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
 #define TRYCU(x) do { if( rc == GPULIN_OK ) { cudaError_t e_ = (x); if( e_ != cudaSuccess ) rc = fail(GPULIN_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while( 0 )
+   TRY(devAlloc(h, &d_sell_off, (size_t)nslices + 1));
    TRY(devAlloc(h, &d_tile_row0, (size_t)h->ntiles + 2));
    TRY(devAlloc(h, &d_endmask, (size_t)h->ntiles * 32 + 32));
    TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
@@ -377,15 +429,17 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &d_cols, (size_t)h->nstored + 8));
    TRY(devAlloc(h, &d_sides, (size_t)nrows + 1));
    TRY(devAlloc(h, &d_dirty, (size_t)nrows + 64));
-   TRY(devAlloc(h, &d_xlist, 2 * (size_t)h->nstream + (size_t)h->nlong + 1));
+   TRY(devAlloc(h, &d_xlist, (size_t)nrows + 1));
    TRY(devAlloc(h, &d_bnd, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)ncols + 2));
-   TRY(devAlloc(h, &d_colflag, (size_t)ncols + 64));
+   TRY(devAlloc(h, &d_colbits, (size_t)ncols / 32 + 2));
+   TRY(devAlloc(h, &d_chglist, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_colbeg, (size_t)ncols + 2));
    TRY(devAlloc(h, &d_colrows, (size_t)nnz + 1));
    TRY(devAlloc(h, &d_ctrl, 1));
    TRY(devAlloc(h, &h->d_tmplb, (size_t)ncols + 1));
    TRY(devAlloc(h, &h->d_tmpub, (size_t)ncols + 1));
+   TRYCU(cudaMemcpy(d_sell_off, sell_off.data(), sizeof(long long) * ((size_t)nslices + 1), cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_tile_row0, tile_row0.data(), sizeof(int) * ((size_t)h->ntiles + 1), cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_endmask, endmask.data(), (size_t)h->ntiles * 32, cudaMemcpyHostToDevice));
    TRYCU(cudaMemset(d_tileflag, 0, (size_t)h->ntiles + 64));
@@ -417,7 +471,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRYCU(cudaMemcpy(d_colbeg, colbeg.data(), sizeof(long long) * ((size_t)ncols + 1), cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_colrows, colrows.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
    TRYCU(cudaMemset(d_dirty, 0, (size_t)nrows + 64));
-   TRYCU(cudaMemset(d_colflag, 0, (size_t)ncols + 64));
+   TRYCU(cudaMemset(d_colbits, 0, sizeof(unsigned) * ((size_t)ncols / 32 + 2)));
    TRYCU(cudaMemset(d_ctrl, 0, sizeof(Ctrl)));
    TRYCU(cudaMemset(d_cand, 0, sizeof(long long) * (2 * (size_t)ncols + 2)));
    TRYCU(cudaMallocHost((void**)&h->h_ctrl, sizeof(Ctrl)));
@@ -440,8 +494,11 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    p.nrows = (int)nrows;
    p.ncols = (int)ncols;
-   p.nstream = h->nstream;
+   p.nsell = h->nsell;
+   p.nsx = nsx;
    p.ntiles = h->ntiles;
+   p.streambase = streambase;
+   p.sell_off = d_sell_off;
    p.tile_row0 = d_tile_row0;
    p.endmask = d_endmask;
    p.tileflag = d_tileflag;
@@ -454,7 +511,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.xlist = d_xlist;
    p.bnd = d_bnd;
    p.cand = d_cand;
-   p.colflag = d_colflag;
+   p.colbits = d_colbits;
+   p.chglist = d_chglist;
    p.colbeg = d_colbeg;
    p.colrows = d_colrows;
    p.ctrl = d_ctrl;
@@ -473,8 +531,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    // ---- launch geometry ------------------------------------------------------------------------------------------
    // persistent grids: as many blocks as stay resident, never more than there is work
-   // flag scan: 16 columns per thread
-   h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols / 16 + APPLY_THREADS) / APPLY_THREADS, (int64_t)h->nsm * 4));
+   h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols + APPLY_THREADS - 1) / APPLY_THREADS, (int64_t)h->nsm * 4));
    {
       int occ = 0;
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_stream_kernel, SWEEP_THREADS, 0) != cudaSuccess || occ < 1 )
@@ -486,9 +543,21 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       // at least two tiles per warp, never more blocks than stay resident
       const int64_t need = ((int64_t)h->ntiles + 2 * wpb - 1) / (2 * wpb);
       h->nstreamblocks = (int)std::min<int64_t>(need, (int64_t)h->nsm * occ);
+      int occs = 0;
+      const char* ve = getenv("GPULIN_SELL_VARIANT");
+      if( ve != nullptr && atoi(ve) >= 0 && atoi(ve) < NSELLVARIANTS )
+         h->sellvariant = atoi(ve);
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, g_sellKernels[h->sellvariant], SELL_THREADS, 0) != cudaSuccess || occs < 1 )
+         occs = 1;
+      const char* oes = getenv("GPULIN_SELL_OCC");
+      if( oes != nullptr && atoi(oes) > 0 )
+         occs = atoi(oes);
+      const int64_t needs = ((int64_t)nslices + (SELL_THREADS / 32) - 1) / (SELL_THREADS / 32);
+      h->nsellblocks = (int)std::min<int64_t>(needs, (int64_t)h->nsm * occs);
       if( getenv("GPULIN_VERBOSE") != nullptr )
-         fprintf(stderr, "gpulin: stream sweep %d tiles, %d blocks x %d threads (%d per SM); %d long rows\n", h->ntiles,
-            h->nstreamblocks, SWEEP_THREADS, occ, h->nlong);
+         fprintf(stderr, "gpulin: %d SELL rows in %d blocks (%d per SM); stream sweep %d rows, %d tiles, %d blocks x %d threads "
+            "(%d per SM); %d long rows\n", h->nsell, h->nsellblocks, occs, h->nstream, h->ntiles, h->nstreamblocks, SWEEP_THREADS,
+            occ, h->nlong);
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_long_kernel, LONG_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nlongblocks = (int)std::min<int64_t>(h->nlong, (int64_t)h->nsm * occ);
@@ -777,8 +846,8 @@ extern "C" int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats)
 {
    if( h == nullptr || stats == nullptr )
       return fail(GPULIN_ERR_ARG, "invalid argument");
-   const int64_t v[10] = {h->nnz, h->nstored, h->nstream, h->ntiles, h->nlong, (int64_t)h->devbytes, h->nstreamblocks,
-      h->nlongblocks, h->nexactblocks, h->maxlen};
+   const int64_t v[10] = {h->nnz, h->nstored, h->nsell, h->nstream, h->nlong, (int64_t)h->devbytes, h->ntiles,
+      h->nsellblocks, h->nstreamblocks, h->maxlen};
    for( int i = 0; i < nstats && i < 10; ++i )
       stats[i] = v[i];
    return GPULIN_OK;

@@ -8,6 +8,7 @@
 
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 namespace gpl {
 
@@ -359,11 +360,34 @@ __device__ __forceinline__ bool rowInfeasible(const Num& n, const RowAcc& a, dou
 struct Sink
 {
    long long*     cand;      // 2*ncols candidate keys
-   unsigned char* colflag;   // per-column "a key moved this round" flag, consumed by the apply kernel
+   unsigned*      colbits;   // one bit per column: "a key moved this round"
+   int*           chglist;   // the columns whose bit was raised this round, in no particular order
+   unsigned*      nchgcols;  // length of chglist
 };
 
+// the first candidate of a round that reaches a column puts it on the list the apply kernel works through.  Split in
+// two so that a thread can have the bit tests of several columns in flight before it looks at the first answer.
+__device__ __forceinline__ bool raiseColumnBit(const Sink& s, int j)
+{
+   const unsigned bit = 1u << (j & 31);
+   return (atomicOr(&s.colbits[j >> 5], bit) & bit) == 0u;
+}
+__device__ __forceinline__ void listChangedColumn(const Sink& s, int j, bool first)
+{
+   if( first )
+   {
+      // one atomic on the list counter per group of lanes that got here together
+      const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+      unsigned pos = 0u;
+      if( g.thread_rank() == 0 )
+         pos = atomicAdd(s.nchgcols, (unsigned)g.size());
+      pos = g.shfl(pos, 0) + g.thread_rank();
+      s.chglist[pos] = j;
+   }
+}
+
 __device__ __forceinline__ void inferUb(const Num& n, const Sink& s, int j, bool integral, double newub, double l,
-   double u, bool force, bool& cutoff)
+   double u, bool force, bool& cutoff, bool& touched)
 {
    newub = adjustedUb(n, integral, newub);
    if( isInf(n, -newub) || isFeasLT(n, newub, l) )
@@ -379,10 +403,10 @@ __device__ __forceinline__ void inferUb(const Num& n, const Sink& s, int j, bool
    // every value that gets here is below the round-start bound, so the column changes this round whichever
    // candidate wins: no need to wait for the atomic's result
    atomicMin(&s.cand[2 * (size_t)j + 1], d2key(newub));
-   s.colflag[j] = 1;
+   touched = true;
 }
 __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool integral, double newlb, double l,
-   double u, bool force, bool& cutoff)
+   double u, bool force, bool& cutoff, bool& touched)
 {
    newlb = adjustedLb(n, integral, newlb);
    if( isInf(n, newlb) || isFeasGT(n, newlb, u) )
@@ -396,28 +420,28 @@ __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool
    if( !isGT(n, newlb, l) )
       return;
    atomicMin(&s.cand[2 * (size_t)j], ~d2key(newlb));
-   s.colflag[j] = 1;
+   touched = true;
 }
 
 // tightenVarUb / tightenVarLb: cons_linear.c:5242-5307 / 5311-5376
 __device__ __forceinline__ void tightenVarUb(const Num& n, const Sink& s, int j, bool integral, double newub, double l,
-   double u, bool force, bool& cutoff)
+   double u, bool force, bool& cutoff, bool& touched)
 {
    newub = adjustedUb(n, integral, newub);
    if( force || isUbBetter(n, newub, l, u) )
-      inferUb(n, s, j, integral, newub, l, u, force, cutoff);
+      inferUb(n, s, j, integral, newub, l, u, force, cutoff, touched);
 }
 __device__ __forceinline__ void tightenVarLb(const Num& n, const Sink& s, int j, bool integral, double newlb, double l,
-   double u, bool force, bool& cutoff)
+   double u, bool force, bool& cutoff, bool& touched)
 {
    newlb = adjustedLb(n, integral, newlb);
    if( force || isLbBetter(n, newlb, l, u) )
-      inferLb(n, s, j, integral, newlb, l, u, force, cutoff);
+      inferLb(n, s, j, integral, newlb, l, u, force, cutoff, touched);
 }
 
 // candidate bounds of one nonzero: tightenVarBoundsEasy (cons_linear.c:5380-5653) or tightenVarBounds (:6700-6974)
 __device__ __forceinline__ void candidates(const Num& n, const Sink& s, const RowInfo& ri, double a, int j, bool integral,
-   double l, double u, bool& cutoff)
+   double l, double u, bool& cutoff, bool& touched)
 {
    const bool pos = a > 0.0;
    if( ri.easy )
@@ -426,16 +450,16 @@ __device__ __forceinline__ void candidates(const Num& n, const Sink& s, const Ro
       if( ri.rhsfin && ((alpha - ri.slackR > n.sumeps) || (ri.force && alpha - ri.slackR > n.eps)) )
       {
          if( pos )
-            tightenVarUb(n, s, j, integral, l + (ri.slackR / a), l, u, ri.force, cutoff);
+            tightenVarUb(n, s, j, integral, l + (ri.slackR / a), l, u, ri.force, cutoff, touched);
          else
-            tightenVarLb(n, s, j, integral, u + ri.slackR / a, l, u, ri.force, cutoff);
+            tightenVarLb(n, s, j, integral, u + ri.slackR / a, l, u, ri.force, cutoff, touched);
       }
       if( ri.lhsfin && ((alpha - ri.slackL > n.sumeps) || (ri.force && alpha - ri.slackL > n.eps)) )
       {
          if( pos )
-            tightenVarLb(n, s, j, integral, u - (ri.slackL / a), l, u, ri.force, cutoff);
+            tightenVarLb(n, s, j, integral, u - (ri.slackL / a), l, u, ri.force, cutoff, touched);
          else
-            tightenVarUb(n, s, j, integral, l - (ri.slackL / a), l, u, ri.force, cutoff);
+            tightenVarUb(n, s, j, integral, l - (ri.slackL / a), l, u, ri.force, cutoff, touched);
       }
       return;
    }
@@ -475,12 +499,12 @@ __device__ __forceinline__ void candidates(const Num& n, const Sink& s, const Ro
       if( pos )
       {
          if( !isInf(n, nb) && ((ri.force && isLT(n, nb, u)) || (integral && isFeasLT(n, nb, u)) || isUbBetter(n, nb, l, u)) )
-            inferUb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+            inferUb(n, s, j, integral, nb, l, u, ri.force, cutoff, touched);
       }
       else
       {
          if( !isInf(n, -nb) && ((ri.force && isGT(n, nb, l)) || (integral && isFeasGT(n, nb, l)) || isLbBetter(n, nb, l, u)) )
-            inferLb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+            inferLb(n, s, j, integral, nb, l, u, ri.force, cutoff, touched);
       }
    }
    if( !maxsettoinf && ri.lhsfin && maxtight && (isLT(n, fabs(ri.lhs), 1.0) || !isEQ(n, maxres / ri.lhs, 1.0)) )
@@ -489,12 +513,12 @@ __device__ __forceinline__ void candidates(const Num& n, const Sink& s, const Ro
       if( pos )
       {
          if( !isInf(n, -nb) && ((ri.force && isGT(n, nb, l)) || (integral && isFeasGT(n, nb, l)) || isLbBetter(n, nb, l, u)) )
-            inferLb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+            inferLb(n, s, j, integral, nb, l, u, ri.force, cutoff, touched);
       }
       else
       {
          if( !isInf(n, nb) && ((ri.force && isLT(n, nb, u)) || (integral && isFeasLT(n, nb, u)) || isUbBetter(n, nb, l, u)) )
-            inferUb(n, s, j, integral, nb, l, u, ri.force, cutoff);
+            inferUb(n, s, j, integral, nb, l, u, ri.force, cutoff, touched);
       }
    }
 }

@@ -43,7 +43,7 @@ struct Ctrl
    int                status;       // GPULIN_FIXPOINT / _CUTOFF / _ROUNDLIMIT
    int                cutoff;       // set by any kernel that proves infeasibility
    unsigned int       ticket;       // apply kernel: blocks finished
-   unsigned int       pad0;
+   unsigned int       nchgcols;     // columns on the change list of the running round
    unsigned long long logcount;     // entries produced
    unsigned long long round_nchg;   // accepted bound changes of the running round
    unsigned long long total_nchg;
@@ -69,8 +69,12 @@ struct DevProblem
 {
    int                 nrows;
    int                 ncols;
-   int                 nstream;    // rows [0,nstream) form the CSR stream (caller's order), rows [nstream,nrows) are long / empty
+   int                 nsell;      // rows [0,nsell): 1..32 nonzeros, SELL-32 slices sorted by length (thread-per-row sweep)
+   int                 nsx;        // rows [nsell,nsx): 33..STREAM_MAXLEN nonzeros, the CSR stream in the caller's order;
+                                   // rows [nsx,nrows): longer or empty, swept block-per-row
    int                 ntiles;     // tiles of the stream (its storage is padded with zero coefficients to a whole tile)
+   long long           streambase; // element offset of the first tile of the stream (a multiple of TILE)
+   const long long*    sell_off;   // per SELL slice: element offset; element k of row r sits at sell_off[r>>5] + (r&31) + 32 k
    // rows (permuted numbering)
    const long long*    rowbeg;     // element offset of the first nonzero
    const int*          rowlen;     // length | ROWLEN_EXACT
@@ -82,12 +86,12 @@ struct DevProblem
    const int*          tile_row0;  // first row that ends at or behind the first nonzero of the tile
    const unsigned char* endmask;   // per tile and lane: bit i = nonzero 8*lane+i is the last of its row
    unsigned char*      tileflag;   // a marked row starts in this tile
-   int*                xlist;      // rows handed to exact_rows_kernel: lists [0,nstream) short, [nstream,2 nstream) medium,
-                                   // [2 nstream, 2 nstream + nlong) long
+   int*                xlist;      // rows handed to exact_rows_kernel, one list per bin: [0,nsell) [nsell,nsx) [nsx,nrows)
    // columns
    const double2*      bnd;        // (lb, ub) at round start
    long long*          cand;       // 2*ncols (+2) candidate keys, see Sink
-   unsigned char*      colflag;
+   unsigned*           colbits;    // bit per column: on the change list
+   int*                chglist;    // columns a candidate reached in the running round
    // column -> rows (permuted row ids)
    const long long*    colbeg;
    const int*          colrows;
@@ -158,7 +162,9 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
    const double thr = slackThreshold(n, ri.force);
    Sink s;
    s.cand = p.cand;
-   s.colflag = p.colflag;
+   s.colbits = p.colbits;
+   s.chglist = p.chglist;
+   s.nchgcols = &p.ctrl->nchgcols;
    for( int k0 = first; k0 < len; k0 += 4 * step )
    {
       double a[4];
@@ -180,15 +186,23 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
          if( k0 + q * step < len )
             b[q] = p.bnd[cj[q] & 0x7fffffff];
       }
+      bool touched[4] = {false, false, false, false};
 #pragma unroll
       for( int q = 0; q < 4; ++q )
       {
          if( k0 + q * step < len )
          {
             if( !ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr) )
-               candidates(n, s, ri, a[q], cj[q] & 0x7fffffff, cj[q] < 0, b[q].x, b[q].y, cutoff);
+               candidates(n, s, ri, a[q], cj[q] & 0x7fffffff, cj[q] < 0, b[q].x, b[q].y, cutoff, touched[q]);
          }
       }
+      bool first[4];
+#pragma unroll
+      for( int q = 0; q < 4; ++q )
+         first[q] = touched[q] && raiseColumnBit(s, cj[q] & 0x7fffffff);
+#pragma unroll
+      for( int q = 0; q < 4; ++q )
+         listChangedColumn(s, cj[q] & 0x7fffffff, first[q]);
    }
 }
 
@@ -384,8 +398,7 @@ __device__ __forceinline__ void addRoundNnz(const DevProblem& p, unsigned long l
 
 // ---- the filter sweep over the CSR stream --------------------------------------------------------------------------
 
-// a marked row whose sums are complete: is it finished, or does it need the exact rules?  (returns 0: not marked /
-// finished, 1: hand over as a short row, 2: hand over as a medium row)
+// a marked row whose sums are complete: is it finished (0), or does it need the exact rules (1)?
 __device__ __forceinline__ int finishRow(const DevProblem& p, int row, const LeanAcc& tot, unsigned char flag, int lenword,
    const double2& sd, unsigned& nnzdone)
 {
@@ -395,9 +408,7 @@ __device__ __forceinline__ int finishRow(const DevProblem& p, int row, const Lea
    const bool exact = (lenword & ROWLEN_EXACT) != 0;
    const int len = lenword & ~ROWLEN_EXACT;
    nnzdone += (unsigned)len;
-   if( exact || !rowClearlyQuiet(p.num, tot, len, sd.x, sd.y) )
-      return len <= SHORT_MAXLEN ? 1 : 2;
-   return 0;
+   return (exact || !rowClearlyQuiet(p.num, tot, len, sd.x, sd.y)) ? 1 : 0;
 }
 
 // appends `row` of every lane with want == true to a work list (one atomic per warp)
@@ -436,7 +447,7 @@ struct TileRegs
 
 __device__ __forceinline__ void loadTile(const DevProblem& p, int t, int lane, TileRegs& r)
 {
-   const long long e0 = (long long)t * TILE + lane * TPL;
+   const long long e0 = p.streambase + (long long)t * TILE + lane * TPL;
    ldStream256(p.vals + e0, r.a[0], r.a[1], r.a[2], r.a[3]);
    ldStream256(p.vals + e0 + 4, r.a[4], r.a[5], r.a[6], r.a[7]);
    ldStream256(p.cols + e0, r.cj);
@@ -469,10 +480,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const De
    // look-back: a marked row that started in the range of the previous warp and ends in this one is ours to finish
    {
       const int r = p.tile_row0[t0];
-      if( r < p.nstream )
+      if( r < p.nsx )
       {
          const long long beg = p.rowbeg[r];
-         const long long first = (long long)t0 * TILE;
+         const long long first = p.streambase + (long long)t0 * TILE;
          if( beg < first && p.dirty[r] == ROW_MARKED )
          {
             LeanAcc part;
@@ -644,11 +655,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const De
                }
                verdict = finishRow(p, row0 + rr, tot[rr], rflag, rlen, rsd, nnzdone);
             }
-            if( __any_sync(0xffffffffu, verdict != 0) )
-            {
-               pushRow(p, verdict == 1, row0 + rr, lane, 0, 0);
-               pushRow(p, verdict == 2, row0 + rr, lane, 1, p.nstream);
-            }
+            pushRow(p, verdict != 0, row0 + rr, lane, 1, p.nsell);
          }
          __syncwarp();
 
@@ -658,9 +665,126 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const De
          {
             const int ropen = row0 + nrows;
             const bool lastIsEnd = ((__shfl_sync(0xffffffffu, em, 31) >> (TPL - 1)) & 1u) != 0u;
-            if( !lastIsEnd && ropen < p.nstream )
+            if( !lastIsEnd && ropen < p.nsx )
                opendirty = p.dirty[ropen] == ROW_MARKED;
          }
+      }
+   }
+   nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
+   if( lane == 0 )
+      addRoundNnz(p, (unsigned long long)nnzdone, gw);
+}
+
+// ---- thread-per-row on SELL-32 slices (rows of 1..32 nonzeros) -------------------------------------------------------
+// Element k of the row of lane t sits at sell_off[slice] + 32 k + t: every load of a warp is one coalesced line, no
+// shuffles at all.  Persistent warps take slices w, w+W, ... in batches of four whose flags / lengths / offsets are
+// fetched with one round trip; the coefficients of the next chunk -- of the same or of the next slice -- stream in
+// while the bounds of the current chunk are gathered.
+constexpr int SELL_THREADS = 256;
+constexpr int SELL_NB = 4;
+
+template <int CH>
+__device__ __forceinline__ void loadChunk(const DevProblem& p, long long base, int c, int len, double (&a)[CH], int (&cj)[CH])
+{
+#pragma unroll
+   for( int k = 0; k < CH; ++k )
+   {
+      if( c + k < len )
+      {
+         a[k] = ldStream(p.vals + base + 32LL * (c + k));
+         cj[k] = ldStream(p.cols + base + 32LL * (c + k));
+      }
+   }
+}
+
+template <int CH, int MINB>
+__global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const DevProblem p)
+{
+   const Num& n = p.num;
+   const int lane = threadIdx.x & 31;
+   const int gw = (blockIdx.x * SELL_THREADS + threadIdx.x) >> 5;
+   const int nw = (gridDim.x * SELL_THREADS) >> 5;
+   const int nslices = (p.nsell + 31) >> 5;
+   unsigned nnzdone = 0;
+   for( int s0 = gw; s0 < nslices; s0 += SELL_NB * nw )
+   {
+      // ---- one round trip: flags, lengths and offsets of the next four slices of this warp
+      int len[SELL_NB];
+      int maxlen[SELL_NB];
+      long long base[SELL_NB];
+      unsigned actm = 0u;
+      unsigned exactm = 0u;
+#pragma unroll
+      for( int i = 0; i < SELL_NB; ++i )
+      {
+         const int slice = s0 + i * nw;
+         const int row = slice * 32 + lane;
+         const bool valid = slice < nslices && row < p.nsell;
+         const unsigned char f = valid ? p.dirty[row] : ROW_CLEAN;
+         const int lw = valid ? p.rowlen[row] : 0;
+         base[i] = (slice < nslices ? p.sell_off[slice] : 0) + lane;
+         const bool act = f == ROW_MARKED;
+         len[i] = act ? (lw & ~ROWLEN_EXACT) : 0;
+         if( act )
+            actm |= 1u << i;
+         if( act && (lw & ROWLEN_EXACT) != 0 )
+            exactm |= 1u << i;
+      }
+#pragma unroll
+      for( int i = 0; i < SELL_NB; ++i )
+         maxlen[i] = __reduce_max_sync(0xffffffffu, len[i]);
+
+      double an[CH];
+      int cjn[CH];
+      loadChunk<CH>(p, base[0], 0, len[0], an, cjn);
+#pragma unroll
+      for( int i = 0; i < SELL_NB; ++i )
+      {
+         const int row = (s0 + i * nw) * 32 + lane;
+         const bool act = ((actm >> i) & 1u) != 0u;
+         double2 sd = make_double2(0.0, 0.0);
+         if( act )
+            sd = p.sides[row];
+         LeanAcc acc;
+         leanInit(acc);
+         for( int c = 0; c < maxlen[i]; c += CH )
+         {
+            double a[CH];
+            int cj[CH];
+            double2 b[CH];
+#pragma unroll
+            for( int k = 0; k < CH; ++k )
+            {
+               a[k] = an[k];
+               cj[k] = cjn[k];
+            }
+            if( c + CH < maxlen[i] )
+               loadChunk<CH>(p, base[i], c + CH, len[i], an, cjn);
+            else if( i + 1 < SELL_NB )
+               loadChunk<CH>(p, base[i + 1], 0, len[i + 1], an, cjn);
+#pragma unroll
+            for( int k = 0; k < CH; ++k )
+            {
+               if( c + k < len[i] )
+                  b[k] = p.bnd[cj[k] & 0x7fffffff];
+            }
+#pragma unroll
+            for( int k = 0; k < CH; ++k )
+            {
+               if( c + k < len[i] )
+                  leanElem(acc, a[k], b[k].x, b[k].y);
+            }
+         }
+         if( maxlen[i] == 0 && i + 1 < SELL_NB )
+            loadChunk<CH>(p, base[i + 1], 0, len[i + 1], an, cjn);
+         bool handoff = false;
+         if( act )
+         {
+            handoff = ((exactm >> i) & 1u) != 0u || !rowClearlyQuiet(n, acc, len[i], sd.x, sd.y);
+            p.dirty[row] = ROW_CLEAN;
+            nnzdone += (unsigned)len[i];
+         }
+         pushRow(p, handoff, row, lane, 0, 0);
       }
    }
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
@@ -676,7 +800,7 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
    const int lane = threadIdx.x & 31;
    const int warp = threadIdx.x >> 5;
    const Num& n = p.num;
-   const int row0 = p.nstream;
+   const int row0 = p.nsx;
    const int nrows = p.nrows - row0;
 
    for( int r = blockIdx.x; r < nrows; r += gridDim.x )
@@ -735,7 +859,7 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
          p.dirty[row] = ROW_CLEAN;
          addRoundNnz(p, (unsigned long long)len, row);
          if( handoff )
-            p.xlist[2 * p.nstream + atomicAdd(&p.ctrl->nexact[2], 1u)] = row;
+            p.xlist[p.nsx + atomicAdd(&p.ctrl->nexact[2], 1u)] = row;
       }
    }
 }
@@ -778,7 +902,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
          {
             const int row = p.xlist[item];
             len = p.rowlen[row] & ~ROWLEN_EXACT;
-            base = p.rowbeg[row];
+            base = p.sell_off[row >> 5] + (row & 31);
             sd = p.sides[row];
          }
          double a[EXACT_Q];
@@ -790,8 +914,8 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
             const int k = gl + EXACT_G * q;
             if( k < len )
             {
-               a[q] = p.vals[base + k];
-               cj[q] = p.cols[base + k];
+               a[q] = p.vals[base + 32LL * k];
+               cj[q] = p.cols[base + 32LL * k];
             }
          }
 #pragma unroll
@@ -819,16 +943,27 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
                const double thr = slackThreshold(n, ri.force);
                Sink sk;
                sk.cand = p.cand;
-               sk.colflag = p.colflag;
+               sk.colbits = p.colbits;
+               sk.chglist = p.chglist;
+               sk.nchgcols = &p.ctrl->nchgcols;
+               bool touched[EXACT_Q];
 #pragma unroll
                for( int q = 0; q < EXACT_Q; ++q )
                {
+                  touched[q] = false;
                   if( gl + EXACT_G * q < len )
                   {
                      if( !ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr) )
-                        candidates(n, sk, ri, a[q], cj[q] & 0x7fffffff, cj[q] < 0, b[q].x, b[q].y, cutoff);
+                        candidates(n, sk, ri, a[q], cj[q] & 0x7fffffff, cj[q] < 0, b[q].x, b[q].y, cutoff, touched[q]);
                   }
                }
+               bool first[EXACT_Q];
+#pragma unroll
+               for( int q = 0; q < EXACT_Q; ++q )
+                  first[q] = touched[q] && raiseColumnBit(sk, cj[q] & 0x7fffffff);
+#pragma unroll
+               for( int q = 0; q < EXACT_Q; ++q )
+                  listChangedColumn(sk, cj[q] & 0x7fffffff, first[q]);
             }
             if( cutoff || (gl == 0 && rowInfeasible(n, ri.acc, ri.lhs, ri.rhs)) )
                p.ctrl->cutoff = 1;
@@ -842,7 +977,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
       const int nw = nthreads >> 5;
       for( unsigned item = gw; item < n1; item += nw )
       {
-         const int row = p.xlist[p.nstream + item];
+         const int row = p.xlist[p.nsell + item];
          const int len = p.rowlen[row] & ~ROWLEN_EXACT;
          const long long beg = p.rowbeg[row];
          const double2 sd = p.sides[row];
@@ -857,7 +992,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
    // ---- long rows: one block per row
    for( unsigned item = blockIdx.x; item < n2; item += gridDim.x )
    {
-      const int row = p.xlist[2 * p.nstream + item];
+      const int row = p.xlist[p.nsx + item];
       const int len = p.rowlen[row] & ~ROWLEN_EXACT;
       const long long beg = p.rowbeg[row];
       const double2 sd = p.sides[row];
@@ -901,35 +1036,43 @@ __device__ __forceinline__ int applyColumn(const DevProblem& p, int j, double2& 
    return (int)lbchg + (int)ubchg;
 }
 
-__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j)
+// marks the rows of column j (entries first, first+step, ... of the calling lane) for the next round
+__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step)
 {
-   // row ids are fetched eight at a time before any flag is stored: the byte stores may alias anything as far as the
+   // row ids are fetched four at a time before any flag is stored: the byte stores may alias anything as far as the
    // compiler knows, and a load-store-load-store chain would cost one memory round trip per row
    const long long e = p.colbeg[j + 1];
-   for( long long q = p.colbeg[j]; q < e; q += 8 )
+   for( long long q = p.colbeg[j] + first; q < e; q += 4 * step )
    {
-      int r[8];
+      int r[4];
+      long long rb[4];
 #pragma unroll
-      for( int t = 0; t < 8; ++t )
+      for( int t = 0; t < 4; ++t )
       {
-         if( q + t < e )
-            r[t] = p.colrows[q + t];
+         if( q + t * step < e )
+            r[t] = p.colrows[q + t * step];
       }
-      long long rb[8];
+      unsigned char fl[4];
 #pragma unroll
-      for( int t = 0; t < 8; ++t )
+      for( int t = 0; t < 4; ++t )
       {
-         if( q + t < e && r[t] < p.nstream )
-            rb[t] = p.rowbeg[r[t]];
+         fl[t] = ROW_MARKED;
+         if( q + t * step < e )
+         {
+            // read before write: many columns mark the same dense rows, and stores to one address serialise
+            fl[t] = p.dirty[r[t]];
+            if( r[t] >= p.nsell && r[t] < p.nsx )
+               rb[t] = p.rowbeg[r[t]];
+         }
       }
 #pragma unroll
-      for( int t = 0; t < 8; ++t )
+      for( int t = 0; t < 4; ++t )
       {
-         if( q + t < e )
+         if( fl[t] != ROW_MARKED )
          {
             p.dirty[r[t]] = ROW_MARKED;
-            if( r[t] < p.nstream )
-               p.tileflag[rb[t] >> 8] = 1;
+            if( r[t] >= p.nsell && r[t] < p.nsx )
+               p.tileflag[(rb[t] - p.streambase) >> 8] = 1;
          }
       }
    }
@@ -957,6 +1100,7 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
    c->total_nnz += nnz;
    c->round_nchg = 0;
    c->ticket = 0;
+   c->nchgcols = 0;
    c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
    c->round = r + 1;
    int cont = 0;
@@ -973,45 +1117,35 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
       cudaGraphSetConditional(handle, (unsigned)cont);
 }
 
-// one column whose candidate keys may have moved: accept, log, mark its rows; returns the number of changed bounds
-__device__ __forceinline__ int applyAndMark(const DevProblem& p, int j, int round, int logcap)
+// appends the accepted changes of column j to the round-ordered change log
+__device__ __forceinline__ void logChanges(const DevProblem& p, int j, int round, int logcap, int nc, bool lbchg, bool ubchg,
+   const double2& nb)
 {
-   bool lbchg;
-   bool ubchg;
-   double2 nb;
-   const int nc = applyColumn(p, j, nb, lbchg, ubchg);
-   if( nc > 0 )
+   unsigned long long pos = atomicAdd(&p.ctrl->logcount, (unsigned long long)nc);
+   if( lbchg )
    {
-      markColumnRows(p, j);
-      if( logcap > 0 )
+      if( pos < (unsigned long long)logcap )
       {
-         unsigned long long pos = atomicAdd(&p.ctrl->logcount, (unsigned long long)nc);
-         if( lbchg )
-         {
-            if( pos < (unsigned long long)logcap )
-            {
-               ChangeRec rec;
-               rec.var = j; rec.round = round; rec.newbound = nb.x; rec.is_upper = 0; rec.reserved = 0;
-               p.log[pos] = rec;
-            }
-            ++pos;
-         }
-         if( ubchg && pos < (unsigned long long)logcap )
-         {
-            ChangeRec rec;
-            rec.var = j; rec.round = round; rec.newbound = nb.y; rec.is_upper = 1; rec.reserved = 0;
-            p.log[pos] = rec;
-         }
+         ChangeRec rec;
+         rec.var = j; rec.round = round; rec.newbound = nb.x; rec.is_upper = 0; rec.reserved = 0;
+         p.log[pos] = rec;
       }
+      ++pos;
    }
-   return nc;
+   if( ubchg && pos < (unsigned long long)logcap )
+   {
+      ChangeRec rec;
+      rec.var = j; rec.round = round; rec.newbound = nb.y; rec.is_upper = 1; rec.reserved = 0;
+      p.log[pos] = rec;
+   }
 }
 
-// DENSE = false: only columns whose flag was raised by the sweep of this round are looked at (single GPU); the flags
-//                are scanned 16 per thread;
+// DENSE = false: the columns on the change list of this round -- cost proportional to the changes (single GPU);
+//                eight lanes per column: one accepts the bounds, all mark the rows of the column;
 // DENSE = true : every column compares its (all-reduced) candidate keys with its bounds (rows sharded over ranks:
 //                a key may have been moved by another rank)
 constexpr int APPLY_THREADS = 256;
+constexpr int APPLY_G = 8;
 
 template <bool DENSE, bool GRAPH>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
@@ -1025,37 +1159,63 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
    const int lane = threadIdx.x & 31;
    const int round = c->round;
    const int logcap = c->logcap;
+   const unsigned nlist = c->nchgcols;
    int mychg = 0;
-   const int stride = gridDim.x * APPLY_THREADS;
+   const int nthreads = gridDim.x * APPLY_THREADS;
    const int gtid = blockIdx.x * APPLY_THREADS + threadIdx.x;
    if( DENSE )
    {
-      for( int j = gtid; j < p.ncols; j += stride )
+      // the local list only serves to lower the bits again
+      for( unsigned i = gtid; i < nlist; i += nthreads )
       {
-         p.colflag[j] = 0;
-         mychg += applyAndMark(p, j, round, logcap);
+         const int j = p.chglist[i];
+         atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
+      }
+      for( int j = gtid; j < p.ncols; j += nthreads )
+      {
+         bool lbchg;
+         bool ubchg;
+         double2 nb;
+         const int nc = applyColumn(p, j, nb, lbchg, ubchg);
+         if( nc > 0 )
+         {
+            markColumnRows(p, j, 0, 1);
+            if( logcap > 0 )
+               logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
+         }
+         mychg += nc;
       }
    }
    else
    {
-      const int nvec = (p.ncols + 15) >> 4;     // colflag is allocated and zeroed beyond ncols
-      for( int v = gtid; v < nvec; v += stride )
+      const int gl = lane & (APPLY_G - 1);
+      const int ngroups = nthreads / APPLY_G;
+      const unsigned trips = (nlist + ngroups - 1) / ngroups;       // warp-uniform
+      for( unsigned it = 0; it < trips; ++it )
       {
-         const uint4 f = reinterpret_cast<const uint4*>(p.colflag)[v];
-         if( (f.x | f.y | f.z | f.w) == 0u )
-            continue;
-         reinterpret_cast<uint4*>(p.colflag)[v] = make_uint4(0u, 0u, 0u, 0u);
-         const unsigned w[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-         for( int q = 0; q < 4; ++q )
+         const unsigned item = it * ngroups + gtid / APPLY_G;
+         const bool valid = item < nlist;
+         int j = 0;
+         int nc = 0;
+         if( valid )
          {
-#pragma unroll
-            for( int t = 0; t < 4; ++t )
+            j = p.chglist[item];
+            if( gl == 0 )
             {
-               if( (w[q] >> (8 * t)) & 0xffu )
-                  mychg += applyAndMark(p, 16 * v + 4 * q + t, round, logcap);
+               bool lbchg;
+               bool ubchg;
+               double2 nb;
+               nc = applyColumn(p, j, nb, lbchg, ubchg);
+               atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
+               if( nc > 0 && logcap > 0 )
+                  logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
+               mychg += nc;
             }
          }
+         // every candidate that reached the column beat the round-start bound, so nc > 0 for listed columns (a
+         // crossing pair clamped back to its old value is the one exception): the group marks without waiting
+         if( valid )
+            markColumnRows(p, j, gl, APPLY_G);
       }
    }
    mychg = __reduce_add_sync(0xffffffffu, mychg);
@@ -1086,8 +1246,9 @@ __global__ void set_bounds_kernel(const DevProblem p, const double* lb, const do
       const double u = ub[j] + 0.0;
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
-      p.colflag[j] = 0;
    }
+   for( int w = blockIdx.x * blockDim.x + threadIdx.x; w < (p.ncols + 31) / 32; w += stride )
+      p.colbits[w] = 0u;
    for( int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nrows; r += stride )
       p.dirty[r] = ROW_MARKED;
    for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.ntiles; t += stride )
@@ -1104,8 +1265,7 @@ __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const i
       const double u = ub[i] + 0.0;
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
-      p.colflag[j] = 0;
-      markColumnRows(p, j);
+      markColumnRows(p, j, 0, 1);
    }
 }
 
@@ -1137,6 +1297,7 @@ __global__ void begin_kernel(Ctrl* c)
    c->status = 0;
    c->cutoff = 0;
    c->ticket = 0;
+   c->nchgcols = 0;
    c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
    c->logcount = 0;
    c->round_nchg = 0;

@@ -218,8 +218,8 @@ class LinearPropagator:
     def layout(self) -> dict:
         st = np.zeros(10, dtype=np.int64)
         _check(self._lib.gpulin_get_layout(self._h, st.ctypes.data, 10))
-        keys = ("nnz", "stored_nnz", "rows_stream", "tiles", "rows_block", "device_bytes", "blocks_stream",
-                "blocks_block", "blocks_exact", "maxlen")
+        keys = ("nnz", "stored_nnz", "rows_thread", "rows_stream", "rows_block", "device_bytes", "tiles",
+                "blocks_thread", "blocks_stream", "maxlen")
         return dict(zip(keys, (int(x) for x in st)))
 
     def algorithmic_bytes(self) -> int:
