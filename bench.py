@@ -203,6 +203,24 @@ def run_ours(args):
             lp.get_bounds_ptr(h_olb.data_ptr(), h_oub.data_ptr(), on_device=False)   # synchronises
             return res
         launches_per_step = lambda res: 2 + 3 * res["nrounds"]                       # noqa: E731
+    elif args.exchange == "peer":
+        # candidates are committed into every rank's key vector through NVLink peer memory by the kernel that produces
+        # them; device-side barriers; the round loop stays in the CUDA graph on every GPU
+        sp = sharded.PeerPropagator(prob, rank, world, local_rank)
+        lp = sp.lp
+        lp.set_stream(stream.cuda_stream)
+        abytes = nnz * 12 + nrows * 20 + ncols * 17
+
+        def step_resident():
+            lp.set_bounds_ptr(d_lb0.data_ptr(), d_ub0.data_ptr(), on_device=True)
+            return lp.propagate(0)
+
+        def step_e2e():
+            lp.set_bounds_ptr(h_lb.data_ptr(), h_ub.data_ptr(), on_device=False)
+            res = lp.propagate(0)
+            lp.get_bounds_ptr(h_olb.data_ptr(), h_oub.data_ptr(), on_device=False)
+            return res
+        launches_per_step = lambda res: 3 + 5 * res["nrounds"]                       # noqa: E731
     else:
         cuts = sharded.partition_rows(prob["rowptr"], world)
         eng = sharded.CudaEngine(prob, (int(cuts[rank]), int(cuts[rank + 1])), local_rank)
@@ -261,12 +279,19 @@ def run_ours(args):
                 data="synthetic",
                 config=dict(workload=wl["desc"], nrows=nrows, ncols=ncols, nnz=nnz, rounds=res["nrounds"],
                             changes=res["nchanges"], verdict=propagator.STATUS_NAMES[res["status"]],
-                            parallelism=("1 GPU" if world == 1 else f"rows sharded over {world} GPUs, 1 int64 MIN all-reduce/round"),
+                            parallelism=("1 GPU" if world == 1 else
+                                         (f"rows sharded over {world} GPUs, candidates committed to all ranks through NVLink peer memory "
+                                          "inside the exact kernel, 2 device barriers/round" if args.exchange == "peer" else
+                                          f"rows sharded over {world} GPUs, 1 int64 MIN all-reduce/round (NCCL)")),
                             l2="inputs larger than L2: 157 MB streamed per full round vs 126 MB L2" if args.workload != "c3small" else "fits L2",
-                            loop="CUDA graph WHILE node (device-side)" if world == 1 else "host loop, NCCL per round"),
+                            loop="CUDA graph WHILE node (device-side)" if (world == 1 or args.exchange == "peer") else "host loop, NCCL per round"),
                 e2e=dict(value=nnz * K / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=16 * ncols,
                          d2h_bytes_per_step=16 * ncols + 32),
                 gpu_launches=K * launches_per_step(res), clocks=clocks.summary(), status_consistent=status_ok)
+    if world > 1 and args.exchange == "peer":
+        ms, rn, rc = lp.round_stats()
+        line["round_us"] = [round(float(x) * 1e3, 1) for x in ms]
+        line["round_nnz_local"] = [int(x) for x in rn]
     if world == 1:
         sweep_ms = statistics.mean(p[0] for p in prof)
         exact_ms = statistics.mean(p[1] for p in prof)
@@ -296,6 +321,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how the ranks merge candidate bounds (peer memory inside the kernel | NCCL all-reduce)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

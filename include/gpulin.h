@@ -178,6 +178,19 @@ int gpulin_round_sweep(gpulin_t* h);
  *  ranks).  If nchanges or cutoff is non-NULL the call synchronises and returns the round's change count / verdict */
 int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int32_t* cutoff);
 
+/* ---- rows sharded over the GPUs of ONE node, candidates exchanged through peer memory (NVLink) ------------------
+ * One process per GPU.  Every rank creates its handle on its own row block, exports three CUDA IPC handles, the host
+ * language all-gathers them, every rank connects.  From then on gpulin_set_bounds / gpulin_propagate are COLLECTIVE
+ * calls (same bounds, same maxrounds on every rank): the exact kernel commits every candidate into the key vector of
+ * every rank with system-scope atomics over NVLink, two device-side barriers per round keep the ranks in step, and the
+ * whole fixpoint loop stays on the device -- no NCCL call and no host round trip per round. */
+
+/** writes this rank's IPC handles (*nbytes bytes; call with out = NULL to query the size) */
+int gpulin_peer_handles(gpulin_t* h, void* out, int64_t* nbytes);
+
+/** opens the other ranks' buffers; allhandles = the nranks handle blobs in rank order */
+int gpulin_peer_connect(gpulin_t* h, int rank, int nranks, const void* allhandles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,11 @@ struct gpulin
    cudaGraphExec_t gexec = nullptr;
    cudaGraphConditionalHandle handle = 0;
    bool        hostloop = false;
+   int         npeers = 1;          // > 1 after gpulin_peer_connect: candidates are committed on every rank
+   int         peerrank = 0;
+   unsigned*   d_sync = nullptr;    // this rank's barrier words (exported)
+   PeerTable*  d_peers = nullptr;
+   void*       peerptr[MAX_PEERS][3] = {};   // opened IPC pointers of the other ranks
    bool        havebounds = false;
    // results of the last propagate call
    gpulin_result last{};
@@ -155,7 +160,7 @@ static const SellKernel g_sellKernels[] = {
 constexpr int NSELLVARIANTS = sizeof(g_sellKernels) / sizeof(g_sellKernels[0]);
 
 // one propagation round on h->stream
-template <bool DENSE, bool GRAPH>
+template <int MODE, bool GRAPH>
 static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
 {
    if( sweep )
@@ -195,7 +200,13 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
          exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
    }
    if( apply )
-      apply_kernel<DENSE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
+   {
+      if( MODE == APPLY_PEERS )
+         peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);      // every rank's candidates have arrived
+      apply_kernel<MODE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
+      if( MODE == APPLY_PEERS )
+         peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);      // nobody commits into keys that are still being read
+   }
    CU(cudaGetLastError());
    return GPULIN_OK;
 }
@@ -218,17 +229,30 @@ static int buildGraph(gpulin* h)
       kp.kernelParams = args;
       CU(cudaGraphAddKernelNode(&beginNode, h->graph, nullptr, 0, &kp));
    }
+   cudaGraphNode_t afterBegin = beginNode;
+   if( h->npeers > 1 )
+   {
+      // all ranks have their bounds in place before anybody commits a candidate
+      cudaKernelNodeParams kp;
+      memset(&kp, 0, sizeof(kp));
+      void* args[1] = {(void*)&h->p};
+      kp.func = (void*)peer_barrier_kernel;
+      kp.gridDim = dim3(1);
+      kp.blockDim = dim3(1);
+      kp.kernelParams = args;
+      CU(cudaGraphAddKernelNode(&afterBegin, h->graph, &beginNode, 1, &kp));
+   }
    cudaGraphNodeParams cp = {};
    cp.type = cudaGraphNodeTypeConditional;
    cp.conditional.handle = h->handle;
    cp.conditional.type = cudaGraphCondTypeWhile;
    cp.conditional.size = 1;
    cudaGraphNode_t whileNode;
-   CU(cudaGraphAddNode(&whileNode, h->graph, &beginNode, 1, &cp));
+   CU(cudaGraphAddNode(&whileNode, h->graph, &afterBegin, 1, &cp));
    cudaGraph_t body = cp.conditional.phGraph_out[0];
 
    CU(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-   const int lrc = launchRoundKernels<false, true>(h, true, true);
+   const int lrc = (h->npeers > 1 ? launchRoundKernels<APPLY_PEERS, true>(h, true, true) : launchRoundKernels<APPLY_LIST, true>(h, true, true));
    cudaGraph_t captured = nullptr;
    CU(cudaStreamEndCapture(h->stream, &captured));
    OK(lrc);
@@ -437,6 +461,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &d_colbeg, (size_t)ncols + 2));
    TRY(devAlloc(h, &d_colrows, (size_t)nnz + 1));
    TRY(devAlloc(h, &d_ctrl, 1));
+   TRY(devAlloc(h, &h->d_sync, 64));
+   TRY(devAlloc(h, &h->d_peers, 1));
    TRY(devAlloc(h, &h->d_tmplb, (size_t)ncols + 1));
    TRY(devAlloc(h, &h->d_tmpub, (size_t)ncols + 1));
    TRYCU(cudaMemcpy(d_sell_off, sell_off.data(), sizeof(long long) * ((size_t)nslices + 1), cudaMemcpyHostToDevice));
@@ -473,6 +499,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRYCU(cudaMemset(d_dirty, 0, (size_t)nrows + 64));
    TRYCU(cudaMemset(d_colbits, 0, sizeof(unsigned) * ((size_t)ncols / 32 + 2)));
    TRYCU(cudaMemset(d_ctrl, 0, sizeof(Ctrl)));
+   TRYCU(cudaMemset(h->d_sync, 0, 64 * sizeof(unsigned)));
    TRYCU(cudaMemset(d_cand, 0, sizeof(long long) * (2 * (size_t)ncols + 2)));
    TRYCU(cudaMallocHost((void**)&h->h_ctrl, sizeof(Ctrl)));
    TRYCU(cudaMallocHost((void**)&h->h_params, 4 * sizeof(int)));
@@ -517,6 +544,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.colrows = d_colrows;
    p.ctrl = d_ctrl;
    p.log = nullptr;
+   p.peers = nullptr;
    gpulin_numerics defnum;
    gpulin_default_numerics(&defnum);
    if( num == nullptr )
@@ -587,6 +615,14 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    if( h->stream != nullptr )
       cudaStreamSynchronize(h->stream);
    destroyGraph(h);
+   for( int r = 0; r < MAX_PEERS; ++r )
+   {
+      for( int k = 0; k < 3; ++k )
+      {
+         if( h->peerptr[r][k] != nullptr )
+            cudaIpcCloseMemHandle(h->peerptr[r][k]);
+      }
+   }
    for( int i = 0; i < h->nalloc; ++i )
       cudaFree(h->d_all[i]);
    if( h->d_log != nullptr )
@@ -728,9 +764,11 @@ extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
    else
    {
       begin_kernel<<<1, 1, 0, h->stream>>>(h->p.ctrl);
+      if( h->npeers > 1 )
+         peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);
       for( ;; )
       {
-         OK((launchRoundKernels<false, false>(h, true, true)));
+         OK((h->npeers > 1 ? launchRoundKernels<APPLY_PEERS, false>(h, true, true) : launchRoundKernels<APPLY_LIST, false>(h, true, true)));
          int cont = 0;
          CU(cudaMemcpyAsync(&h->h_ctrl->cont, &h->p.ctrl->cont, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
          CU(cudaStreamSynchronize(h->stream));
@@ -753,6 +791,8 @@ extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
    h->lastrounds = c->round;
    if( res != nullptr )
       *res = h->last;
+   if( c->peererror )
+      return fail(GPULIN_ERR_STATE, "a peer rank did not reach the round barrier within 5 s");
    return GPULIN_OK;
 }
 
@@ -924,7 +964,7 @@ extern "C" int gpulin_round_sweep(gpulin_t* h)
    if( !h->havebounds )
       return fail(GPULIN_ERR_STATE, "gpulin_round_sweep before gpulin_set_bounds");
    CU(cudaSetDevice(h->device));
-   OK((launchRoundKernels<false, false>(h, true, false)));
+   OK((launchRoundKernels<APPLY_LIST, false>(h, true, false)));
    publish_cutoff_kernel<<<1, 1, 0, h->stream>>>(h->p);
    CU(cudaGetLastError());
    return GPULIN_OK;
@@ -937,9 +977,9 @@ extern "C" int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int
    CU(cudaSetDevice(h->device));
    absorb_cutoff_kernel<<<1, 1, 0, h->stream>>>(h->p);
    if( dense )
-      OK((launchRoundKernels<true, false>(h, false, true)));
+      OK((launchRoundKernels<APPLY_DENSE, false>(h, false, true)));
    else
-      OK((launchRoundKernels<false, false>(h, false, true)));
+      OK((launchRoundKernels<APPLY_LIST, false>(h, false, true)));
    if( nchanges != nullptr || cutoff != nullptr )
    {
       OK(fetchCtrl(h));
@@ -976,12 +1016,12 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    CU(cudaEventRecord(h->evprof[0], h->stream));
    const int keepexact = h->nexactblocks;
    h->nexactblocks = 0;                               // launchRoundKernels skips the exact kernel ...
-   OK((launchRoundKernels<false, false>(h, true, false)));
+   OK((launchRoundKernels<APPLY_LIST, false>(h, true, false)));
    h->nexactblocks = keepexact;
    CU(cudaEventRecord(h->evprof[1], h->stream));
    exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);   // ... which is timed on its own
    CU(cudaEventRecord(h->evprof[2], h->stream));
-   OK((launchRoundKernels<false, false>(h, false, true)));
+   OK((launchRoundKernels<APPLY_LIST, false>(h, false, true)));
    CU(cudaEventRecord(h->evprof[3], h->stream));
    CU(cudaEventSynchronize(h->evprof[3]));
    float t[3] = {0.f, 0.f, 0.f};
@@ -991,6 +1031,65 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    if( exact_ms != nullptr ) *exact_ms = t[1];
    if( apply_ms != nullptr ) *apply_ms = t[2];
    OK(fetchCtrl(h));
+   return GPULIN_OK;
+}
+
+// ---- rows sharded over the GPUs of one node, candidates exchanged through peer memory -------------------------------
+
+extern "C" int gpulin_peer_handles(gpulin_t* h, void* out, int64_t* nbytes)
+{
+   if( h == nullptr || nbytes == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   *nbytes = 3 * (int64_t)sizeof(cudaIpcMemHandle_t);
+   if( out == nullptr )
+      return GPULIN_OK;
+   CU(cudaSetDevice(h->device));
+   cudaIpcMemHandle_t* hd = (cudaIpcMemHandle_t*)out;
+   CU(cudaIpcGetMemHandle(&hd[0], h->p.cand));
+   CU(cudaIpcGetMemHandle(&hd[1], h->p.colbits));
+   CU(cudaIpcGetMemHandle(&hd[2], h->d_sync));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_peer_connect(gpulin_t* h, int rank, int nranks, const void* allhandles)
+{
+   if( h == nullptr || allhandles == nullptr || nranks < 1 || nranks > MAX_PEERS || rank < 0 || rank >= nranks )
+      return fail(GPULIN_ERR_ARG, "invalid argument (at most %d ranks)", MAX_PEERS);
+   if( h->npeers > 1 )
+      return fail(GPULIN_ERR_STATE, "gpulin_peer_connect called twice");
+   CU(cudaSetDevice(h->device));
+   CU(cudaStreamSynchronize(h->stream));
+   const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)allhandles;
+   PeerTable t;
+   memset(&t, 0, sizeof(t));
+   t.n = nranks;
+   t.rank = rank;
+   for( int r = 0; r < nranks; ++r )
+   {
+      if( r == rank )
+      {
+         t.cand[r] = h->p.cand;
+         t.colbits[r] = h->p.colbits;
+         t.sync[r] = h->d_sync;
+         continue;
+      }
+      for( int k = 0; k < 3; ++k )
+      {
+         cudaError_t e = cudaIpcOpenMemHandle(&h->peerptr[r][k], hd[3 * r + k], cudaIpcMemLazyEnablePeerAccess);
+         if( e != cudaSuccess )
+            return fail(GPULIN_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s (peer access between the GPUs is required)",
+               r, cudaGetErrorString(e));
+      }
+      t.cand[r] = (long long*)h->peerptr[r][0];
+      t.colbits[r] = (unsigned*)h->peerptr[r][1];
+      t.sync[r] = (unsigned*)h->peerptr[r][2];
+   }
+   CU(cudaMemcpy(h->d_peers, &t, sizeof(t), cudaMemcpyHostToDevice));
+   h->p.peers = h->d_peers;
+   h->npeers = nranks;
+   h->peerrank = rank;
+   if( !h->hostloop )
+      OK(buildGraph(h));
    return GPULIN_OK;
 }
 

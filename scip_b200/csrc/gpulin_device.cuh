@@ -43,27 +43,52 @@ __device__ __forceinline__ bool isLE(const Num& n, double a, double b) { return 
 __device__ __forceinline__ bool isGT(const Num& n, double a, double b) { return a - b > n.eps; }
 __device__ __forceinline__ bool isGE(const Num& n, double a, double b) { return a - b >= -n.eps; }
 __device__ __forceinline__ bool isEQ(const Num& n, double a, double b) { return fabs(a - b) <= n.eps; }
+// plain maximum / minimum of two doubles that are never NaN here (fmax/fmin cost ~8 instructions each for their NaN rules)
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double relDiff(double a, double b)
 {
-   double q = fmax(1.0, fmax(fabs(a), fabs(b)));
+   double q = dmax(1.0, dmax(fabs(a), fabs(b)));
    return (a - b) / q;
 }
-__device__ __forceinline__ bool isFeasLT(const Num& n, double a, double b) { return relDiff(a, b) < -n.feastol; }
-__device__ __forceinline__ bool isFeasGT(const Num& n, double a, double b) { return relDiff(a, b) > n.feastol; }
+// relDiff(a,b) < -feastol  /  > feastol  (set.c:7254-7372).  The fp64 division is only executed when the product form
+// cannot decide: d/q and feastol are compared with a guard band of 1e-10 relative, far above the rounding of either side.
+__device__ __forceinline__ bool isFeasLT(const Num& n, double a, double b)
+{
+   const double q = dmax(1.0, dmax(fabs(a), fabs(b)));
+   const double d = a - b;
+   const double t = n.feastol * q;
+   if( d < -t * 1.0000000001 )
+      return true;
+   if( d > -t * 0.9999999999 )
+      return false;
+   return d / q < -n.feastol;
+}
+__device__ __forceinline__ bool isFeasGT(const Num& n, double a, double b)
+{
+   const double q = dmax(1.0, dmax(fabs(a), fabs(b)));
+   const double d = a - b;
+   const double t = n.feastol * q;
+   if( d > t * 1.0000000001 )
+      return true;
+   if( d < t * 0.9999999999 )
+      return false;
+   return d / q > n.feastol;
+}
 
 // set.c:7711-7753
 __device__ __forceinline__ bool isLbBetter(const Num& n, double newlb, double oldlb, double oldub)
 {
    if( oldlb < 0.0 && newlb >= 0.0 )
       return true;
-   double m = fmax(fmin(oldub - oldlb, fabs(oldlb)), 1e-3);
+   double m = dmax(dmin(oldub - oldlb, fabs(oldlb)), 1e-3);
    return newlb - oldlb > n.bstreps * m;
 }
 __device__ __forceinline__ bool isUbBetter(const Num& n, double newub, double oldlb, double oldub)
 {
    if( oldub > 0.0 && newub <= 0.0 )
       return true;
-   double m = fmax(fmin(oldub - oldlb, fabs(oldub)), 1e-3);
+   double m = dmax(dmin(oldub - oldlb, fabs(oldub)), 1e-3);
    return newub - oldub < -(n.bstreps * m);
 }
 
@@ -184,7 +209,7 @@ __device__ __noinline__ void accElemSlow(const Num& n, RowAcc& r, double a, doub
    if( isInf(n, -l) || isInf(n, u) )
       r.maxdelta = n.inf;
    else
-      r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
+      r.maxdelta = dmax(r.maxdelta, fabs(a) * (u - l));
 }
 
 // classification + accumulation of one nonzero (a, [l,u]); the common case (finite bounds, no huge product)
@@ -201,7 +226,7 @@ __device__ __forceinline__ void accElem(const Num& n, RowAcc& r, double a, doubl
    {
       dd_add(r.minhi, r.minlo, cmin);
       dd_add(r.maxhi, r.maxlo, cmax);
-      r.maxdelta = fmax(r.maxdelta, fabs(a) * (u - l));
+      r.maxdelta = dmax(r.maxdelta, fabs(a) * (u - l));
    }
    else
       accElemSlow(n, r, a, l, u);
@@ -211,7 +236,7 @@ __device__ __forceinline__ void accMerge(RowAcc& r, const RowAcc& o)
 {
    dd_add_dd(r.minhi, r.minlo, o.minhi, o.minlo);
    dd_add_dd(r.maxhi, r.maxlo, o.maxhi, o.maxlo);
-   r.maxdelta = fmax(r.maxdelta, o.maxdelta);
+   r.maxdelta = dmax(r.maxdelta, o.maxdelta);
    r.cnt = cntMerge(r.cnt, o.cnt);
 }
 
@@ -311,7 +336,7 @@ __device__ __forceinline__ bool rowGates(const Num& n, RowInfo& ri, int len, boo
          cntGet(a.cnt, MAXNEGHUGE), 0.0, false, maxact, t2, s2);
       double slack = (!ri.rhsfin || s1) ? n.inf : (ri.rhs - minact);
       double surplus = (!ri.lhsfin || s2) ? n.inf : (maxact - ri.lhs);
-      if( isLE(n, a.maxdelta, fmin(slack, surplus)) )
+      if( isLE(n, a.maxdelta, dmin(slack, surplus)) )
          return false;
    }
    ri.easy = isLT(n, a.maxdelta, n.maxeasy);
@@ -357,19 +382,56 @@ __device__ __forceinline__ bool rowInfeasible(const Num& n, const RowAcc& a, dou
 // ----    cand[2j]   = ~d2key(lb)   (bitwise NOT reverses the order: a larger lower bound is a smaller key)
 // ----    cand[2j+1] =  d2key(ub)
 // ---- so both sides tighten by MIN -- one ncclMin all-reduce over the whole vector merges the ranks' candidates.
+// Rows sharded over several GPUs of one node: every rank keeps the full key vector, and a candidate is committed into
+// the key vectors of ALL ranks through peer memory (NVLink P2P atomics, system scope) -- the exchange of the round is
+// fused into the kernel that produces the candidates, no collective follows.
+constexpr int MAX_PEERS = 8;
+struct PeerTable
+{
+   int        n;                   // ranks
+   int        rank;                // this rank
+   long long* cand[MAX_PEERS];     // key vector of every rank ([rank] = the local one)
+   unsigned*  colbits[MAX_PEERS];  // changed-column bits of every rank
+   unsigned*  sync[MAX_PEERS];     // [0] barrier arrivals, [1] epoch of the last cutoff
+};
+
 struct Sink
 {
-   long long*     cand;      // 2*ncols candidate keys
-   unsigned*      colbits;   // one bit per column: "a key moved this round"
-   int*           chglist;   // the columns whose bit was raised this round, in no particular order
-   unsigned*      nchgcols;  // length of chglist
+   long long*       cand;      // 2*ncols candidate keys
+   unsigned*        colbits;   // one bit per column: "a key moved this round"
+   int*             chglist;   // the columns whose bit was raised this round, in no particular order
+   unsigned*        nchgcols;  // length of chglist
+   const PeerTable* peers;     // NULL: single GPU
 };
+
+// returns false if a candidate at least as good is already in place (a plain load first: in a round in which many rows
+// propose bounds for the same column only the first few have to pay for an atomic; a stale value only costs an atomic)
+__device__ __forceinline__ bool commitKey(const Sink& s, size_t idx, long long key)
+{
+   if( key >= __ldcg(&s.cand[idx]) )
+      return false;
+   if( s.peers == nullptr )
+      atomicMin(&s.cand[idx], key);
+   else
+   {
+      for( int r = 0; r < s.peers->n; ++r )
+         atomicMin_system(&s.peers->cand[r][idx], key);
+   }
+   return true;
+}
 
 // the first candidate of a round that reaches a column puts it on the list the apply kernel works through.  Split in
 // two so that a thread can have the bit tests of several columns in flight before it looks at the first answer.
+// With peers there is no list: the bit is raised on every rank and the apply kernel scans the bits.
 __device__ __forceinline__ bool raiseColumnBit(const Sink& s, int j)
 {
    const unsigned bit = 1u << (j & 31);
+   if( s.peers != nullptr )
+   {
+      for( int r = 0; r < s.peers->n; ++r )
+         atomicOr_system(&s.peers->colbits[r][j >> 5], bit);
+      return false;
+   }
    return (atomicOr(&s.colbits[j >> 5], bit) & bit) == 0u;
 }
 __device__ __forceinline__ void listChangedColumn(const Sink& s, int j, bool first)
@@ -395,15 +457,15 @@ __device__ __forceinline__ void inferUb(const Num& n, const Sink& s, int j, bool
       cutoff = true;
       return;
    }
-   newub = fmax(newub, l);
+   newub = dmax(newub, l);
    if( force ? isGE(n, newub, u) : !isUbBetter(n, newub, l, u) )
       return;
    if( !isLT(n, newub, u) )
       return;
    // every value that gets here is below the round-start bound, so the column changes this round whichever
    // candidate wins: no need to wait for the atomic's result
-   atomicMin(&s.cand[2 * (size_t)j + 1], d2key(newub));
-   touched = true;
+   if( commitKey(s, 2 * (size_t)j + 1, d2key(newub)) )
+      touched = true;
 }
 __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool integral, double newlb, double l,
    double u, bool force, bool& cutoff, bool& touched)
@@ -414,13 +476,13 @@ __device__ __forceinline__ void inferLb(const Num& n, const Sink& s, int j, bool
       cutoff = true;
       return;
    }
-   newlb = fmin(newlb, u);
+   newlb = dmin(newlb, u);
    if( force ? isLE(n, newlb, l) : !isLbBetter(n, newlb, l, u) )
       return;
    if( !isGT(n, newlb, l) )
       return;
-   atomicMin(&s.cand[2 * (size_t)j], ~d2key(newlb));
-   touched = true;
+   if( commitKey(s, 2 * (size_t)j, ~d2key(newlb)) )
+      touched = true;
 }
 
 // tightenVarUb / tightenVarLb: cons_linear.c:5242-5307 / 5311-5376

@@ -44,6 +44,8 @@ struct Ctrl
    int                cutoff;       // set by any kernel that proves infeasibility
    unsigned int       ticket;       // apply kernel: blocks finished
    unsigned int       nchgcols;     // columns on the change list of the running round
+   unsigned int       epoch;        // peer barriers passed so far (never reset)
+   int                peererror;    // a peer barrier timed out
    unsigned long long logcount;     // entries produced
    unsigned long long round_nchg;   // accepted bound changes of the running round
    unsigned long long total_nchg;
@@ -97,6 +99,7 @@ struct DevProblem
    const int*          colrows;
    Ctrl*               ctrl;
    ChangeRec*          log;
+   const PeerTable*    peers;      // NULL: single GPU; else candidates go to every rank's key vector (see Sink)
    Num                 num;
 };
 
@@ -149,7 +152,7 @@ __device__ __forceinline__ bool passesSlackTest(const RowInfo& ri, double alpha,
 // threshold of the slack test: alpha - slack > sumepsilon, or > epsilon for single-variable rows (:5474, :5566)
 __device__ __forceinline__ double slackThreshold(const Num& n, bool force)
 {
-   return force ? fmin(n.eps, n.sumeps) : n.sumeps;
+   return force ? dmin(n.eps, n.sumeps) : n.sumeps;
 }
 
 // ---- candidate pass over the elements first, first+step, ... < len of a row that passed the gates of tightenBounds
@@ -165,6 +168,7 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
    s.colbits = p.colbits;
    s.chglist = p.chglist;
    s.nchgcols = &p.ctrl->nchgcols;
+   s.peers = p.peers;
    for( int k0 = first; k0 < len; k0 += 4 * step )
    {
       double a[4];
@@ -310,7 +314,7 @@ __device__ __forceinline__ bool rowClearlyQuiet(const Num& n, const LeanAcc& r, 
       return true;                // all variables fixed (:7057)
    const double slack = isInf(n, rhs) ? n.inf : rhs - r.minact;
    const double surplus = isInf(n, -lhs) ? n.inf : r.maxact - lhs;
-   const double m = fmin(slack, surplus);
+   const double m = dmin(slack, surplus);
    // the gate maxdelta <= min(slack, surplus) + eps (:7081) with every rounding in its disfavour
    return md + 2.0 * E + 4.5e-16 * fabs(m) - m <= 0.5 * n.eps;
 }
@@ -946,6 +950,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
                sk.colbits = p.colbits;
                sk.chglist = p.chglist;
                sk.nchgcols = &p.ctrl->nchgcols;
+               sk.peers = p.peers;
                bool touched[EXACT_Q];
 #pragma unroll
                for( int q = 0; q < EXACT_Q; ++q )
@@ -1144,10 +1149,15 @@ __device__ __forceinline__ void logChanges(const DevProblem& p, int j, int round
 //                eight lanes per column: one accepts the bounds, all mark the rows of the column;
 // DENSE = true : every column compares its (all-reduced) candidate keys with its bounds (rows sharded over ranks:
 //                a key may have been moved by another rank)
+//         PEERS: the changed-column bits (raised on every rank by every rank's exact kernel) are scanned, a word per
+//                thread; all ranks hold the same keys and bits, so they all accept the same changes
 constexpr int APPLY_THREADS = 256;
 constexpr int APPLY_G = 8;
+constexpr int APPLY_LIST = 0;
+constexpr int APPLY_DENSE = 1;
+constexpr int APPLY_PEERS = 2;
 
-template <bool DENSE, bool GRAPH>
+template <int MODE, bool GRAPH>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
 {
    __shared__ int s_nchg;
@@ -1163,7 +1173,34 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
    int mychg = 0;
    const int nthreads = gridDim.x * APPLY_THREADS;
    const int gtid = blockIdx.x * APPLY_THREADS + threadIdx.x;
-   if( DENSE )
+   if( MODE == APPLY_PEERS )
+   {
+      const int nwords = (p.ncols + 31) >> 5;
+      for( int w = gtid; w < nwords; w += nthreads )
+      {
+         unsigned bits = p.colbits[w];
+         if( bits == 0u )
+            continue;
+         p.colbits[w] = 0u;
+         while( bits != 0u )
+         {
+            const int j = 32 * w + __ffs(bits) - 1;
+            bits &= bits - 1u;
+            bool lbchg;
+            bool ubchg;
+            double2 nb;
+            const int nc = applyColumn(p, j, nb, lbchg, ubchg);
+            if( nc > 0 )
+            {
+               markColumnRows(p, j, 0, 1);
+               if( logcap > 0 )
+                  logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
+            }
+            mychg += nc;
+         }
+      }
+   }
+   else if( MODE == APPLY_DENSE )
    {
       // the local list only serves to lower the bits again
       for( unsigned i = gtid; i < nlist; i += nthreads )
@@ -1234,6 +1271,43 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
          controlStep<GRAPH>(c, handle);
       }
    }
+}
+
+// ---- barrier over the ranks of a node through peer memory (one thread per rank) -----------------------------------
+// Every rank adds 1 to the arrival word of every rank and spins on its own word.  Two barriers per round: after the
+// exact kernel (all candidates of all ranks are in every key vector) and after the apply kernel (nobody commits into a
+// key vector that is still being read).  The cutoff verdict travels as "epoch of the last cutoff".
+__global__ void peer_barrier_kernel(const DevProblem p)
+{
+   const PeerTable* t = p.peers;
+   Ctrl* c = p.ctrl;
+   if( t == nullptr )
+      return;
+   __threadfence_system();
+   const unsigned epoch = ++c->epoch;
+   if( c->cutoff )
+   {
+      for( int r = 0; r < t->n; ++r )
+         atomicMax_system(&t->sync[r][1], epoch);
+      __threadfence_system();
+   }
+   for( int r = 0; r < t->n; ++r )
+      atomicAdd_system(&t->sync[r][0], 1u);
+   const unsigned target = (unsigned)t->n * epoch;
+   volatile unsigned* mine = t->sync[t->rank];
+   const unsigned long long tstart = globaltimer();
+   while( mine[0] < target )
+   {
+      if( globaltimer() - tstart > 5000000000ull )     // 5 s: a peer is gone -- give up instead of hanging the GPU
+      {
+         c->peererror = 1;
+         c->cutoff = 1;
+         break;
+      }
+   }
+   __threadfence_system();
+   if( mine[1] == epoch )
+      c->cutoff = 1;
 }
 
 // ---- bound (re)initialisation ----------------------------------------------------------------------------------

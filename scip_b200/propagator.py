@@ -60,6 +60,8 @@ _SIGNATURES = {
     "gpulin_set_stream": (ctypes.c_int, [_P, _P]),
     "gpulin_sync": (ctypes.c_int, [_P]),
     "gpulin_exchange_buffer": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_peer_handles": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_peer_connect": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "gpulin_get_keys": (ctypes.c_int, [_P, _P]),
     "gpulin_set_keys": (ctypes.c_int, [_P, _P]),
     "gpulin_mark_all": (ctypes.c_int, [_P]),
@@ -255,6 +257,18 @@ class LinearPropagator:
         keys = np.ascontiguousarray(keys, dtype=np.int64)
         assert keys.shape == (2 * self.ncols + 2,)
         _check(self._lib.gpulin_set_keys(self._h, keys.ctypes.data))
+
+    def peer_handles(self) -> bytes:
+        n = ctypes.c_int64(0)
+        _check(self._lib.gpulin_peer_handles(self._h, None, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value)
+        _check(self._lib.gpulin_peer_handles(self._h, buf, ctypes.byref(n)))
+        return buf.raw
+
+    def peer_connect(self, rank: int, handles):
+        """``handles``: list of the blobs of all ranks in rank order"""
+        blob = b"".join(handles)
+        _check(self._lib.gpulin_peer_connect(self._h, int(rank), len(handles), blob))
 
     def mark_all(self):
         _check(self._lib.gpulin_mark_all(self._h))

@@ -91,6 +91,35 @@ class CudaEngine:
         self.lp.close()
 
 
+class PeerPropagator:
+    """rows sharded over the GPUs of one node, candidates exchanged through peer memory: after the one-time handle
+    exchange every call is a plain (collective) LinearPropagator call -- the round loop runs on the devices"""
+
+    def __init__(self, prob, rank: int, world: int, device: int, group=None, **numerics):
+        import torch.distributed as dist
+        from .propagator import LinearPropagator
+        cuts = partition_rows(prob["rowptr"], world)
+        self.lp = LinearPropagator(prob, device=device, rows=(int(cuts[rank]), int(cuts[rank + 1])), **numerics)
+        self.rank, self.world = rank, world
+        if world > 1:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, self.lp.peer_handles(), group=group)
+            self.lp.peer_connect(rank, blobs)
+            dist.barrier(group=group)
+
+    def set_bounds(self, lb, ub):
+        self.lp.set_bounds(lb, ub)
+
+    def propagate(self, maxrounds: int = 0):
+        return self.lp.propagate(maxrounds)
+
+    def get_bounds(self):
+        return self.lp.get_bounds()
+
+    def close(self):
+        self.lp.close()
+
+
 class ShardedPropagator:
     """drives the rounds of one rank; ``engine`` owns the local rows (CudaEngine on GPUs)"""
 
