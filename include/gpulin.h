@@ -115,6 +115,20 @@ int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, const doubl
  *  loop runs inside one persistent kernel, no host round trip per round (propagateDomains, solve.c:766) */
 int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res);
 
+/** the two halves of gpulin_propagate: enqueue the whole fixpoint loop on the handle's stream and return at once;
+ *  wait for it and fetch the verdict.  Lets one host thread keep several handles (clones) busy concurrently */
+int gpulin_propagate_async(gpulin_t* h, int maxrounds);
+int gpulin_propagate_wait(gpulin_t* h, gpulin_result* res);
+
+/** another set of bound vectors on the SAME matrix (probing, SCIPstartProbing scip_probing.c:120): the clone shares the
+ *  read-only device arrays with `h` and owns bounds, keys, marks, work lists, stream and graph.  Destroy in any order */
+int gpulin_clone(gpulin_t* h, gpulin_t** out);
+
+/** probing start: `h` (a clone of `base` or vice versa) takes over the bounds of `base` with no row marked -- the state
+ *  of a node whose propagation is complete; follow with gpulin_update_bounds (SCIPchgVarLb/UbProbing :302/:346) and
+ *  gpulin_propagate (SCIPpropagateProbing :581); calling it again is SCIPbacktrackProbing (:226) */
+int gpulin_reset_from(gpulin_t* h, gpulin_t* base);
+
 /** copies the current bounds to host memory */
 int gpulin_get_bounds(gpulin_t* h, double* lb, double* ub);
 

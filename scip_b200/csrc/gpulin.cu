@@ -45,8 +45,18 @@ static int fail(int code, const char* fmt, ...)
          return rc_;             \
    } while( 0 )
 
+// the read-only device arrays of the matrix, shared by a handle and its clones (gpulin_clone)
+struct SharedMatrix
+{
+   void*  ptrs[16] = {nullptr};
+   int    n = 0;
+   int    refs = 1;
+   size_t bytes = 0;
+};
+
 struct gpulin
 {
+   SharedMatrix* shared = nullptr;
    int         device = 0;
    int64_t     nrows = 0, ncols = 0, nnz = 0;
    int64_t     nstored = 0;      // nonzeros incl. SELL padding
@@ -92,20 +102,27 @@ struct gpulin
    PeerTable*  d_peers = nullptr;
    void*       peerptr[MAX_PEERS][3] = {};   // opened IPC pointers of the other ranks
    bool        havebounds = false;
+   bool        pending = false;     // gpulin_propagate_async was called, gpulin_propagate_wait not yet
    // results of the last propagate call
    gpulin_result last{};
    int         lastrounds = 0;
 };
 
 template <typename T>
-static int devAlloc(gpulin* h, T** out, size_t count)
+static int devAlloc(gpulin* h, T** out, size_t count, bool shared = false)
 {
    void* ptr = nullptr;
    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
    cudaError_t e = cudaMalloc(&ptr, bytes);
    if( e != cudaSuccess )
       return fail(GPULIN_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-   h->d_all[h->nalloc++] = ptr;
+   if( shared )
+   {
+      h->shared->ptrs[h->shared->n++] = ptr;
+      h->shared->bytes += bytes;
+   }
+   else
+      h->d_all[h->nalloc++] = ptr;
    h->devbytes += bytes;
    *out = (T*)ptr;
    return GPULIN_OK;
@@ -301,6 +318,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    CU(cudaSetDevice(device));
 
    gpulin* h = new gpulin();
+   h->shared = new SharedMatrix();
    h->device = device;
    h->nrows = nrows;
    h->ncols = ncols;
@@ -380,7 +398,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    h->nstored = off;
    if( h->nstored >= (1LL << 40) || h->nstreamelems / TILE >= (1LL << 31) - 64 )
    {
-      delete h;
+      gpulin_destroy(h);
       return fail(GPULIN_ERR_ARG, "matrix too large");
    }
    std::vector<double> pvals((size_t)h->nstored + 8, 0.0);
@@ -443,23 +461,23 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    int rc = GPULIN_OK;
 #define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
 #define TRYCU(x) do { if( rc == GPULIN_OK ) { cudaError_t e_ = (x); if( e_ != cudaSuccess ) rc = fail(GPULIN_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while( 0 )
-   TRY(devAlloc(h, &d_sell_off, (size_t)nslices + 1));
-   TRY(devAlloc(h, &d_tile_row0, (size_t)h->ntiles + 2));
-   TRY(devAlloc(h, &d_endmask, (size_t)h->ntiles * 32 + 32));
+   TRY(devAlloc(h, &d_sell_off, (size_t)nslices + 1, true));
+   TRY(devAlloc(h, &d_tile_row0, (size_t)h->ntiles + 2, true));
+   TRY(devAlloc(h, &d_endmask, (size_t)h->ntiles * 32 + 32, true));
    TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
-   TRY(devAlloc(h, &d_rowlen, (size_t)nrows + 1));
-   TRY(devAlloc(h, &d_rowbeg, (size_t)nrows + 1));
-   TRY(devAlloc(h, &d_vals, (size_t)h->nstored + 8));
-   TRY(devAlloc(h, &d_cols, (size_t)h->nstored + 8));
-   TRY(devAlloc(h, &d_sides, (size_t)nrows + 1));
+   TRY(devAlloc(h, &d_rowlen, (size_t)nrows + 1, true));
+   TRY(devAlloc(h, &d_rowbeg, (size_t)nrows + 1, true));
+   TRY(devAlloc(h, &d_vals, (size_t)h->nstored + 8, true));
+   TRY(devAlloc(h, &d_cols, (size_t)h->nstored + 8, true));
+   TRY(devAlloc(h, &d_sides, (size_t)nrows + 1, true));
    TRY(devAlloc(h, &d_dirty, (size_t)nrows + 64));
    TRY(devAlloc(h, &d_xlist, (size_t)nrows + 1));
    TRY(devAlloc(h, &d_bnd, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)ncols + 2));
    TRY(devAlloc(h, &d_colbits, (size_t)ncols / 32 + 2));
    TRY(devAlloc(h, &d_chglist, (size_t)ncols + 1));
-   TRY(devAlloc(h, &d_colbeg, (size_t)ncols + 2));
-   TRY(devAlloc(h, &d_colrows, (size_t)nnz + 1));
+   TRY(devAlloc(h, &d_colbeg, (size_t)ncols + 2, true));
+   TRY(devAlloc(h, &d_colrows, (size_t)nnz + 1, true));
    TRY(devAlloc(h, &d_ctrl, 1));
    TRY(devAlloc(h, &h->d_sync, 64));
    TRY(devAlloc(h, &h->d_peers, 1));
@@ -625,6 +643,12 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    }
    for( int i = 0; i < h->nalloc; ++i )
       cudaFree(h->d_all[i]);
+   if( h->shared != nullptr && --h->shared->refs == 0 )
+   {
+      for( int i = 0; i < h->shared->n; ++i )
+         cudaFree(h->shared->ptrs[i]);
+      delete h->shared;
+   }
    if( h->d_log != nullptr )
       cudaFree(h->d_log);
    if( h->h_ctrl != nullptr )
@@ -746,7 +770,7 @@ static int fetchCtrl(gpulin* h)
    return GPULIN_OK;
 }
 
-extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
+extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
 {
    if( h == nullptr )
       return fail(GPULIN_ERR_ARG, "handle is NULL");
@@ -778,8 +802,21 @@ extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
       }
    }
    CU(cudaEventRecord(h->ev1, h->stream));
-   OK(fetchCtrl(h));
-   CU(cudaEventSynchronize(h->ev1));
+   // the verdict and the statistics come back with the same stream order, without blocking the caller
+   CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+   h->pending = true;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_propagate_wait(gpulin_t* h, gpulin_result* res)
+{
+   if( h == nullptr )
+      return fail(GPULIN_ERR_ARG, "handle is NULL");
+   if( !h->pending )
+      return fail(GPULIN_ERR_STATE, "gpulin_propagate_wait without gpulin_propagate_async");
+   CU(cudaSetDevice(h->device));
+   CU(cudaStreamSynchronize(h->stream));
+   h->pending = false;
    float ms = 0.0f;
    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
    const Ctrl* c = h->h_ctrl;
@@ -793,6 +830,111 @@ extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
       *res = h->last;
    if( c->peererror )
       return fail(GPULIN_ERR_STATE, "a peer rank did not reach the round barrier within 5 s");
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
+{
+   OK(gpulin_propagate_async(h, maxrounds));
+   return gpulin_propagate_wait(h, res);
+}
+
+// probing: start from the (propagated) state of `base`: bounds and keys are copied, nothing is marked
+extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
+{
+   if( h == nullptr || base == nullptr || h->shared != base->shared )
+      return fail(GPULIN_ERR_ARG, "gpulin_reset_from needs a handle and a clone of it");
+   if( !base->havebounds )
+      return fail(GPULIN_ERR_STATE, "the base handle has no bounds");
+   CU(cudaSetDevice(h->device));
+   CU(cudaMemcpyAsync(const_cast<double2*>(h->p.bnd), base->p.bnd, sizeof(double2) * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->p.cand, base->p.cand, sizeof(long long) * 2 * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
+   CU(cudaMemsetAsync(h->p.dirty, 0, (size_t)h->nrows, h->stream));
+   CU(cudaMemsetAsync(h->p.tileflag, 0, (size_t)h->ntiles, h->stream));
+   CU(cudaMemsetAsync(h->p.colbits, 0, sizeof(unsigned) * ((size_t)h->ncols / 32 + 1), h->stream));
+   h->havebounds = true;
+   return GPULIN_OK;
+}
+
+// a second set of bound vectors on the same matrix: shares the read-only arrays, owns everything a round writes
+extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
+{
+   if( src == nullptr || out == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   *out = nullptr;
+   if( src->npeers > 1 )
+      return fail(GPULIN_ERR_STATE, "a handle connected to peers cannot be cloned");
+   CU(cudaSetDevice(src->device));
+   gpulin* h = new gpulin();
+   h->shared = src->shared;
+   ++h->shared->refs;
+   h->device = src->device;
+   h->nrows = src->nrows; h->ncols = src->ncols; h->nnz = src->nnz; h->nstored = src->nstored;
+   h->nsell = src->nsell; h->nstream = src->nstream; h->nlong = src->nlong; h->ntiles = src->ntiles;
+   h->nstreamelems = src->nstreamelems; h->maxlen = src->maxlen;
+   h->sellvariant = src->sellvariant; h->nsellblocks = src->nsellblocks; h->nstreamblocks = src->nstreamblocks;
+   h->nlongblocks = src->nlongblocks; h->napplyblocks = src->napplyblocks; h->nexactblocks = src->nexactblocks;
+   h->nsm = src->nsm; h->hostloop = src->hostloop; h->perm = src->perm;
+   h->p = src->p;
+   DevProblem& p = h->p;
+   unsigned char* d_dirty; unsigned char* d_tileflag; int* d_xlist; double2* d_bnd; long long* d_cand; unsigned* d_colbits;
+   int* d_chglist; Ctrl* d_ctrl;
+   int rc = GPULIN_OK;
+   TRY(devAlloc(h, &d_dirty, (size_t)h->nrows + 64));
+   TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
+   TRY(devAlloc(h, &d_xlist, (size_t)h->nrows + 1));
+   TRY(devAlloc(h, &d_bnd, (size_t)h->ncols + 1));
+   TRY(devAlloc(h, &d_cand, 2 * (size_t)h->ncols + 2));
+   TRY(devAlloc(h, &d_colbits, (size_t)h->ncols / 32 + 2));
+   TRY(devAlloc(h, &d_chglist, (size_t)h->ncols + 1));
+   TRY(devAlloc(h, &d_ctrl, 1));
+   TRY(devAlloc(h, &h->d_sync, 64));
+   TRY(devAlloc(h, &h->d_peers, 1));
+   TRY(devAlloc(h, &h->d_tmplb, (size_t)h->ncols + 1));
+   TRY(devAlloc(h, &h->d_tmpub, (size_t)h->ncols + 1));
+   TRYCU(cudaMemset(d_dirty, 0, (size_t)h->nrows + 64));
+   TRYCU(cudaMemset(d_tileflag, 0, (size_t)h->ntiles + 64));
+   TRYCU(cudaMemset(d_colbits, 0, sizeof(unsigned) * ((size_t)h->ncols / 32 + 2)));
+   TRYCU(cudaMemset(d_ctrl, 0, sizeof(Ctrl)));
+   TRYCU(cudaMemset(h->d_sync, 0, 64 * sizeof(unsigned)));
+   TRYCU(cudaMemset(d_cand, 0, sizeof(long long) * (2 * (size_t)h->ncols + 2)));
+   TRYCU(cudaMallocHost((void**)&h->h_ctrl, sizeof(Ctrl)));
+   TRYCU(cudaMallocHost((void**)&h->h_params, 4 * sizeof(int)));
+   if( rc == GPULIN_OK )
+      memset(h->h_ctrl, 0, sizeof(Ctrl));
+   TRYCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+   TRYCU(cudaStreamCreateWithFlags(&h->aux[0], cudaStreamNonBlocking));
+   TRYCU(cudaStreamCreateWithFlags(&h->aux[1], cudaStreamNonBlocking));
+   TRYCU(cudaEventCreateWithFlags(&h->evfork, cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evjoin[0], cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evjoin[1], cudaEventDisableTiming));
+   TRYCU(cudaEventCreate(&h->ev0));
+   TRYCU(cudaEventCreate(&h->ev1));
+   if( rc != GPULIN_OK )
+   {
+      gpulin_destroy(h);
+      return rc;
+   }
+   p.dirty = d_dirty;
+   p.tileflag = d_tileflag;
+   p.xlist = d_xlist;
+   p.bnd = d_bnd;
+   p.cand = d_cand;
+   p.colbits = d_colbits;
+   p.chglist = d_chglist;
+   p.ctrl = d_ctrl;
+   p.log = nullptr;
+   p.peers = nullptr;
+   if( !h->hostloop )
+   {
+      rc = buildGraph(h);
+      if( rc != GPULIN_OK )
+      {
+         gpulin_destroy(h);
+         return rc;
+      }
+   }
+   *out = h;
    return GPULIN_OK;
 }
 

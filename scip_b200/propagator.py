@@ -48,6 +48,10 @@ _SIGNATURES = {
     "gpulin_set_bounds_device": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_update_bounds": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P]),
     "gpulin_propagate": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(Result)]),
+    "gpulin_propagate_async": (ctypes.c_int, [_P, ctypes.c_int]),
+    "gpulin_propagate_wait": (ctypes.c_int, [_P, ctypes.POINTER(Result)]),
+    "gpulin_clone": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
+    "gpulin_reset_from": (ctypes.c_int, [_P, _P]),
     "gpulin_get_bounds": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_get_bounds_device": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_set_change_log": (ctypes.c_int, [_P, ctypes.c_int64]),
@@ -198,6 +202,32 @@ class LinearPropagator:
         _check(self._lib.gpulin_propagate(self._h, int(maxrounds), ctypes.byref(res)))
         return dict(status=res.status, nrounds=res.nrounds, nchanges=res.nchanges, nnz_processed=res.nnz_processed,
                     device_ms=res.device_ms)
+
+    def propagate_async(self, maxrounds: int = 0):
+        _check(self._lib.gpulin_propagate_async(self._h, int(maxrounds)))
+
+    def propagate_wait(self) -> dict:
+        res = Result()
+        _check(self._lib.gpulin_propagate_wait(self._h, ctypes.byref(res)))
+        return dict(status=res.status, nrounds=res.nrounds, nchanges=res.nchanges, nnz_processed=res.nnz_processed,
+                    device_ms=res.device_ms)
+
+    def clone(self) -> "LinearPropagator":
+        """another set of bound vectors on the same device matrix (probing)"""
+        other = object.__new__(LinearPropagator)
+        other._lib = self._lib
+        other._h = _P()
+        _check(self._lib.gpulin_clone(self._h, ctypes.byref(other._h)))
+        other.nrows, other.ncols, other.nnz = self.nrows, self.ncols, self.nnz
+        other.numerics, other.device = self.numerics, self.device
+        return other
+
+    def reset_from(self, base: "LinearPropagator"):
+        _check(self._lib.gpulin_reset_from(self._h, base._h))
+
+    def update_bounds_nosync(self, idx, lb, ub):
+        """like update_bounds, but the (numpy, contiguous) arrays must stay alive until the stream has consumed them"""
+        _check(self._lib.gpulin_update_bounds(self._h, len(idx), idx.ctypes.data, lb.ctypes.data, ub.ctypes.data))
 
     def round_stats(self, maxn: int = 1024):
         ms = np.zeros(maxn, dtype=np.float64)
