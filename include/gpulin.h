@@ -129,6 +129,13 @@ int gpulin_clone(gpulin_t* h, gpulin_t** out);
  *  gpulin_propagate (SCIPpropagateProbing :581); calling it again is SCIPbacktrackProbing (:226) */
 int gpulin_reset_from(gpulin_t* h, gpulin_t* base);
 
+/** a batch of probes on the node held by `base` (BASELINE config 5; SCIPapplyProbingVar, prop_probing.c:1254-1279):
+ *  probe i sets column var[i] to [lb[i], ub[i]] and propagates to its fixpoint; `nworkers` clones of the base handle
+ *  (kept inside it) hold that many probes in flight.  Outputs (any may be NULL): verdict, rounds and accepted bound
+ *  changes per probe.  The base handle's bounds are not modified */
+int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
+   const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges);
+
 /** copies the current bounds to host memory */
 int gpulin_get_bounds(gpulin_t* h, double* lb, double* ub);
 

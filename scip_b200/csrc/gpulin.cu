@@ -103,6 +103,10 @@ struct gpulin
    void*       peerptr[MAX_PEERS][3] = {};   // opened IPC pointers of the other ranks
    bool        havebounds = false;
    bool        pending = false;     // gpulin_propagate_async was called, gpulin_propagate_wait not yet
+   bool        lightfetch = false;  // fetch only the head of the control block after a call (probing workers)
+   std::vector<gpulin*> workers;    // clones that gpulin_probe_batch keeps for this (base) handle
+   int         lastvar = -1;        // probing worker: the column of its last probe
+   bool        needreset = true;    // probing worker: its state is not "node + change log"
    // results of the last propagate call
    gpulin_result last{};
    int         lastrounds = 0;
@@ -630,6 +634,9 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    if( h == nullptr )
       return;
    cudaSetDevice(h->device);
+   for( gpulin* w : h->workers )
+      gpulin_destroy(w);
+   h->workers.clear();
    if( h->stream != nullptr )
       cudaStreamSynchronize(h->stream);
    destroyGraph(h);
@@ -803,7 +810,7 @@ extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
    }
    CU(cudaEventRecord(h->ev1, h->stream));
    // the verdict and the statistics come back with the same stream order, without blocking the caller
-   CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, h->lightfetch ? offsetof(Ctrl, round_nnz) : sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
    h->pending = true;
    return GPULIN_OK;
 }
@@ -853,6 +860,78 @@ extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
    CU(cudaMemsetAsync(h->p.tileflag, 0, (size_t)h->ntiles, h->stream));
    CU(cudaMemsetAsync(h->p.colbits, 0, sizeof(unsigned) * ((size_t)h->ncols / 32 + 1), h->stream));
    h->havebounds = true;
+   return GPULIN_OK;
+}
+
+// BASELINE config 5 / SCIPapplyProbingVar (prop_probing.c:1254-1279): probe i starts from the bounds of `base` (the
+// node), sets variable var[i] to [lb[i], ub[i]] and propagates to its fixpoint.  nworkers clones of the base handle keep
+// that many probes in flight on their own streams; a worker returns to the node by undoing its change log.
+extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
+   const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges)
+{
+   if( base == nullptr || nworkers < 1 || nprobes < 0 || (nprobes > 0 && (var == nullptr || lb == nullptr || ub == nullptr)) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( !base->havebounds )
+      return fail(GPULIN_ERR_STATE, "gpulin_probe_batch before gpulin_set_bounds on the base handle");
+   for( int64_t i = 0; i < nprobes; ++i )
+   {
+      if( var[i] < 0 || var[i] >= base->ncols )
+         return fail(GPULIN_ERR_ARG, "probe %lld: column index %d out of range", (long long)i, var[i]);
+   }
+   CU(cudaSetDevice(base->device));
+   CU(cudaStreamSynchronize(base->stream));
+   const int64_t logcap = 1 << 16;
+   while( (int)base->workers.size() < nworkers )
+   {
+      gpulin* w = nullptr;
+      OK(gpulin_clone(base, &w));
+      int rc = gpulin_set_change_log(w, logcap);
+      if( rc != GPULIN_OK )
+      {
+         gpulin_destroy(w);
+         return rc;
+      }
+      w->lightfetch = true;
+      base->workers.push_back(w);
+   }
+   for( gpulin* w : base->workers )
+      w->needreset = true;          // the node may have changed since the last batch
+
+   std::vector<int64_t> inflight((size_t)nworkers, -1);
+   auto finish = [&](int wi) -> int {
+      gpulin* w = base->workers[(size_t)wi];
+      const int64_t i = inflight[(size_t)wi];
+      gpulin_result r;
+      OK(gpulin_propagate_wait(w, &r));
+      if( status != nullptr ) status[i] = r.status;
+      if( nrounds != nullptr ) nrounds[i] = r.nrounds;
+      if( nchanges != nullptr ) nchanges[i] = r.nchanges;
+      // after a fixpoint nothing is marked and the log names every column that moved: cheap backtrack next time
+      w->needreset = !(r.status == GPULIN_FIXPOINT && (int64_t)w->h_ctrl->logcount <= w->logcap);
+      inflight[(size_t)wi] = -1;
+      return GPULIN_OK;
+   };
+   for( int64_t i = 0; i < nprobes; ++i )
+   {
+      const int wi = (int)(i % nworkers);
+      gpulin* w = base->workers[(size_t)wi];
+      if( inflight[(size_t)wi] >= 0 )
+         OK(finish(wi));
+      if( w->needreset )
+         OK(gpulin_reset_from(w, base));
+      else
+         restore_kernel<<<1, 256, 0, w->stream>>>(w->p, base->p, w->lastvar);
+      update_one_kernel<<<1, 32, 0, w->stream>>>(w->p, var[i], lb[i], ub[i]);
+      CU(cudaGetLastError());
+      w->lastvar = var[i];
+      OK(gpulin_propagate_async(w, maxrounds));
+      inflight[(size_t)wi] = i;
+   }
+   for( int wi = 0; wi < nworkers; ++wi )
+   {
+      if( inflight[(size_t)wi] >= 0 )
+         OK(finish(wi));
+   }
    return GPULIN_OK;
 }
 

@@ -1343,6 +1343,33 @@ __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const i
    }
 }
 
+// probing: one bound change passed by value (SCIPchgVarLbProbing / SCIPchgVarUbProbing), rows of the column marked
+__global__ void update_one_kernel(const DevProblem p, int j, double l, double u)
+{
+   if( threadIdx.x == 0 )
+   {
+      l += 0.0;
+      u += 0.0;
+      const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
+      reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+   }
+   markColumnRows(p, j, threadIdx.x, blockDim.x);
+}
+
+// probing backtrack (SCIPbacktrackProbing): the columns the last probe changed -- they are in its change log -- and
+// the probed column itself take the bounds of the node again; everything else was never touched
+__global__ void restore_kernel(const DevProblem p, const DevProblem base, int probedvar)
+{
+   const unsigned long long n = min(p.ctrl->logcount, (unsigned long long)p.ctrl->logcap);
+   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+   for( unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride )
+   {
+      const int j = i < n ? p.log[i].var : probedvar;
+      const_cast<double2*>(p.bnd)[j] = base.bnd[j];
+      reinterpret_cast<longlong2*>(p.cand)[j] = reinterpret_cast<const longlong2*>(base.cand)[j];
+   }
+}
+
 __global__ void get_bounds_kernel(const DevProblem p, double* lb, double* ub)
 {
    const int stride = gridDim.x * blockDim.x;

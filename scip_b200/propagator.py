@@ -52,6 +52,7 @@ _SIGNATURES = {
     "gpulin_propagate_wait": (ctypes.c_int, [_P, ctypes.POINTER(Result)]),
     "gpulin_clone": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "gpulin_reset_from": (ctypes.c_int, [_P, _P]),
+    "gpulin_probe_batch": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, _P, _P, _P, ctypes.c_int, _P, _P, _P]),
     "gpulin_get_bounds": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_get_bounds_device": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_set_change_log": (ctypes.c_int, [_P, ctypes.c_int64]),
@@ -228,6 +229,19 @@ class LinearPropagator:
     def update_bounds_nosync(self, idx, lb, ub):
         """like update_bounds, but the (numpy, contiguous) arrays must stay alive until the stream has consumed them"""
         _check(self._lib.gpulin_update_bounds(self._h, len(idx), idx.ctypes.data, lb.ctypes.data, ub.ctypes.data))
+
+    def probe_batch(self, var, lb, ub, nworkers: int = 32, maxrounds: int = 0) -> dict:
+        """probe i: column var[i] set to [lb[i], ub[i]] on top of this handle's bounds, propagated to its fixpoint"""
+        var = np.ascontiguousarray(var, dtype=np.int32)
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        n = len(var)
+        status = np.zeros(n, dtype=np.int32)
+        nrounds = np.zeros(n, dtype=np.int32)
+        nchanges = np.zeros(n, dtype=np.int64)
+        _check(self._lib.gpulin_probe_batch(self._h, int(nworkers), n, var.ctypes.data, lb.ctypes.data, ub.ctypes.data,
+                                            int(maxrounds), status.ctypes.data, nrounds.ctypes.data, nchanges.ctypes.data))
+        return dict(status=status, nrounds=nrounds, nchanges=nchanges)
 
     def round_stats(self, maxn: int = 1024):
         ms = np.zeros(maxn, dtype=np.float64)

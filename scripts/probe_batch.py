@@ -23,7 +23,7 @@ def main():
     still = nlb[var] < nub[var]
     var, val = var[still].astype(np.int32), val[still].astype(np.float64)
     print(f"{len(var)} of 1024 probe variables are still free at the node")
-    for nworkers in (1, 8, 32, 64):
+    for nworkers in (1, 32):
         pb = ProbingBatch(base, nworkers=nworkers)
         pb.run(var[:64], val[:64], val[:64])
         t0 = time.perf_counter()
@@ -33,6 +33,15 @@ def main():
         print(f"workers {nworkers:3d}: {dt*1e3:8.1f} ms for {len(var)} probes = {dt/len(var)*1e6:7.1f} us/probe; "
               f"cutoffs {int((res['status']==1).sum())}, mean rounds {res['nrounds'].mean():.2f}, "
               f"mean changes {res['nchanges'].mean():.1f}")
+
+
+    for nworkers in (1, 8, 32, 64, 128):
+        base.probe_batch(var[:256], val[:256], val[:256], nworkers=nworkers)
+        t0 = time.perf_counter()
+        res = base.probe_batch(var, val, val, nworkers=nworkers)
+        dt = time.perf_counter() - t0
+        print(f"native, workers {nworkers:3d}: {dt*1e3:8.1f} ms for {len(var)} probes = {dt/len(var)*1e6:7.1f} us/probe; "
+              f"cutoffs {int((res['status']==1).sum())}, mean rounds {res['nrounds'].mean():.2f}")
 
 
 if __name__ == "__main__":

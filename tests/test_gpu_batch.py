@@ -22,6 +22,11 @@ def _check_batch(gpulin, prob, var, lb, ub, nworkers, **numerics):
             again = pb.run(var, lb, ub)                      # the workers are reusable; results are reproducible
         finally:
             pb.close()
+        # the native batch entry point (clones kept inside the handle, backtracking by undoing the change log)
+        nat1 = base.probe_batch(var, lb, ub, nworkers=min(nworkers, 4))
+        nat2 = base.probe_batch(var, lb, ub, nworkers=min(nworkers, 4))     # second batch: workers restore from their logs
+        for k in ("status", "nrounds", "nchanges"):
+            assert np.array_equal(nat1[k], res[k]) and np.array_equal(nat2[k], res[k]), k
         blb, bub = base.get_bounds()
         assert np.array_equal(blb, nlb) and np.array_equal(bub, nub)      # the node itself is untouched
     assert np.array_equal(res["status"], again["status"]) and np.array_equal(res["nchanges"], again["nchanges"])
