@@ -8,7 +8,12 @@
  *      SCIPgetVarsLinear / SCIPgetValsLinear / SCIPgetLhsLinear / SCIPgetRhsLinear (cons_linear.h:263-307), columns =
  *      SCIPvarGetProbindex (pub_var.h:592); tolerances from SCIPinfinity/SCIPepsilon/SCIPsumepsilon/SCIPfeastol/
  *      SCIPgetHugeValue and numerics/boundstreps, constraints/linear/maxeasyactivitydelta;
- *   2. send the local bounds of all variables (SCIPvarGetLbLocal/UbLocal) through gpulin_set_bounds;
+ *   2. bring the device bounds up to date: the first call after a (re)build sends all local bounds
+ *      (SCIPvarGetLbLocal/UbLocal, gpulin_set_bounds); later calls send only the bounds that changed since the last
+ *      call -- an event handler catches SCIP_EVENTTYPE_BOUNDCHANGED of every variable (SCIPcatchVarEvent,
+ *      scip_event.h:254), exactly as cons_linear does for its rows (cons_linear.c:717-754, eventExecLinear :17162) --
+ *      through gpulin_update_bounds, which marks only the rows of those columns (cost proportional to the changes:
+ *      branching, backtracking, other propagators);
  *   3. gpulin_propagate: all rounds to the fixpoint on the GPU (no host round trip per round);
  *   4. replay the round-ordered change log with SCIPinferVarLbProp / SCIPinferVarUbProp (scip_var.c:7589/7705,
  *      force = TRUE: the relative threshold numerics/boundstreps was already applied on the device per inference);
@@ -26,6 +31,8 @@
 
 #include "scip/cons_linear.h"
 #include "scip/pub_cons.h"
+#include "scip/pub_event.h"
+#include "scip/scip_event.h"
 #include "scip/pub_message.h"
 #include "scip/pub_prop.h"
 #include "scip/pub_var.h"
@@ -52,6 +59,9 @@
 #define DEFAULT_MAXROUNDS      -1         /* rounds per call on the device (-1: to the fixpoint) */
 #define DEFAULT_DEVICE         0
 #define DEFAULT_LOGCAPFAC      8          /* change log capacity = factor * number of variables */
+#define DEFAULT_INCREMENTAL    TRUE       /* send only changed bounds (event driven) instead of all bounds per call */
+#define EVENTHDLR_NAME         "gpulinear"
+#define EVENTHDLR_DESC         "collects the variables whose bounds changed since the last call of prop_gpulinear"
 
 struct SCIP_PropData
 {
@@ -75,6 +85,17 @@ struct SCIP_PropData
    int64_t               logcap;
    int                   nlinconss;          /**< active linear constraints when the device copy was built */
    int                   nskipped;           /**< rows not sent to the device (modifiable, local, non-active variables) */
+   SCIP_EVENTHDLR*       eventhdlr;          /**< bound change event handler */
+   int*                  filterpos;          /**< per column: position of the caught event, or -1 */
+   int*                  touched;            /**< columns whose bounds changed since the last call */
+   SCIP_Bool*            istouched;          /**< per column: already in touched[] */
+   int32_t*              updidx;             /**< staging of gpulin_update_bounds */
+   int                   ntouched;
+   SCIP_Bool             fullsync;           /**< the next call must send all bounds */
+   SCIP_Bool             inreplay;           /**< bound changes are our own: the device already has them */
+   SCIP_Bool             incremental;        /**< parameter */
+   SCIP_Longint          nfullsyncs;
+   SCIP_Longint          nupdates;           /**< bounds sent through gpulin_update_bounds */
    int                   maxrounds;          /**< parameter */
    int                   device;             /**< parameter */
    SCIP_Longint          ncalls;
@@ -95,6 +116,25 @@ void freeDeviceCopy(
       gpulin_destroy(propdata->gpu);
       propdata->gpu = NULL;
    }
+   if( propdata->filterpos != NULL )
+   {
+      int j;
+      for( j = 0; j < propdata->ncols; ++j )
+      {
+         if( propdata->filterpos[j] >= 0 )
+         {
+            SCIP_RETCODE rc = SCIPdropVarEvent(scip, propdata->vars[j], SCIP_EVENTTYPE_BOUNDCHANGED, propdata->eventhdlr,
+               (SCIP_EVENTDATA*)(size_t)(j + 1), propdata->filterpos[j]);
+            if( rc != SCIP_OKAY )
+               SCIPwarningMessage(scip, "prop_gpulinear: could not drop the bound change event of column %d\n", j);
+         }
+      }
+   }
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->filterpos, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->touched, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->istouched, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->updidx, propdata->ncols);
+   propdata->ntouched = 0;
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->vars, propdata->ncols);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->lb, propdata->ncols);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->ub, propdata->ncols);
@@ -287,11 +327,66 @@ SCIP_RETCODE buildDeviceCopy(
       return SCIP_ERROR;
    }
 
+   /* from now on every bound change of a column is noted (cf. consCatchAllEvents, cons_linear.c:717) */
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->filterpos, ncols) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->touched, ncols) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->istouched, ncols) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->updidx, ncols) );
+   for( j = 0; j < ncols; ++j )
+   {
+      propdata->filterpos[j] = -1;
+      propdata->istouched[j] = FALSE;
+   }
+   propdata->ntouched = 0;
+   propdata->fullsync = TRUE;
+   if( propdata->incremental && propdata->eventhdlr != NULL )
+   {
+      for( j = 0; j < ncols; ++j )
+      {
+         SCIP_CALL( SCIPcatchVarEvent(scip, propdata->vars[j], SCIP_EVENTTYPE_BOUNDCHANGED, propdata->eventhdlr,
+               (SCIP_EVENTDATA*)(size_t)(j + 1), &propdata->filterpos[j]) );
+      }
+   }
+
    SCIPverbMessage(scip, SCIP_VERBLEVEL_FULL, NULL,
       "prop_gpulinear: device copy of %d linear rows (%d skipped), %d columns, %lld nonzeros\n", nrows, propdata->nskipped,
       ncols, (long long)propdata->nnz);
 
    return SCIP_OKAY;
+}
+
+/** execution method of the event handler: remembers the column (the device copy of its bounds is stale now) */
+static
+SCIP_DECL_EVENTEXEC(eventExecGpulinear)
+{
+   SCIP_PROPDATA* propdata = (SCIP_PROPDATA*)SCIPeventhdlrGetData(eventhdlr);
+   const int j = (int)(size_t)eventdata - 1;
+
+   (void)scip;
+   (void)event;
+   assert(propdata != NULL);
+   if( propdata->inreplay || propdata->istouched == NULL || j < 0 || j >= propdata->ncols )
+      return SCIP_OKAY;
+   if( !propdata->istouched[j] )
+   {
+      propdata->istouched[j] = TRUE;
+      propdata->touched[propdata->ntouched++] = j;
+   }
+   return SCIP_OKAY;
+}
+
+/** a bound SCIP holds differs from what the device holds (SCIP adjusted or rejected a replayed change) */
+static
+void noteMismatch(
+   SCIP_PROPDATA*        propdata,
+   int                   j
+   )
+{
+   if( propdata->istouched != NULL && !propdata->istouched[j] )
+   {
+      propdata->istouched[j] = TRUE;
+      propdata->touched[propdata->ntouched++] = j;
+   }
 }
 
 /*
@@ -325,8 +420,9 @@ SCIP_DECL_PROPEXITSOL(propExitsolGpulinear)
    if( propdata->ncalls > 0 )
    {
       SCIPverbMessage(scip, SCIP_VERBLEVEL_FULL, NULL,
-         "prop_gpulinear: %lld calls, %lld device rounds, %lld bound changes, %.3f ms on the device\n",
-         (long long)propdata->ncalls, (long long)propdata->nrounds, (long long)propdata->nchanges, propdata->devicems);
+         "prop_gpulinear: %lld calls (%lld full bound uploads, %lld single bounds sent), %lld device rounds, %lld bound changes, "
+         "%.3f ms on the device\n", (long long)propdata->ncalls, (long long)propdata->nfullsyncs, (long long)propdata->nupdates,
+         (long long)propdata->nrounds, (long long)propdata->nchanges, propdata->devicems);
    }
    freeDeviceCopy(scip, propdata);
 
@@ -367,13 +463,35 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
 
    *result = SCIP_DIDNOTFIND;
 
-   /* bounds of the current node */
-   for( j = 0; j < propdata->ncols; ++j )
+   /* bounds of the current node: everything after a (re)build or a cutoff, else only what changed since the last call */
+   if( propdata->fullsync || !propdata->incremental )
    {
-      propdata->lb[j] = SCIPvarGetLbLocal(propdata->vars[j]);
-      propdata->ub[j] = SCIPvarGetUbLocal(propdata->vars[j]);
+      for( j = 0; j < propdata->ncols; ++j )
+      {
+         propdata->lb[j] = SCIPvarGetLbLocal(propdata->vars[j]);
+         propdata->ub[j] = SCIPvarGetUbLocal(propdata->vars[j]);
+         propdata->istouched[j] = FALSE;
+      }
+      propdata->ntouched = 0;
+      propdata->fullsync = FALSE;
+      ++propdata->nfullsyncs;
+      rc = gpulin_set_bounds(propdata->gpu, propdata->lb, propdata->ub);
    }
-   rc = gpulin_set_bounds(propdata->gpu, propdata->lb, propdata->ub);
+   else
+   {
+      int n = propdata->ntouched;
+      for( j = 0; j < n; ++j )
+      {
+         const int col = propdata->touched[j];
+         propdata->updidx[j] = col;
+         propdata->lb[j] = SCIPvarGetLbLocal(propdata->vars[col]);
+         propdata->ub[j] = SCIPvarGetUbLocal(propdata->vars[col]);
+         propdata->istouched[col] = FALSE;
+      }
+      propdata->ntouched = 0;
+      propdata->nupdates += n;
+      rc = gpulin_update_bounds(propdata->gpu, n, propdata->updidx, propdata->lb, propdata->ub);
+   }
    if( rc == GPULIN_OK )
       rc = gpulin_propagate(propdata->gpu, propdata->maxrounds < 0 ? 0 : propdata->maxrounds, &res);
    if( rc != GPULIN_OK )
@@ -388,6 +506,8 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
 
    if( res.status == GPULIN_CUTOFF )
    {
+      /* the device bounds moved on a path SCIP never saw: start over from SCIP's bounds next time */
+      propdata->fullsync = TRUE;
       *result = SCIP_CUTOFF;
       return SCIP_OKAY;
    }
@@ -407,25 +527,35 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
       for( e = 0; e < nlog; ++e )
       {
          const gpulin_change* chg = &propdata->changes[e];
+         SCIP_VAR* var = propdata->vars[chg->var];
          SCIP_Bool infeasible;
          SCIP_Bool tightened;
+         SCIP_RETCODE retcode;
 
+         propdata->inreplay = TRUE;      /* the device already holds this bound */
          if( chg->is_upper )
-            SCIP_CALL( SCIPinferVarUbProp(scip, propdata->vars[chg->var], chg->newbound, prop, 1, TRUE, &infeasible, &tightened) );
+            retcode = SCIPinferVarUbProp(scip, var, chg->newbound, prop, 1, TRUE, &infeasible, &tightened);
          else
-            SCIP_CALL( SCIPinferVarLbProp(scip, propdata->vars[chg->var], chg->newbound, prop, 0, TRUE, &infeasible, &tightened) );
+            retcode = SCIPinferVarLbProp(scip, var, chg->newbound, prop, 0, TRUE, &infeasible, &tightened);
+         propdata->inreplay = FALSE;
+         SCIP_CALL( retcode );
          if( infeasible )
          {
+            propdata->fullsync = TRUE;
             *result = SCIP_CUTOFF;
             return SCIP_OKAY;
          }
          if( tightened )
             ++ntightened;
+         /* SCIP may have adjusted or declined the value: then the device copy of this column is stale */
+         if( (chg->is_upper ? SCIPvarGetUbLocal(var) : SCIPvarGetLbLocal(var)) != chg->newbound )
+            noteMismatch(propdata, chg->var);
       }
    }
    else
    {
       /* the log overflowed: hand over the final bounds (no valid replay order: PROPRESPROP may fail for them) */
+      propdata->fullsync = TRUE;
       rc = gpulin_get_bounds(propdata->gpu, propdata->lb, propdata->ub);
       if( rc != GPULIN_OK )
       {
@@ -574,6 +704,9 @@ SCIP_RETCODE SCIPincludePropGpulinear(
          propExecGpulinear, propdata) );
    assert(prop != NULL);
 
+   SCIP_CALL( SCIPincludeEventhdlrBasic(scip, &propdata->eventhdlr, EVENTHDLR_NAME, EVENTHDLR_DESC, eventExecGpulinear,
+         (SCIP_EVENTHDLRDATA*)propdata) );
+
    /* PROPCOPY stays NULL: sub-SCIPs and concurrent copies do not get a GPU propagator */
    SCIP_CALL( SCIPsetPropFree(scip, prop, propFreeGpulinear) );
    SCIP_CALL( SCIPsetPropExitsol(scip, prop, propExitsolGpulinear) );
@@ -582,6 +715,9 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/maxdevicerounds",
          "maximal number of propagation rounds per call on the device (-1: to the fixpoint)",
          &propdata->maxrounds, FALSE, DEFAULT_MAXROUNDS, -1, INT_MAX, NULL, NULL) );
+   SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/incremental",
+         "send only the bounds that changed since the last call (bound change events) instead of all bounds",
+         &propdata->incremental, FALSE, DEFAULT_INCREMENTAL, NULL, NULL) );
    SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/device",
          "CUDA device ordinal",
          &propdata->device, TRUE, DEFAULT_DEVICE, 0, 1023, NULL, NULL) );
