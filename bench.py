@@ -51,6 +51,15 @@ CPU_SAMPLE = dict(desc="set-cover 200k rows x 200k binaries, 2M nnz, seed 1 (1/5
                   gen=lambda synth: synth.setcover(200_000, 200_000, 2_000_000, seed=1))
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -297,8 +306,10 @@ def run_ours(args):
         exact_ms = statistics.mean(p[1] for p in prof)
         apply_ms = statistics.mean(p[2] for p in prof)
         achieved = abytes / (sweep_ms * 1e-3) / 1e9
-        line["roofline"] = dict(bound="hbm", kernel="sweep_short_kernel (filter sweep of one full round)", achieved=achieved,
-                                peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src, traffic=None,
+        kname = {"c3": "sweep_sell_kernel", "c3small": "sweep_sell_kernel", "c4": "sweep_stream_kernel"}[args.workload]
+        line["roofline"] = dict(bound="hbm", kernel=f"{kname} (filter sweep of one full round)", achieved=achieved,
+                                peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src,
+                                traffic=measured_traffic(f"{kname}:{args.workload}"),
                                 algorithmic_bytes=abytes, kernel_us=sweep_ms * 1e3,
                                 full_round_us=(sweep_ms + exact_ms + apply_ms) * 1e3,
                                 full_round_frac=abytes / ((sweep_ms + exact_ms + apply_ms) * 1e-3) / 1e9 / peak)
