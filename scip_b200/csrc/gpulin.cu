@@ -70,6 +70,7 @@ struct gpulin
    int         nlongblocks = 0;
    int         napplyblocks = 0;
    int         nexactblocks = 0;
+   int         nsparseblocks = 0;   // grid of the persistent sparse-rounds kernel (0: disabled)
    int         nsm = 148;
    std::vector<int> perm;        // permuted row -> caller's row
    // device allocations
@@ -227,6 +228,13 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
       apply_kernel<MODE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
       if( MODE == APPLY_PEERS )
          peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);      // nobody commits into keys that are still being read
+      if( MODE == APPLY_LIST && sweep && h->nsparseblocks > 0 )
+      {
+         // rounds with few marked rows are run by one persistent cooperative kernel (returns at once otherwise)
+         void* args[2] = {(void*)&h->p, (void*)&h->handle};
+         CU(cudaLaunchCooperativeKernel((const void*)sparse_rounds_kernel<GRAPH>, dim3(h->nsparseblocks), dim3(SPARSE_THREADS),
+            args, 0, h->stream));
+      }
    }
    CU(cudaGetLastError());
    return GPULIN_OK;
@@ -460,7 +468,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    DevProblem& p = h->p;
    long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
    int* d_tile_row0; unsigned char* d_endmask; unsigned char* d_tileflag;
-   int* d_xlist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned* d_colbits; int* d_chglist; long long* d_colbeg; int* d_colrows;
+   int* d_xlist; int* d_marklist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned* d_colbits; int* d_chglist; long long* d_colbeg; int* d_colrows;
    Ctrl* d_ctrl;
    int rc = GPULIN_OK;
 #define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
@@ -476,6 +484,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &d_sides, (size_t)nrows + 1, true));
    TRY(devAlloc(h, &d_dirty, (size_t)nrows + 64));
    TRY(devAlloc(h, &d_xlist, (size_t)nrows + 1));
+   TRY(devAlloc(h, &d_marklist, (size_t)6 * MARKCAP));
    TRY(devAlloc(h, &d_bnd, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)ncols + 2));
    TRY(devAlloc(h, &d_colbits, (size_t)ncols / 32 + 2));
@@ -558,6 +567,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.sides = d_sides;
    p.dirty = d_dirty;
    p.xlist = d_xlist;
+   p.marklist = d_marklist;
    p.bnd = d_bnd;
    p.cand = d_cand;
    p.colbits = d_colbits;
@@ -614,6 +624,13 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_rows_kernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
+      // the sparse-rounds kernel: one block per SM (all must be co-resident: grid syncs); GPULIN_SPARSE=0 disables it
+      int coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+      const char* se = getenv("GPULIN_SPARSE");
+      if( coop && !(se != nullptr && atoi(se) == 0)
+         && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sparse_rounds_kernel<true>, SPARSE_THREADS, 0) == cudaSuccess && occ >= 1 )
+         h->nsparseblocks = h->nsm;
    }
 
    if( !h->hostloop )
@@ -953,15 +970,17 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    h->nstreamelems = src->nstreamelems; h->maxlen = src->maxlen;
    h->sellvariant = src->sellvariant; h->nsellblocks = src->nsellblocks; h->nstreamblocks = src->nstreamblocks;
    h->nlongblocks = src->nlongblocks; h->napplyblocks = src->napplyblocks; h->nexactblocks = src->nexactblocks;
+   h->nsparseblocks = src->nsparseblocks;
    h->nsm = src->nsm; h->hostloop = src->hostloop; h->perm = src->perm;
    h->p = src->p;
    DevProblem& p = h->p;
    unsigned char* d_dirty; unsigned char* d_tileflag; int* d_xlist; double2* d_bnd; long long* d_cand; unsigned* d_colbits;
-   int* d_chglist; Ctrl* d_ctrl;
+   int* d_chglist; Ctrl* d_ctrl; int* d_marklist;
    int rc = GPULIN_OK;
    TRY(devAlloc(h, &d_dirty, (size_t)h->nrows + 64));
    TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
    TRY(devAlloc(h, &d_xlist, (size_t)h->nrows + 1));
+   TRY(devAlloc(h, &d_marklist, (size_t)6 * MARKCAP));
    TRY(devAlloc(h, &d_bnd, (size_t)h->ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)h->ncols + 2));
    TRY(devAlloc(h, &d_colbits, (size_t)h->ncols / 32 + 2));
@@ -997,6 +1016,7 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    p.dirty = d_dirty;
    p.tileflag = d_tileflag;
    p.xlist = d_xlist;
+   p.marklist = d_marklist;
    p.bnd = d_bnd;
    p.cand = d_cand;
    p.colbits = d_colbits;

@@ -32,6 +32,7 @@ constexpr int TPL = 8;                // nonzeros per lane and tile
 constexpr int STREAM_MAXLEN = 4096;   // longer rows (and empty rows) are swept block-per-row
 constexpr int SHORT_MAXLEN = 32;      // exact kernel: rows up to this length are handled by groups of 8 lanes
 constexpr int NNZ_SLOTS = 64;         // spread counters of the nonzeros swept in a round
+constexpr int MARKCAP = 1 << 15;      // capacity of a mark list; rounds with more marked rows take the dense sweeps
 
 // loop control + statistics, lives in device memory
 struct Ctrl
@@ -52,6 +53,11 @@ struct Ctrl
    unsigned long long total_nnz;
    unsigned long long t_start;      // %globaltimer at the start of the call
    unsigned int       nexact[4];    // rows the filter sweeps handed to the exact kernel in the running round, per list
+   unsigned int       nmark[2][4];  // rows marked (per bin) into mark list buffer 0 / 1; marking writes buffer mb^1
+   unsigned int       mb;           // the buffer the last apply filled = what a sparse round reads
+   unsigned int       stay;         // sparse_rounds_kernel: another sparse round follows
+   unsigned int       nsparse;      // rounds done by sparse_rounds_kernel in this call (statistics)
+   unsigned int       pad1;
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
    unsigned long long hist_time[MAX_HIST];   // %globaltimer at the end of each round
    unsigned long long hist_nnz[MAX_HIST];
@@ -89,6 +95,8 @@ struct DevProblem
    const unsigned char* endmask;   // per tile and lane: bit i = nonzero 8*lane+i is the last of its row
    unsigned char*      tileflag;   // a marked row starts in this tile
    int*                xlist;      // rows handed to exact_rows_kernel, one list per bin: [0,nsell) [nsell,nsx) [nsx,nrows)
+   int*                marklist;   // rows marked by the apply step: [buffer 0|1][bin 0..2][MARKCAP]; complete unless a
+                                   // count exceeds MARKCAP (the dirty flags are the ground truth, the lists a shortcut)
    // columns
    const double2*      bnd;        // (lb, ub) at round start
    long long*          cand;       // 2*ncols (+2) candidate keys, see Sink
@@ -875,20 +883,27 @@ constexpr int EXACT_THREADS = 256;
 constexpr int EXACT_G = 8;                           // lanes per short row
 constexpr int EXACT_Q = SHORT_MAXLEN / EXACT_G;      // elements per lane
 
-__global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProblem p)
+// claims a marked row (sparse rounds: the lists may name a row twice, or a row that a dense sweep finished already)
+__device__ __forceinline__ bool claimRow(const DevProblem& p, int row)
 {
-   __shared__ RowAcc s_acc[EXACT_THREADS / 32];
+   unsigned* word = reinterpret_cast<unsigned*>(p.dirty + (row & ~3));
+   const int shift = 8 * (row & 3);
+   const unsigned old = atomicAnd(word, ~(0xffu << shift));
+   return ((old >> shift) & 0xffu) == ROW_MARKED;
+}
 
-   const unsigned n0 = p.ctrl->nexact[0];
-   const unsigned n1 = p.ctrl->nexact[1];
-   const unsigned n2 = p.ctrl->nexact[2];
-   if( (n0 | n1 | n2) == 0u )
-      return;
+// SPARSE = false: the rows the filter sweeps handed over (xlist);  SPARSE = true: the rows the last apply step marked
+// (marklist) -- in a round with few marked rows the filter pass is skipped and every marked row gets the exact rules
+template <bool SPARSE>
+__device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0, unsigned n0, const int* list1, unsigned n1,
+   const int* list2, unsigned n2, RowAcc* s_acc, int nblockthreads)
+{
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
    const int warp = threadIdx.x >> 5;
-   const int gtid = blockIdx.x * EXACT_THREADS + threadIdx.x;
-   const int nthreads = gridDim.x * EXACT_THREADS;
+   const int gtid = blockIdx.x * nblockthreads + threadIdx.x;
+   const int nthreads = gridDim.x * nblockthreads;
+   unsigned long long nnzdone = 0;
 
    // ---- short rows: EXACT_G lanes per row
    {
@@ -898,16 +913,26 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
       for( unsigned it = 0; it < rounds; ++it )
       {
          const unsigned item = it * ngroups + gtid / EXACT_G;
-         const bool valid = item < n0;
+         bool valid = item < n0;
+         int row = 0;
+         if( valid )
+            row = list0[item];
+         if( SPARSE )
+         {
+            int mine = (valid && gl == 0) ? (claimRow(p, row) ? 1 : 0) : 0;
+            mine = __shfl_sync(0xffffffffu, mine, lane & ~(EXACT_G - 1));
+            valid = mine != 0;
+         }
          int len = 0;
          long long base = 0;
          double2 sd = make_double2(0.0, 0.0);
          if( valid )
          {
-            const int row = p.xlist[item];
             len = p.rowlen[row] & ~ROWLEN_EXACT;
             base = p.sell_off[row >> 5] + (row & 31);
             sd = p.sides[row];
+            if( SPARSE && gl == 0 )
+               nnzdone += (unsigned long long)len;
          }
          double a[EXACT_Q];
          int cj[EXACT_Q];
@@ -982,10 +1007,19 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
       const int nw = nthreads >> 5;
       for( unsigned item = gw; item < n1; item += nw )
       {
-         const int row = p.xlist[p.nsell + item];
+         const int row = list1[item];
+         if( SPARSE )
+         {
+            int mine = lane == 0 ? (claimRow(p, row) ? 1 : 0) : 0;
+            mine = __shfl_sync(0xffffffffu, mine, 0);
+            if( !mine )
+               continue;
+         }
          const int len = p.rowlen[row] & ~ROWLEN_EXACT;
          const long long beg = p.rowbeg[row];
          const double2 sd = p.sides[row];
+         if( SPARSE && lane == 0 )
+            nnzdone += (unsigned long long)len;
          RowAcc acc;
          accInit(acc);
          accumulateExact(p, acc, beg, 1, lane, 32, len);
@@ -997,24 +1031,49 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
    // ---- long rows: one block per row
    for( unsigned item = blockIdx.x; item < n2; item += gridDim.x )
    {
-      const int row = p.xlist[p.nsx + item];
+      const int row = list2[item];
+      __syncthreads();                  // the previous row's shared state has been read by everybody
+      if( SPARSE )
+      {
+         __shared__ int s_mine;
+         if( threadIdx.x == 0 )
+            s_mine = claimRow(p, row) ? 1 : 0;
+         __syncthreads();
+         if( !s_mine )
+            continue;
+      }
       const int len = p.rowlen[row] & ~ROWLEN_EXACT;
       const long long beg = p.rowbeg[row];
       const double2 sd = p.sides[row];
+      if( SPARSE && threadIdx.x == 0 )
+         nnzdone += (unsigned long long)len;
       RowAcc acc;
       accInit(acc);
-      accumulateExact(p, acc, beg, 1, threadIdx.x, EXACT_THREADS, len);
+      accumulateExact(p, acc, beg, 1, threadIdx.x, nblockthreads, len);
       accWarpReduce(acc, lane);
-      __syncthreads();                  // the previous row's s_acc has been read by everybody
       if( lane == 0 )
          s_acc[warp] = acc;
       __syncthreads();
       acc = s_acc[0];
 #pragma unroll 1
-      for( int w = 1; w < EXACT_THREADS / 32; ++w )
+      for( int w = 1; w < nblockthreads / 32; ++w )
          accMerge(acc, s_acc[w]);
-      rowTighten(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, EXACT_THREADS, len);
+      rowTighten(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, nblockthreads, len);
    }
+   if( SPARSE && nnzdone != 0 )
+      addRoundNnz(p, nnzdone, gtid >> 5);
+}
+
+__global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProblem p)
+{
+   __shared__ RowAcc s_acc[EXACT_THREADS / 32];
+
+   const unsigned n0 = p.ctrl->nexact[0];
+   const unsigned n1 = p.ctrl->nexact[1];
+   const unsigned n2 = p.ctrl->nexact[2];
+   if( (n0 | n1 | n2) == 0u )
+      return;
+   exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, EXACT_THREADS);
 }
 
 // ---- accept the new bounds of one column; returns the number of changed bounds (0..2) -------------------------
@@ -1078,6 +1137,18 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
             p.dirty[r[t]] = ROW_MARKED;
             if( r[t] >= p.nsell && r[t] < p.nsx )
                p.tileflag[(rb[t] - p.streambase) >> 8] = 1;
+            // note the row for a sparse round (two columns racing for the same row may both note it: harmless)
+            const int bin = r[t] < p.nsell ? 0 : (r[t] < p.nsx ? 1 : 2);
+            const unsigned wb = p.ctrl->mb ^ 1u;
+            const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+            const unsigned same = g.match_any(bin);
+            const int leader = __ffs(same) - 1;
+            unsigned pos = 0u;
+            if( (int)g.thread_rank() == leader )
+               pos = atomicAdd(&p.ctrl->nmark[wb][bin], (unsigned)__popc(same));
+            pos = g.shfl(pos, leader) + (unsigned)__popc(same & ((1u << g.thread_rank()) - 1u));
+            if( pos < (unsigned)MARKCAP )
+               p.marklist[(wb * 3 + bin) * MARKCAP + pos] = r[t];
          }
       }
    }
@@ -1107,6 +1178,9 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
    c->ticket = 0;
    c->nchgcols = 0;
    c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
+   // the list this apply step filled becomes the one a sparse round reads; the other one is empty again
+   c->nmark[c->mb][0] = c->nmark[c->mb][1] = c->nmark[c->mb][2] = 0;
+   c->mb ^= 1u;
    c->round = r + 1;
    int cont = 0;
    if( c->cutoff )
@@ -1121,6 +1195,9 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
    if( GRAPH )
       cudaGraphSetConditional(handle, (unsigned)cont);
 }
+
+constexpr int APPLY_THREADS = 256;
+constexpr int APPLY_G = 8;
 
 // appends the accepted changes of column j to the round-ordered change log
 __device__ __forceinline__ void logChanges(const DevProblem& p, int j, int round, int logcap, int nc, bool lbchg, bool ubchg,
@@ -1145,14 +1222,48 @@ __device__ __forceinline__ void logChanges(const DevProblem& p, int j, int round
    }
 }
 
+// the columns on the change list of this round, eight lanes per column: one accepts the bounds, all mark the rows of the
+// column; returns the number of bound changes this thread accepted
+__device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlist, int gtid, int nthreads, int round, int logcap)
+{
+   const int gl = gtid & (APPLY_G - 1);
+   const int ngroups = nthreads / APPLY_G;
+   const unsigned trips = (nlist + ngroups - 1) / ngroups;       // warp-uniform
+   int mychg = 0;
+   for( unsigned it = 0; it < trips; ++it )
+   {
+      const unsigned item = it * ngroups + gtid / APPLY_G;
+      const bool valid = item < nlist;
+      int j = 0;
+      if( valid )
+      {
+         j = p.chglist[item];
+         if( gl == 0 )
+         {
+            bool lbchg;
+            bool ubchg;
+            double2 nb;
+            const int nc = applyColumn(p, j, nb, lbchg, ubchg);
+            atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
+            if( nc > 0 && logcap > 0 )
+               logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
+            mychg += nc;
+         }
+      }
+      // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
+      // clamped back to its old value is the one exception): the group marks without waiting for the verdict
+      if( valid )
+         markColumnRows(p, j, gl, APPLY_G);
+   }
+   return mychg;
+}
+
 // DENSE = false: the columns on the change list of this round -- cost proportional to the changes (single GPU);
 //                eight lanes per column: one accepts the bounds, all mark the rows of the column;
 // DENSE = true : every column compares its (all-reduced) candidate keys with its bounds (rows sharded over ranks:
 //                a key may have been moved by another rank)
 //         PEERS: the changed-column bits (raised on every rank by every rank's exact kernel) are scanned, a word per
 //                thread; all ranks hold the same keys and bits, so they all accept the same changes
-constexpr int APPLY_THREADS = 256;
-constexpr int APPLY_G = 8;
 constexpr int APPLY_LIST = 0;
 constexpr int APPLY_DENSE = 1;
 constexpr int APPLY_PEERS = 2;
@@ -1224,37 +1335,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
       }
    }
    else
-   {
-      const int gl = lane & (APPLY_G - 1);
-      const int ngroups = nthreads / APPLY_G;
-      const unsigned trips = (nlist + ngroups - 1) / ngroups;       // warp-uniform
-      for( unsigned it = 0; it < trips; ++it )
-      {
-         const unsigned item = it * ngroups + gtid / APPLY_G;
-         const bool valid = item < nlist;
-         int j = 0;
-         int nc = 0;
-         if( valid )
-         {
-            j = p.chglist[item];
-            if( gl == 0 )
-            {
-               bool lbchg;
-               bool ubchg;
-               double2 nb;
-               nc = applyColumn(p, j, nb, lbchg, ubchg);
-               atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
-               if( nc > 0 && logcap > 0 )
-                  logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
-               mychg += nc;
-            }
-         }
-         // every candidate that reached the column beat the round-start bound, so nc > 0 for listed columns (a
-         // crossing pair clamped back to its old value is the one exception): the group marks without waiting
-         if( valid )
-            markColumnRows(p, j, gl, APPLY_G);
-      }
-   }
+      mychg += applyListPhase(p, nlist, gtid, nthreads, round, logcap);
    mychg = __reduce_add_sync(0xffffffffu, mychg);
    if( lane == 0 && mychg != 0 )
       atomicAdd(&s_nchg, mychg);
@@ -1270,6 +1351,70 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
          __threadfence();
          controlStep<GRAPH>(c, handle);
       }
+   }
+}
+
+// ---- sparse rounds: a persistent cooperative kernel ----------------------------------------------------------------
+// Once the bounds have nearly settled a round touches a few hundred rows, and three launches plus a graph-loop iteration
+// cost more than the work.  This kernel follows the apply step inside the loop body: as long as the last apply marked
+// at most SPARSE_MAXROWS rows (all of them on the mark list) it runs whole rounds by itself -- exact rules for the marked
+// rows, grid sync, apply for the changed columns, grid sync, loop control -- and leaves when a round is not sparse any
+// more or the loop ends.  The filter pass is skipped in these rounds: every marked row gets the exact rules.
+constexpr int SPARSE_THREADS = 256;
+constexpr unsigned SPARSE_MAXROWS = 16384;
+
+template <bool GRAPH>
+__global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
+{
+   __shared__ RowAcc s_acc[SPARSE_THREADS / 32];
+   __shared__ int s_nchg;
+   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+   Ctrl* c = p.ctrl;
+   const int lane = threadIdx.x & 31;
+   const int gtid = blockIdx.x * SPARSE_THREADS + threadIdx.x;
+   const int nthreads = gridDim.x * SPARSE_THREADS;
+
+   for( ;; )
+   {
+      // every thread reads the same state: it was written before the previous grid sync (or by the apply kernel)
+      const unsigned mb = c->mb;
+      const unsigned n0 = c->nmark[mb][0];
+      const unsigned n1 = c->nmark[mb][1];
+      const unsigned n2 = c->nmark[mb][2];
+      const bool sparse = c->cont != 0 && n0 <= (unsigned)MARKCAP && n1 <= (unsigned)MARKCAP && n2 <= (unsigned)MARKCAP
+         && n0 + n1 + n2 <= SPARSE_MAXROWS && n2 <= 64u;
+      if( !sparse )
+         break;
+      if( threadIdx.x == 0 )
+         s_nchg = 0;
+
+      // ---- the exact rules for the marked rows
+      const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
+      exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, SPARSE_THREADS);
+      __threadfence();
+      grid.sync();
+
+      // ---- accept the changes, mark the rows of the changed columns (into the other mark list)
+      const int round = c->round;
+      const unsigned nlist = c->nchgcols;
+      int mychg = applyListPhase(p, nlist, gtid, nthreads, round, c->logcap);
+      mychg = __reduce_add_sync(0xffffffffu, mychg);
+      if( lane == 0 && mychg != 0 )
+         atomicAdd(&s_nchg, mychg);
+      __syncthreads();
+      if( threadIdx.x == 0 && s_nchg != 0 )
+         atomicAdd(&c->round_nchg, (unsigned long long)s_nchg);
+      __threadfence();
+      grid.sync();
+
+      // ---- loop control
+      if( gtid == 0 )
+      {
+         controlStep<GRAPH>(c, handle);
+         ++c->nsparse;
+         __threadfence();
+      }
+      grid.sync();
    }
 }
 
@@ -1400,6 +1545,9 @@ __global__ void begin_kernel(Ctrl* c)
    c->ticket = 0;
    c->nchgcols = 0;
    c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
+   c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
+   c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
+   c->nsparse = 0;
    c->logcount = 0;
    c->round_nchg = 0;
    for( int i = 0; i < NNZ_SLOTS; ++i )
