@@ -306,7 +306,7 @@ def run_ours(args):
         exact_ms = statistics.mean(p[1] for p in prof)
         apply_ms = statistics.mean(p[2] for p in prof)
         achieved = abytes / (sweep_ms * 1e-3) / 1e9
-        kname = {"c3": "sweep_sell_kernel", "c3small": "sweep_sell_kernel", "c4": "sweep_stream_kernel"}[args.workload]
+        kname = {"c3": "sweep_sell_bits_kernel", "c3small": "sweep_sell_kernel", "c4": "sweep_stream_kernel"}[args.workload]
         line["roofline"] = dict(bound="hbm", kernel=f"{kname} (filter sweep of one full round)", achieved=achieved,
                                 peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src,
                                 traffic=measured_traffic(f"{kname}:{args.workload}"),

@@ -71,10 +71,13 @@ struct gpulin
    int         napplyblocks = 0;
    int         nexactblocks = 0;
    int         nsparseblocks = 0;   // grid of the persistent sparse-rounds kernel (0: disabled)
+   int         nsellbitsblocks = 0; // grid of sweep_sell_bits_kernel (0: the gather variant is used)
+   int         sellbitsvariant = 0;
+   size_t      freebytes = 0;       // size of the freebits array
    int         nsm = 148;
    std::vector<int> perm;        // permuted row -> caller's row
    // device allocations
-   void*       d_all[24] = {nullptr};
+   void*       d_all[32] = {nullptr};
    int         nalloc = 0;
    size_t      devbytes = 0;
    double*     d_tmplb = nullptr;   // staging for set/get_bounds
@@ -181,6 +184,25 @@ static const SellKernel g_sellKernels[] = {
 };
 constexpr int NSELLVARIANTS = sizeof(g_sellKernels) / sizeof(g_sellKernels[0]);
 
+// dynamic shared memory of sweep_sell_bits_kernel: bit table, rings, mbarriers + descriptors
+static size_t sellBitsSmem(int nfreewords)
+{
+   return (((size_t)nfreewords * 4 + 127) & ~(size_t)127) + SB_AUX_BYTES;
+}
+
+// instances of the bit-table sweep: {threads per block, nonzeros per thread and chunk, midpoint form, table covers all
+// columns}; the first two are the product (chosen by nfreecols >= ncols), GPULIN_SELLBITS_VARIANT selects one for experiments
+typedef void (*SellBitsKernel)(const DevProblem);
+struct SellBitsVariant { SellBitsKernel kernel; int threads; bool allcols; };
+static const SellBitsVariant g_sellBitsKernels[] = {
+   {sweep_sell_bits_kernel<1024, 2, true, false>, 1024, false},   // 0
+   {sweep_sell_bits_kernel<1024, 2, true, true>, 1024, true},     // 1
+   {sweep_sell_bits_kernel<1024, 2, false, false>, 1024, false},  // 2: lb/ub form (leanElem)
+   {sweep_sell_bits_kernel<768, 3, true, true>, 768, true},       // 3
+   {sweep_sell_bits_kernel<768, 4, true, false>, 768, false},     // 4
+};
+constexpr int NSELLBITSVARIANTS = sizeof(g_sellBitsKernels) / sizeof(g_sellBitsKernels[0]);
+
 // one propagation round on h->stream
 template <int MODE, bool GRAPH>
 static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
@@ -214,7 +236,10 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
       }
       else if( h->nstreamblocks > 0 )
          sweep_stream_kernel<<<h->nstreamblocks, SWEEP_THREADS, 0, h->stream>>>(h->p);
-      if( h->nsellblocks > 0 )
+      if( h->nsellbitsblocks > 0 )
+         g_sellBitsKernels[h->sellbitsvariant].kernel<<<h->nsellbitsblocks, g_sellBitsKernels[h->sellbitsvariant].threads,
+            sellBitsSmem(h->p.nfreewords), h->stream>>>(h->p);
+      else if( h->nsellblocks > 0 )
          g_sellKernels[h->sellvariant]<<<h->nsellblocks, SELL_THREADS, 0, h->stream>>>(h->p);
       for( int i = 0; i < side; ++i )
          CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
@@ -468,6 +493,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    DevProblem& p = h->p;
    long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
    int* d_tile_row0; unsigned char* d_endmask; unsigned char* d_tileflag;
+   unsigned* d_freebits; double2* d_bndf;
    int* d_xlist; int* d_marklist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned* d_colbits; int* d_chglist; long long* d_colbeg; int* d_colrows;
    Ctrl* d_ctrl;
    int rc = GPULIN_OK;
@@ -488,6 +514,10 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &d_bnd, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)ncols + 2));
    TRY(devAlloc(h, &d_colbits, (size_t)ncols / 32 + 2));
+   const int nallwords = (int)((((size_t)ncols + 31) / 32 + 3) & ~(size_t)3);
+   h->freebytes = sizeof(unsigned) * ((size_t)nallwords + 4);
+   TRY(devAlloc(h, &d_freebits, (size_t)nallwords + 4));
+   TRY(devAlloc(h, &d_bndf, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_chglist, (size_t)ncols + 1));
    TRY(devAlloc(h, &d_colbeg, (size_t)ncols + 2, true));
    TRY(devAlloc(h, &d_colrows, (size_t)nnz + 1, true));
@@ -569,6 +599,10 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.xlist = d_xlist;
    p.marklist = d_marklist;
    p.bnd = d_bnd;
+   p.freebits = d_freebits;
+   p.bndf = d_bndf;
+   p.nfreewords = std::min(nallwords, SELLBITS_MAXWORDS);
+   p.nfreecols = (int)std::min<int64_t>(ncols, (int64_t)p.nfreewords * 32);
    p.cand = d_cand;
    p.colbits = d_colbits;
    p.chglist = d_chglist;
@@ -614,6 +648,18 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
          occs = atoi(oes);
       const int64_t needs = ((int64_t)nslices + (SELL_THREADS / 32) - 1) / (SELL_THREADS / 32);
       h->nsellblocks = (int)std::min<int64_t>(needs, (int64_t)h->nsm * occs);
+      // the shared-memory bit-table variant: one block of 1024 threads per SM; worth its prologue (the table is staged
+      // by every block) once there is more than a handful of slices per block; GPULIN_SELLBITS=0 disables it
+      const char* be = getenv("GPULIN_SELLBITS");
+      const bool allcols = h->p.nfreecols >= h->p.ncols;
+      h->sellbitsvariant = allcols ? 1 : 0;
+      const char* bv = getenv("GPULIN_SELLBITS_VARIANT");
+      if( bv != nullptr && atoi(bv) >= 0 && atoi(bv) < NSELLBITSVARIANTS && (allcols || !g_sellBitsKernels[atoi(bv)].allcols) )
+         h->sellbitsvariant = atoi(bv);
+      if( h->nsellblocks > 0 && !(be != nullptr && atoi(be) == 0) && nslices >= h->nsm * 32
+         && cudaFuncSetAttribute(g_sellBitsKernels[h->sellbitsvariant].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+               (int)sellBitsSmem(SELLBITS_MAXWORDS)) == cudaSuccess )
+         h->nsellbitsblocks = h->nsm;
       if( getenv("GPULIN_VERBOSE") != nullptr )
          fprintf(stderr, "gpulin: %d SELL rows in %d blocks (%d per SM); stream sweep %d rows, %d tiles, %d blocks x %d threads "
             "(%d per SM); %d long rows\n", h->nsell, h->nsellblocks, occs, h->nstream, h->ntiles, h->nstreamblocks, SWEEP_THREADS,
@@ -873,6 +919,8 @@ extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
    CU(cudaSetDevice(h->device));
    CU(cudaMemcpyAsync(const_cast<double2*>(h->p.bnd), base->p.bnd, sizeof(double2) * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemcpyAsync(h->p.cand, base->p.cand, sizeof(long long) * 2 * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->p.freebits, base->p.freebits, h->freebytes, cudaMemcpyDeviceToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->p.bndf, base->p.bndf, sizeof(double2) * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemsetAsync(h->p.dirty, 0, (size_t)h->nrows, h->stream));
    CU(cudaMemsetAsync(h->p.tileflag, 0, (size_t)h->ntiles, h->stream));
    CU(cudaMemsetAsync(h->p.colbits, 0, sizeof(unsigned) * ((size_t)h->ncols / 32 + 1), h->stream));
@@ -975,13 +1023,18 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    h->p = src->p;
    DevProblem& p = h->p;
    unsigned char* d_dirty; unsigned char* d_tileflag; int* d_xlist; double2* d_bnd; long long* d_cand; unsigned* d_colbits;
-   int* d_chglist; Ctrl* d_ctrl; int* d_marklist;
+   int* d_chglist; Ctrl* d_ctrl; int* d_marklist; unsigned* d_freebits; double2* d_bndf;
    int rc = GPULIN_OK;
    TRY(devAlloc(h, &d_dirty, (size_t)h->nrows + 64));
    TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
    TRY(devAlloc(h, &d_xlist, (size_t)h->nrows + 1));
    TRY(devAlloc(h, &d_marklist, (size_t)6 * MARKCAP));
    TRY(devAlloc(h, &d_bnd, (size_t)h->ncols + 1));
+   h->freebytes = src->freebytes;
+   h->nsellbitsblocks = src->nsellbitsblocks;
+   h->sellbitsvariant = src->sellbitsvariant;
+   TRY(devAlloc(h, &d_freebits, h->freebytes / sizeof(unsigned)));
+   TRY(devAlloc(h, &d_bndf, (size_t)h->ncols + 1));
    TRY(devAlloc(h, &d_cand, 2 * (size_t)h->ncols + 2));
    TRY(devAlloc(h, &d_colbits, (size_t)h->ncols / 32 + 2));
    TRY(devAlloc(h, &d_chglist, (size_t)h->ncols + 1));
@@ -1018,6 +1071,8 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    p.xlist = d_xlist;
    p.marklist = d_marklist;
    p.bnd = d_bnd;
+   p.freebits = d_freebits;
+   p.bndf = d_bndf;
    p.cand = d_cand;
    p.colbits = d_colbits;
    p.chglist = d_chglist;

@@ -99,6 +99,10 @@ struct DevProblem
                                    // count exceeds MARKCAP (the dirty flags are the ground truth, the lists a shortcut)
    // columns
    const double2*      bnd;        // (lb, ub) at round start
+   double2*            bndf;       // ((lb+ub)/2, (ub-lb)/2) per column: what sweep_sell_bits_kernel gathers instead of bnd
+   unsigned*           freebits;   // bit per column: bnd == (0,1) exactly; nfreewords words (a multiple of 4) are staged into
+   int                 nfreewords; // shared memory by sweep_sell_bits_kernel, they cover the columns [0, nfreecols)
+   int                 nfreecols;
    long long*          cand;       // 2*ncols (+2) candidate keys, see Sink
    unsigned*           colbits;    // bit per column: on the change list
    int*                chglist;    // columns a candidate reached in the running round
@@ -709,13 +713,14 @@ __device__ __forceinline__ void loadChunk(const DevProblem& p, long long base, i
    }
 }
 
-template <int CH, int MINB>
-__global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const DevProblem p)
+// BITS: the bounds of a column whose bit is set in the shared-memory table s_free are (0,1) -- no gather
+template <int CH, bool BITS>
+__device__ __forceinline__ void sellSweep(const DevProblem& p, const unsigned* s_free, int nblockthreads)
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
-   const int gw = (blockIdx.x * SELL_THREADS + threadIdx.x) >> 5;
-   const int nw = (gridDim.x * SELL_THREADS) >> 5;
+   const int gw = (blockIdx.x * nblockthreads + threadIdx.x) >> 5;
+   const int nw = (gridDim.x * nblockthreads) >> 5;
    const int nslices = (p.nsell + 31) >> 5;
    unsigned nnzdone = 0;
    for( int s0 = gw; s0 < nslices; s0 += SELL_NB * nw )
@@ -778,7 +783,17 @@ __global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const De
             for( int k = 0; k < CH; ++k )
             {
                if( c + k < len[i] )
-                  b[k] = p.bnd[cj[k] & 0x7fffffff];
+               {
+                  const int j = cj[k] & 0x7fffffff;
+                  if( BITS )
+                  {
+                     b[k] = make_double2(0.0, 1.0);
+                     if( j >= p.nfreecols || ((s_free[j >> 5] >> (j & 31)) & 1u) == 0u )
+                        b[k] = p.bnd[j];
+                  }
+                  else
+                     b[k] = p.bnd[j];
+               }
             }
 #pragma unroll
             for( int k = 0; k < CH; ++k )
@@ -799,6 +814,253 @@ __global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const De
          pushRow(p, handoff, row, lane, 0, 0);
       }
    }
+   nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
+   if( lane == 0 )
+      addRoundNnz(p, (unsigned long long)nnzdone, gw);
+}
+
+template <int CH, int MINB>
+__global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const DevProblem p)
+{
+   sellSweep<CH, false>(p, nullptr, SELL_THREADS);
+}
+
+// ---- the SELL sweep with a shared-memory bit table -------------------------------------------------------------------
+// The gather variant above is bound by the L1/L2 path, not by HBM: a random 16-byte bound gather costs one L1 wavefront
+// and one L2 sector per nonzero (10M gathers >= 40 us on C3).  Most columns of a MIP are binaries at their original
+// bounds: freebits holds one bit per column, "the bounds are exactly (0,1)", kept up to date by everybody who writes bnd
+// (noteBounds).  One block per SM stages the table into shared memory with bulk copies (TMA, 125 KB for 1M columns;
+// columns beyond nfreecols and columns whose bit is clear are gathered as before): 32 random words cost ~4 bank-conflict
+// cycles per warp instead of 32 wavefronts.  (A variant that also staged the matrix through per-warp cp.async / TMA rings
+// in the remaining shared memory was tried and was slower: with the table resident, ~100 KB of ring per SM do not hold
+// more bytes in flight than the registers do, and the ring bookkeeping costs more instructions than it saves latency.)
+constexpr int SB_MAXSMEM = 227 * 1024;
+constexpr int SB_AUX_BYTES = 256;                          // the mbarrier of the table + alignment
+constexpr int SELLBITS_MAXWORDS = ((SB_MAXSMEM - SB_AUX_BYTES) / 4) & ~31;
+
+__device__ __forceinline__ unsigned smemAddr(const void* ptr)
+{
+   return (unsigned)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbarInit(unsigned bar, unsigned count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned bar, unsigned bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned bar, unsigned parity)
+{
+   unsigned ok;
+   do
+   {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+   } while( ok == 0u );
+}
+// global -> shared bulk copy through the async proxy (TMA, 1-D); bytes and both addresses are multiples of 16
+__device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// The filter sums in midpoint / half-width form: with m_k = a_k (l_k + u_k)/2 and h_k = |a_k| (u_k - l_k)/2 the term of
+// the minimal activity is m_k - h_k and that of the maximal activity m_k + h_k, whatever the sign of a_k -- no selects:
+//    minact = M - H,  maxact = M + H,  maxdelta = 2 max_k h_k,   M = sum m_k,  H = sum h_k           (7 instructions per nonzero)
+// The table bndf holds ((l+u)/2, (u-l)/2) per column.  Error against the exact rules: every m_k, h_k carries at most three
+// roundings, a sum of n terms n - 1 more, so each activity is within (n + 4) u C of the exact value, C = sum |m_k| + h_k
+// (tracked as Mabs + H, an upper bound of every |a_k l_k|, |a_k u_k| as well) -- covered by rowClearlyQuiet's
+// E = (n^2 + 8) 2.3e-16 cabs with cabs >= C.  An infinite or NaN bound makes C huge or NaN: not quiet.
+struct MidAcc
+{
+   double M;
+   double Mabs;
+   double H;
+   float  hmax;     // max_k h_k, rounded up
+};
+
+__device__ __forceinline__ void midInit(MidAcc& r)
+{
+   r.M = r.Mabs = r.H = 0.0;
+   r.hmax = 0.0f;
+}
+
+__device__ __forceinline__ void midElem(MidAcc& r, double a, double mid, double hw)
+{
+   const double m = a * mid;
+   const double h = fabs(a) * hw;
+   r.M += m;
+   r.Mabs += fabs(m);
+   r.H += h;
+   r.hmax = fmaxf(r.hmax, __double2float_ru(h));
+}
+
+__device__ __forceinline__ LeanAcc midToLean(const MidAcc& r)
+{
+   LeanAcc o;
+   o.minact = r.M - r.H;
+   o.maxact = r.M + r.H;
+   o.maxdelta = __fmul_ru(2.0f, r.hmax);
+   o.cabshi = __double2hiint(r.Mabs + r.H) & 0x7fffffff;
+   return o;
+}
+
+// bound pair of a column unless `skip` (a predicated load: no branch, no reconvergence point)
+__device__ __forceinline__ void gatherUnless(unsigned skip, const double2* addr, double2& b)
+{
+   asm("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %2, 0;\n\t@q ld.global.v2.f64 {%0, %1}, [%3];\n\t}"
+       : "+d"(b.x), "+d"(b.y) : "r"(skip), "l"(addr));
+}
+
+// MID: sums in midpoint / half-width form from bndf (else leanElem from bnd)
+//      ALLCOLS: the table covers every column (no range checks);  HD: the maximal half width is kept as a double
+template <int NT, int CH, bool MID, bool ALLCOLS = false, bool HD = false>
+__global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
+{
+   extern __shared__ __align__(128) unsigned char s_raw[];
+   const Num& n = p.num;
+   const unsigned tabbytes = (unsigned)p.nfreewords * 4u;
+   const unsigned* s_free = reinterpret_cast<const unsigned*>(s_raw);
+   const unsigned tabbar = smemAddr(s_raw + ((tabbytes + 127u) & ~127u));
+   if( threadIdx.x == 0 )
+   {
+      mbarInit(tabbar, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbarExpectTx(tabbar, tabbytes);
+      for( unsigned o = 0; o < tabbytes; o += 16384u )
+         bulkLoad(smemAddr(s_raw) + o, reinterpret_cast<const unsigned char*>(p.freebits) + o, min(16384u, tabbytes - o), tabbar);
+   }
+   __syncthreads();
+
+   const int lane = threadIdx.x & 31;
+   const int gw = (blockIdx.x * NT + threadIdx.x) >> 5;
+   const int nw = (gridDim.x * NT) >> 5;
+   const int nslices = (p.nsell + 31) >> 5;
+   const int lastword = p.nfreewords - 1;
+   unsigned nnzdone = 0;
+   bool tabready = false;
+   for( int s0 = gw; s0 < nslices; s0 += SELL_NB * nw )
+   {
+      // ---- one round trip: flags, lengths and offsets of the next four slices of this warp
+      int len[SELL_NB];
+      int maxlen[SELL_NB];
+      long long base[SELL_NB];
+      unsigned actm = 0u;
+      unsigned exactm = 0u;
+#pragma unroll
+      for( int i = 0; i < SELL_NB; ++i )
+      {
+         const int slice = s0 + i * nw;
+         const int row = slice * 32 + lane;
+         const bool valid = slice < nslices && row < p.nsell;
+         const unsigned char f = valid ? p.dirty[row] : ROW_CLEAN;
+         const int lw = valid ? p.rowlen[row] : 0;
+         base[i] = (slice < nslices ? p.sell_off[slice] : 0) + lane;
+         const bool act = f == ROW_MARKED;
+         len[i] = act ? (lw & ~ROWLEN_EXACT) : 0;
+         if( act )
+            actm |= 1u << i;
+         if( act && (lw & ROWLEN_EXACT) != 0 )
+            exactm |= 1u << i;
+      }
+#pragma unroll
+      for( int i = 0; i < SELL_NB; ++i )
+         maxlen[i] = __reduce_max_sync(0xffffffffu, len[i]);
+
+      double an[CH];
+      int cjn[CH];
+      loadChunk<CH>(p, base[0], 0, len[0], an, cjn);
+      if( !tabready )
+      {
+         mbarWait(tabbar, 0u);      // the first coefficients are on their way while the table arrives
+         tabready = true;
+      }
+#pragma unroll
+      for( int i = 0; i < SELL_NB; ++i )
+      {
+         const int row = (s0 + i * nw) * 32 + lane;
+         const bool act = ((actm >> i) & 1u) != 0u;
+         double2 sd = make_double2(0.0, 0.0);
+         if( act )
+            sd = p.sides[row];
+         MidAcc macc;
+         LeanAcc lacc;
+         midInit(macc);
+         leanInit(lacc);
+         double hmaxd = 0.0;
+         for( int c = 0; c < maxlen[i]; c += CH )
+         {
+            double a[CH];
+            int cj[CH];
+            double2 b[CH];
+#pragma unroll
+            for( int k = 0; k < CH; ++k )
+            {
+               a[k] = an[k];
+               cj[k] = cjn[k] & 0x7fffffff;
+            }
+            if( c + CH < maxlen[i] )
+               loadChunk<CH>(p, base[i], c + CH, len[i], an, cjn);
+            else if( i + 1 < SELL_NB )
+               loadChunk<CH>(p, base[i + 1], 0, len[i + 1], an, cjn);
+#pragma unroll
+            for( int k = 0; k < CH; ++k )
+            {
+               if( c + k < len[i] )
+               {
+                  const unsigned w = s_free[ALLCOLS ? cj[k] >> 5 : min(cj[k] >> 5, lastword)];
+                  const unsigned fr = (ALLCOLS || cj[k] < p.nfreecols) ? (w >> (cj[k] & 31)) & 1u : 0u;
+                  if( MID )
+                  {
+                     b[k] = make_double2(0.5, 0.5);
+                     gatherUnless(fr, p.bndf + cj[k], b[k]);
+                  }
+                  else
+                  {
+                     b[k] = make_double2(0.0, 1.0);
+                     gatherUnless(fr, p.bnd + cj[k], b[k]);
+                  }
+               }
+            }
+#pragma unroll
+            for( int k = 0; k < CH; ++k )
+            {
+               if( c + k < len[i] )
+               {
+                  if( MID && HD )
+                  {
+                     const double m = a[k] * b[k].x;
+                     const double hh = fabs(a[k]) * b[k].y;
+                     macc.M += m;
+                     macc.Mabs += fabs(m);
+                     macc.H += hh;
+                     hmaxd = hh > hmaxd ? hh : hmaxd;
+                  }
+                  else if( MID )
+                     midElem(macc, a[k], b[k].x, b[k].y);
+                  else
+                     leanElem(lacc, a[k], b[k].x, b[k].y);
+               }
+            }
+         }
+         if( maxlen[i] == 0 && i + 1 < SELL_NB )
+            loadChunk<CH>(p, base[i + 1], 0, len[i + 1], an, cjn);
+         bool handoff = false;
+         if( act )
+         {
+            if( HD )
+               macc.hmax = __double2float_ru(hmaxd);
+            handoff = ((exactm >> i) & 1u) != 0u || !rowClearlyQuiet(n, MID ? midToLean(macc) : lacc, len[i], sd.x, sd.y);
+            p.dirty[row] = ROW_CLEAN;
+            nnzdone += (unsigned)len[i];
+         }
+         pushRow(p, handoff, row, lane, 0, 0);
+      }
+   }
+   if( !tabready && threadIdx.x < 32 )
+      mbarWait(tabbar, 0u);         // the block must not retire under the copies it issued
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
    if( lane == 0 )
       addRoundNnz(p, (unsigned long long)nnzdone, gw);
@@ -1076,6 +1338,25 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProb
    exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, EXACT_THREADS);
 }
 
+// ---- everybody who writes bnd[j] keeps the column's bit in freebits: set iff the bounds are exactly (0,1) ------------
+__device__ __forceinline__ bool isFree01(double l, double u)
+{
+   return l == 0.0 && u == 1.0;
+}
+__device__ __forceinline__ double2 midHalfWidth(double l, double u)
+{
+   return make_double2(0.5 * l + 0.5 * u, 0.5 * u - 0.5 * l);
+}
+__device__ __forceinline__ void noteBounds(const DevProblem& p, int j, double l, double u)
+{
+   p.bndf[j] = midHalfWidth(l, u);
+   const unsigned m = 1u << (j & 31);
+   if( isFree01(l, u) )
+      atomicOr(&p.freebits[j >> 5], m);
+   else
+      atomicAnd(&p.freebits[j >> 5], ~m);
+}
+
 // ---- accept the new bounds of one column; returns the number of changed bounds (0..2) -------------------------
 __device__ __forceinline__ int applyColumn(const DevProblem& p, int j, double2& nb, bool& lbchg, bool& ubchg)
 {
@@ -1096,7 +1377,10 @@ __device__ __forceinline__ int applyColumn(const DevProblem& p, int j, double2& 
    ubchg = (nu != old.y);
    nb = make_double2(nl, nu);
    if( lbchg || ubchg )
+   {
       const_cast<double2*>(p.bnd)[j] = nb;
+      noteBounds(p, j, nl, nu);
+   }
    return (int)lbchg + (int)ubchg;
 }
 
@@ -1137,9 +1421,13 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
             p.dirty[r[t]] = ROW_MARKED;
             if( r[t] >= p.nsell && r[t] < p.nsx )
                p.tileflag[(rb[t] - p.streambase) >> 8] = 1;
-            // note the row for a sparse round (two columns racing for the same row may both note it: harmless)
+            // note the row for a sparse round (two columns racing for the same row may both note it: harmless); once
+            // a list has overflowed the round will be a dense one and nobody needs the list (a stale count only costs
+            // an atomic)
             const int bin = r[t] < p.nsell ? 0 : (r[t] < p.nsx ? 1 : 2);
             const unsigned wb = p.ctrl->mb ^ 1u;
+            if( __ldcg(&p.ctrl->nmark[wb][bin]) > (unsigned)MARKCAP )
+               continue;
             const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
             const unsigned same = g.match_any(bin);
             const int leader = __ffs(same) - 1;
@@ -1197,7 +1485,8 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
 }
 
 constexpr int APPLY_THREADS = 256;
-constexpr int APPLY_G = 8;
+constexpr int APPLY_G = 4;           // lanes per changed column in the apply kernel (rounds with many changes)
+constexpr int SPARSE_G = 8;          // ... in the sparse-rounds kernel (few changes: latency counts)
 
 // appends the accepted changes of column j to the round-ordered change log
 __device__ __forceinline__ void logChanges(const DevProblem& p, int j, int round, int logcap, int nc, bool lbchg, bool ubchg,
@@ -1224,15 +1513,16 @@ __device__ __forceinline__ void logChanges(const DevProblem& p, int j, int round
 
 // the columns on the change list of this round, eight lanes per column: one accepts the bounds, all mark the rows of the
 // column; returns the number of bound changes this thread accepted
+template <int G>
 __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlist, int gtid, int nthreads, int round, int logcap)
 {
-   const int gl = gtid & (APPLY_G - 1);
-   const int ngroups = nthreads / APPLY_G;
+   const int gl = gtid & (G - 1);
+   const int ngroups = nthreads / G;
    const unsigned trips = (nlist + ngroups - 1) / ngroups;       // warp-uniform
    int mychg = 0;
    for( unsigned it = 0; it < trips; ++it )
    {
-      const unsigned item = it * ngroups + gtid / APPLY_G;
+      const unsigned item = it * ngroups + gtid / G;
       const bool valid = item < nlist;
       int j = 0;
       if( valid )
@@ -1253,7 +1543,7 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
       if( valid )
-         markColumnRows(p, j, gl, APPLY_G);
+         markColumnRows(p, j, gl, G);
    }
    return mychg;
 }
@@ -1335,7 +1625,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
       }
    }
    else
-      mychg += applyListPhase(p, nlist, gtid, nthreads, round, logcap);
+      mychg += applyListPhase<APPLY_G>(p, nlist, gtid, nthreads, round, logcap);
    mychg = __reduce_add_sync(0xffffffffu, mychg);
    if( lane == 0 && mychg != 0 )
       atomicAdd(&s_nchg, mychg);
@@ -1361,7 +1651,8 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
 // rows, grid sync, apply for the changed columns, grid sync, loop control -- and leaves when a round is not sparse any
 // more or the loop ends.  The filter pass is skipped in these rounds: every marked row gets the exact rules.
 constexpr int SPARSE_THREADS = 256;
-constexpr unsigned SPARSE_MAXROWS = 16384;
+constexpr unsigned SPARSE_MAXROWS = 1u << 14;      // short rows (8 lanes each)
+constexpr unsigned SPARSE_MAXMEDIUM = 1u << 12;    // rows of 33..4096 nonzeros (a warp each)
 
 template <bool GRAPH>
 __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
@@ -1382,7 +1673,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const Dev
       const unsigned n1 = c->nmark[mb][1];
       const unsigned n2 = c->nmark[mb][2];
       const bool sparse = c->cont != 0 && n0 <= (unsigned)MARKCAP && n1 <= (unsigned)MARKCAP && n2 <= (unsigned)MARKCAP
-         && n0 + n1 + n2 <= SPARSE_MAXROWS && n2 <= 64u;
+         && n0 <= SPARSE_MAXROWS && n1 <= SPARSE_MAXMEDIUM && n2 <= 64u;
       if( !sparse )
          break;
       if( threadIdx.x == 0 )
@@ -1397,7 +1688,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const Dev
       // ---- accept the changes, mark the rows of the changed columns (into the other mark list)
       const int round = c->round;
       const unsigned nlist = c->nchgcols;
-      int mychg = applyListPhase(p, nlist, gtid, nthreads, round, c->logcap);
+      int mychg = applyListPhase<SPARSE_G>(p, nlist, gtid, nthreads, round, c->logcap);
       mychg = __reduce_add_sync(0xffffffffu, mychg);
       if( lane == 0 && mychg != 0 )
          atomicAdd(&s_nchg, mychg);
@@ -1458,13 +1749,24 @@ __global__ void peer_barrier_kernel(const DevProblem p)
 // ---- bound (re)initialisation ----------------------------------------------------------------------------------
 __global__ void set_bounds_kernel(const DevProblem p, const double* lb, const double* ub)
 {
-   const int stride = gridDim.x * blockDim.x;
-   for( int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.ncols; j += stride )
+   const int stride = gridDim.x * blockDim.x;          // a multiple of 32: a warp owns the 32 columns of one word
+   const int nallwords = max(p.nfreewords, (p.ncols + 31) / 32);
+   for( int j0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < nallwords * 32; j0 += stride )
    {
-      const double l = lb[j] + 0.0;
-      const double u = ub[j] + 0.0;
-      const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
-      reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+      const int j = j0 + (threadIdx.x & 31);
+      bool fr = false;
+      if( j < p.ncols )
+      {
+         const double l = lb[j] + 0.0;
+         const double u = ub[j] + 0.0;
+         const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
+         reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+         p.bndf[j] = midHalfWidth(l, u);
+         fr = isFree01(l, u);
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, fr);
+      if( (threadIdx.x & 31) == 0 )
+         p.freebits[j0 >> 5] = word;
    }
    for( int w = blockIdx.x * blockDim.x + threadIdx.x; w < (p.ncols + 31) / 32; w += stride )
       p.colbits[w] = 0u;
@@ -1484,6 +1786,7 @@ __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const i
       const double u = ub[i] + 0.0;
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+      noteBounds(p, j, l, u);
       markColumnRows(p, j, 0, 1);
    }
 }
@@ -1497,6 +1800,7 @@ __global__ void update_one_kernel(const DevProblem p, int j, double l, double u)
       u += 0.0;
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+      noteBounds(p, j, l, u);
    }
    markColumnRows(p, j, threadIdx.x, blockDim.x);
 }
@@ -1510,8 +1814,10 @@ __global__ void restore_kernel(const DevProblem p, const DevProblem base, int pr
    for( unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride )
    {
       const int j = i < n ? p.log[i].var : probedvar;
-      const_cast<double2*>(p.bnd)[j] = base.bnd[j];
+      const double2 b = base.bnd[j];
+      const_cast<double2*>(p.bnd)[j] = b;
       reinterpret_cast<longlong2*>(p.cand)[j] = reinterpret_cast<const longlong2*>(base.cand)[j];
+      noteBounds(p, j, b.x, b.y);
    }
 }
 
