@@ -109,6 +109,8 @@ struct gpulin
    bool        pending = false;     // gpulin_propagate_async was called, gpulin_propagate_wait not yet
    bool        lightfetch = false;  // fetch only the head of the control block after a call (probing workers)
    std::vector<gpulin*> workers;    // clones that gpulin_probe_batch keeps for this (base) handle
+   void*       d_proberes = nullptr; // verdicts of the probes of a batch (ProbeResult[proberescap])
+   int64_t     proberescap = 0;
    int         lastvar = -1;        // probing worker: the column of its last probe
    bool        needreset = true;    // probing worker: its state is not "node + change log"
    // results of the last propagate call
@@ -700,6 +702,9 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    for( gpulin* w : h->workers )
       gpulin_destroy(w);
    h->workers.clear();
+   if( h->d_proberes != nullptr )
+      cudaFree(h->d_proberes);
+   h->d_proberes = nullptr;
    if( h->stream != nullptr )
       cudaStreamSynchronize(h->stream);
    destroyGraph(h);
@@ -922,6 +927,7 @@ extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
    CU(cudaMemcpyAsync(h->p.freebits, base->p.freebits, h->freebytes, cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemcpyAsync(h->p.bndf, base->p.bndf, sizeof(double2) * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemsetAsync(h->p.dirty, 0, (size_t)h->nrows, h->stream));
+   CU(cudaMemsetAsync(&h->p.ctrl->poisoned, 0, sizeof(unsigned), h->stream));
    CU(cudaMemsetAsync(h->p.tileflag, 0, (size_t)h->ntiles, h->stream));
    CU(cudaMemsetAsync(h->p.colbits, 0, sizeof(unsigned) * ((size_t)h->ncols / 32 + 1), h->stream));
    h->havebounds = true;
@@ -962,40 +968,60 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
    for( gpulin* w : base->workers )
       w->needreset = true;          // the node may have changed since the last batch
 
-   std::vector<int64_t> inflight((size_t)nworkers, -1);
-   auto finish = [&](int wi) -> int {
-      gpulin* w = base->workers[(size_t)wi];
-      const int64_t i = inflight[(size_t)wi];
-      gpulin_result r;
-      OK(gpulin_propagate_wait(w, &r));
-      if( status != nullptr ) status[i] = r.status;
-      if( nrounds != nullptr ) nrounds[i] = r.nrounds;
-      if( nchanges != nullptr ) nchanges[i] = r.nchanges;
-      // after a fixpoint nothing is marked and the log names every column that moved: cheap backtrack next time
-      w->needreset = !(r.status == GPULIN_FIXPOINT && (int64_t)w->h_ctrl->logcount <= w->logcap);
-      inflight[(size_t)wi] = -1;
-      return GPULIN_OK;
-   };
+   // ---- one launch per probe (probe_kernel), round-robin over the workers' streams; the verdicts come back in one copy
+   if( nprobes > base->proberescap )
+   {
+      if( base->d_proberes != nullptr )
+         cudaFree(base->d_proberes);
+      base->d_proberes = nullptr;
+      base->proberescap = 0;
+      CU(cudaMalloc(&base->d_proberes, sizeof(ProbeResult) * (size_t)nprobes));
+      base->proberescap = nprobes;
+   }
+   ProbeResult* d_res = (ProbeResult*)base->d_proberes;
+   const bool general = getenv("GPULIN_PROBE_GENERAL") != nullptr;     // experiments: every probe through the general loop
+   for( int64_t i = 0; i < nprobes && !general; ++i )
+   {
+      gpulin* w = base->workers[(size_t)(i % nworkers)];
+      if( w->needreset )
+      {
+         OK(gpulin_reset_from(w, base));
+         w->lastvar = -1;
+         w->needreset = false;
+      }
+      probe_kernel<<<1, PROBE_THREADS, 0, w->stream>>>(w->p, base->p, w->lastvar, var[i], lb[i], ub[i], maxrounds, (int)w->logcap,
+         d_res + i);
+      w->lastvar = var[i];
+   }
+   CU(cudaGetLastError());
+   for( int wi = 0; wi < nworkers; ++wi )
+      CU(cudaStreamSynchronize(base->workers[(size_t)wi]->stream));
+   std::vector<ProbeResult> res((size_t)nprobes);
+   if( nprobes > 0 && !general )
+      CU(cudaMemcpy(res.data(), d_res, sizeof(ProbeResult) * (size_t)nprobes, cudaMemcpyDeviceToHost));
+   // ---- probes that outgrew the block are rerun through the general loop on worker 0
    for( int64_t i = 0; i < nprobes; ++i )
    {
-      const int wi = (int)(i % nworkers);
-      gpulin* w = base->workers[(size_t)wi];
-      if( inflight[(size_t)wi] >= 0 )
-         OK(finish(wi));
-      if( w->needreset )
-         OK(gpulin_reset_from(w, base));
-      else
-         restore_kernel<<<1, 256, 0, w->stream>>>(w->p, base->p, w->lastvar);
+      if( !general && res[(size_t)i].status != GPULIN_PROBE_OVERFLOW )
+         continue;
+      if( !general )
+         base->workers[(size_t)(i % nworkers)]->needreset = true;
+      gpulin* w = base->workers[0];
+      OK(gpulin_reset_from(w, base));
+      w->needreset = true;
       update_one_kernel<<<1, 32, 0, w->stream>>>(w->p, var[i], lb[i], ub[i]);
       CU(cudaGetLastError());
-      w->lastvar = var[i];
-      OK(gpulin_propagate_async(w, maxrounds));
-      inflight[(size_t)wi] = i;
+      gpulin_result r;
+      OK(gpulin_propagate(w, maxrounds, &r));
+      res[(size_t)i].status = r.status;
+      res[(size_t)i].nrounds = r.nrounds;
+      res[(size_t)i].nchanges = r.nchanges;
    }
-   for( int wi = 0; wi < nworkers; ++wi )
+   for( int64_t i = 0; i < nprobes; ++i )
    {
-      if( inflight[(size_t)wi] >= 0 )
-         OK(finish(wi));
+      if( status != nullptr ) status[i] = res[(size_t)i].status;
+      if( nrounds != nullptr ) nrounds[i] = res[(size_t)i].nrounds;
+      if( nchanges != nullptr ) nchanges[i] = res[(size_t)i].nchanges;
    }
    return GPULIN_OK;
 }

@@ -57,7 +57,7 @@ struct Ctrl
    unsigned int       mb;           // the buffer the last apply filled = what a sparse round reads
    unsigned int       stay;         // sparse_rounds_kernel: another sparse round follows
    unsigned int       nsparse;      // rounds done by sparse_rounds_kernel in this call (statistics)
-   unsigned int       pad1;
+   unsigned int       poisoned;     // probing worker: its state is not "node + change log" any more (see probe_kernel)
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
    unsigned long long hist_time[MAX_HIST];   // %globaltimer at the end of each round
    unsigned long long hist_nnz[MAX_HIST];
@@ -1706,6 +1706,160 @@ __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const Dev
          __threadfence();
       }
       grid.sync();
+   }
+}
+
+// ---- one probe = one launch of one block ----------------------------------------------------------------------------
+// SCIPbacktrackProbing + SCIPchgVarLb/UbProbing + SCIPpropagateProbing (scip_probing.c:226/:302/:346/:581) for a worker
+// clone: undo the change log of the previous probe of this worker, set the probed bound, mark the rows of the column and
+// run sparse rounds (exact rules for the marked rows, apply, loop control) inside the block until the fixpoint, a
+// cutoff or the round limit -- no other launch, no host round trip; the verdict goes to out[0].  A probe is a small
+// cascade (a few dozen rows); one that outgrows the block (more than PROBE_MAXROWS marked rows in a round, a long row,
+// a full change log) stops with GPULIN_PROBE_OVERFLOW and marks the worker as poisoned: the host reruns such probes
+// through the general loop after a reset.  Whatever is still marked when the probe ends is unmarked again, so that the
+// next probe of this worker starts from "node + change log".
+constexpr int PROBE_THREADS = 256;
+constexpr unsigned PROBE_MAXROWS = 4096;
+constexpr unsigned PROBE_MAXMEDIUM = 64;
+constexpr int GPULIN_PROBE_OVERFLOW = 3;
+
+struct ProbeResult
+{
+   int       status;
+   int       nrounds;
+   long long nchanges;
+};
+
+__global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p, const DevProblem base, int restorevar, int j,
+   double l, double u, int maxrounds, int logcap, ProbeResult* out)
+{
+   __shared__ RowAcc s_acc[PROBE_THREADS / 32];
+   __shared__ int s_nchg;
+   Ctrl* c = p.ctrl;
+   const int tid = threadIdx.x;
+   const int lane = tid & 31;
+
+   if( c->poisoned )
+   {
+      if( tid == 0 )
+      {
+         out->status = GPULIN_PROBE_OVERFLOW;
+         out->nrounds = 0;
+         out->nchanges = 0;
+      }
+      return;
+   }
+
+   // ---- back to the node: the columns the previous probe changed are in its log
+   if( restorevar >= 0 )
+   {
+      const unsigned long long n = min(c->logcount, (unsigned long long)c->logcap);
+      for( unsigned long long i = tid; i <= n; i += PROBE_THREADS )
+      {
+         const int jj = i < n ? p.log[i].var : restorevar;
+         const double2 b = base.bnd[jj];
+         const_cast<double2*>(p.bnd)[jj] = b;
+         reinterpret_cast<longlong2*>(p.cand)[jj] = reinterpret_cast<const longlong2*>(base.cand)[jj];
+         noteBounds(p, jj, b.x, b.y);
+      }
+   }
+   __syncthreads();
+
+   // ---- start of the call (begin_kernel), the probed bound, the rows of its column
+   if( tid == 0 )
+   {
+      c->maxrounds = maxrounds;
+      c->logcap = logcap;
+      c->round = 0;
+      c->cont = 1;
+      c->status = 0;
+      c->cutoff = 0;
+      c->ticket = 0;
+      c->nchgcols = 0;
+      c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
+      c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
+      c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
+      c->mb = 0;
+      c->nsparse = 0;
+      c->logcount = 0;
+      c->round_nchg = 0;
+      for( int i = 0; i < NNZ_SLOTS; ++i )
+         c->round_nnz[i] = 0;
+      c->total_nchg = 0;
+      c->total_nnz = 0;
+      c->t_start = globaltimer();
+      l += 0.0;
+      u += 0.0;
+      const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
+      reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+      noteBounds(p, j, l, u);
+   }
+   __syncthreads();
+   markColumnRows(p, j, tid, PROBE_THREADS);       // into mark list 1
+   __syncthreads();
+   if( tid == 0 )
+      c->mb = 1;
+   __syncthreads();
+
+   bool overflow = false;
+   for( ;; )
+   {
+      const unsigned mb = c->mb;
+      const unsigned n0 = c->nmark[mb][0];
+      const unsigned n1 = c->nmark[mb][1];
+      const unsigned n2 = c->nmark[mb][2];
+      if( c->cont == 0 )
+         break;
+      if( n0 > PROBE_MAXROWS || n1 > PROBE_MAXMEDIUM || n2 > 0u || c->logcount > (unsigned long long)c->logcap )
+      {
+         overflow = true;
+         break;
+      }
+      if( tid == 0 )
+         s_nchg = 0;
+      const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
+      exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, PROBE_THREADS);
+      __syncthreads();
+      int mychg = applyListPhase<SPARSE_G>(p, c->nchgcols, tid, PROBE_THREADS, c->round, c->logcap);
+      mychg = __reduce_add_sync(0xffffffffu, mychg);
+      if( lane == 0 && mychg != 0 )
+         atomicAdd(&s_nchg, mychg);
+      __syncthreads();
+      if( tid == 0 )
+      {
+         c->round_nchg = (unsigned long long)s_nchg;
+         controlStep<false>(c, 0);
+      }
+      __syncthreads();
+   }
+
+   // ---- whatever is still marked (cutoff, round limit, overflow) is unmarked: the next probe starts from the node
+   {
+      const unsigned mb = c->mb;
+      const unsigned n0 = c->nmark[mb][0];
+      const unsigned n1 = c->nmark[mb][1];
+      const unsigned n2 = c->nmark[mb][2];
+      const bool listed = n0 <= (unsigned)MARKCAP && n1 <= (unsigned)MARKCAP && n2 <= (unsigned)MARKCAP;
+      if( listed )
+      {
+         const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
+         for( unsigned i = tid; i < n0; i += PROBE_THREADS )
+            p.dirty[ml[i]] = ROW_CLEAN;
+         for( unsigned i = tid; i < n1; i += PROBE_THREADS )
+            p.dirty[ml[MARKCAP + i]] = ROW_CLEAN;
+         for( unsigned i = tid; i < n2; i += PROBE_THREADS )
+            p.dirty[ml[2 * MARKCAP + i]] = ROW_CLEAN;
+      }
+      __syncthreads();
+      if( tid == 0 )
+      {
+         c->nmark[mb][0] = c->nmark[mb][1] = c->nmark[mb][2] = 0;
+         if( !listed || c->logcount > (unsigned long long)c->logcap )
+            c->poisoned = 1;
+         out->status = overflow ? GPULIN_PROBE_OVERFLOW : c->status;
+         out->nrounds = c->round;
+         out->nchanges = (long long)c->total_nchg;
+      }
    }
 }
 
