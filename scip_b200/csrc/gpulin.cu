@@ -107,10 +107,15 @@ struct gpulin
    void*       peerptr[MAX_PEERS][3] = {};   // opened IPC pointers of the other ranks
    bool        havebounds = false;
    bool        pending = false;     // gpulin_propagate_async was called, gpulin_propagate_wait not yet
-   bool        lightfetch = false;  // fetch only the head of the control block after a call (probing workers)
+   bool        lightfetch = false;  // (unused: every call fetches only the head of the control block now)
+   bool        histfetched = false; // the pinned mirror holds the per-round history of the last call
    std::vector<gpulin*> workers;    // clones that gpulin_probe_batch keeps for this (base) handle
    void*       d_proberes = nullptr; // verdicts of the probes of a batch (ProbeResult[proberescap])
    int64_t     proberescap = 0;
+   int64_t     smallcols = -1;      // columns updated since the last clean fixpoint (< 0: the marks are not all on the list)
+   bool        smallcall = false;   // the pending call was started by probe_kernel
+   bool        smallcalls = true;   // GPULIN_SMALL=0 disables that path
+   int         lastmaxrounds = 0;
    int         lastvar = -1;        // probing worker: the column of its last probe
    bool        needreset = true;    // probing worker: its state is not "node + change log"
    // results of the last propagate call
@@ -204,6 +209,8 @@ static const SellBitsVariant g_sellBitsKernels[] = {
    {sweep_sell_bits_kernel<768, 4, true, false>, 768, false},     // 4
 };
 constexpr int NSELLBITSVARIANTS = sizeof(g_sellBitsKernels) / sizeof(g_sellBitsKernels[0]);
+
+constexpr int64_t SMALLCALL_MAXCOLS = 256;      // gpulin_propagate after at most this many updated columns starts in one block
 
 // one propagation round on h->stream
 template <int MODE, bool GRAPH>
@@ -367,6 +374,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && nsm > 0 )
          h->nsm = nsm;
    }
+   h->smallcalls = !(getenv("GPULIN_SMALL") != nullptr && atoi(getenv("GPULIN_SMALL")) == 0);
    const char* loopenv = getenv("GPULIN_LOOP");
    h->hostloop = (loopenv != nullptr && strcmp(loopenv, "host") == 0);
 
@@ -784,6 +792,7 @@ extern "C" int gpulin_set_bounds_device(gpulin_t* h, const double* d_lb, const d
       return fail(GPULIN_ERR_ARG, "NULL argument");
    CU(cudaSetDevice(h->device));
    set_bounds_kernel<<<gridFor(h, std::max(h->ncols, h->nrows)), 256, 0, h->stream>>>(h->p, d_lb, d_ub);
+   h->smallcols = -1;
    CU(cudaGetLastError());
    h->havebounds = true;
    return GPULIN_OK;
@@ -813,6 +822,23 @@ extern "C" int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, 
          return fail(GPULIN_ERR_ARG, "column index %d out of range", idx[i]);
    }
    CU(cudaSetDevice(h->device));
+   if( n <= SmallUpdate::CAP )
+   {
+      // a handful of bounds (the usual call at a branch-and-bound node): passed by value, no staging copies
+      SmallUpdate su;
+      su.n = (int)n;
+      for( int64_t i = 0; i < n; ++i )
+      {
+         su.idx[i] = idx[i];
+         su.lb[i] = lb[i];
+         su.ub[i] = ub[i];
+      }
+      update_small_kernel<<<1, 32 * SmallUpdate::CAP, 0, h->stream>>>(h->p, su);
+      CU(cudaGetLastError());
+      if( h->smallcols >= 0 )
+         h->smallcols += n;
+      return GPULIN_OK;
+   }
    if( n > h->updcap )
    {
       CU(cudaStreamSynchronize(h->stream));
@@ -835,6 +861,8 @@ extern "C" int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, 
    CU(cudaMemcpyAsync(h->d_updub, ub, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
    update_bounds_kernel<<<gridFor(h, n), 256, 0, h->stream>>>(h->p, n, h->d_updidx, h->d_updlb, h->d_updub);
    CU(cudaGetLastError());
+   if( h->smallcols >= 0 )
+      h->smallcols += n;
    return GPULIN_OK;
 }
 
@@ -852,11 +880,21 @@ extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
    if( !h->havebounds )
       return fail(GPULIN_ERR_STATE, "gpulin_propagate before gpulin_set_bounds");
    CU(cudaSetDevice(h->device));
+   h->lastmaxrounds = maxrounds;
+   h->smallcall = h->smallcols >= 0 && h->smallcols <= SMALLCALL_MAXCOLS && h->npeers <= 1 && !h->hostloop && h->smallcalls;
+   h->smallcols = -1;
    h->h_params[0] = maxrounds;
    h->h_params[1] = (int)h->logcap;
-   CU(cudaMemcpyAsync(&h->p.ctrl->maxrounds, h->h_params, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   if( !h->smallcall )       // (probe_kernel takes both as arguments)
+      CU(cudaMemcpyAsync(&h->p.ctrl->maxrounds, h->h_params, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
    CU(cudaEventRecord(h->ev0, h->stream));
-   if( !h->hostloop )
+   if( h->smallcall )
+   {
+      // few bounds moved since the last fixpoint: one block runs the whole call (and hands over if the cascade grows)
+      probe_kernel<<<1, PROBE_THREADS, 0, h->stream>>>(h->p, h->p, -1, -1, 0.0, 0.0, maxrounds, (int)h->logcap, 1, nullptr);
+      CU(cudaGetLastError());
+   }
+   else if( !h->hostloop )
    {
       CU(cudaGraphLaunch(h->gexec, h->stream));
    }
@@ -878,7 +916,9 @@ extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
    }
    CU(cudaEventRecord(h->ev1, h->stream));
    // the verdict and the statistics come back with the same stream order, without blocking the caller
-   CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, h->lightfetch ? offsetof(Ctrl, round_nnz) : sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+   // (the per-round history is fetched when gpulin_get_round_stats asks for it)
+   CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, offsetof(Ctrl, round_nnz), cudaMemcpyDeviceToHost, h->stream));
+   h->histfetched = false;
    h->pending = true;
    return GPULIN_OK;
 }
@@ -894,6 +934,19 @@ extern "C" int gpulin_propagate_wait(gpulin_t* h, gpulin_result* res)
    h->pending = false;
    float ms = 0.0f;
    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+   if( h->smallcall && h->h_ctrl->status == GPULIN_PROBE_OVERFLOW )
+   {
+      // the cascade outgrew the block: the general loop continues the call (begin_kernel sees Ctrl::resume)
+      h->smallcall = false;
+      CU(cudaEventRecord(h->ev0, h->stream));
+      CU(cudaGraphLaunch(h->gexec, h->stream));       // (probe_kernel left maxrounds and logcap in the control block)
+      CU(cudaEventRecord(h->ev1, h->stream));
+      CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, offsetof(Ctrl, round_nnz), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      float ms2 = 0.0f;
+      CU(cudaEventElapsedTime(&ms2, h->ev0, h->ev1));
+      ms += ms2;
+   }
    const Ctrl* c = h->h_ctrl;
    h->last.status = c->status;
    h->last.nrounds = c->round;
@@ -901,6 +954,7 @@ extern "C" int gpulin_propagate_wait(gpulin_t* h, gpulin_result* res)
    h->last.nnz_processed = (int64_t)c->total_nnz;
    h->last.device_ms = (double)ms;
    h->lastrounds = c->round;
+   h->smallcols = (c->status == GPULIN_FIXPOINT && !c->peererror) ? 0 : -1;     // nothing is marked after a fixpoint
    if( res != nullptr )
       *res = h->last;
    if( c->peererror )
@@ -928,6 +982,8 @@ extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
    CU(cudaMemcpyAsync(h->p.bndf, base->p.bndf, sizeof(double2) * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemsetAsync(h->p.dirty, 0, (size_t)h->nrows, h->stream));
    CU(cudaMemsetAsync(&h->p.ctrl->poisoned, 0, sizeof(unsigned), h->stream));
+   CU(cudaMemsetAsync(&h->p.ctrl->nmark[0][0], 0, sizeof(unsigned) * 8, h->stream));
+   h->smallcols = 0;               // the state of a node whose propagation is complete
    CU(cudaMemsetAsync(h->p.tileflag, 0, (size_t)h->ntiles, h->stream));
    CU(cudaMemsetAsync(h->p.colbits, 0, sizeof(unsigned) * ((size_t)h->ncols / 32 + 1), h->stream));
    h->havebounds = true;
@@ -990,7 +1046,7 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
          w->needreset = false;
       }
       probe_kernel<<<1, PROBE_THREADS, 0, w->stream>>>(w->p, base->p, w->lastvar, var[i], lb[i], ub[i], maxrounds, (int)w->logcap,
-         d_res + i);
+         0, d_res + i);
       w->lastvar = var[i];
    }
    CU(cudaGetLastError());
@@ -1187,6 +1243,13 @@ extern "C" int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int
 {
    if( h == nullptr || n == nullptr )
       return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( !h->histfetched )
+   {
+      CU(cudaSetDevice(h->device));
+      CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      h->histfetched = true;
+   }
    const Ctrl* c = h->h_ctrl;
    const int m = std::min(std::min(h->lastrounds, (int)MAX_HIST), (int)maxn);
    unsigned long long prev = c->t_start;
@@ -1260,12 +1323,15 @@ extern "C" int gpulin_mark_all(gpulin_t* h)
       return fail(GPULIN_ERR_ARG, "handle is NULL");
    CU(cudaSetDevice(h->device));
    mark_all_kernel<<<gridFor(h, h->nrows), 256, 0, h->stream>>>(h->p);
+   h->smallcols = -1;
    CU(cudaGetLastError());
    return GPULIN_OK;
 }
 
 extern "C" int gpulin_round_begin(gpulin_t* h)
 {
+   if( h != nullptr )
+      h->smallcols = -1;
    if( h == nullptr )
       return fail(GPULIN_ERR_ARG, "handle is NULL");
    if( !h->havebounds )

@@ -55,7 +55,7 @@ struct Ctrl
    unsigned int       nexact[4];    // rows the filter sweeps handed to the exact kernel in the running round, per list
    unsigned int       nmark[2][4];  // rows marked (per bin) into mark list buffer 0 / 1; marking writes buffer mb^1
    unsigned int       mb;           // the buffer the last apply filled = what a sparse round reads
-   unsigned int       stay;         // sparse_rounds_kernel: another sparse round follows
+   unsigned int       resume;       // the next begin_kernel continues the call small_rounds started (round count, totals, log)
    unsigned int       nsparse;      // rounds done by sparse_rounds_kernel in this call (statistics)
    unsigned int       poisoned;     // probing worker: its state is not "node + change log" any more (see probe_kernel)
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
@@ -1730,8 +1730,11 @@ struct ProbeResult
    long long nchanges;
 };
 
+// The same kernel serves small incremental calls on any handle (j < 0, keepmarks): the rows gpulin_update_bounds marked
+// since the last fixpoint are on mark list mb^1; if the cascade outgrows the block the marks stay and the general loop
+// continues the call (Ctrl::resume).
 __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p, const DevProblem base, int restorevar, int j,
-   double l, double u, int maxrounds, int logcap, ProbeResult* out)
+   double l, double u, int maxrounds, int logcap, int keepmarks, ProbeResult* out)
 {
    __shared__ RowAcc s_acc[PROBE_THREADS / 32];
    __shared__ int s_nchg;
@@ -1777,9 +1780,6 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p
       c->ticket = 0;
       c->nchgcols = 0;
       c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
-      c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
-      c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
-      c->mb = 0;
       c->nsparse = 0;
       c->logcount = 0;
       c->round_nchg = 0;
@@ -1788,27 +1788,41 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p
       c->total_nchg = 0;
       c->total_nnz = 0;
       c->t_start = globaltimer();
-      l += 0.0;
-      u += 0.0;
-      const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
-      reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
-      noteBounds(p, j, l, u);
+      c->resume = 0;
+      if( j >= 0 )
+      {
+         c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
+         c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
+         c->mb = 0;
+         l += 0.0;
+         u += 0.0;
+         const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
+         reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+         noteBounds(p, j, l, u);
+      }
    }
    __syncthreads();
-   markColumnRows(p, j, tid, PROBE_THREADS);       // into mark list 1
+   bool overflow = false;
+   if( j >= 0 )
+      markColumnRows(p, j, tid, PROBE_THREADS);       // into mark list 1
+   else
+   {
+      // rows left marked by an earlier call are not on the list that is read now: the general loop has to look
+      const unsigned mb = c->mb;
+      overflow = (c->nmark[mb][0] | c->nmark[mb][1] | c->nmark[mb][2]) != 0u;
+   }
    __syncthreads();
    if( tid == 0 )
-      c->mb = 1;
+      c->mb ^= 1u;
    __syncthreads();
 
-   bool overflow = false;
    for( ;; )
    {
       const unsigned mb = c->mb;
       const unsigned n0 = c->nmark[mb][0];
       const unsigned n1 = c->nmark[mb][1];
       const unsigned n2 = c->nmark[mb][2];
-      if( c->cont == 0 )
+      if( c->cont == 0 || overflow )
          break;
       if( n0 > PROBE_MAXROWS || n1 > PROBE_MAXMEDIUM || n2 > 0u || c->logcount > (unsigned long long)c->logcap )
       {
@@ -1833,6 +1847,25 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p
       __syncthreads();
    }
 
+   if( keepmarks )
+   {
+      // a call on an ordinary handle: marked rows stay marked; after an overflow the general loop takes over
+      if( tid == 0 )
+      {
+         if( overflow )
+         {
+            c->resume = 1;
+            c->status = GPULIN_PROBE_OVERFLOW;
+         }
+         if( out != nullptr )
+         {
+            out->status = c->status;
+            out->nrounds = c->round;
+            out->nchanges = (long long)c->total_nchg;
+         }
+      }
+      return;
+   }
    // ---- whatever is still marked (cutoff, round limit, overflow) is unmarked: the next probe starts from the node
    {
       const unsigned mb = c->mb;
@@ -1945,6 +1978,40 @@ __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const i
    }
 }
 
+// a handful of bound changes passed by value (no staging copy): a warp per column
+struct SmallUpdate
+{
+   static constexpr int CAP = 8;
+   int    n;
+   int    idx[CAP];
+   double lb[CAP];
+   double ub[CAP];
+};
+
+__global__ void update_small_kernel(const DevProblem p, const SmallUpdate su)
+{
+   const int w = threadIdx.x >> 5;
+   const int lane = threadIdx.x & 31;
+   if( w >= su.n )
+      return;
+   const int j = su.idx[w];
+   // two entries may name the same column: the later one wins, like in update_bounds_kernel's sequential semantics
+   for( int k = w + 1; k < su.n; ++k )
+   {
+      if( su.idx[k] == j )
+         return;
+   }
+   if( lane == 0 )
+   {
+      const double l = su.lb[w] + 0.0;
+      const double u = su.ub[w] + 0.0;
+      const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
+      reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+      noteBounds(p, j, l, u);
+   }
+   markColumnRows(p, j, lane, 32);
+}
+
 // probing: one bound change passed by value (SCIPchgVarLbProbing / SCIPchgVarUbProbing), rows of the column marked
 __global__ void update_one_kernel(const DevProblem p, int j, double l, double u)
 {
@@ -1998,6 +2065,17 @@ __global__ void mark_all_kernel(const DevProblem p)
 // start of a gpulin_propagate call: reset the loop state
 __global__ void begin_kernel(Ctrl* c)
 {
+   if( c->resume )
+   {
+      // the call was started by probe_kernel (a small incremental call that outgrew its block): rounds, totals and the
+      // change log go on; the marked rows are found through their flags
+      c->resume = 0;
+      c->cont = 1;
+      c->status = 0;
+      c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
+      c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
+      return;
+   }
    c->round = 0;
    c->cont = 1;
    c->status = 0;

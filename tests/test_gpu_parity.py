@@ -176,6 +176,40 @@ def test_update_bounds_marks_only_affected_rows(gpulin):
         assert_bounds_match(glb, gub, want["lb"], want["ub"], prob["vartype"], what="after update_bounds")
 
 
+@pytest.mark.parametrize("small", ["1", "0"])
+def test_dive_of_incremental_calls_matches_oracle(gpulin, monkeypatch, small):
+    """a dive (SCIPchgVarLb/UbProbing + SCIPpropagateProbing, step after step): every call after a few updated bounds runs
+    in one block (probe_kernel, GPULIN_SMALL=1, the default) or through the general loop (=0); both equal the oracle"""
+    monkeypatch.setenv("GPULIN_SMALL", small)
+    prob = synth.setcover(20_000, 20_000, 200_000, seed=12)
+    rng = np.random.default_rng(12)
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.set_change_log(100_000)
+        lp.propagate()
+        lb, ub = lp.get_bounds()
+        for step in range(12):
+            free = np.flatnonzero(lb < ub)
+            if len(free) == 0:
+                break
+            nfix = 1 if step < 8 else 40            # the last steps fix many columns: the cascade outgrows one block
+            var = free[rng.permutation(len(free))[:nfix]]
+            val = rng.integers(0, 2, size=len(var)).astype(np.float64)
+            lp.update_bounds(var, val, val)
+            res = lp.propagate()
+            lb[var] = val
+            ub[var] = val
+            want = oracle.propagate(prob, lb=lb, ub=ub)
+            assert res["status"] == want["status"], f"step {step}"
+            if want["status"] == oracle.STATUS_CUTOFF:
+                break
+            assert res["nrounds"] == want["nrounds"] and res["nchanges"] == want["nchanges"], f"step {step}"
+            log, n = lp.changes(100_000)
+            assert n == res["nchanges"]
+            glb, gub = lp.get_bounds()
+            assert_bounds_match(glb, gub, want["lb"], want["ub"], prob["vartype"], what=f"dive step {step}")
+            lb, ub = glb, gub
+
+
 def test_change_log_replays_to_the_fixpoint(gpulin):
     prob, _ = load_golden("dcmulti", "1e-9")
     with gpulin.LinearPropagator(prob, boundstreps=1e-9) as lp:
