@@ -443,7 +443,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       off += plen[(size_t)i];
    }
    h->nstored = off;
-   if( h->nstored >= (1LL << 40) || h->nstreamelems / TILE >= (1LL << 31) - 64 )
+   if( h->nstored >= (1LL << 40) || h->nstreamelems / TILE >= (1LL << 31) - 64 || nrows >= (1LL << 30) )
    {
       gpulin_destroy(h);
       return fail(GPULIN_ERR_ARG, "matrix too large");
@@ -495,7 +495,18 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       {
          const int64_t r = perm[(size_t)i];
          for( int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k )
-            colrows[(size_t)fill[(size_t)colidx[k]]++] = (int)i;
+         {
+            // flags: a tightened lower / upper bound of the column can matter for a finite side of this row
+            const double a = vals[k];
+            const bool rhsfin = rhs[r] < num->infinity;
+            const bool lhsfin = lhs[r] > -num->infinity;
+            int e = (int)i;
+            if( (a > 0.0 && rhsfin) || (a < 0.0 && lhsfin) )
+               e |= COLROW_LB;
+            if( (a > 0.0 && lhsfin) || (a < 0.0 && rhsfin) )
+               e |= COLROW_UB;
+            colrows[(size_t)fill[(size_t)colidx[k]]++] = e;
+         }
       }
    }
 

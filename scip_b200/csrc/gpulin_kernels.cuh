@@ -1385,7 +1385,15 @@ __device__ __forceinline__ int applyColumn(const DevProblem& p, int j, double2& 
 }
 
 // marks the rows of column j (entries first, first+step, ... of the calling lane) for the next round
-__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step)
+// An entry of colrows carries two flags: a tightened lower / upper bound of the column can matter for a finite side of
+// the row (the rule by which eventExecLinear resets boundstightened, cons_linear.c:17239-17252: a larger lower bound
+// raises the minimal activity if a > 0 -- that matters if rhs is finite -- or lowers the maximal one if a < 0 -- lhs).
+// A row for which the change cannot matter keeps all its residual activities and its verdict: it is not marked.
+constexpr int COLROW_LB = 0x40000000;
+constexpr int COLROW_UB = (int)0x80000000u;
+constexpr int COLROW_ANY = COLROW_LB | COLROW_UB;
+
+__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step, int which = COLROW_ANY)
 {
    // row ids are fetched four at a time before any flag is stored: the byte stores may alias anything as far as the
    // compiler knows, and a load-store-load-store chain would cost one memory round trip per row
@@ -1397,6 +1405,7 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
 #pragma unroll
       for( int t = 0; t < 4; ++t )
       {
+         r[t] = 0;
          if( q + t * step < e )
             r[t] = p.colrows[q + t * step];
       }
@@ -1405,7 +1414,9 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
       for( int t = 0; t < 4; ++t )
       {
          fl[t] = ROW_MARKED;
-         if( q + t * step < e )
+         const bool matters = (r[t] & which) != 0;
+         r[t] &= ~COLROW_ANY;
+         if( q + t * step < e && matters )
          {
             // read before write: many columns mark the same dense rows, and stores to one address serialise
             fl[t] = p.dirty[r[t]];
@@ -1525,25 +1536,32 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
       const unsigned item = it * ngroups + gtid / G;
       const bool valid = item < nlist;
       int j = 0;
+      int which = 0;
       if( valid )
       {
+         // which of the two bounds moves says which rows can care; every lane of the group reads the two words itself
+         // (one broadcast load each) BEFORE the first lane accepts the bounds
          j = p.chglist[item];
-         if( gl == 0 )
-         {
-            bool lbchg;
-            bool ubchg;
-            double2 nb;
-            const int nc = applyColumn(p, j, nb, lbchg, ubchg);
-            atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
-            if( nc > 0 && logcap > 0 )
-               logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
-            mychg += nc;
-         }
+         const longlong2 k = reinterpret_cast<const longlong2*>(p.cand)[j];
+         const double2 old = p.bnd[j];
+         which = (key2d(~k.x) != old.x ? COLROW_LB : 0) | (key2d(k.y) != old.y ? COLROW_UB : 0);
+      }
+      __syncwarp();
+      if( valid && gl == 0 )
+      {
+         bool lbchg;
+         bool ubchg;
+         double2 nb;
+         const int nc = applyColumn(p, j, nb, lbchg, ubchg);
+         atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
+         if( nc > 0 && logcap > 0 )
+            logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
+         mychg += nc;
       }
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
       if( valid )
-         markColumnRows(p, j, gl, G);
+         markColumnRows(p, j, gl, G, which);
    }
    return mychg;
 }
@@ -1593,7 +1611,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
             const int nc = applyColumn(p, j, nb, lbchg, ubchg);
             if( nc > 0 )
             {
-               markColumnRows(p, j, 0, 1);
+               markColumnRows(p, j, 0, 1, (lbchg ? COLROW_LB : 0) | (ubchg ? COLROW_UB : 0));
                if( logcap > 0 )
                   logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
             }
@@ -1617,7 +1635,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
          const int nc = applyColumn(p, j, nb, lbchg, ubchg);
          if( nc > 0 )
          {
-            markColumnRows(p, j, 0, 1);
+            markColumnRows(p, j, 0, 1, (lbchg ? COLROW_LB : 0) | (ubchg ? COLROW_UB : 0));
             if( logcap > 0 )
                logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
          }
