@@ -1326,7 +1326,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
       addRoundNnz(p, nnzdone, gtid >> 5);
 }
 
-__global__ void __launch_bounds__(EXACT_THREADS) exact_rows_kernel(const DevProblem p)
+__global__ void __launch_bounds__(EXACT_THREADS, 3) exact_rows_kernel(const DevProblem p)
 {
    __shared__ RowAcc s_acc[EXACT_THREADS / 32];
 
