@@ -259,7 +259,14 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
    {
       if( MODE == APPLY_PEERS )
          peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);      // every rank's candidates have arrived
-      apply_kernel<MODE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
+      if( MODE == APPLY_PEERS )
+      {
+         // the bits every rank raised on this rank become the change list; then the same list-driven apply as on one GPU
+         peer_collect_kernel<<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p);
+         apply_kernel<APPLY_LIST, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
+      }
+      else
+         apply_kernel<MODE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
       if( MODE == APPLY_PEERS )
          peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);      // nobody commits into keys that are still being read
       if( MODE == APPLY_LIST && sweep && h->nsparseblocks > 0 )

@@ -1662,6 +1662,43 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
    }
 }
 
+// ---- rows sharded over peers: the changed-column bits (raised on every rank by every rank's exact kernel) become the
+// ---- change list, so that the list-driven apply step (4 lanes per column) serves this mode as well: a word per thread,
+// ---- one atomic on the list counter per warp
+__global__ void __launch_bounds__(APPLY_THREADS) peer_collect_kernel(const DevProblem p)
+{
+   const int lane = threadIdx.x & 31;
+   const int nwords = (p.ncols + 31) >> 5;
+   const int nthreads = gridDim.x * APPLY_THREADS;
+   const int gtid = blockIdx.x * APPLY_THREADS + threadIdx.x;
+   for( int w0 = gtid - lane; w0 < nwords; w0 += nthreads )      // warp-uniform trip count
+   {
+      const int w = w0 + lane;
+      unsigned bits = w < nwords ? p.colbits[w] : 0u;
+      const int mine = __popc(bits);
+      int incl = mine;
+#pragma unroll
+      for( int d = 1; d < 32; d <<= 1 )
+      {
+         const int o = __shfl_up_sync(0xffffffffu, incl, d);
+         if( lane >= d )
+            incl += o;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if( total == 0 )
+         continue;
+      unsigned base = 0u;
+      if( lane == 31 )
+         base = atomicAdd(&p.ctrl->nchgcols, (unsigned)total);
+      base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - mine);
+      while( bits != 0u )
+      {
+         p.chglist[base++] = 32 * w + __ffs(bits) - 1;
+         bits &= bits - 1u;
+      }
+   }
+}
+
 // ---- sparse rounds: a persistent cooperative kernel ----------------------------------------------------------------
 // Once the bounds have nearly settled a round touches a few hundred rows, and three launches plus a graph-loop iteration
 // cost more than the work.  This kernel follows the apply step inside the loop body: as long as the last apply marked
