@@ -218,6 +218,8 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
 {
    if( sweep )
    {
+      if( MODE == APPLY_PEERS )
+         lists_to_work_kernel<<<std::min(h->napplyblocks, 64), APPLY_THREADS, 0, h->stream>>>(h->p);
       // the three bins are independent: the smaller ones run on side streams beside the largest
       const int nkinds = (h->nsellblocks > 0) + (h->nstreamblocks > 0) + (h->nlongblocks > 0);
       int side = 0;

@@ -58,6 +58,8 @@ struct Ctrl
    unsigned int       resume;       // the next begin_kernel continues the call small_rounds started (round count, totals, log)
    unsigned int       nsparse;      // rounds done by sparse_rounds_kernel in this call (statistics)
    unsigned int       poisoned;     // probing worker: its state is not "node + change log" any more (see probe_kernel)
+   unsigned int       listsvalid;   // an apply step of this call has run: every marked row is on mark list mb (or a count overflowed)
+   unsigned int       skipsweep;    // the running round takes its rows from the mark list (lists_to_work_kernel): no filter sweep
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
    unsigned long long hist_time[MAX_HIST];   // %globaltimer at the end of each round
    unsigned long long hist_nnz[MAX_HIST];
@@ -473,6 +475,8 @@ __device__ __forceinline__ void loadTile(const DevProblem& p, int t, int lane, T
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const DevProblem p)
 {
+   if( p.ctrl->skipsweep )
+      return;
    static_assert(TPL == 8 && TILE == 256, "the tile layout is wired into the vector loads");
    // per warp: the sums of the rows that end in the current tile, in row order (at most one row per nonzero)
    __shared__ LeanAcc s_tot[SWEEP_THREADS / 32][TILE];
@@ -822,6 +826,8 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, const unsigned* s
 template <int CH, int MINB>
 __global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const DevProblem p)
 {
+   if( p.ctrl->skipsweep )
+      return;
    sellSweep<CH, false>(p, nullptr, SELL_THREADS);
 }
 
@@ -919,6 +925,8 @@ __device__ __forceinline__ void gatherUnless(unsigned skip, const double2* addr,
 template <int NT, int CH, bool MID, bool ALLCOLS = false, bool HD = false>
 __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
 {
+   if( p.ctrl->skipsweep )
+      return;
    extern __shared__ __align__(128) unsigned char s_raw[];
    const Num& n = p.num;
    const unsigned tabbytes = (unsigned)p.nfreewords * 4u;
@@ -1069,6 +1077,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
 // ---- block-per-row for rows longer than STREAM_MAXLEN (and empty rows) ---------------------------------------------
 __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProblem p)
 {
+   if( p.ctrl->skipsweep )
+      return;
    __shared__ LeanAcc s_lean[LONG_THREADS / 32];
 
    const int lane = threadIdx.x & 31;
@@ -1481,6 +1491,7 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
    c->nmark[c->mb][0] = c->nmark[c->mb][1] = c->nmark[c->mb][2] = 0;
    c->mb ^= 1u;
    c->round = r + 1;
+   c->listsvalid = 1;
    int cont = 0;
    if( c->cutoff )
       c->status = 1;
@@ -1660,6 +1671,41 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
          controlStep<GRAPH>(c, handle);
       }
    }
+}
+
+// ---- rows sharded over peers, a round with few marked rows: the rows on the mark list go straight to the work lists of
+// ---- the exact kernel and the filter sweeps of this round return at once (the cooperative sparse-rounds kernel is not
+// ---- used with peers: every round needs its two barriers over the ranks).  The decision is local to the rank.
+__global__ void __launch_bounds__(APPLY_THREADS) lists_to_work_kernel(const DevProblem p)
+{
+   Ctrl* c = p.ctrl;
+   const unsigned mb = c->mb;
+   const unsigned n0 = c->nmark[mb][0];
+   const unsigned n1 = c->nmark[mb][1];
+   const unsigned n2 = c->nmark[mb][2];
+   const bool sparse = c->listsvalid != 0 && n0 <= 16384u && n1 <= 4096u && n2 <= 64u;
+   if( !sparse )
+   {
+      if( blockIdx.x == 0 && threadIdx.x == 0 )
+         c->skipsweep = 0;
+      return;
+   }
+   if( blockIdx.x == 0 && threadIdx.x == 0 )
+      c->skipsweep = 1;
+   const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
+   const unsigned total = n0 + n1 + n2;
+   unsigned long long nnzdone = 0;
+   for( unsigned i = blockIdx.x * APPLY_THREADS + threadIdx.x; i < total; i += gridDim.x * APPLY_THREADS )
+   {
+      const int bin = i < n0 ? 0 : (i < n0 + n1 ? 1 : 2);
+      const int row = bin == 0 ? ml[i] : (bin == 1 ? ml[MARKCAP + (i - n0)] : ml[2 * MARKCAP + (i - n0 - n1)]);
+      if( !claimRow(p, row) )
+         continue;
+      nnzdone += (unsigned long long)(p.rowlen[row] & ~ROWLEN_EXACT);
+      const unsigned pos = atomicAdd(&c->nexact[bin], 1u);
+      p.xlist[(bin == 0 ? 0 : (bin == 1 ? p.nsell : p.nsx)) + pos] = row;
+   }
+   addRoundNnz(p, nnzdone, (int)(blockIdx.x * APPLY_THREADS + threadIdx.x) >> 5);
 }
 
 // ---- rows sharded over peers: the changed-column bits (raised on every rank by every rank's exact kernel) become the
@@ -2127,6 +2173,8 @@ __global__ void begin_kernel(Ctrl* c)
       c->resume = 0;
       c->cont = 1;
       c->status = 0;
+      c->listsvalid = 0;
+      c->skipsweep = 0;
       c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
       c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
       return;
@@ -2141,6 +2189,8 @@ __global__ void begin_kernel(Ctrl* c)
    c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
    c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
    c->nsparse = 0;
+   c->listsvalid = 0;
+   c->skipsweep = 0;
    c->logcount = 0;
    c->round_nchg = 0;
    for( int i = 0; i < NNZ_SLOTS; ++i )
