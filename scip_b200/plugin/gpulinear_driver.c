@@ -1,7 +1,7 @@
 /* gpulinear_driver.c -- a minimal SCIP application with prop_gpulinear linked in (SCIP has no dlopen plugin loader:
  * plugins are linked into the application, cf. examples/Eventhdlr/src/cmain.c of the reference).
  *
- *    gpulinear_driver (--lpb X.lpb | --read X.mps) [--cpu] [--boundstreps B] [--out X.lpr] [--solve] [--verbose]
+ *    gpulinear_driver (--lpb X.lpb | --read X.mps) [--cpu] [--boundstreps B] [--out X.lpr] [--solve] [--presolve] [--verbose]
  *
  * Root-node propagation to the fixpoint with presolving / LP / heuristics / all other propagators off.  By default the
  * bound tightening of the linear constraint handler is switched off (constraints/linear/tightenboundsfreq = -1) and
@@ -113,6 +113,8 @@ static SCIP_RETCODE run(int argc, char** argv)
    int usecpu = 0;
    int solve = 0;
    int quiet = 1;
+   int presolve = 0;
+   int rowsof[5] = {-1, -1, -1, -1, -1};
    char pname[128];
    double t0, t1;
    int infeasible;
@@ -127,9 +129,10 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--cpu") == 0 ) usecpu = 1;
       else if( strcmp(argv[i], "--solve") == 0 ) solve = 1;
       else if( strcmp(argv[i], "--verbose") == 0 ) quiet = 0;
+      else if( strcmp(argv[i], "--presolve") == 0 ) presolve = 1;
       else
       {
-         fprintf(stderr, "usage: gpulinear_driver (--lpb F | --read F) [--cpu] [--boundstreps B] [--out F.lpr] [--solve] [--verbose]\n");
+         fprintf(stderr, "usage: gpulinear_driver (--lpb F | --read F) [--cpu] [--boundstreps B] [--out F.lpr] [--solve] [--presolve] [--verbose]\n");
          return SCIP_ERROR;
       }
    }
@@ -141,8 +144,11 @@ static SCIP_RETCODE run(int argc, char** argv)
    if( !usecpu )
       SCIP_CALL( SCIPincludePropGpulinear(scip) );
 
-   SCIP_CALL( SCIPsetIntParam(scip, "presolving/maxrounds", 0) );
-   SCIP_CALL( SCIPsetIntParam(scip, "presolving/maxrestarts", 0) );
+   if( !presolve )
+   {
+      SCIP_CALL( SCIPsetIntParam(scip, "presolving/maxrounds", 0) );
+      SCIP_CALL( SCIPsetIntParam(scip, "presolving/maxrestarts", 0) );
+   }
    SCIP_CALL( SCIPsetIntParam(scip, "propagating/maxrounds", -1) );
    SCIP_CALL( SCIPsetIntParam(scip, "propagating/maxroundsroot", -1) );
    SCIP_CALL( SCIPsetIntParam(scip, "lp/solvefreq", -1) );
@@ -184,16 +190,21 @@ static SCIP_RETCODE run(int argc, char** argv)
    t1 = wallclock();
 
    infeasible = (SCIPgetStatus(scip) == SCIP_STATUS_INFEASIBLE);
+   if( !usecpu )
+   {
+      for( i = 0; i < 5; ++i )
+         rowsof[i] = SCIPgetNRowsGpulinear(scip, i);
+   }
    linhdlr = SCIPfindConshdlr(scip, "linear");
    gpuprop = SCIPfindProp(scip, "gpulinear");
    printf("{\"mode\": \"%s\", \"status\": \"%s\", \"scip_status\": %d, \"ncols\": %d, \"nodes\": %lld, \"linear_prop_calls\": %lld, "
       "\"linear_domreds\": %lld, \"linear_prop_time_s\": %.9g, \"gpu_prop_calls\": %lld, \"gpu_domreds\": %lld, "
-      "\"gpu_prop_time_s\": %.9g, \"solve_time_s\": %.9g, \"primal\": %.15g}\n",
+      "\"gpu_prop_time_s\": %.9g, \"solve_time_s\": %.9g, \"primal\": %.15g, \"gpu_rows\": [%d, %d, %d, %d, %d]}\n",
       usecpu ? "cpu" : "gpu", infeasible ? "infeasible" : "ok", (int)SCIPgetStatus(scip), g_nvars, (long long)SCIPgetNNodes(scip),
       (long long)SCIPconshdlrGetNPropCalls(linhdlr), (long long)SCIPconshdlrGetNDomredsFound(linhdlr),
       SCIPconshdlrGetPropTime(linhdlr), gpuprop != NULL ? (long long)SCIPpropGetNCalls(gpuprop) : 0LL,
       gpuprop != NULL ? (long long)SCIPpropGetNDomredsFound(gpuprop) : 0LL, gpuprop != NULL ? SCIPpropGetTime(gpuprop) : 0.0,
-      t1 - t0, SCIPgetPrimalbound(scip));
+      t1 - t0, SCIPgetPrimalbound(scip), rowsof[0], rowsof[1], rowsof[2], rowsof[3], rowsof[4]);
 
    if( outfile != NULL )
    {

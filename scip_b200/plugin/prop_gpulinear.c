@@ -4,9 +4,12 @@
  * -> tightenBounds (:6980).  As a propagator with non-negative priority it is called by SCIPpropExec (prop.c:646) before
  * the constraint handlers (solve.c:524).  What it does per call (SCIP_DECL_PROPEXEC, type_prop.h:217):
  *
- *   1. (re)build the device copy of the linear rows when the set of linear constraints changed: rows through
- *      SCIPgetVarsLinear / SCIPgetValsLinear / SCIPgetLhsLinear / SCIPgetRhsLinear (cons_linear.h:263-307), columns =
- *      SCIPvarGetProbindex (pub_var.h:592); tolerances from SCIPinfinity/SCIPepsilon/SCIPsumepsilon/SCIPfeastol/
+ *   1. (re)build the device copy of the linear rows when the set of constraints changed: rows through
+ *      SCIPgetVarsLinear / SCIPgetValsLinear / SCIPgetLhsLinear / SCIPgetRhsLinear (cons_linear.h:263-307) and -- with
+ *      propagating/gpulinear/allrows, the way SCIP's own matrix view does it (matrix.c:541-696) -- the linear rows
+ *      behind knapsack, setppc, logicor and varbound constraints, into which presolving upgrades most linear
+ *      constraints; every row is rewritten to active variables (SCIPgetProbvarLinearSum, scip_var.h:962: negated and
+ *      aggregated variables, the constant goes to the sides), columns = SCIPvarGetProbindex (pub_var.h:592); tolerances from SCIPinfinity/SCIPepsilon/SCIPsumepsilon/SCIPfeastol/
  *      SCIPgetHugeValue and numerics/boundstreps, constraints/linear/maxeasyactivitydelta;
  *   2. bring the device bounds up to date: the first call after a (re)build sends all local bounds
  *      (SCIPvarGetLbLocal/UbLocal, gpulin_set_bounds); later calls send only the bounds that changed since the last
@@ -30,6 +33,10 @@
 #include "gpulin.h"
 
 #include "scip/cons_linear.h"
+#include "scip/cons_knapsack.h"
+#include "scip/cons_logicor.h"
+#include "scip/cons_setppc.h"
+#include "scip/cons_varbound.h"
 #include "scip/pub_cons.h"
 #include "scip/pub_event.h"
 #include "scip/scip_event.h"
@@ -59,6 +66,7 @@
 #define DEFAULT_MAXROUNDS      -1         /* rounds per call on the device (-1: to the fixpoint) */
 #define DEFAULT_DEVICE         0
 #define DEFAULT_LOGCAPFAC      8          /* change log capacity = factor * number of variables */
+#define DEFAULT_ALLROWS        TRUE       /* read the rows of knapsack / setppc / logicor / varbound constraints as well */
 #define DEFAULT_INCREMENTAL    TRUE       /* send only changed bounds (event driven) instead of all bounds per call */
 #define EVENTHDLR_NAME         "gpulinear"
 #define EVENTHDLR_DESC         "collects the variables whose bounds changed since the last call of prop_gpulinear"
@@ -83,7 +91,9 @@ struct SCIP_PropData
    int                   nrows;
    int64_t               nnz;
    int64_t               logcap;
-   int                   nlinconss;          /**< active linear constraints when the device copy was built */
+   int                   nlinconss;          /**< active constraints of all row sources when the device copy was built */
+   int                   nrowsof[5];         /**< rows per source: linear, knapsack, setppc, logicor, varbound */
+   SCIP_Bool             allrows;            /**< parameter: also read knapsack / setppc / logicor / varbound rows */
    int                   nskipped;           /**< rows not sent to the device (modifiable, local, non-active variables) */
    SCIP_EVENTHDLR*       eventhdlr;          /**< bound change event handler */
    int*                  filterpos;          /**< per column: position of the caught event, or -1 */
@@ -155,133 +165,300 @@ void freeDeviceCopy(
    propdata->nlinconss = -1;
 }
 
-/** can this linear constraint be propagated on the device?  (cf. tightenBounds :7010: modifiable rows are skipped) */
+#define NROWSOURCES 5
+static const char* const rowsourcenames[NROWSOURCES] = {"linear", "knapsack", "setppc", "logicor", "varbound"};
+
+/** number of active constraints of all row sources (the cheap staleness check of the device copy) */
 static
-SCIP_Bool rowIsUsable(
+int countSourceConss(
    SCIP*                 scip,
-   SCIP_CONS*            cons
+   SCIP_Bool             allrows
    )
 {
-   SCIP_VAR** vars;
-   int nvars;
-   int v;
-
-   if( SCIPconsIsModifiable(cons) || SCIPconsIsLocal(cons) || !SCIPconsIsPropagationEnabled(cons) )
-      return FALSE;
-   vars = SCIPgetVarsLinear(scip, cons);
-   nvars = SCIPgetNVarsLinear(scip, cons);
-   for( v = 0; v < nvars; ++v )
+   int n = 0;
+   int s;
+   for( s = 0; s < (allrows ? NROWSOURCES : 1); ++s )
    {
-      if( SCIPvarGetProbindex(vars[v]) < 0 )
-         return FALSE;
+      SCIP_CONSHDLR* conshdlr = SCIPfindConshdlr(scip, rowsourcenames[s]);
+      if( conshdlr != NULL )
+         n += SCIPconshdlrGetNActiveConss(conshdlr);
    }
-   return TRUE;
+   return n;
 }
 
-/** builds the device copy of all usable linear rows */
+/** the row  lhs <= sum vals[i] vars[i] <= rhs  of a constraint of source `src`, rewritten to active variables; the
+ *  buffers grow as needed.  *usable = FALSE for rows the device must not propagate (cf. tightenBounds :7010: modifiable
+ *  rows are skipped; local rows are only valid in a subtree) */
+static
+SCIP_RETCODE getActiveRow(
+   SCIP*                 scip,
+   SCIP_CONS*            cons,
+   int                   src,
+   SCIP_VAR***           vars,
+   SCIP_Real**           vals,
+   int*                  size,
+   int*                  nvars,
+   SCIP_Real*            lhs,
+   SCIP_Real*            rhs,
+   SCIP_Bool*            usable
+   )
+{
+   SCIP_VAR** cvars = NULL;
+   SCIP_Real constant = 0.0;
+   int n = 0;
+   int required = 0;
+   int v;
+
+   *usable = FALSE;
+   *nvars = 0;
+   if( SCIPconsIsModifiable(cons) || SCIPconsIsLocal(cons) || !SCIPconsIsPropagationEnabled(cons) )
+      return SCIP_OKAY;
+
+   switch( src )
+   {
+   case 0:
+      n = SCIPgetNVarsLinear(scip, cons);
+      cvars = SCIPgetVarsLinear(scip, cons);
+      break;
+   case 1:
+      n = SCIPgetNVarsKnapsack(scip, cons);
+      cvars = SCIPgetVarsKnapsack(scip, cons);
+      break;
+   case 2:
+      n = SCIPgetNVarsSetppc(scip, cons);
+      cvars = SCIPgetVarsSetppc(scip, cons);
+      break;
+   case 3:
+      n = SCIPgetNVarsLogicor(scip, cons);
+      cvars = SCIPgetVarsLogicor(scip, cons);
+      break;
+   default:
+      n = 2;
+      break;
+   }
+   if( n > *size )
+   {
+      const int newsize = SCIPcalcMemGrowSize(scip, n);
+      SCIP_CALL( SCIPreallocBufferArray(scip, vars, newsize) );
+      SCIP_CALL( SCIPreallocBufferArray(scip, vals, newsize) );
+      *size = newsize;
+   }
+   switch( src )
+   {
+   case 0:
+   {
+      const SCIP_Real* cvals = SCIPgetValsLinear(scip, cons);
+      for( v = 0; v < n; ++v )
+      {
+         (*vars)[v] = cvars[v];
+         (*vals)[v] = cvals[v];
+      }
+      *lhs = SCIPgetLhsLinear(scip, cons);
+      *rhs = SCIPgetRhsLinear(scip, cons);
+      break;
+   }
+   case 1:
+   {
+      /* sum w x <= capacity (cons_knapsack.h:145-177) */
+      const SCIP_Longint* weights = SCIPgetWeightsKnapsack(scip, cons);
+      for( v = 0; v < n; ++v )
+      {
+         (*vars)[v] = cvars[v];
+         (*vals)[v] = (SCIP_Real)weights[v];
+      }
+      *lhs = -SCIPinfinity(scip);
+      *rhs = (SCIP_Real)SCIPgetCapacityKnapsack(scip, cons);
+      break;
+   }
+   case 2:
+   {
+      /* sum x == / <= / >= 1 (cons_setppc.h:87-89) */
+      const SCIP_SETPPCTYPE type = SCIPgetTypeSetppc(scip, cons);
+      for( v = 0; v < n; ++v )
+      {
+         (*vars)[v] = cvars[v];
+         (*vals)[v] = 1.0;
+      }
+      *lhs = type == SCIP_SETPPCTYPE_PACKING ? -SCIPinfinity(scip) : 1.0;
+      *rhs = type == SCIP_SETPPCTYPE_COVERING ? SCIPinfinity(scip) : 1.0;
+      break;
+   }
+   case 3:
+      /* sum x >= 1 */
+      for( v = 0; v < n; ++v )
+      {
+         (*vars)[v] = cvars[v];
+         (*vals)[v] = 1.0;
+      }
+      *lhs = 1.0;
+      *rhs = SCIPinfinity(scip);
+      break;
+   default:
+      /* lhs <= x + c y <= rhs (cons_varbound.h:140-168) */
+      (*vars)[0] = SCIPgetVarVarbound(scip, cons);
+      (*vals)[0] = 1.0;
+      (*vars)[1] = SCIPgetVbdvarVarbound(scip, cons);
+      (*vals)[1] = SCIPgetVbdcoefVarbound(scip, cons);
+      *lhs = SCIPgetLhsVarbound(scip, cons);
+      *rhs = SCIPgetRhsVarbound(scip, cons);
+      break;
+   }
+
+   /* active variables: x' = 1 - x, x = a y + c, ... ; the constant moves to the sides (matrix.c: getActiveVariables) */
+   SCIP_CALL( SCIPgetProbvarLinearSum(scip, *vars, *vals, &n, *size, &constant, &required) );
+   if( required > *size )
+   {
+      const int newsize = SCIPcalcMemGrowSize(scip, required);
+      SCIP_CALL( SCIPreallocBufferArray(scip, vars, newsize) );
+      SCIP_CALL( SCIPreallocBufferArray(scip, vals, newsize) );
+      *size = newsize;
+      SCIP_CALL( SCIPgetProbvarLinearSum(scip, *vars, *vals, &n, *size, &constant, &required) );
+      assert(required <= *size);
+   }
+   for( v = 0; v < n; ++v )
+   {
+      if( SCIPvarGetProbindex((*vars)[v]) < 0 )
+         return SCIP_OKAY;
+   }
+   if( !SCIPisInfinity(scip, -(*lhs)) )
+      *lhs -= constant;
+   if( !SCIPisInfinity(scip, *rhs) )
+      *rhs -= constant;
+   *nvars = n;
+   *usable = TRUE;
+   return SCIP_OKAY;
+}
+
+/** builds the device copy of all usable rows */
 static
 SCIP_RETCODE buildDeviceCopy(
    SCIP*                 scip,
    SCIP_PROPDATA*        propdata
    )
 {
-   SCIP_CONSHDLR* conshdlr;
-   SCIP_CONS** conss;
    SCIP_VAR** probvars;
+   SCIP_VAR** rowvars;
+   SCIP_Real* rowvals;
    gpulin_numerics num;
    uint8_t* vartype;
    int64_t* fill;
    int64_t k;
-   int nconss;
+   int rowsize;
+   int nsources;
    int ncols;
    int nrows;
+   int pass;
+   int src;
    int c;
    int j;
    int rc;
 
    freeDeviceCopy(scip, propdata);
 
-   conshdlr = SCIPfindConshdlr(scip, "linear");
-   if( conshdlr == NULL )
-      return SCIP_OKAY;
-   conss = SCIPconshdlrGetConss(conshdlr);
-   nconss = SCIPconshdlrGetNActiveConss(conshdlr);
-   propdata->nlinconss = nconss;
+   nsources = propdata->allrows ? NROWSOURCES : 1;
+   propdata->nlinconss = countSourceConss(scip, propdata->allrows);
    propdata->nskipped = 0;
+   if( propdata->nlinconss == 0 )
+      return SCIP_OKAY;
 
    probvars = SCIPgetVars(scip);
    ncols = SCIPgetNVars(scip);
+   rowsize = 64;
+   SCIP_CALL( SCIPallocBufferArray(scip, &rowvars, rowsize) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &rowvals, rowsize) );
+   vartype = NULL;
+   fill = NULL;
+
+   /* two passes over the constraints of all sources: count, then fill */
    nrows = 0;
    k = 0;
-   for( c = 0; c < nconss; ++c )
+   for( pass = 0; pass < 2; ++pass )
    {
-      if( rowIsUsable(scip, conss[c]) )
+      if( pass == 1 )
       {
-         ++nrows;
-         k += SCIPgetNVarsLinear(scip, conss[c]);
+         if( nrows == 0 || ncols == 0 )
+         {
+            SCIPfreeBufferArray(scip, &rowvals);
+            SCIPfreeBufferArray(scip, &rowvars);
+            return SCIP_OKAY;
+         }
+         propdata->ncols = ncols;
+         propdata->nrows = nrows;
+         propdata->nnz = k;
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->vars, ncols) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lb, ncols) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->ub, ncols) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colptr, ncols + 1) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowcons, nrows) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lhs, nrows) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rhs, nrows) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowptr, nrows + 1) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colidx, propdata->nnz) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->vals, propdata->nnz) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colrows, propdata->nnz) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colpos, propdata->nnz) );
+         SCIP_CALL( SCIPallocBufferArray(scip, &vartype, ncols) );
+         SCIP_CALL( SCIPallocBufferArray(scip, &fill, ncols + 1) );
+         for( j = 0; j < ncols; ++j )
+         {
+            assert(SCIPvarGetProbindex(probvars[j]) == j);
+            propdata->vars[j] = probvars[j];
+            vartype[j] = SCIPvarIsIntegral(probvars[j]) ? GPULIN_VAR_INTEGRAL : GPULIN_VAR_CONTINUOUS;
+            propdata->colptr[j] = 0;
+         }
+         propdata->colptr[ncols] = 0;
+         nrows = 0;
+         k = 0;
       }
-      else
-         ++propdata->nskipped;
-   }
-   if( nrows == 0 || ncols == 0 )
-      return SCIP_OKAY;
-
-   propdata->ncols = ncols;
-   propdata->nrows = nrows;
-   propdata->nnz = k;
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->vars, ncols) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lb, ncols) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->ub, ncols) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colptr, ncols + 1) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowcons, nrows) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lhs, nrows) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rhs, nrows) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowptr, nrows + 1) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colidx, propdata->nnz) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->vals, propdata->nnz) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colrows, propdata->nnz) );
-   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colpos, propdata->nnz) );
-   SCIP_CALL( SCIPallocBufferArray(scip, &vartype, ncols) );
-   SCIP_CALL( SCIPallocBufferArray(scip, &fill, ncols + 1) );
-
-   for( j = 0; j < ncols; ++j )
-   {
-      assert(SCIPvarGetProbindex(probvars[j]) == j);
-      propdata->vars[j] = probvars[j];
-      vartype[j] = SCIPvarIsIntegral(probvars[j]) ? GPULIN_VAR_INTEGRAL : GPULIN_VAR_CONTINUOUS;
-      propdata->colptr[j] = 0;
-   }
-   propdata->colptr[ncols] = 0;
-
-   /* rows */
-   nrows = 0;
-   k = 0;
-   for( c = 0; c < nconss; ++c )
-   {
-      SCIP_VAR** vars;
-      SCIP_Real* vals;
-      int nvars;
-      int v;
-
-      if( !rowIsUsable(scip, conss[c]) )
-         continue;
-      vars = SCIPgetVarsLinear(scip, conss[c]);
-      vals = SCIPgetValsLinear(scip, conss[c]);
-      nvars = SCIPgetNVarsLinear(scip, conss[c]);
-      propdata->rowcons[nrows] = conss[c];
-      propdata->rowptr[nrows] = k;
-      propdata->lhs[nrows] = SCIPgetLhsLinear(scip, conss[c]);
-      propdata->rhs[nrows] = SCIPgetRhsLinear(scip, conss[c]);
-      for( v = 0; v < nvars; ++v )
+      for( src = 0; src < nsources; ++src )
       {
-         propdata->colidx[k] = SCIPvarGetProbindex(vars[v]);
-         propdata->vals[k] = vals[v];
-         ++propdata->colptr[propdata->colidx[k] + 1];
-         ++k;
+         SCIP_CONSHDLR* conshdlr = SCIPfindConshdlr(scip, rowsourcenames[src]);
+         SCIP_CONS** conss;
+         int nconss;
+
+         if( pass == 0 )
+            propdata->nrowsof[src] = 0;
+         if( conshdlr == NULL )
+            continue;
+         conss = SCIPconshdlrGetConss(conshdlr);
+         nconss = SCIPconshdlrGetNActiveConss(conshdlr);
+         for( c = 0; c < nconss; ++c )
+         {
+            SCIP_Real lhs;
+            SCIP_Real rhs;
+            SCIP_Bool usable;
+            int nvars;
+            int v;
+
+            SCIP_CALL( getActiveRow(scip, conss[c], src, &rowvars, &rowvals, &rowsize, &nvars, &lhs, &rhs, &usable) );
+            if( !usable )
+            {
+               if( pass == 0 )
+                  ++propdata->nskipped;
+               continue;
+            }
+            if( pass == 1 )
+            {
+               propdata->rowcons[nrows] = conss[c];
+               propdata->rowptr[nrows] = k;
+               propdata->lhs[nrows] = lhs;
+               propdata->rhs[nrows] = rhs;
+               for( v = 0; v < nvars; ++v )
+               {
+                  propdata->colidx[k + v] = SCIPvarGetProbindex(rowvars[v]);
+                  propdata->vals[k + v] = rowvals[v];
+                  ++propdata->colptr[propdata->colidx[k + v] + 1];
+               }
+            }
+            else
+               ++propdata->nrowsof[src];
+            k += nvars;
+            ++nrows;
+         }
       }
-      ++nrows;
    }
    propdata->rowptr[nrows] = k;
+   assert(nrows == propdata->nrows && k == propdata->nnz);
 
    /* column -> rows, for PROPRESPROP */
    for( j = 0; j < ncols; ++j )
@@ -311,6 +488,8 @@ SCIP_RETCODE buildDeviceCopy(
       propdata->lhs, propdata->rhs, vartype, &num, &propdata->gpu);
    SCIPfreeBufferArray(scip, &fill);
    SCIPfreeBufferArray(scip, &vartype);
+   SCIPfreeBufferArray(scip, &rowvals);
+   SCIPfreeBufferArray(scip, &rowvars);
    if( rc != GPULIN_OK )
    {
       SCIPerrorMessage("prop_gpulinear: gpulin_create failed (%d): %s\n", rc, gpulin_last_error());
@@ -349,8 +528,9 @@ SCIP_RETCODE buildDeviceCopy(
    }
 
    SCIPverbMessage(scip, SCIP_VERBLEVEL_FULL, NULL,
-      "prop_gpulinear: device copy of %d linear rows (%d skipped), %d columns, %lld nonzeros\n", nrows, propdata->nskipped,
-      ncols, (long long)propdata->nnz);
+      "prop_gpulinear: device copy of %d rows (%d linear, %d knapsack, %d setppc, %d logicor, %d varbound; %d skipped), "
+      "%d columns, %lld nonzeros\n", nrows, propdata->nrowsof[0], propdata->nrowsof[1], propdata->nrowsof[2],
+      propdata->nrowsof[3], propdata->nrowsof[4], propdata->nskipped, ncols, (long long)propdata->nnz);
 
    return SCIP_OKAY;
 }
@@ -434,8 +614,8 @@ static
 SCIP_DECL_PROPEXEC(propExecGpulinear)
 {
    SCIP_PROPDATA* propdata;
-   SCIP_CONSHDLR* conshdlr;
    gpulin_result res;
+   int nsourceconss;
    int64_t nlog;
    int64_t e;
    int ntightened;
@@ -448,13 +628,12 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
    propdata = SCIPpropGetData(prop);
    assert(propdata != NULL);
 
-   conshdlr = SCIPfindConshdlr(scip, "linear");
-   if( conshdlr == NULL || SCIPconshdlrGetNActiveConss(conshdlr) == 0 )
+   nsourceconss = countSourceConss(scip, propdata->allrows);
+   if( nsourceconss == 0 )
       return SCIP_OKAY;
 
-   /* staleness: rebuild when the number of active linear constraints or of variables changed */
-   if( propdata->gpu == NULL || propdata->nlinconss != SCIPconshdlrGetNActiveConss(conshdlr)
-      || propdata->ncols != SCIPgetNVars(scip) )
+   /* staleness: rebuild when the number of active constraints of the row sources or of variables changed */
+   if( propdata->gpu == NULL || propdata->nlinconss != nsourceconss || propdata->ncols != SCIPgetNVars(scip) )
    {
       SCIP_CALL( buildDeviceCopy(scip, propdata) );
       if( propdata->gpu == NULL )
@@ -718,9 +897,29 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/incremental",
          "send only the bounds that changed since the last call (bound change events) instead of all bounds",
          &propdata->incremental, FALSE, DEFAULT_INCREMENTAL, NULL, NULL) );
+   SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/allrows",
+         "also propagate the linear rows behind knapsack, setppc, logicor and varbound constraints (cf. matrix.c)",
+         &propdata->allrows, FALSE, DEFAULT_ALLROWS, NULL, NULL) );
    SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/device",
          "CUDA device ordinal",
          &propdata->device, TRUE, DEFAULT_DEVICE, 0, 1023, NULL, NULL) );
 
    return SCIP_OKAY;
+}
+
+/** rows on the device by source (0 linear, 1 knapsack, 2 setppc, 3 logicor, 4 varbound) */
+int SCIPgetNRowsGpulinear(
+   SCIP*                 scip,               /**< SCIP data structure */
+   int                   source              /**< row source */
+   )
+{
+   SCIP_PROP* prop = SCIPfindProp(scip, PROP_NAME);
+   SCIP_PROPDATA* propdata;
+
+   if( prop == NULL || source < 0 || source >= NROWSOURCES )
+      return -1;
+   propdata = SCIPpropGetData(prop);
+   if( propdata == NULL || propdata->gpu == NULL )
+      return -1;
+   return propdata->nrowsof[source];
 }

@@ -23,6 +23,13 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP*                 scip                /**< SCIP data structure */
    );
 
+/** rows on the device by source (0 linear, 1 knapsack, 2 setppc, 3 logicor, 4 varbound; cf. SCIPmatrixGetNRows,
+ *  pub_matrix.h); -1 if there is no device copy or the propagator is not included */
+int SCIPgetNRowsGpulinear(
+   SCIP*                 scip,               /**< SCIP data structure */
+   int                   source              /**< row source */
+   );
+
 #ifdef __cplusplus
 }
 #endif

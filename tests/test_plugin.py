@@ -66,3 +66,41 @@ def test_plugin_in_tree_search_with_conflict_analysis():
     gpu = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve")
     assert gpu["scip_status"] == cpu["scip_status"]
     assert gpu["gpu_prop_calls"] > 100 and gpu["linear_domreds"] == 0
+
+
+@needs_driver
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["p0548", "misc03", "lseu", "enigma"])
+def test_plugin_reads_upgraded_rows_after_presolve(tmp_path, name):
+    """with presolving on, most linear constraints are upgraded to knapsack / setppc / logicor / varbound constraints
+    (consPresolLinear); the plugin reads their rows like SCIP's matrix view does (matrix.c:541-696), rewritten to active
+    variables.  Root node: same verdict as the reference's own propagators, and -- the GPU rows are an additional
+    propagator on the same transformed problem -- bounds at least as tight"""
+    outs = {}
+    info = {}
+    for mode in ("cpu", "gpu"):
+        out = str(tmp_path / f"{mode}.lpr")
+        args = ["--lpb", os.path.join(GOLDEN, name + ".lpb"), "--presolve", "--boundstreps", "1e-9", "--out", out]
+        info[mode] = run_driver(*(args + (["--cpu"] if mode == "cpu" else [])))
+        outs[mode] = oracle.read_lpr(out)
+    assert outs["gpu"]["infeasible"] == outs["cpu"]["infeasible"]
+    rows = info["gpu"]["gpu_rows"]
+    if info["gpu"]["gpu_prop_calls"] > 0:
+        assert sum(rows) > 0 and sum(rows[1:]) > 0, rows      # upgraded rows are on the device
+    if not outs["cpu"]["infeasible"]:
+        tol = 1e-9 * np.maximum(1.0, np.abs(outs["cpu"]["lb"]))
+        assert np.all(outs["gpu"]["lb"] >= outs["cpu"]["lb"] - tol)
+        tol = 1e-9 * np.maximum(1.0, np.abs(outs["cpu"]["ub"]))
+        assert np.all(outs["gpu"]["ub"] <= outs["cpu"]["ub"] + tol)
+
+
+@needs_driver
+@pytest.mark.gpu
+def test_plugin_in_tree_search_after_presolve():
+    """the tree search of enigma on the presolved problem (set partitioning / knapsack rows on the device, negated
+    variables rewritten to active ones): same status and optimal value as the reference alone"""
+    cpu = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--cpu", "--solve", "--presolve")
+    gpu = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", "--presolve")
+    assert gpu["scip_status"] == cpu["scip_status"]
+    assert abs(gpu["primal"] - cpu["primal"]) <= 1e-6
+    assert gpu["gpu_prop_calls"] > 10
