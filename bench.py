@@ -158,6 +158,31 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def probing_batch_extra(propagator, synth, device):
+    """BASELINE configs[4] on one GPU (reported beside the headline, not part of it): 1024 probes -- one free binary fixed
+    to 0 or 1 each, SCIPapplyProbingVar's pattern -- on the 5M-nnz set-cover matrix at its root fixpoint, 32 workers,
+    one launch of one block per probe; wall clock of the whole batch through the C ABI with host buffers"""
+    prob = synth.setcover(500_000, 500_000, 5_000_000, seed=3)
+    with propagator.LinearPropagator(prob, device=device) as base:
+        base.propagate()
+        lb, ub = base.get_bounds()
+        free = np.flatnonzero(lb < ub)
+        rng = np.random.default_rng(3)
+        var = free[rng.integers(0, len(free), size=1024)].astype(np.int32)
+        val = rng.integers(0, 2, size=1024).astype(np.float64)
+        base.probe_batch(var[:256], val[:256], val[:256], nworkers=32)
+        times = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            res = base.probe_batch(var, val, val, nworkers=32)
+            times.append(time.perf_counter() - t0)
+    t = min(times)
+    return dict(workload="1024 probing bound vectors on a 5M-nnz set-cover MIP (500k x 500k, seed 3), 32 workers",
+                ms_per_batch=t * 1e3, us_per_probe=t / len(var) * 1e6, probes=int(len(var)),
+                cutoffs=int((res["status"] == 1).sum()), mean_rounds=float(res["nrounds"].mean()),
+                mean_changes=float(res["nchanges"].mean()))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
@@ -319,6 +344,8 @@ def run_ours(args):
         if not args.no_cpu:
             cb, _, _ = cpu_reference_steps(1, 0)
             line["cpu_baseline"] = cb
+        if not args.no_extras:
+            line["extras"] = dict(c5_probing_batch=probing_batch_extra(propagator, synth, local_rank))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -332,6 +359,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra measurements (BASELINE configs[4], N=1 only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the ranks merge candidate bounds (peer memory inside the kernel | NCCL all-reduce)")
     args = ap.parse_args()

@@ -99,6 +99,109 @@ static SCIP_RETCODE readLpb(SCIP* scip, const char* fn)
    return SCIP_OKAY;
 }
 
+/* --probe-batch N: a checker propagator (delayed: it runs once the root node is propagated) probes up to N unfixed
+ * integral variables the way SCIPapplyProbingVar does (prop_probing.c:1254-1279: SCIPstartProbing, SCIPchgVarLb/UbProbing,
+ * SCIPpropagateProbing, SCIPendProbing), then hands the same probes to SCIPprobeBatchGpulinear and compares the verdicts */
+static int g_nprobecheck = 0;
+static int g_probedone = 0;
+static int g_inprobecheck = 0;
+static int g_usecpu = 0;
+
+static SCIP_DECL_PROPEXEC(propExecProbecheck)
+{
+   SCIP_VAR** vars = SCIPgetVars(scip);
+   SCIP_VAR** pv;
+   SCIP_Real* plb;
+   SCIP_Real* pub;
+   SCIP_Bool* cutscip;
+   SCIP_Bool* cutbatch;
+   SCIP_Longint* ndom;
+   SCIP_Longint* nchg;
+   SCIP_Bool nodecutoff = FALSE;
+   int nvars = SCIPgetNVars(scip);
+   int n = 0;
+   int nmismatch = 0;
+   int ncutscip = 0;
+   int ncutbatch = 0;
+   int nactive = 0;
+   double t0, t1, t2;
+   int i;
+
+   (void)prop;
+   (void)proptiming;
+   *result = SCIP_DIDNOTRUN;
+   if( g_probedone || g_inprobecheck || SCIPgetDepth(scip) != 0 || SCIPinProbing(scip) )
+      return SCIP_OKAY;
+   g_probedone = 1;
+   g_inprobecheck = 1;
+   SCIP_CALL( SCIPallocBufferArray(scip, &pv, g_nprobecheck) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &plb, g_nprobecheck) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &pub, g_nprobecheck) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &cutscip, g_nprobecheck) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &cutbatch, g_nprobecheck) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &ndom, g_nprobecheck) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &nchg, g_nprobecheck) );
+   for( i = 0; i < nvars && n < g_nprobecheck; ++i )
+   {
+      const SCIP_Real lb = SCIPvarGetLbLocal(vars[i]);
+      const SCIP_Real ub = SCIPvarGetUbLocal(vars[i]);
+      if( !SCIPvarIsIntegral(vars[i]) || ub - lb < 0.5 || SCIPisInfinity(scip, -lb) || SCIPisInfinity(scip, ub) )
+         continue;
+      pv[n] = vars[i];
+      if( n % 2 == 0 )
+      {
+         /* upper part of the domain */
+         plb[n] = SCIPfeasFloor(scip, 0.5 * (lb + ub)) + 1.0;
+         pub[n] = ub;
+      }
+      else
+      {
+         plb[n] = lb;
+         pub[n] = SCIPfeasFloor(scip, 0.5 * (lb + ub));
+      }
+      ++n;
+   }
+   t0 = wallclock();
+   for( i = 0; i < n; ++i )
+   {
+      SCIP_CALL( SCIPstartProbing(scip) );
+      if( plb[i] > SCIPvarGetLbLocal(pv[i]) )
+         SCIP_CALL( SCIPchgVarLbProbing(scip, pv[i], plb[i]) );
+      if( pub[i] < SCIPvarGetUbLocal(pv[i]) )
+         SCIP_CALL( SCIPchgVarUbProbing(scip, pv[i], pub[i]) );
+      SCIP_CALL( SCIPpropagateProbing(scip, -1, &cutscip[i], &ndom[i]) );
+      SCIP_CALL( SCIPendProbing(scip) );
+      ncutscip += cutscip[i] ? 1 : 0;
+   }
+   t1 = wallclock();
+   t2 = t1;
+   if( !g_usecpu )
+   {
+      SCIP_CALL( SCIPprobeBatchGpulinear(scip, n, pv, plb, pub, &nodecutoff, cutbatch, NULL, nchg) );
+      t2 = wallclock();
+      for( i = 0; i < n; ++i )
+      {
+         ncutbatch += cutbatch[i] ? 1 : 0;
+         nactive += nchg[i] > 0 ? 1 : 0;
+         if( cutbatch[i] != cutscip[i] )
+            ++nmismatch;
+      }
+   }
+   printf("PROBEBATCH {\"probes\": %d, \"cutoffs_scip\": %d, \"cutoffs_batch\": %d, \"mismatches\": %d, \"node_cutoff\": %d, "
+      "\"probes_with_changes\": %d, \"scip_probing_s\": %.9g, \"batch_s\": %.9g}\n", n, ncutscip, ncutbatch, nmismatch,
+      (int)nodecutoff, nactive, t1 - t0, t2 - t1);
+   SCIPfreeBufferArray(scip, &nchg);
+   SCIPfreeBufferArray(scip, &ndom);
+   SCIPfreeBufferArray(scip, &cutbatch);
+   SCIPfreeBufferArray(scip, &cutscip);
+   SCIPfreeBufferArray(scip, &pub);
+   SCIPfreeBufferArray(scip, &plb);
+   SCIPfreeBufferArray(scip, &pv);
+   g_inprobecheck = 0;
+   *result = SCIP_DIDNOTFIND;
+   return SCIP_OKAY;
+}
+
 static SCIP_RETCODE run(int argc, char** argv)
 {
    static const char* offprops[] = { "dualfix", "genvbounds", "nlobbt", "obbt", "probing", "pseudoobj", "redcost",
@@ -130,6 +233,7 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--solve") == 0 ) solve = 1;
       else if( strcmp(argv[i], "--verbose") == 0 ) quiet = 0;
       else if( strcmp(argv[i], "--presolve") == 0 ) presolve = 1;
+      else if( strcmp(argv[i], "--probe-batch") == 0 && i + 1 < argc ) g_nprobecheck = atoi(argv[++i]);
       else
       {
          fprintf(stderr, "usage: gpulinear_driver (--lpb F | --read F) [--cpu] [--boundstreps B] [--out F.lpr] [--solve] [--presolve] [--verbose]\n");
@@ -143,6 +247,13 @@ static SCIP_RETCODE run(int argc, char** argv)
    SCIP_CALL( SCIPincludeDefaultPlugins(scip) );
    if( !usecpu )
       SCIP_CALL( SCIPincludePropGpulinear(scip) );
+   g_usecpu = usecpu;
+   if( g_nprobecheck > 0 )
+   {
+      SCIP_PROP* checkprop = NULL;
+      SCIP_CALL( SCIPincludePropBasic(scip, &checkprop, "probecheck", "compares SCIP's probing cycle with the batched GPU entry",
+            -1000, 1, TRUE, SCIP_PROPTIMING_BEFORELP, propExecProbecheck, NULL) );
+   }
 
    if( !presolve )
    {

@@ -923,3 +923,105 @@ int SCIPgetNRowsGpulinear(
       return -1;
    return propdata->nrowsof[source];
 }
+
+/** a batch of independent probes on the current node, see prop_gpulinear.h */
+SCIP_RETCODE SCIPprobeBatchGpulinear(
+   SCIP*                 scip,               /**< SCIP data structure */
+   int                   nprobes,            /**< number of probes */
+   SCIP_VAR**            vars,               /**< active problem variable of each probe */
+   SCIP_Real*            lbs,                /**< lower bound of the variable in its probe */
+   SCIP_Real*            ubs,                /**< upper bound of the variable in its probe */
+   SCIP_Bool*            nodecutoff,         /**< the node itself is infeasible: no probe was run */
+   SCIP_Bool*            cutoff,             /**< per probe: the probe is infeasible */
+   int*                  nrounds,            /**< per probe: propagation rounds */
+   SCIP_Longint*         nchgbds             /**< per probe: bound changes found */
+   )
+{
+   SCIP_PROP* prop = SCIPfindProp(scip, PROP_NAME);
+   SCIP_PROPDATA* propdata;
+   SCIP_RESULT result;
+   int32_t* cols;
+   int32_t* status;
+   int32_t* rounds;
+   int64_t* nchanges;
+   int iter;
+   int rc;
+   int i;
+
+   if( prop == NULL )
+   {
+      SCIPerrorMessage("prop_gpulinear is not included\n");
+      return SCIP_PLUGINNOTFOUND;
+   }
+   propdata = SCIPpropGetData(prop);
+   assert(propdata != NULL);
+   if( nodecutoff != NULL )
+      *nodecutoff = FALSE;
+
+   /* the node first: device copy up to date, node bounds on the device, node fixpoint replayed into SCIP; a second
+    * pass takes the values SCIP adjusted during the replay back to the device */
+   for( iter = 0; iter < 4; ++iter )
+   {
+      SCIP_CALL( propExecGpulinear(scip, prop, SCIP_PROPTIMING_BEFORELP, &result) );
+      if( result == SCIP_CUTOFF )
+      {
+         if( nodecutoff != NULL )
+            *nodecutoff = TRUE;
+         return SCIP_OKAY;
+      }
+      if( result != SCIP_REDUCEDDOM && propdata->ntouched == 0 && !propdata->fullsync )
+         break;
+   }
+   for( i = 0; i < nprobes; ++i )
+   {
+      if( cutoff != NULL )
+         cutoff[i] = FALSE;
+      if( nrounds != NULL )
+         nrounds[i] = 0;
+      if( nchgbds != NULL )
+         nchgbds[i] = 0;
+   }
+   if( propdata->gpu == NULL || nprobes == 0 )
+      return SCIP_OKAY;
+
+   SCIP_CALL( SCIPallocBufferArray(scip, &cols, nprobes) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &status, nprobes) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &rounds, nprobes) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &nchanges, nprobes) );
+   rc = GPULIN_OK;
+   for( i = 0; i < nprobes; ++i )
+   {
+      cols[i] = SCIPvarGetProbindex(vars[i]);
+      if( cols[i] < 0 || cols[i] >= propdata->ncols || propdata->vars[cols[i]] != vars[i] )
+      {
+         SCIPerrorMessage("SCIPprobeBatchGpulinear: probe %d: <%s> is not an active problem variable\n", i, SCIPvarGetName(vars[i]));
+         rc = GPULIN_ERR_ARG;
+         break;
+      }
+   }
+   if( rc == GPULIN_OK )
+      rc = gpulin_probe_batch(propdata->gpu, 32, nprobes, cols, lbs, ubs, propdata->maxrounds < 0 ? 0 : propdata->maxrounds,
+         status, rounds, nchanges);
+   if( rc == GPULIN_OK )
+   {
+      for( i = 0; i < nprobes; ++i )
+      {
+         if( cutoff != NULL )
+            cutoff[i] = (status[i] == GPULIN_CUTOFF);
+         if( nrounds != NULL )
+            nrounds[i] = rounds[i];
+         if( nchgbds != NULL )
+            nchgbds[i] = nchanges[i];
+      }
+   }
+   SCIPfreeBufferArray(scip, &nchanges);
+   SCIPfreeBufferArray(scip, &rounds);
+   SCIPfreeBufferArray(scip, &status);
+   SCIPfreeBufferArray(scip, &cols);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("SCIPprobeBatchGpulinear failed (%d): %s\n", rc, gpulin_last_error());
+      return SCIP_ERROR;
+   }
+   return SCIP_OKAY;
+}

@@ -13,6 +13,7 @@
 #include "scip/def.h"
 #include "scip/type_retcode.h"
 #include "scip/type_scip.h"
+#include "scip/type_var.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -28,6 +29,25 @@ SCIP_RETCODE SCIPincludePropGpulinear(
 int SCIPgetNRowsGpulinear(
    SCIP*                 scip,               /**< SCIP data structure */
    int                   source              /**< row source */
+   );
+
+/** a batch of independent probes on the current node -- the cycle SCIPstartProbing / SCIPchgVarLb/UbProbing /
+ *  SCIPpropagateProbing / SCIPbacktrackProbing (scip_probing.c:120,302,346,581,226) that SCIPapplyProbingVar
+ *  (prop_probing.c:1254-1279) runs once per candidate, for all candidates at once: probe i sets vars[i] to
+ *  [lbs[i], ubs[i]] on top of the node's bounds and propagates the device rows to the fixpoint (gpulin_probe_batch: one
+ *  launch per probe, many probes in flight).  The node itself is propagated first (like a call of the propagator; its
+ *  reductions are applied, *nodecutoff reports an infeasible node).  Outputs per probe (each array may be NULL):
+ *  cutoff, propagation rounds, number of bound changes.  Stage SOLVING, at a node or in probing. */
+SCIP_RETCODE SCIPprobeBatchGpulinear(
+   SCIP*                 scip,               /**< SCIP data structure */
+   int                   nprobes,            /**< number of probes */
+   SCIP_VAR**            vars,               /**< active problem variable of each probe */
+   SCIP_Real*            lbs,                /**< lower bound of the variable in its probe */
+   SCIP_Real*            ubs,                /**< upper bound of the variable in its probe */
+   SCIP_Bool*            nodecutoff,         /**< the node itself is infeasible: no probe was run */
+   SCIP_Bool*            cutoff,             /**< per probe: the probe is infeasible */
+   int*                  nrounds,            /**< per probe: propagation rounds */
+   SCIP_Longint*         nchgbds             /**< per probe: bound changes found */
    );
 
 #ifdef __cplusplus

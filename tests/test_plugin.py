@@ -104,3 +104,20 @@ def test_plugin_in_tree_search_after_presolve():
     assert gpu["scip_status"] == cpu["scip_status"]
     assert abs(gpu["primal"] - cpu["primal"]) <= 1e-6
     assert gpu["gpu_prop_calls"] > 10
+
+
+@needs_driver
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["enigma", "p0548", "misc03", "lseu", "gt2"])
+def test_batched_probing_entry_matches_scip_probing(name):
+    """SCIPprobeBatchGpulinear (all probes of a node in one call: gpulin_probe_batch, one launch per probe) against SCIP's own
+    probing cycle, probe by probe (SCIPstartProbing / SCIPchgVarLb|UbProbing / SCIPpropagateProbing / SCIPendProbing as in
+    SCIPapplyProbingVar, prop_probing.c:1254-1279), at the propagated root node: same verdict for every probe"""
+    res = subprocess.run([DRIVER, "--lpb", os.path.join(GOLDEN, name + ".lpb"), "--boundstreps", "1e-9", "--probe-batch", "400"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("PROBEBATCH ")]
+    assert len(lines) == 1, res.stdout[-2000:]
+    info = json.loads(lines[0][len("PROBEBATCH "):])
+    assert info["probes"] > 0 and info["node_cutoff"] == 0
+    assert info["mismatches"] == 0 and info["cutoffs_batch"] == info["cutoffs_scip"], info
