@@ -158,7 +158,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def probing_batch_extra(propagator, synth, device):
+def probing_batch_extra(propagator, synth, device, with_cpu=True):
     """BASELINE configs[4] on one GPU (reported beside the headline, not part of it): 1024 probes -- one free binary fixed
     to 0 or 1 each, SCIPapplyProbingVar's pattern -- on the 5M-nnz set-cover matrix at its root fixpoint, 32 workers,
     one launch of one block per probe; wall clock of the whole batch through the C ABI with host buffers"""
@@ -177,10 +177,34 @@ def probing_batch_extra(propagator, synth, device):
             res = base.probe_batch(var, val, val, nworkers=32)
             times.append(time.perf_counter() - t0)
     t = min(times)
-    return dict(workload="1024 probing bound vectors on a 5M-nnz set-cover MIP (500k x 500k, seed 3), 32 workers",
-                ms_per_batch=t * 1e3, us_per_probe=t / len(var) * 1e6, probes=int(len(var)),
-                cutoffs=int((res["status"] == 1).sum()), mean_rounds=float(res["nrounds"].mean()),
-                mean_changes=float(res["nchanges"].mean()))
+    out = dict(workload="1024 probing bound vectors on a 5M-nnz set-cover MIP (500k x 500k, seed 3), 32 workers",
+               ms_per_batch=t * 1e3, us_per_probe=t / len(var) * 1e6, probes=int(len(var)),
+               cutoffs=int((res["status"] == 1).sum()), mean_rounds=float(res["nrounds"].mean()),
+               mean_changes=float(res["nchanges"].mean()))
+    if with_cpu:
+        out["cpu_reference"] = cpu_probing_reference(synth)
+    return out
+
+
+def cpu_probing_reference(synth):
+    """the reference's own probing cycle (SCIPstartProbing / SCIPchgVarLb|UbProbing / SCIPpropagateProbing / SCIPendProbing,
+    oracle/ref_driver.c --probe) at the propagated root of a bounded sample of the same family, 1 core"""
+    import oracle
+    from scip_b200.lpb import write_lpb
+    if not oracle.have_reference():
+        return dict(unavailable="oracle/_ref is not built")
+    prob = synth.setcover(200_000, 200_000, 2_000_000, seed=3)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "sample.lpb")
+        write_lpb(path, prob)
+        out = subprocess.run([oracle.REF_DRIVER, "--lpb", path, "--probe", "512"], capture_output=True, text=True,
+                             timeout=600).stdout
+    lines = [ln for ln in out.splitlines() if ln.startswith("PROBING ")]
+    if not lines:
+        return dict(unavailable="ref_driver printed no PROBING line")
+    info = json.loads(lines[0][len("PROBING "):])
+    return dict(us_per_probe=info["probing_s"] / max(info["probes"], 1) * 1e6, probes=info["probes"], cores=1, kind="reference",
+                sample="set-cover 200k x 200k, 2M nnz, seed 3; 512 probes at the propagated root, SCIP 11 built from /root/reference")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -345,7 +369,7 @@ def run_ours(args):
             cb, _, _ = cpu_reference_steps(1, 0)
             line["cpu_baseline"] = cb
         if not args.no_extras:
-            line["extras"] = dict(c5_probing_batch=probing_batch_extra(propagator, synth, local_rank))
+            line["extras"] = dict(c5_probing_batch=probing_batch_extra(propagator, synth, local_rank, with_cpu=not args.no_cpu))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -307,6 +307,59 @@ static SCIP_RETCODE applyParitySettings(SCIP* scip, double boundstreps, int quie
    return SCIP_OKAY;
 }
 
+/* --probe N: once the root node is propagated (a delayed propagator), the reference's own probing cycle for up to N
+ * unfixed integral variables -- SCIPstartProbing / SCIPchgVarLb|UbProbing / SCIPpropagateProbing / SCIPendProbing, what
+ * SCIPapplyProbingVar does per candidate (prop_probing.c:1254-1279) -- timed: the CPU baseline of BASELINE configs[4] */
+static int g_nprobe = 0;
+static int g_probedone = 0;
+static int g_inprobe = 0;
+
+static SCIP_DECL_PROPEXEC(propExecProbe)
+{
+   SCIP_VAR** vars = SCIPgetVars(scip);
+   int nvars = SCIPgetNVars(scip);
+   int n = 0;
+   int ncut = 0;
+   SCIP_Longint ndomtotal = 0;
+   double t0, t1;
+   int i;
+
+   (void)prop;
+   (void)proptiming;
+   *result = SCIP_DIDNOTRUN;
+   if( g_probedone || g_inprobe || SCIPgetDepth(scip) != 0 || SCIPinProbing(scip) )
+      return SCIP_OKAY;
+   g_probedone = 1;
+   g_inprobe = 1;
+   t0 = wallclock();
+   /* every (nvars / N)-th candidate, so that the probes are spread over the columns */
+   for( i = 0; i < nvars && n < g_nprobe; i += (nvars > 8 * g_nprobe ? 7 : 1) )
+   {
+      const SCIP_Real lb = SCIPvarGetLbLocal(vars[i]);
+      const SCIP_Real ub = SCIPvarGetUbLocal(vars[i]);
+      SCIP_Bool cutoff;
+      SCIP_Longint ndom;
+      if( !SCIPvarIsIntegral(vars[i]) || ub - lb < 0.5 || SCIPisInfinity(scip, -lb) || SCIPisInfinity(scip, ub) )
+         continue;
+      SCIP_CALL( SCIPstartProbing(scip) );
+      if( n % 2 == 0 )
+         SCIP_CALL( SCIPchgVarLbProbing(scip, vars[i], SCIPfeasFloor(scip, 0.5 * (lb + ub)) + 1.0) );
+      else
+         SCIP_CALL( SCIPchgVarUbProbing(scip, vars[i], SCIPfeasFloor(scip, 0.5 * (lb + ub))) );
+      SCIP_CALL( SCIPpropagateProbing(scip, -1, &cutoff, &ndom) );
+      SCIP_CALL( SCIPendProbing(scip) );
+      ncut += cutoff ? 1 : 0;
+      ndomtotal += ndom;
+      ++n;
+   }
+   t1 = wallclock();
+   printf("PROBING {\"probes\": %d, \"cutoffs\": %d, \"domreds\": %lld, \"probing_s\": %.9g}\n", n, ncut,
+      (long long)ndomtotal, t1 - t0);
+   g_inprobe = 0;
+   *result = SCIP_DIDNOTFIND;
+   return SCIP_OKAY;
+}
+
 static SCIP_RETCODE run(int argc, char** argv)
 {
    SCIP* scip = NULL;
@@ -332,6 +385,7 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--dump-lpb") == 0 && i + 1 < argc ) dumpfile = argv[++i];
       else if( strcmp(argv[i], "--boundstreps") == 0 && i + 1 < argc ) boundstreps = atof(argv[++i]);
       else if( strcmp(argv[i], "--verbose") == 0 ) quiet = 0;
+      else if( strcmp(argv[i], "--probe") == 0 && i + 1 < argc ) g_nprobe = atoi(argv[++i]);
       else
       {
          fprintf(stderr, "usage: ref_driver (--read FILE | --lpb FILE) [--out OUT.lpr] [--dump-lpb OUT.lpb] [--boundstreps X] [--verbose]\n");
@@ -346,6 +400,12 @@ static SCIP_RETCODE run(int argc, char** argv)
 
    SCIP_CALL( SCIPcreate(&scip) );
    SCIP_CALL( SCIPincludeDefaultPlugins(scip) );
+   if( g_nprobe > 0 )
+   {
+      SCIP_PROP* probeprop = NULL;
+      SCIP_CALL( SCIPincludePropBasic(scip, &probeprop, "refprobe", "times the reference's probing cycle at the propagated root",
+            -1000, 1, TRUE, SCIP_PROPTIMING_BEFORELP, propExecProbe, NULL) );
+   }
    memset(&propdata, 0, sizeof(propdata));
    propdata.dumpfile = dumpfile;
    SCIP_CALL( SCIPincludePropBasic(scip, &prop, "refdump", "dumps linear rows at the first root propagation call",
