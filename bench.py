@@ -260,7 +260,7 @@ def run_ours(args):
             res = lp.propagate(0)
             lp.get_bounds_ptr(h_olb.data_ptr(), h_oub.data_ptr(), on_device=False)   # synchronises
             return res
-        launches_per_step = lambda res: 2 + 3 * res["nrounds"]                       # noqa: E731
+        launches_per_step = lambda res: 1 + lp.call_stats()["launches"]             # noqa: E731  (set_bounds + the call)
     elif args.exchange == "peer":
         # candidates are committed into every rank's key vector through NVLink peer memory by the kernel that produces
         # them; device-side barriers; the round loop stays in the CUDA graph on every GPU
@@ -278,7 +278,7 @@ def run_ours(args):
             res = lp.propagate(0)
             lp.get_bounds_ptr(h_olb.data_ptr(), h_oub.data_ptr(), on_device=False)
             return res
-        launches_per_step = lambda res: 3 + 5 * res["nrounds"]                       # noqa: E731
+        launches_per_step = lambda res: 1 + lp.call_stats()["launches"]             # noqa: E731
     else:
         cuts = sharded.partition_rows(prob["rowptr"], world)
         eng = sharded.CudaEngine(prob, (int(cuts[rank]), int(cuts[rank + 1])), local_rank)

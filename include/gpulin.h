@@ -158,6 +158,12 @@ int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg,
  *  [7..8] persistent blocks of the thread-per-row / tile sweep, [9] longest row */
 int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 
+/** what the last gpulin_propagate call launched: [0] kernel launches, [1] rounds run by the dense kernels (filter sweep(s)
+ *  + exact + apply [+ barriers with peers]), [2] rounds run inside the persistent sparse-rounds kernel, [3] 1 if the call
+ *  was started by the one-block kernel (few updated bounds since the last fixpoint), [4] 1 if that kernel handed over to
+ *  the general loop */
+int gpulin_get_call_stats(gpulin_t* h, int64_t* stats, int32_t nstats);
+
 /** algorithmic bytes of one full round: nnz*12 + nrows*20 + ncols*17 */
 int gpulin_algorithmic_bytes(gpulin_t* h, int64_t* bytes);
 

@@ -115,6 +115,9 @@ struct gpulin
    int64_t     smallcols = -1;      // columns updated since the last clean fixpoint (< 0: the marks are not all on the list)
    bool        smallcall = false;   // the pending call was started by probe_kernel
    bool        smallcalls = true;   // GPULIN_SMALL=0 disables that path
+   bool        lastsmall = false;   // the last call was started by probe_kernel ...
+   bool        lastresumed = false; // ... and handed over to the general loop after smallrounds rounds
+   int         smallrounds = 0;
    int         lastmaxrounds = 0;
    int         lastvar = -1;        // probing worker: the column of its last probe
    bool        needreset = true;    // probing worker: its state is not "node + change log"
@@ -954,8 +957,12 @@ extern "C" int gpulin_propagate_wait(gpulin_t* h, gpulin_result* res)
    h->pending = false;
    float ms = 0.0f;
    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+   h->lastsmall = h->smallcall;
+   h->lastresumed = false;
    if( h->smallcall && h->h_ctrl->status == GPULIN_PROBE_OVERFLOW )
    {
+      h->lastresumed = true;
+      h->smallrounds = h->h_ctrl->round;
       // the cascade outgrew the block: the general loop continues the call (begin_kernel sees Ctrl::resume)
       h->smallcall = false;
       CU(cudaEventRecord(h->ev0, h->stream));
@@ -1294,6 +1301,37 @@ extern "C" int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats)
    const int64_t v[10] = {h->nnz, h->nstored, h->nsell, h->nstream, h->nlong, (int64_t)h->devbytes, h->ntiles,
       h->nsellblocks, h->nstreamblocks, h->maxlen};
    for( int i = 0; i < nstats && i < 10; ++i )
+      stats[i] = v[i];
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_call_stats(gpulin_t* h, int64_t* stats, int32_t nstats)
+{
+   if( h == nullptr || stats == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   const Ctrl* c = h->h_ctrl;
+   const int64_t rounds = h->lastrounds;
+   const int nkinds = (h->nsellblocks > 0) + (h->nstreamblocks > 0) + (h->nlongblocks > 0);
+   int64_t launches = 0;
+   int64_t dense = 0;
+   int64_t sparse = 0;
+   if( h->lastsmall && !h->lastresumed )
+      launches = 1;                                      // probe_kernel ran every round
+   else if( h->npeers > 1 )
+   {
+      dense = rounds;
+      launches = 2 + rounds * (1 + nkinds + 1 + 1 + 1 + 1 + 1);   // begin, barrier; lists, sweeps, exact, barrier, collect, apply, barrier
+   }
+   else
+   {
+      sparse = c->nsparse;
+      dense = rounds - sparse - (h->lastresumed ? (int64_t)h->smallrounds : 0);
+      if( dense < 0 )
+         dense = 0;
+      launches = (h->lastresumed ? 1 : 0) + 1 + dense * (nkinds + 2 + (h->nsparseblocks > 0 ? 1 : 0));
+   }
+   const int64_t v[5] = {launches, dense, sparse, h->lastsmall ? 1 : 0, h->lastresumed ? 1 : 0};
+   for( int i = 0; i < nstats && i < 5; ++i )
       stats[i] = v[i];
    return GPULIN_OK;
 }

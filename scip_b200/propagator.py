@@ -59,6 +59,7 @@ _SIGNATURES = {
     "gpulin_get_changes": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_get_round_stats": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_get_layout": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
+    "gpulin_get_call_stats": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
     "gpulin_algorithmic_bytes": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_profile_round": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                             ctypes.POINTER(ctypes.c_double)]),
@@ -267,6 +268,12 @@ class LinearPropagator:
         keys = ("nnz", "stored_nnz", "rows_thread", "rows_stream", "rows_block", "device_bytes", "tiles",
                 "blocks_thread", "blocks_stream", "maxlen")
         return dict(zip(keys, (int(x) for x in st)))
+
+    def call_stats(self) -> dict:
+        """what the last propagate call launched (kernel launches, dense / sparse rounds, one-block call, hand-over)"""
+        st = np.zeros(5, dtype=np.int64)
+        _check(self._lib.gpulin_get_call_stats(self._h, st.ctypes.data, 5))
+        return dict(zip(("launches", "dense_rounds", "sparse_rounds", "small_call", "resumed"), (int(x) for x in st)))
 
     def algorithmic_bytes(self) -> int:
         b = ctypes.c_int64(0)
