@@ -204,23 +204,31 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
          if( k0 + q * step < len )
             b[q] = p.bnd[cj[q] & 0x7fffffff];
       }
-      bool touched[4] = {false, false, false, false};
+      // which of the four nonzeros have to go through the candidate rules?  Few do (the slack test), and the rules are
+      // long: ONE copy of them serves the four slots (the instruction cache was the bottleneck of the exact kernel
+      // when every slot had its own)
+      unsigned pass = 0u;
 #pragma unroll
       for( int q = 0; q < 4; ++q )
       {
-         if( k0 + q * step < len )
-         {
-            if( !ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr) )
-               candidates(n, s, ri, a[q], cj[q] & 0x7fffffff, cj[q] < 0, b[q].x, b[q].y, cutoff, touched[q]);
-         }
+         if( k0 + q * step < len && (!ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr)) )
+            pass |= 1u << q;
       }
-      bool first[4];
-#pragma unroll
-      for( int q = 0; q < 4; ++q )
-         first[q] = touched[q] && raiseColumnBit(s, cj[q] & 0x7fffffff);
-#pragma unroll
-      for( int q = 0; q < 4; ++q )
-         listChangedColumn(s, cj[q] & 0x7fffffff, first[q]);
+      while( pass != 0u )
+      {
+         const int q = __ffs(pass) - 1;
+         pass &= pass - 1u;
+         double aq = a[0];
+         int cq = cj[0];
+         double2 bq = b[0];
+         if( q == 1 ) { aq = a[1]; cq = cj[1]; bq = b[1]; }
+         if( q == 2 ) { aq = a[2]; cq = cj[2]; bq = b[2]; }
+         if( q == 3 ) { aq = a[3]; cq = cj[3]; bq = b[3]; }
+         bool touched = false;
+         candidates(n, s, ri, aq, cq & 0x7fffffff, cq < 0, bq.x, bq.y, cutoff, touched);
+         const bool firsttouch = touched && raiseColumnBit(s, cq & 0x7fffffff);
+         listChangedColumn(s, cq & 0x7fffffff, firsttouch);
+      }
    }
 }
 
@@ -1248,24 +1256,29 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
                sk.chglist = p.chglist;
                sk.nchgcols = &p.ctrl->nchgcols;
                sk.peers = p.peers;
-               bool touched[EXACT_Q];
+               static_assert(EXACT_Q == 4, "the slot selection below is written for four slots");
+               unsigned pass = 0u;
 #pragma unroll
                for( int q = 0; q < EXACT_Q; ++q )
                {
-                  touched[q] = false;
-                  if( gl + EXACT_G * q < len )
-                  {
-                     if( !ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr) )
-                        candidates(n, sk, ri, a[q], cj[q] & 0x7fffffff, cj[q] < 0, b[q].x, b[q].y, cutoff, touched[q]);
-                  }
+                  if( gl + EXACT_G * q < len && (!ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr)) )
+                     pass |= 1u << q;
                }
-               bool first[EXACT_Q];
-#pragma unroll
-               for( int q = 0; q < EXACT_Q; ++q )
-                  first[q] = touched[q] && raiseColumnBit(sk, cj[q] & 0x7fffffff);
-#pragma unroll
-               for( int q = 0; q < EXACT_Q; ++q )
-                  listChangedColumn(sk, cj[q] & 0x7fffffff, first[q]);
+               while( pass != 0u )      // one copy of the candidate rules for the four slots (see rowCandidates)
+               {
+                  const int q = __ffs(pass) - 1;
+                  pass &= pass - 1u;
+                  double aq = a[0];
+                  int cq = cj[0];
+                  double2 bq = b[0];
+                  if( q == 1 ) { aq = a[1]; cq = cj[1]; bq = b[1]; }
+                  if( q == 2 ) { aq = a[2]; cq = cj[2]; bq = b[2]; }
+                  if( q == 3 ) { aq = a[3]; cq = cj[3]; bq = b[3]; }
+                  bool touched = false;
+                  candidates(n, sk, ri, aq, cq & 0x7fffffff, cq < 0, bq.x, bq.y, cutoff, touched);
+                  const bool firsttouch = touched && raiseColumnBit(sk, cq & 0x7fffffff);
+                  listChangedColumn(sk, cq & 0x7fffffff, firsttouch);
+               }
             }
             if( cutoff || (gl == 0 && rowInfeasible(n, ri.acc, ri.lhs, ri.rhs)) )
                p.ctrl->cutoff = 1;
