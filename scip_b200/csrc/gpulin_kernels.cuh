@@ -171,64 +171,102 @@ __device__ __forceinline__ double slackThreshold(const Num& n, bool force)
 
 // ---- candidate pass over the elements first, first+step, ... < len of a row that passed the gates of tightenBounds
 // ---- (rare once the bounds have settled): the row is read a second time, from L2.  Easy rows only look at nonzeros
-// ---- whose alpha = |a| (ub - lb) exceeds the slack (tightenVarBoundsEasy :5474/:5566).
+// ---- whose alpha = |a| (ub - lb) exceeds the slack (tightenVarBoundsEasy :5474/:5566).  Few nonzeros pass that test and
+// ---- the candidate rules are long, so the passing ones are COMPACTED first: every warp collects their positions in a
+// ---- small queue in shared memory and works through the queue 32 at a time, one nonzero per lane -- the rules run with
+// ---- full warps, and there is one copy of them instead of one per unroll slot (the instruction cache and 1-2 active
+// ---- lanes per pass were what made the exact kernel slow).  `first - lane` must be uniform over the warp.
+constexpr int CAND_QCAP = 160;      // < 32 left over + 4 x 32 new positions
+struct CandQueue
+{
+   int k[CAND_QCAP];
+};
+
 __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo& ri, long long base, int stride,
-   int first, int step, int len, bool& cutoff)
+   int first, int step, int len, bool& cutoff, CandQueue& queue)
 {
    const Num& n = p.num;
    const double thr = slackThreshold(n, ri.force);
+   const int lane = threadIdx.x & 31;
+   const unsigned below = (1u << lane) - 1u;
    Sink s;
    s.cand = p.cand;
    s.colbits = p.colbits;
    s.chglist = p.chglist;
    s.nchgcols = &p.ctrl->nchgcols;
    s.peers = p.peers;
-   for( int k0 = first; k0 < len; k0 += 4 * step )
+   int cnt = 0;                        // positions in the queue (warp-uniform)
+   int kb = first - lane;              // warp-uniform
+   for( ;; )
    {
-      double a[4];
-      int cj[4];
-      double2 b[4];
-#pragma unroll
-      for( int q = 0; q < 4; ++q )
+      if( kb < len )
       {
-         const int k = k0 + q * step;
-         if( k < len )
+         const int k0 = kb + lane;
+         double a[4];
+         int cj[4];
+         double2 b[4];
+#pragma unroll
+         for( int q = 0; q < 4; ++q )
          {
-            a[q] = p.vals[base + (long long)stride * k];
-            cj[q] = p.cols[base + (long long)stride * k];
+            const int k = k0 + q * step;
+            if( k < len )
+            {
+               a[q] = p.vals[base + (long long)stride * k];
+               cj[q] = p.cols[base + (long long)stride * k];
+            }
          }
-      }
 #pragma unroll
-      for( int q = 0; q < 4; ++q )
-      {
-         if( k0 + q * step < len )
-            b[q] = p.bnd[cj[q] & 0x7fffffff];
-      }
-      // which of the four nonzeros have to go through the candidate rules?  Few do (the slack test), and the rules are
-      // long: ONE copy of them serves the four slots (the instruction cache was the bottleneck of the exact kernel
-      // when every slot had its own)
-      unsigned pass = 0u;
+         for( int q = 0; q < 4; ++q )
+         {
+            if( k0 + q * step < len )
+               b[q] = p.bnd[cj[q] & 0x7fffffff];
+         }
 #pragma unroll
-      for( int q = 0; q < 4; ++q )
-      {
-         if( k0 + q * step < len && (!ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr)) )
-            pass |= 1u << q;
+         for( int q = 0; q < 4; ++q )
+         {
+            const bool pass = k0 + q * step < len && (!ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr));
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if( pass )
+               queue.k[cnt + __popc(m & below)] = k0 + q * step;
+            cnt += __popc(m);
+         }
+         kb += 4 * step;
       }
-      while( pass != 0u )
+      const bool last = kb >= len;
+      int head = 0;
+      while( cnt - head >= 32 || (last && cnt > head) )
       {
-         const int q = __ffs(pass) - 1;
-         pass &= pass - 1u;
-         double aq = a[0];
-         int cq = cj[0];
-         double2 bq = b[0];
-         if( q == 1 ) { aq = a[1]; cq = cj[1]; bq = b[1]; }
-         if( q == 2 ) { aq = a[2]; cq = cj[2]; bq = b[2]; }
-         if( q == 3 ) { aq = a[3]; cq = cj[3]; bq = b[3]; }
+         const int take = min(cnt - head, 32);
+         __syncwarp();
          bool touched = false;
-         candidates(n, s, ri, aq, cq & 0x7fffffff, cq < 0, bq.x, bq.y, cutoff, touched);
-         const bool firsttouch = touched && raiseColumnBit(s, cq & 0x7fffffff);
-         listChangedColumn(s, cq & 0x7fffffff, firsttouch);
+         int col = 0;
+         if( lane < take )
+         {
+            const int k = queue.k[head + lane];
+            const double a = p.vals[base + (long long)stride * k];
+            const int cj = p.cols[base + (long long)stride * k];
+            col = cj & 0x7fffffff;
+            const double2 b = p.bnd[col];
+            candidates(n, s, ri, a, col, cj < 0, b.x, b.y, cutoff, touched);
+         }
+         const bool firsttouch = touched && raiseColumnBit(s, col);
+         listChangedColumn(s, col, firsttouch);
+         head += take;
       }
+      if( head > 0 )
+      {
+         // what is left (fewer than 32 positions) moves to the front
+         const int rest = cnt - head;
+         int mv = 0;
+         if( lane < rest )
+            mv = queue.k[head + lane];
+         __syncwarp();
+         if( lane < rest )
+            queue.k[lane] = mv;
+         cnt = rest;
+      }
+      if( last )
+         break;
    }
 }
 
@@ -344,7 +382,7 @@ __device__ __forceinline__ bool rowClearlyQuiet(const Num& n, const LeanAcc& r, 
 // gates, candidate pass and verdict of one row whose exact activities are known (elements first, first+step, ... of
 // the calling thread)
 __device__ __forceinline__ void rowTighten(const DevProblem& p, const RowAcc& acc, double lhs, double rhs, long long base,
-   int stride, int first, int step, int len)
+   int stride, int first, int step, int len, CandQueue& queue)
 {
    RowInfo ri;
    ri.acc = acc;
@@ -352,7 +390,7 @@ __device__ __forceinline__ void rowTighten(const DevProblem& p, const RowAcc& ac
    ri.rhs = rhs;
    bool cutoff = false;
    if( rowGates(p.num, ri, len, cutoff) )
-      rowCandidates(p, ri, base, stride, first, step, len, cutoff);
+      rowCandidates(p, ri, base, stride, first, step, len, cutoff, queue);
    if( cutoff || rowInfeasible(p.num, ri.acc, lhs, rhs) )
       p.ctrl->cutoff = 1;
 }
@@ -1176,7 +1214,7 @@ __device__ __forceinline__ bool claimRow(const DevProblem& p, int row)
 // (marklist) -- in a round with few marked rows the filter pass is skipped and every marked row gets the exact rules
 template <bool SPARSE>
 __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0, unsigned n0, const int* list1, unsigned n1,
-   const int* list2, unsigned n2, RowAcc* s_acc, int nblockthreads)
+   const int* list2, unsigned n2, RowAcc* s_acc, CandQueue* s_queue, int nblockthreads)
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
@@ -1309,7 +1347,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
          accInit(acc);
          accumulateExact(p, acc, beg, 1, lane, 32, len);
          accWarpReduce(acc, lane);
-         rowTighten(p, acc, sd.x, sd.y, beg, 1, lane, 32, len);
+         rowTighten(p, acc, sd.x, sd.y, beg, 1, lane, 32, len, s_queue[warp]);
       }
    }
 
@@ -1343,22 +1381,23 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
 #pragma unroll 1
       for( int w = 1; w < nblockthreads / 32; ++w )
          accMerge(acc, s_acc[w]);
-      rowTighten(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, nblockthreads, len);
+      rowTighten(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, nblockthreads, len, s_queue[warp]);
    }
    if( SPARSE && nnzdone != 0 )
       addRoundNnz(p, nnzdone, gtid >> 5);
 }
 
-__global__ void __launch_bounds__(EXACT_THREADS, 3) exact_rows_kernel(const DevProblem p)
+__global__ void __launch_bounds__(EXACT_THREADS, 2) exact_rows_kernel(const DevProblem p)
 {
    __shared__ RowAcc s_acc[EXACT_THREADS / 32];
+   __shared__ CandQueue s_queue[EXACT_THREADS / 32];
 
    const unsigned n0 = p.ctrl->nexact[0];
    const unsigned n1 = p.ctrl->nexact[1];
    const unsigned n2 = p.ctrl->nexact[2];
    if( (n0 | n1 | n2) == 0u )
       return;
-   exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, EXACT_THREADS);
+   exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, s_queue, EXACT_THREADS);
 }
 
 // ---- everybody who writes bnd[j] keeps the column's bit in freebits: set iff the bounds are exactly (0,1) ------------
@@ -1772,6 +1811,7 @@ template <bool GRAPH>
 __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
 {
    __shared__ RowAcc s_acc[SPARSE_THREADS / 32];
+   __shared__ CandQueue s_queue[SPARSE_THREADS / 32];
    __shared__ int s_nchg;
    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
    Ctrl* c = p.ctrl;
@@ -1795,7 +1835,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const Dev
 
       // ---- the exact rules for the marked rows
       const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
-      exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, SPARSE_THREADS);
+      exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, s_queue, SPARSE_THREADS);
       __threadfence();
       grid.sync();
 
@@ -1851,6 +1891,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p
    double l, double u, int maxrounds, int logcap, int keepmarks, ProbeResult* out)
 {
    __shared__ RowAcc s_acc[PROBE_THREADS / 32];
+   __shared__ CandQueue s_queue[PROBE_THREADS / 32];
    __shared__ int s_nchg;
    Ctrl* c = p.ctrl;
    const int tid = threadIdx.x;
@@ -1946,7 +1987,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p
       if( tid == 0 )
          s_nchg = 0;
       const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
-      exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, PROBE_THREADS);
+      exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, s_queue, PROBE_THREADS);
       __syncthreads();
       int mychg = applyListPhase<SPARSE_G>(p, c->nchgcols, tid, PROBE_THREADS, c->round, c->logcap);
       mychg = __reduce_add_sync(0xffffffffu, mychg);
