@@ -229,7 +229,13 @@ __device__ __forceinline__ void accElem(const Num& n, RowAcc& r, double a, doubl
       r.maxdelta = dmax(r.maxdelta, fabs(a) * (u - l));
    }
    else
-      accElemSlow(n, r, a, l, u);
+   {
+      // through a copy: the accumulator itself never has its address taken and stays in registers (passing `r` would
+      // pin it to local memory: a load and a store around every nonzero)
+      RowAcc t = r;
+      accElemSlow(n, t, a, l, u);
+      r = t;
+   }
 }
 
 __device__ __forceinline__ void accMerge(RowAcc& r, const RowAcc& o)
