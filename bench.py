@@ -160,8 +160,9 @@ def run_reference_arm(args):
 
 def probing_batch_extra(propagator, synth, device, with_cpu=True):
     """BASELINE configs[4] on one GPU (reported beside the headline, not part of it): 1024 probes -- one free binary fixed
-    to 0 or 1 each, SCIPapplyProbingVar's pattern -- on the 5M-nnz set-cover matrix at its root fixpoint, 32 workers,
-    one launch of one block per probe; wall clock of the whole batch through the C ABI with host buffers"""
+    to 0 or 1 each, SCIPapplyProbingVar's pattern -- on the 5M-nnz set-cover matrix at its root fixpoint, 64 workers, one
+    launch per worker (its probes run one after the other, each inside one block); wall clock of the whole batch through
+    the C ABI with host buffers"""
     prob = synth.setcover(500_000, 500_000, 5_000_000, seed=3)
     with propagator.LinearPropagator(prob, device=device) as base:
         base.propagate()
@@ -170,14 +171,14 @@ def probing_batch_extra(propagator, synth, device, with_cpu=True):
         rng = np.random.default_rng(3)
         var = free[rng.integers(0, len(free), size=1024)].astype(np.int32)
         val = rng.integers(0, 2, size=1024).astype(np.float64)
-        base.probe_batch(var[:256], val[:256], val[:256], nworkers=32)
+        base.probe_batch(var[:256], val[:256], val[:256], nworkers=64)
         times = []
         for _ in range(5):
             t0 = time.perf_counter()
-            res = base.probe_batch(var, val, val, nworkers=32)
+            res = base.probe_batch(var, val, val, nworkers=64)
             times.append(time.perf_counter() - t0)
     t = min(times)
-    out = dict(workload="1024 probing bound vectors on a 5M-nnz set-cover MIP (500k x 500k, seed 3), 32 workers",
+    out = dict(workload="1024 probing bound vectors on a 5M-nnz set-cover MIP (500k x 500k, seed 3), 64 workers",
                ms_per_batch=t * 1e3, us_per_probe=t / len(var) * 1e6, probes=int(len(var)),
                cutoffs=int((res["status"] == 1).sum()), mean_rounds=float(res["nrounds"].mean()),
                mean_changes=float(res["nchanges"].mean()))

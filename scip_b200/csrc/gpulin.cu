@@ -111,7 +111,12 @@ struct gpulin
    bool        histfetched = false; // the pinned mirror holds the per-round history of the last call
    std::vector<gpulin*> workers;    // clones that gpulin_probe_batch keeps for this (base) handle
    void*       d_proberes = nullptr; // verdicts of the probes of a batch (ProbeResult[proberescap])
+   int*        d_probevar = nullptr; // the probes of a batch on the device
+   double*     d_probelb = nullptr;
+   double*     d_probeub = nullptr;
    int64_t     proberescap = 0;
+   uint64_t    version = 1;         // counts the calls that can change this handle's bounds (workers compare it)
+   uint64_t    syncedversion = 0;   // probing worker: version of the base handle it last took the bounds from
    int64_t     smallcols = -1;      // columns updated since the last clean fixpoint (< 0: the marks are not all on the list)
    bool        smallcall = false;   // the pending call was started by probe_kernel
    bool        smallcalls = true;   // GPULIN_SMALL=0 disables that path
@@ -733,9 +738,13 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    for( gpulin* w : h->workers )
       gpulin_destroy(w);
    h->workers.clear();
-   if( h->d_proberes != nullptr )
-      cudaFree(h->d_proberes);
+   cudaFree(h->d_proberes);
+   cudaFree(h->d_probevar);
+   cudaFree(h->d_probelb);
+   cudaFree(h->d_probeub);
    h->d_proberes = nullptr;
+   h->d_probevar = nullptr;
+   h->d_probelb = h->d_probeub = nullptr;
    if( h->stream != nullptr )
       cudaStreamSynchronize(h->stream);
    destroyGraph(h);
@@ -816,6 +825,7 @@ extern "C" int gpulin_set_bounds_device(gpulin_t* h, const double* d_lb, const d
    CU(cudaSetDevice(h->device));
    set_bounds_kernel<<<gridFor(h, std::max(h->ncols, h->nrows)), 256, 0, h->stream>>>(h->p, d_lb, d_ub);
    h->smallcols = -1;
+   ++h->version;
    CU(cudaGetLastError());
    h->havebounds = true;
    return GPULIN_OK;
@@ -845,6 +855,7 @@ extern "C" int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, 
          return fail(GPULIN_ERR_ARG, "column index %d out of range", idx[i]);
    }
    CU(cudaSetDevice(h->device));
+   ++h->version;
    if( n <= SmallUpdate::CAP )
    {
       // a handful of bounds (the usual call at a branch-and-bound node): passed by value, no staging copies
@@ -904,6 +915,7 @@ extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
       return fail(GPULIN_ERR_STATE, "gpulin_propagate before gpulin_set_bounds");
    CU(cudaSetDevice(h->device));
    h->lastmaxrounds = maxrounds;
+   ++h->version;
    h->smallcall = h->smallcols >= 0 && h->smallcols <= SMALLCALL_MAXCOLS && h->npeers <= 1 && !h->hostloop && h->smallcalls;
    h->smallcols = -1;
    h->h_params[0] = maxrounds;
@@ -998,6 +1010,8 @@ extern "C" int gpulin_propagate(gpulin_t* h, int maxrounds, gpulin_result* res)
 // probing: start from the (propagated) state of `base`: bounds and keys are copied, nothing is marked
 extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
 {
+   if( h != nullptr )
+      ++h->version;
    if( h == nullptr || base == nullptr || h->shared != base->shared )
       return fail(GPULIN_ERR_ARG, "gpulin_reset_from needs a handle and a clone of it");
    if( !base->havebounds )
@@ -1049,32 +1063,50 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
       base->workers.push_back(w);
    }
    for( gpulin* w : base->workers )
-      w->needreset = true;          // the node may have changed since the last batch
+   {
+      if( w->syncedversion != base->version )
+         w->needreset = true;       // the node has changed since this worker last took its bounds over
+   }
 
-   // ---- one launch per probe (probe_kernel), round-robin over the workers' streams; the verdicts come back in one copy
+   // ---- one launch per WORKER (probe_list_kernel): worker w runs the probes w, w + nworkers, ... one after the other, every
+   // ---- probe inside one block; the probes go to the device in one copy each way
    if( nprobes > base->proberescap )
    {
-      if( base->d_proberes != nullptr )
-         cudaFree(base->d_proberes);
+      cudaFree(base->d_proberes);
+      cudaFree(base->d_probevar);
+      cudaFree(base->d_probelb);
+      cudaFree(base->d_probeub);
       base->d_proberes = nullptr;
+      base->d_probevar = nullptr;
+      base->d_probelb = base->d_probeub = nullptr;
       base->proberescap = 0;
       CU(cudaMalloc(&base->d_proberes, sizeof(ProbeResult) * (size_t)nprobes));
+      CU(cudaMalloc((void**)&base->d_probevar, sizeof(int) * (size_t)nprobes));
+      CU(cudaMalloc((void**)&base->d_probelb, sizeof(double) * (size_t)nprobes));
+      CU(cudaMalloc((void**)&base->d_probeub, sizeof(double) * (size_t)nprobes));
       base->proberescap = nprobes;
    }
    ProbeResult* d_res = (ProbeResult*)base->d_proberes;
    const bool general = getenv("GPULIN_PROBE_GENERAL") != nullptr;     // experiments: every probe through the general loop
-   for( int64_t i = 0; i < nprobes && !general; ++i )
+   if( nprobes > 0 && !general )
    {
-      gpulin* w = base->workers[(size_t)(i % nworkers)];
+      CU(cudaMemcpy(base->d_probevar, var, sizeof(int) * (size_t)nprobes, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(base->d_probelb, lb, sizeof(double) * (size_t)nprobes, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(base->d_probeub, ub, sizeof(double) * (size_t)nprobes, cudaMemcpyHostToDevice));
+   }
+   for( int wi = 0; wi < nworkers && wi < nprobes && !general; ++wi )
+   {
+      gpulin* w = base->workers[(size_t)wi];
       if( w->needreset )
       {
          OK(gpulin_reset_from(w, base));
          w->lastvar = -1;
          w->needreset = false;
+         w->syncedversion = base->version;
       }
-      probe_kernel<<<1, PROBE_THREADS, 0, w->stream>>>(w->p, base->p, w->lastvar, var[i], lb[i], ub[i], maxrounds, (int)w->logcap,
-         0, d_res + i);
-      w->lastvar = var[i];
+      probe_list_kernel<<<1, PROBE_THREADS, 0, w->stream>>>(w->p, base->p, w->lastvar, base->d_probevar, base->d_probelb,
+         base->d_probeub, wi, nworkers, (int)nprobes, maxrounds, (int)w->logcap, d_res);
+      w->lastvar = var[wi + ((nprobes - 1 - wi) / nworkers) * nworkers];
    }
    CU(cudaGetLastError());
    for( int wi = 0; wi < nworkers; ++wi )
@@ -1367,6 +1399,8 @@ extern "C" int gpulin_get_keys(gpulin_t* h, int64_t* keys)
 
 extern "C" int gpulin_set_keys(gpulin_t* h, const int64_t* keys)
 {
+   if( h != nullptr )
+      ++h->version;
    if( h == nullptr || keys == nullptr )
       return fail(GPULIN_ERR_ARG, "invalid argument");
    CU(cudaSetDevice(h->device));
@@ -1418,6 +1452,8 @@ extern "C" int gpulin_round_sweep(gpulin_t* h)
 
 extern "C" int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int32_t* cutoff)
 {
+   if( h != nullptr )
+      ++h->version;
    if( h == nullptr )
       return fail(GPULIN_ERR_ARG, "handle is NULL");
    CU(cudaSetDevice(h->device));

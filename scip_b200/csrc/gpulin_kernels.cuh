@@ -1887,12 +1887,9 @@ struct ProbeResult
 // The same kernel serves small incremental calls on any handle (j < 0, keepmarks): the rows gpulin_update_bounds marked
 // since the last fixpoint are on mark list mb^1; if the cascade outgrows the block the marks stay and the general loop
 // continues the call (Ctrl::resume).
-__global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p, const DevProblem base, int restorevar, int j,
-   double l, double u, int maxrounds, int logcap, int keepmarks, ProbeResult* out)
+__device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem& base, int restorevar, int j, double l, double u,
+   int maxrounds, int logcap, int keepmarks, ProbeResult* out, RowAcc* s_acc, CandQueue* s_queue, int& s_nchg)
 {
-   __shared__ RowAcc s_acc[PROBE_THREADS / 32];
-   __shared__ CandQueue s_queue[PROBE_THREADS / 32];
-   __shared__ int s_nchg;
    Ctrl* c = p.ctrl;
    const int tid = threadIdx.x;
    const int lane = tid & 31;
@@ -2048,6 +2045,33 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p
          out->nrounds = c->round;
          out->nchanges = (long long)c->total_nchg;
       }
+   }
+}
+
+__global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p, const DevProblem base, int restorevar, int j,
+   double l, double u, int maxrounds, int logcap, int keepmarks, ProbeResult* out)
+{
+   __shared__ RowAcc s_acc[PROBE_THREADS / 32];
+   __shared__ CandQueue s_queue[PROBE_THREADS / 32];
+   __shared__ int s_nchg;
+   probeBody(p, base, restorevar, j, l, u, maxrounds, logcap, keepmarks, out, s_acc, s_queue, s_nchg);
+}
+
+// the probes first, first + stride, ... < n of a batch, one after the other on this worker: one launch per worker and
+// batch instead of one per probe (the host's launch rate was what bounded a batch)
+__global__ void __launch_bounds__(PROBE_THREADS) probe_list_kernel(const DevProblem p, const DevProblem base, int restorevar,
+   const int* vars, const double* lbs, const double* ubs, int first, int stride, int n, int maxrounds, int logcap,
+   ProbeResult* out)
+{
+   __shared__ RowAcc s_acc[PROBE_THREADS / 32];
+   __shared__ CandQueue s_queue[PROBE_THREADS / 32];
+   __shared__ int s_nchg;
+   for( int i = first; i < n; i += stride )
+   {
+      const int j = vars[i];
+      probeBody(p, base, restorevar, j, lbs[i], ubs[i], maxrounds, logcap, 0, out + i, s_acc, s_queue, s_nchg);
+      restorevar = j;
+      __syncthreads();
    }
 }
 

@@ -35,7 +35,7 @@ def main():
               f"mean changes {res['nchanges'].mean():.1f}")
 
 
-    for nworkers in (1, 8, 32, 64, 128):
+    for nworkers in (1, 8, 32, 64, 128, 256):
         base.probe_batch(var[:256], val[:256], val[:256], nworkers=nworkers)
         t0 = time.perf_counter()
         res = base.probe_batch(var, val, val, nworkers=nworkers)
