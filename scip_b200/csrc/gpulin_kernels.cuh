@@ -53,7 +53,7 @@ struct Ctrl
    unsigned long long total_nnz;
    unsigned long long t_start;      // %globaltimer at the start of the call
    unsigned int       nexact[4];    // rows the filter sweeps handed to the exact kernel in the running round, per list
-   unsigned int       nmark[2][4];  // rows marked (per bin) into mark list buffer 0 / 1; marking writes buffer mb^1
+   alignas(16) unsigned int nmark[2][4];  // (16-byte aligned: read as one word) rows marked (per bin) into mark list buffer 0 / 1; marking writes buffer mb^1
    unsigned int       mb;           // the buffer the last apply filled = what a sparse round reads
    unsigned int       resume;       // the next begin_kernel continues the call small_rounds started (round count, totals, log)
    unsigned int       nsparse;      // rounds done by sparse_rounds_kernel in this call (statistics)
@@ -1455,7 +1455,18 @@ constexpr int COLROW_LB = 0x40000000;
 constexpr int COLROW_UB = (int)0x80000000u;
 constexpr int COLROW_ANY = COLROW_LB | COLROW_UB;
 
-__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step, int which = COLROW_ANY)
+// `listfull` (in/out, sticky): a mark list of this round has overflowed -- the next round will be a dense one and nobody
+// needs the lists any more.  Then the rows of the thread-per-row class are marked with a blind store (no load in the
+// dependent chain); rows of the other classes are still read first: many columns mark the same long rows, and stores to
+// one address serialise.
+__device__ __forceinline__ bool markListsFull(const DevProblem& p)
+{
+   const unsigned wb = p.ctrl->mb ^ 1u;
+   const uint4 n = __ldcg(reinterpret_cast<const uint4*>(&p.ctrl->nmark[wb][0]));
+   return n.x > (unsigned)MARKCAP || n.y > (unsigned)MARKCAP || n.z > (unsigned)MARKCAP;
+}
+
+__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step, int which, bool& listfull)
 {
    // row ids are fetched four at a time before any flag is stored: the byte stores may alias anything as far as the
    // compiler knows, and a load-store-load-store chain would cost one memory round trip per row
@@ -1480,10 +1491,14 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
          r[t] &= ~COLROW_ANY;
          if( q + t * step < e && matters )
          {
-            // read before write: many columns mark the same dense rows, and stores to one address serialise
-            fl[t] = p.dirty[r[t]];
-            if( r[t] >= p.nsell && r[t] < p.nsx )
-               rb[t] = p.rowbeg[r[t]];
+            if( listfull && r[t] < p.nsell )
+               fl[t] = ROW_CLEAN;          // blind store below
+            else
+            {
+               fl[t] = p.dirty[r[t]];
+               if( r[t] >= p.nsell && r[t] < p.nsx )
+                  rb[t] = p.rowbeg[r[t]];
+            }
          }
       }
 #pragma unroll
@@ -1494,13 +1509,11 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
             p.dirty[r[t]] = ROW_MARKED;
             if( r[t] >= p.nsell && r[t] < p.nsx )
                p.tileflag[(rb[t] - p.streambase) >> 8] = 1;
-            // note the row for a sparse round (two columns racing for the same row may both note it: harmless); once
-            // a list has overflowed the round will be a dense one and nobody needs the list (a stale count only costs
-            // an atomic)
+            if( listfull )
+               continue;
+            // note the row for a sparse round (two columns racing for the same row may both note it: harmless)
             const int bin = r[t] < p.nsell ? 0 : (r[t] < p.nsx ? 1 : 2);
             const unsigned wb = p.ctrl->mb ^ 1u;
-            if( __ldcg(&p.ctrl->nmark[wb][bin]) > (unsigned)MARKCAP )
-               continue;
             const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
             const unsigned same = g.match_any(bin);
             const int leader = __ffs(same) - 1;
@@ -1510,9 +1523,17 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
             pos = g.shfl(pos, leader) + (unsigned)__popc(same & ((1u << g.thread_rank()) - 1u));
             if( pos < (unsigned)MARKCAP )
                p.marklist[(wb * 3 + bin) * MARKCAP + pos] = r[t];
+            else
+               listfull = true;
          }
       }
    }
+}
+
+__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step, int which = COLROW_ANY)
+{
+   bool listfull = false;
+   markColumnRows(p, j, first, step, which, listfull);
 }
 
 // loop control (propagateDomains, solve.c:766-787), run by one thread after the last column was applied
@@ -1594,12 +1615,15 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
    const int ngroups = nthreads / G;
    const unsigned trips = (nlist + ngroups - 1) / ngroups;       // warp-uniform
    int mychg = 0;
+   bool listfull = false;
    for( unsigned it = 0; it < trips; ++it )
    {
       const unsigned item = it * ngroups + gtid / G;
       const bool valid = item < nlist;
       int j = 0;
       int which = 0;
+      if( !listfull )
+         listfull = markListsFull(p);        // one load per trip, beside the loads below (not once per marked row)
       if( valid )
       {
          // which of the two bounds moves says which rows can care; every lane of the group reads the two words itself
@@ -1624,7 +1648,7 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
       if( valid )
-         markColumnRows(p, j, gl, G, which);
+         markColumnRows(p, j, gl, G, which, listfull);
    }
    return mychg;
 }
