@@ -663,7 +663,12 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    // ---- launch geometry ------------------------------------------------------------------------------------------
    // persistent grids: as many blocks as stay resident, never more than there is work
-   h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols + APPLY_THREADS - 1) / APPLY_THREADS, (int64_t)h->nsm * 4));
+   {
+      int occa = 0;
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occa, apply_kernel<APPLY_LIST, true>, APPLY_THREADS, 0) != cudaSuccess || occa < 1 )
+         occa = 2;
+      h->napplyblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols + APPLY_THREADS - 1) / APPLY_THREADS, (int64_t)h->nsm * occa));
+   }
    {
       int occ = 0;
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_stream_kernel, SWEEP_THREADS, 0) != cudaSuccess || occ < 1 )

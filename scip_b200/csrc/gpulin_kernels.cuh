@@ -1466,12 +1466,12 @@ __device__ __forceinline__ bool markListsFull(const DevProblem& p)
    return n.x > (unsigned)MARKCAP || n.y > (unsigned)MARKCAP || n.z > (unsigned)MARKCAP;
 }
 
-__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step, int which, bool& listfull)
+__device__ __forceinline__ void markRowRange(const DevProblem& p, long long qbeg, long long e, int first, int step, int which,
+   bool& listfull)
 {
    // row ids are fetched four at a time before any flag is stored: the byte stores may alias anything as far as the
    // compiler knows, and a load-store-load-store chain would cost one memory round trip per row
-   const long long e = p.colbeg[j + 1];
-   for( long long q = p.colbeg[j] + first; q < e; q += 4 * step )
+   for( long long q = qbeg + first; q < e; q += 4 * step )
    {
       int r[4];
       long long rb[4];
@@ -1528,6 +1528,11 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
          }
       }
    }
+}
+
+__device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step, int which, bool& listfull)
+{
+   markRowRange(p, p.colbeg[j], p.colbeg[j + 1], first, step, which, listfull);
 }
 
 __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int first, int step, int which = COLROW_ANY)
@@ -1616,24 +1621,49 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
    const unsigned trips = (nlist + ngroups - 1) / ngroups;       // warp-uniform
    int mychg = 0;
    bool listfull = false;
+   // software pipeline over the trips of a group: the column index is fetched two trips ahead, its keys, bounds and row
+   // range one trip ahead -- the apply step is nothing but dependent loads (chglist -> cand / bnd / colbeg -> colrows ->
+   // flags), and with a handful of trips per group their latencies add up
+   const unsigned item0 = gtid / G;
+   int jB = item0 < nlist ? p.chglist[item0] : -1;                       // column of trip `it`
+   int jA = item0 + ngroups < nlist ? p.chglist[item0 + ngroups] : -1;   // column of trip `it + 1`
+   longlong2 kB = make_longlong2(0, 0);
+   double2 oldB = make_double2(0.0, 0.0);
+   long long cb0 = 0;
+   long long cb1 = 0;
+   if( jB >= 0 )
+   {
+      kB = reinterpret_cast<const longlong2*>(p.cand)[jB];
+      oldB = p.bnd[jB];
+      cb0 = p.colbeg[jB];
+      cb1 = p.colbeg[jB + 1];
+   }
    for( unsigned it = 0; it < trips; ++it )
    {
-      const unsigned item = it * ngroups + gtid / G;
-      const bool valid = item < nlist;
-      int j = 0;
-      int which = 0;
-      if( !listfull )
-         listfull = markListsFull(p);        // one load per trip, beside the loads below (not once per marked row)
-      if( valid )
+      const int j = jB;
+      const bool valid = j >= 0;
+      const longlong2 k = kB;
+      const double2 old = oldB;
+      const long long q0 = cb0;
+      const long long q1 = cb1;
+      // next trips
+      jB = jA;
       {
-         // which of the two bounds moves says which rows can care; every lane of the group reads the two words itself
-         // (one broadcast load each) BEFORE the first lane accepts the bounds
-         j = p.chglist[item];
-         const longlong2 k = reinterpret_cast<const longlong2*>(p.cand)[j];
-         const double2 old = p.bnd[j];
-         which = (key2d(~k.x) != old.x ? COLROW_LB : 0) | (key2d(k.y) != old.y ? COLROW_UB : 0);
+         const unsigned item2 = (it + 2) * ngroups + item0;
+         jA = (it + 2 < trips && item2 < nlist) ? p.chglist[item2] : -1;
       }
-      __syncwarp();
+      if( jB >= 0 )
+      {
+         kB = reinterpret_cast<const longlong2*>(p.cand)[jB];
+         oldB = p.bnd[jB];
+         cb0 = p.colbeg[jB];
+         cb1 = p.colbeg[jB + 1];
+      }
+      if( !listfull )
+         listfull = markListsFull(p);        // one load per trip, beside the loads above (not once per marked row)
+      // which of the two bounds moves says which rows can care (every lane of the group holds the two words itself,
+      // read BEFORE the first lane accepts the bounds)
+      const int which = valid ? ((key2d(~k.x) != old.x ? COLROW_LB : 0) | (key2d(k.y) != old.y ? COLROW_UB : 0)) : 0;
       if( valid && gl == 0 )
       {
          bool lbchg;
@@ -1648,7 +1678,7 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
       if( valid )
-         markColumnRows(p, j, gl, G, which, listfull);
+         markRowRange(p, q0, q1, gl, G, which, listfull);
    }
    return mychg;
 }
