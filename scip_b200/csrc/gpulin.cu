@@ -71,6 +71,7 @@ struct gpulin
    int         napplyblocks = 0;
    int         nexactblocks = 0;
    int         nsparseblocks = 0;   // grid of the persistent sparse-rounds kernel (0: disabled)
+   int         nsellunit = 0;       // SELL rows [0,nsellunit): all coefficients +1 / -1
    int         nsellbitsblocks = 0; // grid of sweep_sell_bits_kernel (0: the gather variant is used)
    int         sellbitsvariant = 0;
    size_t      freebytes = 0;       // size of the freebits array
@@ -210,11 +211,14 @@ static size_t sellBitsSmem(int nfreewords)
 typedef void (*SellBitsKernel)(const DevProblem);
 struct SellBitsVariant { SellBitsKernel kernel; int threads; bool allcols; };
 static const SellBitsVariant g_sellBitsKernels[] = {
-   {sweep_sell_bits_kernel<1024, 2, true, false>, 1024, false},   // 0
-   {sweep_sell_bits_kernel<1024, 2, true, true>, 1024, true},     // 1
-   {sweep_sell_bits_kernel<1024, 2, false, false>, 1024, false},  // 2: lb/ub form (leanElem)
+   {sweep_sell_bits_kernel<1024, 2, true, false, false, 4>, 1024, false},   // 0
+   {sweep_sell_bits_kernel<1024, 2, true, true, false, 4>, 1024, true},     // 1
+   {sweep_sell_bits_kernel<1024, 2, false, false>, 1024, false},  // 2: lb/ub form (leanElem), unit slices like all others
    {sweep_sell_bits_kernel<768, 3, true, true>, 768, true},       // 3
    {sweep_sell_bits_kernel<768, 4, true, false>, 768, false},     // 4
+   {sweep_sell_bits_kernel<1024, 2, true, true, false, 0>, 1024, true},     // 5: unit slices like all others
+   {sweep_sell_bits_kernel<1024, 2, true, true, false, 2>, 1024, true},     // 6
+   {sweep_sell_bits_kernel<1024, 2, true, true, false, 3>, 1024, true},     // 7
 };
 constexpr int NSELLBITSVARIANTS = sizeof(g_sellBitsKernels) / sizeof(g_sellBitsKernels[0]);
 
@@ -350,8 +354,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    if( nrows < 0 || ncols < 0 || nnz < 0 || (nrows > 0 && rowptr == nullptr) || (nnz > 0 && (colidx == nullptr || vals == nullptr))
       || (nrows > 0 && (lhs == nullptr || rhs == nullptr)) || (ncols > 0 && vartype == nullptr) )
       return fail(GPULIN_ERR_ARG, "invalid problem arrays");
-   if( nrows >= (1LL << 31) - 64 || ncols >= (1LL << 31) - 64 )
-      return fail(GPULIN_ERR_ARG, "more than 2^31 rows or columns are not supported");
+   if( nrows >= (1LL << 30) || ncols >= (1LL << 30) )
+      return fail(GPULIN_ERR_ARG, "more than 2^30 rows or columns are not supported");
    if( nrows > 0 && (rowptr[0] != 0 || rowptr[nrows] != nnz) )
       return fail(GPULIN_ERR_ARG, "rowptr does not span [0,nnz]");
    for( int64_t r = 0; r < nrows; ++r )
@@ -420,7 +424,26 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       else
          longrows.push_back((int)r);
    }
-   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return len[(size_t)a] < len[(size_t)b]; });
+   // the SELL rows whose coefficients are all +1 or -1 come first, in whole slices (the filter sweep does not read their
+   // values, see sweep_sell_bits_kernel); what does not fill a slice stays with the others
+   {
+      std::vector<int> unitrows;
+      std::vector<int> otherrows;
+      for( int r : perm )
+      {
+         bool unit = true;
+         for( int64_t k = rowptr[r]; k < rowptr[r + 1] && unit; ++k )
+            unit = std::fabs(vals[k]) == 1.0;
+         (unit ? unitrows : otherrows).push_back(r);
+      }
+      auto bylen = [&](int a, int b) { return len[(size_t)a] < len[(size_t)b]; };
+      std::stable_sort(unitrows.begin(), unitrows.end(), bylen);
+      h->nsellunit = (int)(unitrows.size() / 32 * 32);
+      otherrows.insert(otherrows.end(), unitrows.begin() + h->nsellunit, unitrows.end());
+      std::stable_sort(otherrows.begin(), otherrows.end(), bylen);
+      perm.assign(unitrows.begin(), unitrows.begin() + h->nsellunit);
+      perm.insert(perm.end(), otherrows.begin(), otherrows.end());
+   }
    std::stable_sort(longrows.begin(), longrows.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
    h->nsell = (int)perm.size();
    h->nstream = (int)streamrows.size();
@@ -477,7 +500,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       {
          const int j = colidx[b + k];
          pvals[(size_t)(base + stride * k)] = vals[b + k];
-         pcols[(size_t)(base + stride * k)] = j | (vartype[j] != 0 ? (int)0x80000000u : 0);
+         pcols[(size_t)(base + stride * k)] = j | (vartype[j] != 0 ? COL_INTEGRAL : 0) | (vals[b + k] < 0.0 ? COL_NEGCOEF : 0);
       }
    }
    std::vector<double2> sides((size_t)nrows + 1);
@@ -621,6 +644,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.nrows = (int)nrows;
    p.ncols = (int)ncols;
    p.nsell = h->nsell;
+   p.nsellunit = h->nsellunit;
    p.nsx = nsx;
    p.ntiles = h->ntiles;
    p.streambase = streambase;

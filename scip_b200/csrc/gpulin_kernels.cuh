@@ -33,6 +33,9 @@ constexpr int STREAM_MAXLEN = 4096;   // longer rows (and empty rows) are swept 
 constexpr int SHORT_MAXLEN = 32;      // exact kernel: rows up to this length are handled by groups of 8 lanes
 constexpr int NNZ_SLOTS = 64;         // spread counters of the nonzeros swept in a round
 constexpr int MARKCAP = 1 << 15;      // capacity of a mark list; rounds with more marked rows take the dense sweeps
+constexpr int COL_INTEGRAL = (int)0x80000000u;   // cols[] word: the column is integral
+constexpr int COL_NEGCOEF = 0x40000000;          // cols[] word: the coefficient of this nonzero is negative
+constexpr int COL_MASK = 0x3fffffff;             // cols[] word: the column index
 
 // loop control + statistics, lives in device memory
 struct Ctrl
@@ -80,6 +83,8 @@ struct DevProblem
    int                 nrows;
    int                 ncols;
    int                 nsell;      // rows [0,nsell): 1..32 nonzeros, SELL-32 slices sorted by length (thread-per-row sweep)
+   int                 nsellunit;  // rows [0,nsellunit) (a multiple of 32): every coefficient is +1 or -1 -- the filter sweep
+                                   // takes the sign from the column word and does not read their values at all
    int                 nsx;        // rows [nsell,nsx): 33..STREAM_MAXLEN nonzeros, the CSR stream in the caller's order;
                                    // rows [nsx,nrows): longer or empty, swept block-per-row
    int                 ntiles;     // tiles of the stream (its storage is padded with zero coefficients to a whole tile)
@@ -91,7 +96,7 @@ struct DevProblem
    const double2*      sides;      // (lhs, rhs)
    unsigned char*      dirty;      // marked for propagation
    const double*       vals;
-   const int*          cols;       // column index | (integral << 31)
+   const int*          cols;       // column index | COL_NEGCOEF (coefficient < 0) | COL_INTEGRAL
    // tiles
    const int*          tile_row0;  // first row that ends at or behind the first nonzero of the tile
    const unsigned char* endmask;   // per tile and lane: bit i = nonzero 8*lane+i is the last of its row
@@ -219,7 +224,7 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
          for( int q = 0; q < 4; ++q )
          {
             if( k0 + q * step < len )
-               b[q] = p.bnd[cj[q] & 0x7fffffff];
+               b[q] = p.bnd[cj[q] & COL_MASK];
          }
 #pragma unroll
          for( int q = 0; q < 4; ++q )
@@ -245,7 +250,7 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
             const int k = queue.k[head + lane];
             const double a = p.vals[base + (long long)stride * k];
             const int cj = p.cols[base + (long long)stride * k];
-            col = cj & 0x7fffffff;
+            col = cj & COL_MASK;
             const double2 b = p.bnd[col];
             candidates(n, s, ri, a, col, cj < 0, b.x, b.y, cutoff, touched);
          }
@@ -418,7 +423,7 @@ __device__ __forceinline__ void accumulateExact(const DevProblem& p, RowAcc& acc
       for( int q = 0; q < 4; ++q )
       {
          if( k0 + q * step < len )
-            b[q] = p.bnd[cj[q] & 0x7fffffff];
+            b[q] = p.bnd[cj[q] & COL_MASK];
       }
 #pragma unroll
       for( int q = 0; q < 4; ++q )
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const De
             leanInit(part);
             for( long long e = beg + lane; e < first; e += 32 )
             {
-               const double2 b = p.bnd[p.cols[e] & 0x7fffffff];
+               const double2 b = p.bnd[p.cols[e] & COL_MASK];
                leanElem(part, p.vals[e], b.x, b.y);
             }
             leanWarpReduce(part);
@@ -591,7 +596,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const De
          double2 b[TPL];
 #pragma unroll
          for( int k = 0; k < TPL; ++k )
-            b[k] = p.bnd[cur.cj[k] & 0x7fffffff];
+            b[k] = p.bnd[cur.cj[k] & COL_MASK];
          double a[TPL];
 #pragma unroll
          for( int k = 0; k < TPL; ++k )
@@ -834,7 +839,7 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, const unsigned* s
             {
                if( c + k < len[i] )
                {
-                  const int j = cj[k] & 0x7fffffff;
+                  const int j = cj[k] & COL_MASK;
                   if( BITS )
                   {
                      b[k] = make_double2(0.0, 1.0);
@@ -966,36 +971,42 @@ __device__ __forceinline__ void gatherUnless(unsigned skip, const double2* addr,
        : "+d"(b.x), "+d"(b.y) : "r"(skip), "l"(addr));
 }
 
+// coefficient of a nonzero of a unit row (+1 or -1), from the sign flag of its column word
+__device__ __forceinline__ double unitCoef(int colword)
+{
+   return __hiloint2double(0x3ff00000 | ((colword << 1) & (int)0x80000000u), 0);
+}
+
+// one chunk of CH nonzeros of a row of a SELL slice; UNIT: the column words only (the values are not read)
+template <int CH, bool UNIT>
+__device__ __forceinline__ void loadChunkBits(const DevProblem& p, long long base, int c, int len, double (&a)[CH], int (&cj)[CH])
+{
+#pragma unroll
+   for( int k = 0; k < CH; ++k )
+   {
+      if( c + k < len )
+      {
+         if( !UNIT )
+            a[k] = ldStream(p.vals + base + 32LL * (c + k));
+         cj[k] = ldStream(p.cols + base + 32LL * (c + k));
+      }
+   }
+}
+
+// the slices [sbeg, send) of the SELL bin, thread per row
 // MID: sums in midpoint / half-width form from bndf (else leanElem from bnd)
 //      ALLCOLS: the table covers every column (no range checks);  HD: the maximal half width is kept as a double
-template <int NT, int CH, bool MID, bool ALLCOLS = false, bool HD = false>
-__global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
+//      UNIT: every coefficient of these slices is +1 or -1 (rows [0, nsellunit)): 4 instead of 12 bytes per nonzero
+template <int NT, int CH, bool MID, bool ALLCOLS, bool HD, bool UNIT>
+__device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigned* s_free, unsigned tabbar, bool& tabready,
+   int sbeg, int send, unsigned& nnzdone)
 {
-   if( p.ctrl->skipsweep )
-      return;
-   extern __shared__ __align__(128) unsigned char s_raw[];
    const Num& n = p.num;
-   const unsigned tabbytes = (unsigned)p.nfreewords * 4u;
-   const unsigned* s_free = reinterpret_cast<const unsigned*>(s_raw);
-   const unsigned tabbar = smemAddr(s_raw + ((tabbytes + 127u) & ~127u));
-   if( threadIdx.x == 0 )
-   {
-      mbarInit(tabbar, 1u);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbarExpectTx(tabbar, tabbytes);
-      for( unsigned o = 0; o < tabbytes; o += 16384u )
-         bulkLoad(smemAddr(s_raw) + o, reinterpret_cast<const unsigned char*>(p.freebits) + o, min(16384u, tabbytes - o), tabbar);
-   }
-   __syncthreads();
-
    const int lane = threadIdx.x & 31;
    const int gw = (blockIdx.x * NT + threadIdx.x) >> 5;
    const int nw = (gridDim.x * NT) >> 5;
-   const int nslices = (p.nsell + 31) >> 5;
    const int lastword = p.nfreewords - 1;
-   unsigned nnzdone = 0;
-   bool tabready = false;
-   for( int s0 = gw; s0 < nslices; s0 += SELL_NB * nw )
+   for( int s0 = sbeg + gw; s0 < send; s0 += SELL_NB * nw )
    {
       // ---- one round trip: flags, lengths and offsets of the next four slices of this warp
       int len[SELL_NB];
@@ -1008,10 +1019,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
       {
          const int slice = s0 + i * nw;
          const int row = slice * 32 + lane;
-         const bool valid = slice < nslices && row < p.nsell;
+         const bool valid = slice < send && row < p.nsell;
          const unsigned char f = valid ? p.dirty[row] : ROW_CLEAN;
          const int lw = valid ? p.rowlen[row] : 0;
-         base[i] = (slice < nslices ? p.sell_off[slice] : 0) + lane;
+         base[i] = (slice < send ? p.sell_off[slice] : 0) + lane;
          const bool act = f == ROW_MARKED;
          len[i] = act ? (lw & ~ROWLEN_EXACT) : 0;
          if( act )
@@ -1025,7 +1036,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
 
       double an[CH];
       int cjn[CH];
-      loadChunk<CH>(p, base[0], 0, len[0], an, cjn);
+      loadChunkBits<CH, UNIT>(p, base[0], 0, len[0], an, cjn);
       if( !tabready )
       {
          mbarWait(tabbar, 0u);      // the first coefficients are on their way while the table arrives
@@ -1052,13 +1063,13 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
 #pragma unroll
             for( int k = 0; k < CH; ++k )
             {
-               a[k] = an[k];
-               cj[k] = cjn[k] & 0x7fffffff;
+               a[k] = UNIT ? unitCoef(cjn[k]) : an[k];
+               cj[k] = cjn[k] & COL_MASK;
             }
             if( c + CH < maxlen[i] )
-               loadChunk<CH>(p, base[i], c + CH, len[i], an, cjn);
+               loadChunkBits<CH, UNIT>(p, base[i], c + CH, len[i], an, cjn);
             else if( i + 1 < SELL_NB )
-               loadChunk<CH>(p, base[i + 1], 0, len[i + 1], an, cjn);
+               loadChunkBits<CH, UNIT>(p, base[i + 1], 0, len[i + 1], an, cjn);
 #pragma unroll
             for( int k = 0; k < CH; ++k )
             {
@@ -1100,7 +1111,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
             }
          }
          if( maxlen[i] == 0 && i + 1 < SELL_NB )
-            loadChunk<CH>(p, base[i + 1], 0, len[i + 1], an, cjn);
+            loadChunkBits<CH, UNIT>(p, base[i + 1], 0, len[i + 1], an, cjn);
          bool handoff = false;
          if( act )
          {
@@ -1113,6 +1124,37 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
          pushRow(p, handoff, row, lane, 0, 0);
       }
    }
+}
+
+// CHU: nonzeros per thread and chunk in the unit slices (0: they take the general path)
+template <int NT, int CH, bool MID, bool ALLCOLS = false, bool HD = false, int CHU = 0>
+__global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
+{
+   if( p.ctrl->skipsweep )
+      return;
+   extern __shared__ __align__(128) unsigned char s_raw[];
+   const unsigned tabbytes = (unsigned)p.nfreewords * 4u;
+   const unsigned* s_free = reinterpret_cast<const unsigned*>(s_raw);
+   const unsigned tabbar = smemAddr(s_raw + ((tabbytes + 127u) & ~127u));
+   if( threadIdx.x == 0 )
+   {
+      mbarInit(tabbar, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbarExpectTx(tabbar, tabbytes);
+      for( unsigned o = 0; o < tabbytes; o += 16384u )
+         bulkLoad(smemAddr(s_raw) + o, reinterpret_cast<const unsigned char*>(p.freebits) + o, min(16384u, tabbytes - o), tabbar);
+   }
+   __syncthreads();
+
+   const int lane = threadIdx.x & 31;
+   const int gw = (blockIdx.x * NT + threadIdx.x) >> 5;
+   const int nslices = (p.nsell + 31) >> 5;
+   const int nunitslices = (CHU > 0 && MID) ? p.nsellunit >> 5 : 0;
+   unsigned nnzdone = 0;
+   bool tabready = false;
+   if( CHU > 0 && MID )
+      sellBitsRange<NT, (CHU > 0 ? CHU : 1), MID, ALLCOLS, HD, true>(p, s_free, tabbar, tabready, 0, nunitslices, nnzdone);
+   sellBitsRange<NT, CH, MID, ALLCOLS, HD, false>(p, s_free, tabbar, tabready, nunitslices, nslices, nnzdone);
    if( !tabready && threadIdx.x < 32 )
       mbarWait(tabbar, 0u);         // the block must not retire under the copies it issued
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
@@ -1166,7 +1208,7 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
          for( int k = 0; k < 4; ++k )
          {
             if( i0 + k * LONG_THREADS + threadIdx.x < len )
-               b[k] = p.bnd[cj[k] & 0x7fffffff];
+               b[k] = p.bnd[cj[k] & COL_MASK];
          }
 #pragma unroll
          for( int k = 0; k < 4; ++k )
@@ -1269,7 +1311,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
          for( int q = 0; q < EXACT_Q; ++q )
          {
             if( gl + EXACT_G * q < len )
-               b[q] = p.bnd[cj[q] & 0x7fffffff];
+               b[q] = p.bnd[cj[q] & COL_MASK];
          }
          RowInfo ri;
          accInit(ri.acc);
@@ -1313,9 +1355,9 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
                   if( q == 2 ) { aq = a[2]; cq = cj[2]; bq = b[2]; }
                   if( q == 3 ) { aq = a[3]; cq = cj[3]; bq = b[3]; }
                   bool touched = false;
-                  candidates(n, sk, ri, aq, cq & 0x7fffffff, cq < 0, bq.x, bq.y, cutoff, touched);
-                  const bool firsttouch = touched && raiseColumnBit(sk, cq & 0x7fffffff);
-                  listChangedColumn(sk, cq & 0x7fffffff, firsttouch);
+                  candidates(n, sk, ri, aq, cq & COL_MASK, cq < 0, bq.x, bq.y, cutoff, touched);
+                  const bool firsttouch = touched && raiseColumnBit(sk, cq & COL_MASK);
+                  listChangedColumn(sk, cq & COL_MASK, firsttouch);
                }
             }
             if( cutoff || (gl == 0 && rowInfeasible(n, ri.acc, ri.lhs, ri.rhs)) )
