@@ -11,7 +11,8 @@ of the candidate keys per round (NCCL).
 
 metric  propagation_fixpoint_nnz_per_s = nonzeros of the instance / time to reach the propagation fixpoint
 value   bounds resident in HBM when the timed region starts (device-side reset of the bounds inside it)
-e2e     the same through the C ABI with HOST buffers: H2D of lb/ub, fixpoint, D2H of lb/ub + verdict, every step
+e2e     the same through the C ABI with HOST buffers, as the plugin calls it at a node: H2D of lb/ub (pinned), fixpoint,
+        D2H of the verdict + the round-ordered change log (N > 1: of the bound vectors), every step
 roofline  the dominant kernel (the filter sweep of one full round): algorithmic bytes (nnz*12 + nrows*20 + ncols*17,
         SURVEY.md 8d) / its CUDA-event time, against the measured HBM copy peak of MEASURED_PEAKS.json
 cpu_baseline / --impl reference   the UNMODIFIED reference (oracle/_ref, SCIP's cons_linear propagation) on the host
@@ -251,6 +252,12 @@ def run_ours(args):
         lp = propagator.LinearPropagator(prob, device=local_rank)
         lp.set_stream(stream.cuda_stream)
         abytes = lp.algorithmic_bytes()
+        # the call the plugin makes at a node (prop_gpulinear.c): bounds in, verdict + round-ordered change log out; the
+        # log is on in both arms (it is part of the product path)
+        logcap = 2 * ncols
+        lp.set_change_log(logcap)
+        h_chg = torch.empty(logcap * 24, dtype=torch.uint8).pin_memory()
+        d2h_bytes = [0]
 
         def step_resident():
             lp.set_bounds_ptr(d_lb0.data_ptr(), d_ub0.data_ptr(), on_device=True)
@@ -258,8 +265,8 @@ def run_ours(args):
 
         def step_e2e():
             lp.set_bounds_ptr(h_lb.data_ptr(), h_ub.data_ptr(), on_device=False)
-            res = lp.propagate(0)
-            lp.get_bounds_ptr(h_olb.data_ptr(), h_oub.data_ptr(), on_device=False)   # synchronises
+            res = lp.propagate(0)                                                    # verdict: 32 bytes, synchronises
+            d2h_bytes[0] = 24 * min(lp.changes_ptr(h_chg.data_ptr(), logcap), logcap) + 32
             return res
         launches_per_step = lambda res: 1 + lp.call_stats()["launches"]             # noqa: E731  (set_bounds + the call)
     elif args.exchange == "peer":
@@ -345,7 +352,8 @@ def run_ours(args):
                             l2="inputs larger than L2: 157 MB streamed per full round vs 126 MB L2" if args.workload != "c3small" else "fits L2",
                             loop="CUDA graph WHILE node (device-side)" if (world == 1 or args.exchange == "peer") else "host loop, NCCL per round"),
                 e2e=dict(value=nnz * K / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=16 * ncols,
-                         d2h_bytes_per_step=16 * ncols + 32),
+                         d2h_bytes_per_step=(d2h_bytes[0] if world == 1 else 16 * ncols + 32),
+                         result=("verdict + change log (gpulin_get_changes)" if world == 1 else "verdict + bound vectors")),
                 gpu_launches=K * launches_per_step(res), clocks=clocks.summary(), status_consistent=status_ok)
     if world > 1 and args.exchange == "peer":
         ms, rn, rc = lp.round_stats()

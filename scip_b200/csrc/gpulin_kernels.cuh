@@ -1653,6 +1653,40 @@ __device__ __forceinline__ void logChanges(const DevProblem& p, int j, int round
    }
 }
 
+// the same for a whole warp (all 32 lanes call it): one atomic on the log counter per warp instead of one per column --
+// a round with 250k changed columns spent 0.19 ms on that one address
+__device__ __forceinline__ void logChangesWarp(const DevProblem& p, int j, int round, int logcap, bool lbchg, bool ubchg,
+   const double2& nb)
+{
+   const unsigned lane = threadIdx.x & 31u;
+   const unsigned below = (1u << lane) - 1u;
+   const unsigned mlb = __ballot_sync(0xffffffffu, lbchg);
+   const unsigned mub = __ballot_sync(0xffffffffu, ubchg);
+   const int total = __popc(mlb) + __popc(mub);
+   if( total == 0 )
+      return;
+   unsigned long long pos = 0;
+   if( lane == 0 )
+      pos = atomicAdd(&p.ctrl->logcount, (unsigned long long)total);
+   pos = __shfl_sync(0xffffffffu, pos, 0) + (unsigned long long)(__popc(mlb & below) + __popc(mub & below));
+   if( lbchg )
+   {
+      if( pos < (unsigned long long)logcap )
+      {
+         ChangeRec rec;
+         rec.var = j; rec.round = round; rec.newbound = nb.x; rec.is_upper = 0; rec.reserved = 0;
+         p.log[pos] = rec;
+      }
+      ++pos;
+   }
+   if( ubchg && pos < (unsigned long long)logcap )
+   {
+      ChangeRec rec;
+      rec.var = j; rec.round = round; rec.newbound = nb.y; rec.is_upper = 1; rec.reserved = 0;
+      p.log[pos] = rec;
+   }
+}
+
 // the columns on the change list of this round, eight lanes per column: one accepts the bounds, all mark the rows of the
 // column; returns the number of bound changes this thread accepted
 template <int G>
@@ -1706,17 +1740,17 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
       // which of the two bounds moves says which rows can care (every lane of the group holds the two words itself,
       // read BEFORE the first lane accepts the bounds)
       const int which = valid ? ((key2d(~k.x) != old.x ? COLROW_LB : 0) | (key2d(k.y) != old.y ? COLROW_UB : 0)) : 0;
+      bool lbchg = false;
+      bool ubchg = false;
+      double2 nb = make_double2(0.0, 0.0);
       if( valid && gl == 0 )
       {
-         bool lbchg;
-         bool ubchg;
-         double2 nb;
          const int nc = applyColumn(p, j, nb, lbchg, ubchg);
          atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
-         if( nc > 0 && logcap > 0 )
-            logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
          mychg += nc;
       }
+      if( logcap > 0 )
+         logChangesWarp(p, j, round, logcap, lbchg, ubchg, nb);
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
       if( valid )
@@ -2144,7 +2178,7 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
    }
 }
 
-__global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p, const DevProblem base, int restorevar, int j,
+__global__ void __launch_bounds__(PROBE_THREADS, 1) probe_kernel(const DevProblem p, const DevProblem base, int restorevar, int j,
    double l, double u, int maxrounds, int logcap, int keepmarks, ProbeResult* out)
 {
    __shared__ RowAcc s_acc[PROBE_THREADS / 32];
@@ -2155,7 +2189,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const DevProblem p
 
 // the probes first, first + stride, ... < n of a batch, one after the other on this worker: one launch per worker and
 // batch instead of one per probe (the host's launch rate was what bounded a batch)
-__global__ void __launch_bounds__(PROBE_THREADS) probe_list_kernel(const DevProblem p, const DevProblem base, int restorevar,
+__global__ void __launch_bounds__(PROBE_THREADS, 1) probe_list_kernel(const DevProblem p, const DevProblem base, int restorevar,
    const int* vars, const double* lbs, const double* ubs, int first, int stride, int n, int maxrounds, int logcap,
    ProbeResult* out)
 {

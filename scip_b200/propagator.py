@@ -262,6 +262,13 @@ class LinearPropagator:
         _check(self._lib.gpulin_get_changes(self._h, out.ctypes.data, maxn, ctypes.byref(n)))
         return out[:min(n.value, maxn)], n.value
 
+    def changes_ptr(self, out_ptr: int, maxn: int) -> int:
+        """The change log of the last call into a caller-owned (e.g. pinned) buffer of gpulin_change records; returns the
+        number of changes produced."""
+        n = ctypes.c_int64(0)
+        _check(self._lib.gpulin_get_changes(self._h, out_ptr, maxn, ctypes.byref(n)))
+        return n.value
+
     def layout(self) -> dict:
         st = np.zeros(10, dtype=np.int64)
         _check(self._lib.gpulin_get_layout(self._h, st.ctypes.data, 10))
