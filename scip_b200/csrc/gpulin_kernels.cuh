@@ -1687,11 +1687,71 @@ __device__ __forceinline__ void logChangesWarp(const DevProblem& p, int j, int r
    }
 }
 
+// Buffered variant for rounds with many changes (apply_kernel): the records of a warp collect in its shared-memory buffer
+// over the trips and go to the log in one piece -- one atomic per LOGBUF records or so, and coalesced stores.
+constexpr int LOGBUF = 96;           // records per warp; a trip adds at most 2 * 32 / APPLY_G = 16
+struct WarpLog
+{
+   ChangeRec* buf;                   // LOGBUF records of this warp (NULL: unbuffered, logChangesWarp)
+   int        n;                     // records in the buffer (warp-uniform)
+};
+
+__device__ __forceinline__ void flushWarpLog(const DevProblem& p, WarpLog& w, int logcap)
+{
+   if( w.n == 0 )
+      return;
+   const unsigned lane = threadIdx.x & 31u;
+   unsigned long long base = 0;
+   if( lane == 0 )
+      base = atomicAdd(&p.ctrl->logcount, (unsigned long long)w.n);
+   base = __shfl_sync(0xffffffffu, base, 0);
+   __syncwarp();
+   for( int i = (int)lane; i < w.n; i += 32 )
+   {
+      if( base + (unsigned long long)i < (unsigned long long)logcap )
+         p.log[base + (unsigned long long)i] = w.buf[i];
+   }
+   __syncwarp();
+   w.n = 0;
+}
+
+__device__ __forceinline__ void logChangesBuffered(const DevProblem& p, WarpLog& w, int j, int round, int logcap, bool lbchg,
+   bool ubchg, const double2& nb)
+{
+   const unsigned lane = threadIdx.x & 31u;
+   const unsigned below = (1u << lane) - 1u;
+   const unsigned mlb = __ballot_sync(0xffffffffu, lbchg);
+   const unsigned mub = __ballot_sync(0xffffffffu, ubchg);
+   const int total = __popc(mlb) + __popc(mub);
+   if( total == 0 )
+      return;
+   if( w.n + total > LOGBUF )
+      flushWarpLog(p, w, logcap);
+   int pos = w.n + __popc(mlb & below) + __popc(mub & below);
+   if( lbchg )
+   {
+      ChangeRec rec;
+      rec.var = j; rec.round = round; rec.newbound = nb.x; rec.is_upper = 0; rec.reserved = 0;
+      w.buf[pos++] = rec;
+   }
+   if( ubchg )
+   {
+      ChangeRec rec;
+      rec.var = j; rec.round = round; rec.newbound = nb.y; rec.is_upper = 1; rec.reserved = 0;
+      w.buf[pos] = rec;
+   }
+   w.n += total;
+}
+
 // the columns on the change list of this round, eight lanes per column: one accepts the bounds, all mark the rows of the
 // column; returns the number of bound changes this thread accepted
 template <int G>
-__device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlist, int gtid, int nthreads, int round, int logcap)
+__device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlist, int gtid, int nthreads, int round, int logcap,
+   ChangeRec* warplogbuf = nullptr)
 {
+   WarpLog wlog;
+   wlog.buf = warplogbuf;
+   wlog.n = 0;
    const int gl = gtid & (G - 1);
    const int ngroups = nthreads / G;
    const unsigned trips = (nlist + ngroups - 1) / ngroups;       // warp-uniform
@@ -1750,12 +1810,19 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
          mychg += nc;
       }
       if( logcap > 0 )
-         logChangesWarp(p, j, round, logcap, lbchg, ubchg, nb);
+      {
+         if( wlog.buf != nullptr )
+            logChangesBuffered(p, wlog, j, round, logcap, lbchg, ubchg, nb);
+         else
+            logChangesWarp(p, j, round, logcap, lbchg, ubchg, nb);
+      }
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
       if( valid )
          markRowRange(p, q0, q1, gl, G, which, listfull);
    }
+   if( wlog.buf != nullptr )
+      flushWarpLog(p, wlog, logcap);
    return mychg;
 }
 
@@ -1773,6 +1840,7 @@ template <int MODE, bool GRAPH>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
 {
    __shared__ int s_nchg;
+   __shared__ ChangeRec s_log[MODE == APPLY_LIST ? APPLY_THREADS / 32 : 1][MODE == APPLY_LIST ? LOGBUF : 1];
    if( threadIdx.x == 0 )
       s_nchg = 0;
    __syncthreads();
@@ -1836,7 +1904,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
       }
    }
    else
-      mychg += applyListPhase<APPLY_G>(p, nlist, gtid, nthreads, round, logcap);
+      mychg += applyListPhase<APPLY_G>(p, nlist, gtid, nthreads, round, logcap, s_log[MODE == APPLY_LIST ? threadIdx.x >> 5 : 0]);
    mychg = __reduce_add_sync(0xffffffffu, mychg);
    if( lane == 0 && mychg != 0 )
       atomicAdd(&s_nchg, mychg);
