@@ -155,7 +155,9 @@ int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg,
 
 /** storage statistics: [0] nnz, [1] stored nonzeros incl. padding, [2] rows swept thread-per-row (SELL-32 slices),
  *  [3] rows in the tiled CSR stream, [4] rows swept block-per-row, [5] bytes on device, [6] tiles of the stream,
- *  [7..8] persistent blocks of the thread-per-row / tile sweep, [9] longest row */
+ *  [7..8] persistent blocks of the thread-per-row / tile sweep, [9] longest row, [10] thread-per-row rows whose
+ *  coefficients are all +1 / -1 (stored first; the filter sweep does not read their values), [11] blocks of the
+ *  bit-table variant of the thread-per-row sweep (0: the gather variant is used) */
 int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 
 /** what the last gpulin_propagate call launched: [0] kernel launches, [1] rounds run by the dense kernels (filter sweep(s)

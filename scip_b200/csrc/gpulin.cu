@@ -71,6 +71,7 @@ struct gpulin
    int         napplyblocks = 0;
    int         nexactblocks = 0;
    int         nsparseblocks = 0;   // grid of the persistent sparse-rounds kernel (0: disabled)
+   void        (*exactkernel)(const DevProblem) = nullptr;
    int         nsellunit = 0;       // SELL rows [0,nsellunit): all coefficients +1 / -1
    int         nsellbitsblocks = 0; // grid of sweep_sell_bits_kernel (0: the gather variant is used)
    int         sellbitsvariant = 0;
@@ -267,7 +268,7 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
       for( int i = 0; i < side; ++i )
          CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
       if( h->nexactblocks > 0 )
-         exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
+         h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
    }
    if( apply )
    {
@@ -734,7 +735,9 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_long_kernel, LONG_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nlongblocks = (int)std::min<int64_t>(h->nlong, (int64_t)h->nsm * occ);
-      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_rows_kernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
+      // two resident blocks per SM with 128 registers, or three with 80 (GPULIN_EXACT_OCC=3; spills)
+      h->exactkernel = (getenv("GPULIN_EXACT_OCC") != nullptr && atoi(getenv("GPULIN_EXACT_OCC")) == 3) ? exact_rows_kernel<3> : exact_rows_kernel<2>;
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->exactkernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
       // the sparse-rounds kernel: one block per SM (all must be co-resident: grid syncs); GPULIN_SPARSE=0 disables it
@@ -1187,7 +1190,7 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    h->nsell = src->nsell; h->nstream = src->nstream; h->nlong = src->nlong; h->ntiles = src->ntiles;
    h->nstreamelems = src->nstreamelems; h->maxlen = src->maxlen;
    h->sellvariant = src->sellvariant; h->nsellblocks = src->nsellblocks; h->nstreamblocks = src->nstreamblocks;
-   h->nlongblocks = src->nlongblocks; h->napplyblocks = src->napplyblocks; h->nexactblocks = src->nexactblocks;
+   h->nlongblocks = src->nlongblocks; h->napplyblocks = src->napplyblocks; h->nexactblocks = src->nexactblocks; h->exactkernel = src->exactkernel;
    h->nsparseblocks = src->nsparseblocks;
    h->nsm = src->nsm; h->hostloop = src->hostloop; h->perm = src->perm;
    h->p = src->p;
@@ -1359,9 +1362,9 @@ extern "C" int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats)
 {
    if( h == nullptr || stats == nullptr )
       return fail(GPULIN_ERR_ARG, "invalid argument");
-   const int64_t v[10] = {h->nnz, h->nstored, h->nsell, h->nstream, h->nlong, (int64_t)h->devbytes, h->ntiles,
-      h->nsellblocks, h->nstreamblocks, h->maxlen};
-   for( int i = 0; i < nstats && i < 10; ++i )
+   const int64_t v[12] = {h->nnz, h->nstored, h->nsell, h->nstream, h->nlong, (int64_t)h->devbytes, h->ntiles,
+      h->nsellblocks, h->nstreamblocks, h->maxlen, h->nsellunit, h->nsellbitsblocks};
+   for( int i = 0; i < nstats && i < 12; ++i )
       stats[i] = v[i];
    return GPULIN_OK;
 }
@@ -1530,7 +1533,7 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    OK((launchRoundKernels<APPLY_LIST, false>(h, true, false)));
    h->nexactblocks = keepexact;
    CU(cudaEventRecord(h->evprof[1], h->stream));
-   exact_rows_kernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);   // ... which is timed on its own
+   h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);   // ... which is timed on its own
    CU(cudaEventRecord(h->evprof[2], h->stream));
    OK((launchRoundKernels<APPLY_LIST, false>(h, false, true)));
    CU(cudaEventRecord(h->evprof[3], h->stream));

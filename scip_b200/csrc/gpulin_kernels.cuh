@@ -1429,7 +1429,8 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
       addRoundNnz(p, nnzdone, gtid >> 5);
 }
 
-__global__ void __launch_bounds__(EXACT_THREADS, 2) exact_rows_kernel(const DevProblem p)
+template <int MINB>
+__global__ void __launch_bounds__(EXACT_THREADS, MINB) exact_rows_kernel(const DevProblem p)
 {
    __shared__ RowAcc s_acc[EXACT_THREADS / 32];
    __shared__ CandQueue s_queue[EXACT_THREADS / 32];

@@ -270,10 +270,10 @@ class LinearPropagator:
         return n.value
 
     def layout(self) -> dict:
-        st = np.zeros(10, dtype=np.int64)
-        _check(self._lib.gpulin_get_layout(self._h, st.ctypes.data, 10))
+        st = np.zeros(12, dtype=np.int64)
+        _check(self._lib.gpulin_get_layout(self._h, st.ctypes.data, 12))
         keys = ("nnz", "stored_nnz", "rows_thread", "rows_stream", "rows_block", "device_bytes", "tiles",
-                "blocks_thread", "blocks_stream", "maxlen")
+                "blocks_thread", "blocks_stream", "maxlen", "rows_unit", "blocks_bittable")
         return dict(zip(keys, (int(x) for x in st)))
 
     def call_stats(self) -> dict:

@@ -193,6 +193,57 @@ def mixed_knapsack(nrows=200_000, ncols=2_000_000, nnz=50_000_000, seed=2, dense
                 vartype=vartype, name=f"mixedknap_{nrows}x{ncols}_s{seed}")
 
 
+def unit_network(nrows=200_000, ncols=150_000, nnz=1_000_000, seed=4, minlen=2, maxlen=8, fix_frac=0.15,
+                 unbounded_frac=0.03):
+    """Rows with coefficients +1 / -1 only (precedence, flow-balance, cardinality shapes) over binaries, small general
+    integers and continuous variables, some of them without an upper bound; <=, >=, ranged and equality rows around
+    a planted point.  Exercises the unit-row storage class of the filter sweep (sign flags, no values read) together
+    with bound gathers, integrality rounding and infinite contributions."""
+    rng = np.random.default_rng(seed)
+    lens = _row_lengths(rng, nrows, minlen, maxlen, nnz)
+    rowptr, rowid, cols = _draw_columns(rng, lens, ncols)
+    nnz = int(rowptr[-1])
+    first = rowptr[:-1]
+    vals = np.where(rng.random(nnz) < 0.45, -1.0, 1.0)
+
+    t = rng.random(ncols)
+    vartype = (t < 0.85).astype(np.uint8)
+    lb = np.zeros(ncols)
+    ub = np.ones(ncols)
+    isint = (t >= 0.6) & (t < 0.85)
+    ub[isint] = rng.choice(np.array([3.0, 10.0]), size=int(isint.sum()))
+    cont = t >= 0.85
+    ub[cont] = 7.5
+    lb[cont & (rng.random(ncols) < 0.3)] = -2.25
+    xstar = lb + rng.random(ncols) * (ub - lb)
+    xstar = np.where(vartype != 0, np.round(xstar), xstar)
+    unb = cont & (rng.random(ncols) < unbounded_frac / 0.15)
+    ub[unb] = INF
+
+    actx = np.add.reduceat(vals * xstar[cols], first)
+    kind = rng.random(nrows)
+    s1 = rng.integers(0, 3, size=nrows).astype(np.float64)
+    s2 = rng.integers(0, 3, size=nrows).astype(np.float64)
+    lhs = np.full(nrows, -INF)
+    rhs = np.full(nrows, INF)
+    le = kind < 0.4
+    ge = (kind >= 0.4) & (kind < 0.7)
+    rg = (kind >= 0.7) & (kind < 0.9)
+    eq = kind >= 0.9
+    rhs[le] = actx[le] + s1[le]
+    lhs[ge] = actx[ge] - s1[ge]
+    lhs[rg] = actx[rg] - s1[rg]
+    rhs[rg] = actx[rg] + s2[rg]
+    lhs[eq] = actx[eq]
+    rhs[eq] = actx[eq]
+
+    fixed = rng.random(ncols) < fix_frac
+    lb = np.where(fixed, xstar, lb)
+    ub = np.where(fixed, xstar, ub)
+    return dict(rowptr=rowptr, colidx=cols.astype(np.int32), vals=vals, lhs=lhs, rhs=rhs, lb=lb + 0.0, ub=ub + 0.0,
+                vartype=vartype, name=f"unitnet_{nrows}x{ncols}_s{seed}")
+
+
 def probing_batch(prob, nvec=1024, seed=3):
     """Config C5: ``nvec`` bound vectors = base bounds + one seeded unfixed variable fixed to 0 or 1 each (the
     SCIPapplyProbingVar pattern, prop_probing.c:1254-1279).  Returns (lb[nvec,ncols], ub[nvec,ncols], var, val)."""

@@ -49,6 +49,27 @@ def test_setcover_100k(gpulin, seed):
     assert got["nchanges"] > 0
 
 
+@pytest.mark.parametrize("seed,bs", [(4, 1e-9), (5, 0.05)])
+def test_unit_rows_with_signs_take_the_bit_table_sweep(gpulin, seed, bs):
+    # +1 / -1 rows over binaries, integers and (partly unbounded) continuous variables, large enough for the bit-table
+    # variant of the thread-per-row sweep: the unit rows are stored first and their values are never read by the filter
+    prob = synth.unit_network(200_000, 150_000, 1_000_000, seed=seed)
+    with gpulin.LinearPropagator(prob) as lp:
+        lay = lp.layout()
+    assert lay["rows_unit"] >= 199_000 and lay["rows_unit"] % 32 == 0 and lay["blocks_bittable"] > 0
+    got, _ = gpu_vs_oracle(gpulin, prob, maxrounds=500, what=f"unitnet seed {seed}", boundstreps=bs)
+    assert got["nchanges"] > 0
+
+
+def test_unit_and_weighted_rows_mixed_in_the_thread_per_row_bin(gpulin):
+    # a set-cover instance (85 % unit rows, 15 % knapsack rows with weights) whose SELL bin holds both storage classes
+    prob = synth.setcover(200_000, 200_000, 2_000_000, seed=6)
+    with gpulin.LinearPropagator(prob) as lp:
+        lay = lp.layout()
+    assert 0 < lay["rows_unit"] < lay["rows_thread"] and lay["blocks_bittable"] > 0
+    gpu_vs_oracle(gpulin, prob, what="setcover 200k")
+
+
 def test_setcover_infeasible(gpulin):
     prob = synth.setcover(50_000, 50_000, 500_000, seed=5, infeasible=True)
     got, want = gpu_vs_oracle(gpulin, prob, what="setcover infeasible")
