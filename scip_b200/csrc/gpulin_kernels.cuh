@@ -187,8 +187,13 @@ struct CandQueue
    int k[CAND_QCAP];
 };
 
+// ALPHA (warp per row: first == lane, step == 32): alpha[q] = |a| (ub - lb) of the elements lane + 32 q, q < 8, was kept
+// from the activity pass -- the slack test of the first 256 nonzeros needs no load at all, only the few nonzeros that
+// pass it are fetched again (from L1)
+constexpr int ALPHA_SLOTS = 8;
+template <bool ALPHA>
 __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo& ri, long long base, int stride,
-   int first, int step, int len, bool& cutoff, CandQueue& queue)
+   int first, int step, int len, bool& cutoff, CandQueue& queue, const double (&alpha)[ALPHA_SLOTS])
 {
    const Num& n = p.num;
    const double thr = slackThreshold(n, ri.force);
@@ -207,29 +212,42 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
       if( kb < len )
       {
          const int k0 = kb + lane;
-         double a[4];
-         int cj[4];
-         double2 b[4];
-#pragma unroll
-         for( int q = 0; q < 4; ++q )
+         double al[4];
+         if( ALPHA && kb < 32 * ALPHA_SLOTS )
          {
-            const int k = k0 + q * step;
-            if( k < len )
+#pragma unroll
+            for( int q = 0; q < 4; ++q )
+               al[q] = kb == 0 ? alpha[q] : alpha[4 + q];
+         }
+         else
+         {
+            double a[4];
+            int cj[4];
+            double2 b[4];
+#pragma unroll
+            for( int q = 0; q < 4; ++q )
             {
-               a[q] = p.vals[base + (long long)stride * k];
-               cj[q] = p.cols[base + (long long)stride * k];
+               const int k = k0 + q * step;
+               if( k < len )
+               {
+                  a[q] = p.vals[base + (long long)stride * k];
+                  cj[q] = p.cols[base + (long long)stride * k];
+               }
             }
+#pragma unroll
+            for( int q = 0; q < 4; ++q )
+            {
+               if( k0 + q * step < len )
+                  b[q] = p.bnd[cj[q] & COL_MASK];
+            }
+#pragma unroll
+            for( int q = 0; q < 4; ++q )
+               al[q] = k0 + q * step < len ? fabs(a[q]) * (b[q].y - b[q].x) : 0.0;
          }
 #pragma unroll
          for( int q = 0; q < 4; ++q )
          {
-            if( k0 + q * step < len )
-               b[q] = p.bnd[cj[q] & COL_MASK];
-         }
-#pragma unroll
-         for( int q = 0; q < 4; ++q )
-         {
-            const bool pass = k0 + q * step < len && (!ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr));
+            const bool pass = k0 + q * step < len && (!ri.easy || passesSlackTest(ri, al[q], thr));
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if( pass )
                queue.k[cnt + __popc(m & below)] = k0 + q * step;
@@ -386,8 +404,9 @@ __device__ __forceinline__ bool rowClearlyQuiet(const Num& n, const LeanAcc& r, 
 
 // gates, candidate pass and verdict of one row whose exact activities are known (elements first, first+step, ... of
 // the calling thread)
+template <bool ALPHA>
 __device__ __forceinline__ void rowTighten(const DevProblem& p, const RowAcc& acc, double lhs, double rhs, long long base,
-   int stride, int first, int step, int len, CandQueue& queue)
+   int stride, int first, int step, int len, CandQueue& queue, const double (&alpha)[ALPHA_SLOTS])
 {
    RowInfo ri;
    ri.acc = acc;
@@ -395,14 +414,15 @@ __device__ __forceinline__ void rowTighten(const DevProblem& p, const RowAcc& ac
    ri.rhs = rhs;
    bool cutoff = false;
    if( rowGates(p.num, ri, len, cutoff) )
-      rowCandidates(p, ri, base, stride, first, step, len, cutoff, queue);
+      rowCandidates<ALPHA>(p, ri, base, stride, first, step, len, cutoff, queue, alpha);
    if( cutoff || rowInfeasible(p.num, ri.acc, lhs, rhs) )
       p.ctrl->cutoff = 1;
 }
 
 // exact activities of the elements first, first+step, ... < len (four independent loads in flight)
+template <bool ALPHA>
 __device__ __forceinline__ void accumulateExact(const DevProblem& p, RowAcc& acc, long long base, int stride, int first,
-   int step, int len)
+   int step, int len, double (&alpha)[ALPHA_SLOTS])
 {
    for( int k0 = first; k0 < len; k0 += 4 * step )
    {
@@ -430,6 +450,18 @@ __device__ __forceinline__ void accumulateExact(const DevProblem& p, RowAcc& acc
       {
          if( k0 + q * step < len )
             accElem(p.num, acc, a[q], b[q].x, b[q].y);
+      }
+      if( ALPHA && k0 < 8 * step )      // the first two trips (step == 32: k0 == first, first + 128)
+      {
+#pragma unroll
+         for( int q = 0; q < 4; ++q )
+         {
+            const double al = k0 + q * step < len ? fabs(a[q]) * (b[q].y - b[q].x) : 0.0;
+            if( k0 < 4 * step )
+               alpha[q] = al;
+            else
+               alpha[4 + q] = al;
+         }
       }
    }
 }
@@ -1387,9 +1419,13 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
             nnzdone += (unsigned long long)len;
          RowAcc acc;
          accInit(acc);
-         accumulateExact(p, acc, beg, 1, lane, 32, len);
+         double alpha[ALPHA_SLOTS];
+#pragma unroll
+         for( int q = 0; q < ALPHA_SLOTS; ++q )
+            alpha[q] = 0.0;
+         accumulateExact<true>(p, acc, beg, 1, lane, 32, len, alpha);
          accWarpReduce(acc, lane);
-         rowTighten(p, acc, sd.x, sd.y, beg, 1, lane, 32, len, s_queue[warp]);
+         rowTighten<true>(p, acc, sd.x, sd.y, beg, 1, lane, 32, len, s_queue[warp], alpha);
       }
    }
 
@@ -1414,7 +1450,8 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
          nnzdone += (unsigned long long)len;
       RowAcc acc;
       accInit(acc);
-      accumulateExact(p, acc, beg, 1, threadIdx.x, nblockthreads, len);
+      double noalpha[ALPHA_SLOTS];
+      accumulateExact<false>(p, acc, beg, 1, threadIdx.x, nblockthreads, len, noalpha);
       accWarpReduce(acc, lane);
       if( lane == 0 )
          s_acc[warp] = acc;
@@ -1423,7 +1460,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
 #pragma unroll 1
       for( int w = 1; w < nblockthreads / 32; ++w )
          accMerge(acc, s_acc[w]);
-      rowTighten(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, nblockthreads, len, s_queue[warp]);
+      rowTighten<false>(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, nblockthreads, len, s_queue[warp], noalpha);
    }
    if( SPARSE && nnzdone != 0 )
       addRoundNnz(p, nnzdone, gtid >> 5);
