@@ -217,6 +217,7 @@ static SCIP_RETCODE run(int argc, char** argv)
    int solve = 0;
    int quiet = 1;
    int presolve = 0;
+   int activeonly = 0;
    int rowsof[5] = {-1, -1, -1, -1, -1};
    char pname[128];
    double t0, t1;
@@ -233,6 +234,7 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--solve") == 0 ) solve = 1;
       else if( strcmp(argv[i], "--verbose") == 0 ) quiet = 0;
       else if( strcmp(argv[i], "--presolve") == 0 ) presolve = 1;
+      else if( strcmp(argv[i], "--active-rows-only") == 0 ) activeonly = 1;
       else if( strcmp(argv[i], "--probe-batch") == 0 && i + 1 < argc ) g_nprobecheck = atoi(argv[++i]);
       else
       {
@@ -283,7 +285,11 @@ static SCIP_RETCODE run(int argc, char** argv)
    if( quiet )
       SCIP_CALL( SCIPsetIntParam(scip, "display/verblevel", 0) );
    if( !usecpu )
+   {
       SCIP_CALL( SCIPsetIntParam(scip, "constraints/linear/tightenboundsfreq", -1) );   /* the replaced path is off */
+      if( activeonly )
+         SCIP_CALL( SCIPsetBoolParam(scip, "propagating/gpulinear/stablecopy", FALSE) );
+   }
 
    if( readfile != NULL )
       SCIP_CALL( SCIPreadProb(scip, readfile, NULL) );
@@ -310,12 +316,13 @@ static SCIP_RETCODE run(int argc, char** argv)
    gpuprop = SCIPfindProp(scip, "gpulinear");
    printf("{\"mode\": \"%s\", \"status\": \"%s\", \"scip_status\": %d, \"ncols\": %d, \"nodes\": %lld, \"linear_prop_calls\": %lld, "
       "\"linear_domreds\": %lld, \"linear_prop_time_s\": %.9g, \"gpu_prop_calls\": %lld, \"gpu_domreds\": %lld, "
-      "\"gpu_prop_time_s\": %.9g, \"solve_time_s\": %.9g, \"primal\": %.15g, \"gpu_rows\": [%d, %d, %d, %d, %d]}\n",
+      "\"gpu_prop_time_s\": %.9g, \"solve_time_s\": %.9g, \"primal\": %.15g, \"gpu_rows\": [%d, %d, %d, %d, %d], \"gpu_builds\": %lld}\n",
       usecpu ? "cpu" : "gpu", infeasible ? "infeasible" : "ok", (int)SCIPgetStatus(scip), g_nvars, (long long)SCIPgetNNodes(scip),
       (long long)SCIPconshdlrGetNPropCalls(linhdlr), (long long)SCIPconshdlrGetNDomredsFound(linhdlr),
       SCIPconshdlrGetPropTime(linhdlr), gpuprop != NULL ? (long long)SCIPpropGetNCalls(gpuprop) : 0LL,
       gpuprop != NULL ? (long long)SCIPpropGetNDomredsFound(gpuprop) : 0LL, gpuprop != NULL ? SCIPpropGetTime(gpuprop) : 0.0,
-      t1 - t0, SCIPgetPrimalbound(scip), rowsof[0], rowsof[1], rowsof[2], rowsof[3], rowsof[4]);
+      t1 - t0, SCIPgetPrimalbound(scip), rowsof[0], rowsof[1], rowsof[2], rowsof[3], rowsof[4],
+      usecpu ? 0LL : (long long)SCIPgetNBuildsGpulinear(scip));
 
    if( outfile != NULL )
    {

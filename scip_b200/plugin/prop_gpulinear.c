@@ -66,6 +66,7 @@
 #define DEFAULT_MAXROUNDS      -1         /* rounds per call on the device (-1: to the fixpoint) */
 #define DEFAULT_DEVICE         0
 #define DEFAULT_LOGCAPFAC      8          /* change log capacity = factor * number of variables */
+#define DEFAULT_STABLECOPY     TRUE       /* device copy of all existing global rows, not only of those active at the node of the build */
 #define DEFAULT_ALLROWS        TRUE       /* read the rows of knapsack / setppc / logicor / varbound constraints as well */
 #define DEFAULT_INCREMENTAL    TRUE       /* send only changed bounds (event driven) instead of all bounds per call */
 #define EVENTHDLR_NAME         "gpulinear"
@@ -94,6 +95,8 @@ struct SCIP_PropData
    int                   nlinconss;          /**< active constraints of all row sources when the device copy was built */
    int                   nrowsof[5];         /**< rows per source: linear, knapsack, setppc, logicor, varbound */
    SCIP_Bool             allrows;            /**< parameter: also read knapsack / setppc / logicor / varbound rows */
+   SCIP_Bool             stablecopy;         /**< parameter: the device copy holds every existing global row (see countSourceConss) */
+   SCIP_Longint          nbuilds;            /**< device copies built so far */
    int                   nskipped;           /**< rows not sent to the device (modifiable, local, non-active variables) */
    SCIP_EVENTHDLR*       eventhdlr;          /**< bound change event handler */
    int*                  filterpos;          /**< per column: position of the caught event, or -1 */
@@ -168,11 +171,21 @@ void freeDeviceCopy(
 #define NROWSOURCES 5
 static const char* const rowsourcenames[NROWSOURCES] = {"linear", "knapsack", "setppc", "logicor", "varbound"};
 
-/** number of active constraints of all row sources (the cheap staleness check of the device copy) */
+/** number of constraints of all row sources (the cheap staleness check of the device copy).
+ *
+ *  stable = FALSE: the ACTIVE constraints.  In a tree search that number moves from node to node: the handlers delete
+ *  constraints locally that have become redundant in a subtree (cons_linear does so in propagateCons, :7743-7753, also when
+ *  its bound tightening is off) and backtracking brings them back -- the device copy would be rebuilt at most nodes.
+ *  stable = TRUE: the EXISTING constraints (active or not, SCIPconshdlrGetNConss).  The device copy then holds every
+ *  existing row that is not deleted, not local and not modifiable.  Such a row is globally valid whether or not it is
+ *  active at the current node, so propagating it is always correct; a row that is only switched off because it is
+ *  redundant in this subtree cannot tighten anything anyway.  The number changes only when constraints are created or
+ *  freed (conflict constraints, restarts). */
 static
 int countSourceConss(
    SCIP*                 scip,
-   SCIP_Bool             allrows
+   SCIP_Bool             allrows,
+   SCIP_Bool             stable
    )
 {
    int n = 0;
@@ -181,7 +194,7 @@ int countSourceConss(
    {
       SCIP_CONSHDLR* conshdlr = SCIPfindConshdlr(scip, rowsourcenames[s]);
       if( conshdlr != NULL )
-         n += SCIPconshdlrGetNActiveConss(conshdlr);
+         n += stable ? SCIPconshdlrGetNConss(conshdlr) : SCIPconshdlrGetNActiveConss(conshdlr);
    }
    return n;
 }
@@ -211,7 +224,7 @@ SCIP_RETCODE getActiveRow(
 
    *usable = FALSE;
    *nvars = 0;
-   if( SCIPconsIsModifiable(cons) || SCIPconsIsLocal(cons) || !SCIPconsIsPropagationEnabled(cons) )
+   if( SCIPconsIsDeleted(cons) || SCIPconsIsModifiable(cons) || SCIPconsIsLocal(cons) || !SCIPconsIsPropagationEnabled(cons) )
       return SCIP_OKAY;
 
    switch( src )
@@ -356,8 +369,9 @@ SCIP_RETCODE buildDeviceCopy(
    freeDeviceCopy(scip, propdata);
 
    nsources = propdata->allrows ? NROWSOURCES : 1;
-   propdata->nlinconss = countSourceConss(scip, propdata->allrows);
+   propdata->nlinconss = countSourceConss(scip, propdata->allrows, propdata->stablecopy);
    propdata->nskipped = 0;
+   ++propdata->nbuilds;
    if( propdata->nlinconss == 0 )
       return SCIP_OKAY;
 
@@ -421,7 +435,7 @@ SCIP_RETCODE buildDeviceCopy(
          if( conshdlr == NULL )
             continue;
          conss = SCIPconshdlrGetConss(conshdlr);
-         nconss = SCIPconshdlrGetNActiveConss(conshdlr);
+         nconss = propdata->stablecopy ? SCIPconshdlrGetNConss(conshdlr) : SCIPconshdlrGetNActiveConss(conshdlr);
          for( c = 0; c < nconss; ++c )
          {
             SCIP_Real lhs;
@@ -600,8 +614,9 @@ SCIP_DECL_PROPEXITSOL(propExitsolGpulinear)
    if( propdata->ncalls > 0 )
    {
       SCIPverbMessage(scip, SCIP_VERBLEVEL_FULL, NULL,
-         "prop_gpulinear: %lld calls (%lld full bound uploads, %lld single bounds sent), %lld device rounds, %lld bound changes, "
-         "%.3f ms on the device\n", (long long)propdata->ncalls, (long long)propdata->nfullsyncs, (long long)propdata->nupdates,
+         "prop_gpulinear: %lld calls (%lld device copies built, %lld full bound uploads, %lld single bounds sent), %lld device rounds, "
+         "%lld bound changes, %.3f ms on the device\n", (long long)propdata->ncalls, (long long)propdata->nbuilds,
+         (long long)propdata->nfullsyncs, (long long)propdata->nupdates,
          (long long)propdata->nrounds, (long long)propdata->nchanges, propdata->devicems);
    }
    freeDeviceCopy(scip, propdata);
@@ -628,11 +643,11 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
    propdata = SCIPpropGetData(prop);
    assert(propdata != NULL);
 
-   nsourceconss = countSourceConss(scip, propdata->allrows);
+   nsourceconss = countSourceConss(scip, propdata->allrows, propdata->stablecopy);
    if( nsourceconss == 0 )
       return SCIP_OKAY;
 
-   /* staleness: rebuild when the number of active constraints of the row sources or of variables changed */
+   /* staleness: rebuild when the number of constraints of the row sources (see countSourceConss) or of variables changed */
    if( propdata->gpu == NULL || propdata->nlinconss != nsourceconss || propdata->ncols != SCIPgetNVars(scip) )
    {
       SCIP_CALL( buildDeviceCopy(scip, propdata) );
@@ -900,6 +915,9 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/allrows",
          "also propagate the linear rows behind knapsack, setppc, logicor and varbound constraints (cf. matrix.c)",
          &propdata->allrows, FALSE, DEFAULT_ALLROWS, NULL, NULL) );
+   SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/stablecopy",
+         "keep one device copy of all existing global rows across the tree (FALSE: of the rows active at the node of the build, rebuilt whenever that number changes)",
+         &propdata->stablecopy, FALSE, DEFAULT_STABLECOPY, NULL, NULL) );
    SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/device",
          "CUDA device ordinal",
          &propdata->device, TRUE, DEFAULT_DEVICE, 0, 1023, NULL, NULL) );
@@ -922,6 +940,20 @@ int SCIPgetNRowsGpulinear(
    if( propdata == NULL || propdata->gpu == NULL )
       return -1;
    return propdata->nrowsof[source];
+}
+
+/** device copies built so far (a rebuild follows every change of the number of source constraints) */
+SCIP_Longint SCIPgetNBuildsGpulinear(
+   SCIP*                 scip                /**< SCIP data structure */
+   )
+{
+   SCIP_PROP* prop = SCIPfindProp(scip, PROP_NAME);
+   SCIP_PROPDATA* propdata;
+
+   if( prop == NULL )
+      return -1;
+   propdata = SCIPpropGetData(prop);
+   return propdata == NULL ? -1 : propdata->nbuilds;
 }
 
 /** a batch of independent probes on the current node, see prop_gpulinear.h */

@@ -31,6 +31,12 @@ int SCIPgetNRowsGpulinear(
    int                   source              /**< row source */
    );
 
+/** device copies built so far (a rebuild follows every change of the number of source constraints); -1 if the
+ *  propagator is not included */
+SCIP_Longint SCIPgetNBuildsGpulinear(
+   SCIP*                 scip                /**< SCIP data structure */
+   );
+
 /** a batch of independent probes on the current node -- the cycle SCIPstartProbing / SCIPchgVarLb/UbProbing /
  *  SCIPpropagateProbing / SCIPbacktrackProbing (scip_probing.c:120,302,346,581,226) that SCIPapplyProbingVar
  *  (prop_probing.c:1254-1279) runs once per candidate, for all candidates at once: probe i sets vars[i] to

@@ -70,6 +70,22 @@ def test_plugin_in_tree_search_with_conflict_analysis():
 
 @needs_driver
 @pytest.mark.gpu
+def test_device_copy_is_stable_across_the_tree():
+    """constraint handlers delete rows locally that became redundant in a subtree (cons_linear.c:7743-7753) and backtracking
+    brings them back: a device copy of the ACTIVE rows (--active-rows-only, the first policy of this plugin) is rebuilt
+    whenever their number moves; the default copy of all EXISTING global rows is built once per change of the constraint
+    set -- same verdict and optimum either way"""
+    stable = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve")
+    active = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", "--active-rows-only")
+    print("device copies built: stable", stable["gpu_builds"], "active-only", active["gpu_builds"],
+          "calls", stable["gpu_prop_calls"], active["gpu_prop_calls"])
+    assert stable["scip_status"] == active["scip_status"]
+    assert abs(stable["primal"] - active["primal"]) <= 1e-6
+    assert 1 <= stable["gpu_builds"] <= active["gpu_builds"]
+
+
+@needs_driver
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["p0548", "misc03", "lseu", "enigma"])
 def test_plugin_reads_upgraded_rows_after_presolve(tmp_path, name):
     """with presolving on, most linear constraints are upgraded to knapsack / setppc / logicor / varbound constraints
