@@ -27,6 +27,7 @@
  * (PROPCOPY = NULL): copies do not get a GPU.
  */
 #include <assert.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "prop_gpulinear.h"
@@ -66,6 +67,7 @@
 #define DEFAULT_MAXROUNDS      -1         /* rounds per call on the device (-1: to the fixpoint) */
 #define DEFAULT_DEVICE         0
 #define DEFAULT_LOGCAPFAC      8          /* change log capacity = factor * number of variables */
+#define DEFAULT_DETERMINISTIC  TRUE       /* replay the changes of a round in a fixed order */
 #define DEFAULT_STABLECOPY     TRUE       /* device copy of all existing global rows, not only of those active at the node of the build */
 #define DEFAULT_ALLROWS        TRUE       /* read the rows of knapsack / setppc / logicor / varbound constraints as well */
 #define DEFAULT_INCREMENTAL    TRUE       /* send only changed bounds (event driven) instead of all bounds per call */
@@ -95,6 +97,7 @@ struct SCIP_PropData
    int                   nlinconss;          /**< active constraints of all row sources when the device copy was built */
    int                   nrowsof[5];         /**< rows per source: linear, knapsack, setppc, logicor, varbound */
    SCIP_Bool             allrows;            /**< parameter: also read knapsack / setppc / logicor / varbound rows */
+   SCIP_Bool             deterministic;      /**< parameter: sort the change log inside every round before the replay */
    SCIP_Bool             stablecopy;         /**< parameter: the device copy holds every existing global row (see countSourceConss) */
    SCIP_Longint          nbuilds;            /**< device copies built so far */
    int                   nskipped;           /**< rows not sent to the device (modifiable, local, non-active variables) */
@@ -624,6 +627,24 @@ SCIP_DECL_PROPEXITSOL(propExitsolGpulinear)
    return SCIP_OKAY;
 }
 
+/** order of the replay: by round (the order that makes every change explainable), inside a round by column and bound.
+ *  The device appends the changes of a round in whatever order its atomics land; SCIP's search (inference order,
+ *  conflict analysis) should not depend on that */
+static
+int compareChanges(
+   const void*           a,
+   const void*           b
+   )
+{
+   const gpulin_change* x = (const gpulin_change*)a;
+   const gpulin_change* y = (const gpulin_change*)b;
+   if( x->round != y->round )
+      return x->round < y->round ? -1 : 1;
+   if( x->var != y->var )
+      return x->var < y->var ? -1 : 1;
+   return x->is_upper - y->is_upper;
+}
+
 /** execution method of propagator */
 static
 SCIP_DECL_PROPEXEC(propExecGpulinear)
@@ -718,6 +739,8 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
    if( nlog <= propdata->logcap )
    {
       /* replay in round order: every change is implied by one row and the bounds SCIP knows at that point */
+      if( propdata->deterministic && nlog > 1 )
+         qsort(propdata->changes, (size_t)nlog, sizeof(gpulin_change), compareChanges);
       for( e = 0; e < nlog; ++e )
       {
          const gpulin_change* chg = &propdata->changes[e];
@@ -915,6 +938,9 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/allrows",
          "also propagate the linear rows behind knapsack, setppc, logicor and varbound constraints (cf. matrix.c)",
          &propdata->allrows, FALSE, DEFAULT_ALLROWS, NULL, NULL) );
+   SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/deterministic",
+         "replay the bound changes of a device round sorted by variable (the device logs them in the order its atomics land)",
+         &propdata->deterministic, FALSE, DEFAULT_DETERMINISTIC, NULL, NULL) );
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/stablecopy",
          "keep one device copy of all existing global rows across the tree (FALSE: of the rows active at the node of the build, rebuilt whenever that number changes)",
          &propdata->stablecopy, FALSE, DEFAULT_STABLECOPY, NULL, NULL) );

@@ -70,6 +70,16 @@ def test_plugin_in_tree_search_with_conflict_analysis():
 
 @needs_driver
 @pytest.mark.gpu
+def test_tree_search_is_reproducible():
+    """the device logs the changes of a round in the order its atomics land; the plugin replays them sorted, so two runs
+    of the same search visit the same nodes"""
+    a = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", "--presolve")
+    b = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", "--presolve")
+    assert (a["nodes"], a["gpu_prop_calls"], a["gpu_domreds"]) == (b["nodes"], b["gpu_prop_calls"], b["gpu_domreds"])
+
+
+@needs_driver
+@pytest.mark.gpu
 def test_device_copy_is_stable_across_the_tree():
     """constraint handlers delete rows locally that became redundant in a subtree (cons_linear.c:7743-7753) and backtracking
     brings them back: a device copy of the ACTIVE rows (--active-rows-only, the first policy of this plugin) is rebuilt
