@@ -153,6 +153,12 @@ int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n
  *  device time [ms] (%globaltimer stamps taken by the kernels), nonzeros swept, bound changes accepted */
 int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n);
 
+/** redundancy feedback -- replaces the verdict at the end of propagateCons (cons_linear.c:7743-7753: a row whose activity
+ *  bounds lie inside its sides, GE(minactivity, lhs) and LE(maxactivity, rhs), is deleted locally with SCIPdelConsLocal):
+ *  the rows (caller's numbering, ascending) that are redundant for the bounds on the device, e.g. after gpulin_propagate.
+ *  *n = their number (may exceed maxn; only maxn are written). */
+int gpulin_get_redundant_rows(gpulin_t* h, int32_t* rows, int64_t maxn, int64_t* n);
+
 /** storage statistics: [0] nnz, [1] stored nonzeros incl. padding, [2] rows swept thread-per-row (SELL-32 slices),
  *  [3] rows in the tiled CSR stream, [4] rows swept block-per-row, [5] bytes on device, [6] tiles of the stream,
  *  [7..8] persistent blocks of the thread-per-row / tile sweep, [9] longest row, [10] thread-per-row rows whose

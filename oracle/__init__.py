@@ -115,6 +115,21 @@ def sweep(prob, lb, ub, rowbegin=0, rowend=None, **numerics):
     return int(c), nlb, nub
 
 
+def redundant_rows(prob, lb, ub, **numerics):
+    """bool[nrows]: rows that are redundant for the bounds lb/ub (the verdict of propagateCons, cons_linear.c:7743)"""
+    p, keep = _problem(prob)
+    num = _numerics(**numerics)
+    lb = np.ascontiguousarray(lb, dtype=np.float64) + 0.0
+    ub = np.ascontiguousarray(ub, dtype=np.float64) + 0.0
+    out = np.zeros(int(p.nrows), dtype=np.uint8)
+    fn = _lib().oracle_redundant_rows
+    fn.restype = ctypes.c_int64
+    fn.argtypes = [ctypes.POINTER(_Problem), ctypes.POINTER(_Numerics), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    fn(ctypes.byref(p), ctypes.byref(num), lb.ctypes.data, ub.ctypes.data, out.ctypes.data)
+    del keep
+    return out.astype(bool)
+
+
 def dd_sum21(ahi, alo, b):
     hi, lo = ctypes.c_double(0), ctypes.c_double(0)
     _lib().oracle_dd_sum21(ctypes.byref(hi), ctypes.byref(lo), ahi, alo, b)

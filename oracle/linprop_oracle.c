@@ -564,6 +564,35 @@ int oracle_sweep(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const double
    return 0;
 }
 
+/* the redundancy verdict of propagateCons, cons_linear.c:7715-7753: with the activities of the given bounds
+ * (goodrelax = TRUE) a row that is not infeasible (FeasGT(minact, rhs) / FeasLT(maxact, lhs)) is redundant iff
+ * GE(minact, lhs) and LE(maxact, rhs) -- the reference then deletes it locally (SCIPdelConsLocal, :7749) */
+int64_t oracle_redundant_rows(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const double* lb, const double* ub,
+   uint8_t* redundant)
+{
+   int64_t r;
+   int64_t count = 0;
+   for( r = 0; r < p->nrows; ++r )
+   {
+      ROWACT ra;
+      double minact;
+      double maxact;
+      int t1, t2, s1, s2;
+      rowActivities(p, n, lb, ub, r, &ra);
+      getMinActivity(n, ra.minact, ra.minposinf, ra.minneginf, ra.minposhuge, ra.minneghuge, 0.0, 1, &minact, &t1, &s1);
+      getMaxActivity(n, ra.maxact, ra.maxposinf, ra.maxneginf, ra.maxposhuge, ra.maxneghuge, 0.0, 1, &maxact, &t2, &s2);
+      redundant[r] = 0;
+      if( isFeasGT(n, minact, p->rhs[r]) || isFeasLT(n, maxact, p->lhs[r]) )
+         continue;
+      if( isGE(n, minact, p->lhs[r]) && isLE(n, maxact, p->rhs[r]) )
+      {
+         redundant[r] = 1;
+         ++count;
+      }
+   }
+   return count;
+}
+
 int oracle_propagate(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, double* lb, double* ub, int maxrounds,
    int* nrounds, int64_t* nchanges)
 {

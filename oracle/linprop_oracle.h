@@ -73,6 +73,16 @@ int oracle_sweep(
    int64_t                rowend
    );
 
+/** redundant[r] = 1 iff row r is redundant for the bounds lb/ub in the sense of propagateCons (cons_linear.c:7743:
+ *  not infeasible, GE(minactivity, lhs) and LE(maxactivity, rhs)); returns their number */
+int64_t oracle_redundant_rows(
+   const ORACLE_PROBLEM*  prob,
+   const ORACLE_NUMERICS* num,
+   const double*          lb,
+   const double*          ub,
+   uint8_t*               redundant   /* nrows, out */
+   );
+
 /** double-double helpers exported for the known-answer tests (dbldblarith.h:154-187) */
 void oracle_dd_sum21(double* rhi, double* rlo, double ahi, double alo, double b);
 

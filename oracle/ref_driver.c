@@ -370,6 +370,7 @@ static SCIP_RETCODE run(int argc, char** argv)
    const char* lpbfile = NULL;
    const char* outfile = NULL;
    const char* dumpfile = NULL;
+   const char* redfile = NULL;
    double boundstreps = -1.0;
    int quiet = 1;
    int i;
@@ -386,6 +387,7 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--boundstreps") == 0 && i + 1 < argc ) boundstreps = atof(argv[++i]);
       else if( strcmp(argv[i], "--verbose") == 0 ) quiet = 0;
       else if( strcmp(argv[i], "--probe") == 0 && i + 1 < argc ) g_nprobe = atoi(argv[++i]);
+      else if( strcmp(argv[i], "--redundant") == 0 && i + 1 < argc ) redfile = argv[++i];
       else
       {
          fprintf(stderr, "usage: ref_driver (--read FILE | --lpb FILE) [--out OUT.lpr] [--dump-lpb OUT.lpb] [--boundstreps X] [--verbose]\n");
@@ -475,6 +477,27 @@ static SCIP_RETCODE run(int argc, char** argv)
          SCIP_VAR* tv = SCIPvarGetTransVar(propdata.origvars[i]);
          double b = (tv != NULL) ? SCIPvarGetUbGlobal(tv) : SCIPvarGetUbGlobal(propdata.origvars[i]);
          fwrite(&b, 8, 1, f);
+      }
+      fclose(f);
+   }
+
+   /* --redundant OUT: one byte per original constraint (= row of the .lpb, in order): 1 if the reference removed it during
+    * the root propagation -- propagateCons deletes rows it finds redundant (cons_linear.c:7743-7753; at depth 0
+    * SCIPdelConsLocal is a global deletion) */
+   if( redfile != NULL )
+   {
+      SCIP_CONS** oconss = SCIPgetOrigConss(scip);
+      int noconss = SCIPgetNOrigConss(scip);
+      f = fopen(redfile, "wb");
+      if( f == NULL )
+         return SCIP_ERROR;
+      for( i = 0; i < noconss; ++i )
+      {
+         SCIP_CONS* tcons = NULL;
+         unsigned char gone;
+         SCIP_CALL( SCIPgetTransformedCons(scip, oconss[i], &tcons) );
+         gone = (unsigned char)((tcons == NULL || SCIPconsIsDeleted(tcons) || !SCIPconsIsActive(tcons)) ? 1 : 0);
+         fwrite(&gone, 1, 1, f);
       }
       fclose(f);
    }

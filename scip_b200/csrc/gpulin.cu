@@ -72,6 +72,8 @@ struct gpulin
    int         nexactblocks = 0;
    int         nsparseblocks = 0;   // grid of the persistent sparse-rounds kernel (0: disabled)
    void        (*exactkernel)(const DevProblem) = nullptr;
+   unsigned char* d_redflags = nullptr; // gpulin_get_redundant_rows: one flag per row, device / pinned host (allocated on first use)
+   unsigned char* h_redflags = nullptr;
    int         nsellunit = 0;       // SELL rows [0,nsellunit): all coefficients +1 / -1
    int         nsellbitsblocks = 0; // grid of sweep_sell_bits_kernel (0: the gather variant is used)
    int         sellbitsvariant = 0;
@@ -802,6 +804,9 @@ extern "C" void gpulin_destroy(gpulin_t* h)
       cudaFreeHost(h->h_ctrl);
    if( h->h_params != nullptr )
       cudaFreeHost(h->h_params);
+   cudaFree(h->d_redflags);
+   if( h->h_redflags != nullptr )
+      cudaFreeHost(h->h_redflags);
    cudaFree(h->d_updidx);
    cudaFree(h->d_updlb);
    cudaFree(h->d_updub);
@@ -1327,6 +1332,38 @@ extern "C" int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn,
       CU(cudaMemcpyAsync(out, h->d_log, sizeof(ChangeRec) * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
    }
+   return GPULIN_OK;
+}
+
+// rows that are redundant for the bounds on the device, in the caller's row numbering, ascending
+extern "C" int gpulin_get_redundant_rows(gpulin_t* h, int32_t* rows, int64_t maxn, int64_t* n)
+{
+   if( h == nullptr || n == nullptr || maxn < 0 || (maxn > 0 && rows == nullptr) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( !h->havebounds )
+      return fail(GPULIN_ERR_STATE, "no bounds on the device");
+   *n = 0;
+   if( h->nrows == 0 )
+      return GPULIN_OK;
+   CU(cudaSetDevice(h->device));
+   if( h->d_redflags == nullptr )
+      CU(cudaMalloc((void**)&h->d_redflags, (size_t)h->nrows));
+   if( h->h_redflags == nullptr )
+      CU(cudaMallocHost((void**)&h->h_redflags, (size_t)h->nrows));
+   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((h->nrows + 7) / 8, (int64_t)h->nsm * 8));
+   redundant_rows_kernel<<<blocks, 256, 0, h->stream>>>(h->p, h->d_redflags);
+   CU(cudaMemcpyAsync(h->h_redflags, h->d_redflags, (size_t)h->nrows, cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaStreamSynchronize(h->stream));
+   std::vector<int32_t> found;
+   for( int64_t i = 0; i < h->nrows; ++i )
+   {
+      if( h->h_redflags[(size_t)i] )
+         found.push_back(h->perm[(size_t)i]);
+   }
+   std::sort(found.begin(), found.end());
+   *n = (int64_t)found.size();
+   for( int64_t i = 0; i < *n && i < maxn; ++i )
+      rows[i] = found[(size_t)i];
    return GPULIN_OK;
 }
 

@@ -382,6 +382,21 @@ __device__ __forceinline__ bool rowInfeasible(const Num& n, const RowAcc& a, dou
    return isFeasGT(n, minact, rhs) || isFeasLT(n, maxact, lhs);
 }
 
+// redundancy verdict of propagateCons (cons_linear.c:7743-7753): a row that is not infeasible is redundant for the current
+// bounds iff GE(minactivity, lhs) and LE(maxactivity, rhs), goodrelax = TRUE -- the reference then deletes it locally
+__device__ __forceinline__ bool rowRedundant(const Num& n, const RowAcc& a, double lhs, double rhs)
+{
+   double minact, maxact;
+   bool t1, t2, s1, s2;
+   getMinActivity(n, a.minhi, a.minlo, cntGet(a.cnt, MINPOSINF), cntGet(a.cnt, MINNEGINF), cntGet(a.cnt, MINPOSHUGE),
+      cntGet(a.cnt, MINNEGHUGE), 0.0, true, minact, t1, s1);
+   getMaxActivity(n, a.maxhi, a.maxlo, cntGet(a.cnt, MAXPOSINF), cntGet(a.cnt, MAXNEGINF), cntGet(a.cnt, MAXPOSHUGE),
+      cntGet(a.cnt, MAXNEGHUGE), 0.0, true, maxact, t2, s2);
+   if( isFeasGT(n, minact, rhs) || isFeasLT(n, maxact, lhs) )
+      return false;
+   return isGE(n, minact, lhs) && isLE(n, maxact, rhs);
+}
+
 // ---- commit filter: SCIPinferVarUbCons/LbCons (scip_var.c:7071-7157 / 6965-7051) followed by the last drop of
 // ---- SCIPnodeAddBoundinfer (tree.c:2020-2059), judged against the round-start bounds [l,u]; a surviving value
 // ---- is merged with atomicMin on its int64 key.  Candidate layout per column j (one 16-byte pair):

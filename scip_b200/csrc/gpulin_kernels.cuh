@@ -1480,6 +1480,30 @@ __global__ void __launch_bounds__(EXACT_THREADS, MINB) exact_rows_kernel(const D
    exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, s_queue, EXACT_THREADS);
 }
 
+// ---- redundancy feedback (propagateCons, cons_linear.c:7743-7753): flags[r] = 1 iff row r (permuted numbering) is
+// ---- redundant for the bounds on the device -- exact activities (double-double, inf / huge counters), a warp per row
+// ---- whatever its class; not on the propagation path (the plugin asks once per node at most)
+__global__ void __launch_bounds__(256) redundant_rows_kernel(const DevProblem p, unsigned char* flags)
+{
+   const int lane = threadIdx.x & 31;
+   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int nw = (gridDim.x * blockDim.x) >> 5;
+   for( int row = gw; row < p.nrows; row += nw )
+   {
+      const int len = p.rowlen[row] & ~ROWLEN_EXACT;
+      const bool sell = row < p.nsell;
+      const long long base = sell ? p.sell_off[row >> 5] + (row & 31) : p.rowbeg[row];
+      const double2 sd = p.sides[row];
+      RowAcc acc;
+      accInit(acc);
+      double noalpha[ALPHA_SLOTS];
+      accumulateExact<false>(p, acc, base, sell ? 32 : 1, lane, 32, len, noalpha);
+      accWarpReduce(acc, lane);
+      if( lane == 0 )
+         flags[row] = rowRedundant(p.num, acc, sd.x, sd.y) ? 1 : 0;
+   }
+}
+
 // ---- everybody who writes bnd[j] keeps the column's bit in freebits: set iff the bounds are exactly (0,1) ------------
 __device__ __forceinline__ bool isFree01(double l, double u)
 {

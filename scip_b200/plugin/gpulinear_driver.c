@@ -218,6 +218,7 @@ static SCIP_RETCODE run(int argc, char** argv)
    int quiet = 1;
    int presolve = 0;
    int activeonly = 0;
+   int delredundant = 0;
    int rowsof[5] = {-1, -1, -1, -1, -1};
    char pname[128];
    double t0, t1;
@@ -235,6 +236,7 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--verbose") == 0 ) quiet = 0;
       else if( strcmp(argv[i], "--presolve") == 0 ) presolve = 1;
       else if( strcmp(argv[i], "--active-rows-only") == 0 ) activeonly = 1;
+      else if( strcmp(argv[i], "--del-redundant") == 0 ) delredundant = 1;
       else if( strcmp(argv[i], "--probe-batch") == 0 && i + 1 < argc ) g_nprobecheck = atoi(argv[++i]);
       else
       {
@@ -289,6 +291,8 @@ static SCIP_RETCODE run(int argc, char** argv)
       SCIP_CALL( SCIPsetIntParam(scip, "constraints/linear/tightenboundsfreq", -1) );   /* the replaced path is off */
       if( activeonly )
          SCIP_CALL( SCIPsetBoolParam(scip, "propagating/gpulinear/stablecopy", FALSE) );
+      if( delredundant )
+         SCIP_CALL( SCIPsetBoolParam(scip, "propagating/gpulinear/delredundant", TRUE) );
    }
 
    if( readfile != NULL )

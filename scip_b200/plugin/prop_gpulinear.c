@@ -67,6 +67,7 @@
 #define DEFAULT_MAXROUNDS      -1         /* rounds per call on the device (-1: to the fixpoint) */
 #define DEFAULT_DEVICE         0
 #define DEFAULT_LOGCAPFAC      8          /* change log capacity = factor * number of variables */
+#define DEFAULT_DELREDUNDANT   FALSE      /* delete rows locally that the device finds redundant (cons_linear does so itself for its rows) */
 #define DEFAULT_DETERMINISTIC  TRUE       /* replay the changes of a round in a fixed order */
 #define DEFAULT_STABLECOPY     TRUE       /* device copy of all existing global rows, not only of those active at the node of the build */
 #define DEFAULT_ALLROWS        TRUE       /* read the rows of knapsack / setppc / logicor / varbound constraints as well */
@@ -97,6 +98,9 @@ struct SCIP_PropData
    int                   nlinconss;          /**< active constraints of all row sources when the device copy was built */
    int                   nrowsof[5];         /**< rows per source: linear, knapsack, setppc, logicor, varbound */
    SCIP_Bool             allrows;            /**< parameter: also read knapsack / setppc / logicor / varbound rows */
+   SCIP_Bool             delredundant;       /**< parameter: SCIPdelConsLocal for rows the device proves redundant */
+   SCIP_Longint          ndelconss;          /**< constraints deleted locally on the device's verdict */
+   int32_t*              redrows;            /**< buffer for gpulin_get_redundant_rows */
    SCIP_Bool             deterministic;      /**< parameter: sort the change log inside every round before the replay */
    SCIP_Bool             stablecopy;         /**< parameter: the device copy holds every existing global row (see countSourceConss) */
    SCIP_Longint          nbuilds;            /**< device copies built so far */
@@ -155,6 +159,7 @@ void freeDeviceCopy(
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->lb, propdata->ncols);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->ub, propdata->ncols);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->colptr, propdata->ncols + 1);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->redrows, propdata->nrows);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->rowcons, propdata->nrows);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->lhs, propdata->nrows);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->rhs, propdata->nrows);
@@ -645,6 +650,40 @@ int compareChanges(
    return x->is_upper - y->is_upper;
 }
 
+/** the end of propagateCons (cons_linear.c:7743-7753): rows whose activity bounds lie inside their sides for the bounds of
+ *  this node are deleted locally.  Only when the device bounds are SCIP's bounds (no mismatch pending). */
+static
+SCIP_RETCODE deleteRedundantRows(
+   SCIP*                 scip,
+   SCIP_PROPDATA*        propdata
+   )
+{
+   int64_t n = 0;
+   int64_t i;
+   int rc;
+
+   if( !propdata->delredundant || propdata->fullsync || propdata->ntouched > 0 || SCIPinProbing(scip) )
+      return SCIP_OKAY;
+   if( propdata->redrows == NULL )
+      SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->redrows, propdata->nrows) );
+   rc = gpulin_get_redundant_rows(propdata->gpu, propdata->redrows, propdata->nrows, &n);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("prop_gpulinear: gpulin_get_redundant_rows failed (%d): %s\n", rc, gpulin_last_error());
+      return SCIP_ERROR;
+   }
+   for( i = 0; i < n && i < propdata->nrows; ++i )
+   {
+      SCIP_CONS* cons = propdata->rowcons[propdata->redrows[i]];
+      if( SCIPconsIsActive(cons) && !SCIPconsIsDeleted(cons) )
+      {
+         SCIP_CALL( SCIPdelConsLocal(scip, cons) );
+         ++propdata->ndelconss;
+      }
+   }
+   return SCIP_OKAY;
+}
+
 /** execution method of propagator */
 static
 SCIP_DECL_PROPEXEC(propExecGpulinear)
@@ -727,7 +766,10 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
       return SCIP_OKAY;
    }
    if( res.nchanges == 0 )
+   {
+      SCIP_CALL( deleteRedundantRows(scip, propdata) );
       return SCIP_OKAY;
+   }
 
    ntightened = 0;
    rc = gpulin_get_changes(propdata->gpu, propdata->changes, propdata->logcap, &nlog);
@@ -808,6 +850,8 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
    }
    if( ntightened > 0 )
       *result = SCIP_REDUCEDDOM;
+
+   SCIP_CALL( deleteRedundantRows(scip, propdata) );
 
    return SCIP_OKAY;
 }
@@ -938,6 +982,9 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/allrows",
          "also propagate the linear rows behind knapsack, setppc, logicor and varbound constraints (cf. matrix.c)",
          &propdata->allrows, FALSE, DEFAULT_ALLROWS, NULL, NULL) );
+   SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/delredundant",
+         "delete rows locally that the device finds redundant for the node's bounds (the end of propagateCons; cons_linear does this itself for its own rows)",
+         &propdata->delredundant, FALSE, DEFAULT_DELREDUNDANT, NULL, NULL) );
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/deterministic",
          "replay the bound changes of a device round sorted by variable (the device logs them in the order its atomics land)",
          &propdata->deterministic, FALSE, DEFAULT_DETERMINISTIC, NULL, NULL) );

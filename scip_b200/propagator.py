@@ -57,6 +57,7 @@ _SIGNATURES = {
     "gpulin_get_bounds_device": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_set_change_log": (ctypes.c_int, [_P, ctypes.c_int64]),
     "gpulin_get_changes": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_get_redundant_rows": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_get_round_stats": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_get_layout": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
     "gpulin_get_call_stats": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
@@ -268,6 +269,13 @@ class LinearPropagator:
         n = ctypes.c_int64(0)
         _check(self._lib.gpulin_get_changes(self._h, out_ptr, maxn, ctypes.byref(n)))
         return n.value
+
+    def redundant_rows(self):
+        """rows (caller's numbering, ascending) that are redundant for the bounds on the device (cons_linear.c:7743)"""
+        out = np.zeros(max(self.nrows, 1), dtype=np.int32)
+        n = ctypes.c_int64(0)
+        _check(self._lib.gpulin_get_redundant_rows(self._h, out.ctypes.data, self.nrows, ctypes.byref(n)))
+        return out[:n.value].copy()
 
     def layout(self) -> dict:
         st = np.zeros(12, dtype=np.int64)

@@ -30,6 +30,13 @@ def load_golden(name, bs):
     return prob, ref
 
 
+def load_golden_redundant(name):
+    """bool[nrows]: rows of <name>.lpb the reference removed as redundant during its root propagation
+    (tests/golden/make_golden_redundant.py, numerics/boundstreps = 1e-9)"""
+    with open(os.path.join(GOLDEN, name + ".bs1e-9.red"), "rb") as f:
+        return np.frombuffer(f.read(), dtype=np.uint8).astype(bool)
+
+
 def rel_diff(a, b):
     return np.abs(a - b) / np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
 

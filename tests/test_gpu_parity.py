@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import assert_bounds_match, golden_names, load_golden
+from conftest import assert_bounds_match, golden_names, load_golden, load_golden_redundant
 from scip_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -40,6 +40,42 @@ def test_reference_fixpoint_exact_protocol(gpulin, name):
 def test_oracle_parity_on_golden_inputs(gpulin, name, bs):
     prob, _ = load_golden(name, "1e-9")
     gpu_vs_oracle(gpulin, prob, maxrounds=1000, what=f"{name} bs={bs}", boundstreps=bs)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_redundant_rows_match_the_reference_and_the_oracle(gpulin, name):
+    """redundancy feedback (gpulin_get_redundant_rows) after the fixpoint: the rows the reference deletes with
+    SCIPdelConsLocal in propagateCons (cons_linear.c:7743-7753), and the oracle's verdict on the same bounds"""
+    prob, ref = load_golden(name, "1e-9")
+    with gpulin.LinearPropagator(prob, boundstreps=1e-9) as lp:
+        lp.set_bounds(prob["lb"], prob["ub"])
+        res = lp.propagate(1000)
+        if ref["infeasible"]:
+            assert res["status"] == gpulin.CUTOFF
+            return
+        got = np.zeros(len(prob["lhs"]), dtype=bool)
+        got[lp.redundant_rows()] = True
+        lb, ub = lp.get_bounds()
+    assert np.array_equal(got, load_golden_redundant(name)), name
+    assert np.array_equal(got, oracle.redundant_rows(prob, lb, ub, boundstreps=1e-9)), name
+
+
+@pytest.mark.parametrize("gen", ["setcover", "mixedknap", "unitnet"])
+def test_redundant_rows_on_synthetic_instances(gpulin, gen):
+    prob = {"setcover": lambda: synth.setcover(100_000, 100_000, 1_000_000, seed=2),
+            "mixedknap": lambda: synth.mixed_knapsack(4000, 40_000, 1_000_000, seed=21, dense_range=(1500, 6000), eq_frac=0.2),
+            "unitnet": lambda: synth.unit_network(50_000, 40_000, 250_000, seed=8)}[gen]()
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.set_bounds(prob["lb"], prob["ub"])
+        before = lp.redundant_rows()
+        assert np.array_equal(before, np.flatnonzero(oracle.redundant_rows(prob, prob["lb"], prob["ub"])))
+        res = lp.propagate(500)
+        assert res["status"] == gpulin.FIXPOINT
+        after = lp.redundant_rows()
+        lb, ub = lp.get_bounds()
+    assert np.array_equal(after, np.flatnonzero(oracle.redundant_rows(prob, lb, ub)))
+    assert set(before.tolist()) <= set(after.tolist())      # tightening never makes a redundant row matter again
+    assert gen == "mixedknap" or len(after) > 0
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])

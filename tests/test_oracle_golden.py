@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import assert_bounds_match, golden_names, load_golden
+from conftest import assert_bounds_match, golden_names, load_golden, load_golden_redundant
 
 NAMES = golden_names()
 
@@ -67,3 +67,15 @@ def test_sweep_row_slices_compose():
     c2, l2, u2 = oracle.sweep(prob, lb, ub, n // 2, n, boundstreps=1e-9)
     assert c0 == (c1 | c2)
     assert np.array_equal(np.maximum(l1, l2), l0) and np.array_equal(np.minimum(u1, u2), u0)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_redundant_rows_are_the_rows_the_reference_deletes(name):
+    # propagateCons removes a row whose activity bounds lie inside its sides (cons_linear.c:7743-7753); at the reference's
+    # own root fixpoint the restated verdict marks exactly the rows the reference deleted
+    prob, ref = load_golden(name, "1e-9")
+    if ref["infeasible"]:
+        pytest.skip("infeasible at the root: the reference stops at the cutoff")
+    deleted = load_golden_redundant(name)
+    assert deleted.shape == (len(prob["lhs"]),)
+    assert np.array_equal(oracle.redundant_rows(prob, ref["lb"], ref["ub"], boundstreps=1e-9), deleted)

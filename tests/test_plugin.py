@@ -70,6 +70,20 @@ def test_plugin_in_tree_search_with_conflict_analysis():
 
 @needs_driver
 @pytest.mark.gpu
+@pytest.mark.parametrize("presolve", [False, True])
+def test_redundancy_feedback_in_tree_search(presolve):
+    """propagating/gpulinear/delredundant: rows the device proves redundant for a node's bounds are deleted locally
+    (SCIPdelConsLocal, the end of propagateCons cons_linear.c:7743-7753) -- same verdict and optimum"""
+    extra = ["--presolve"] if presolve else []
+    base = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", *extra)
+    red = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", "--del-redundant", *extra)
+    assert red["scip_status"] == base["scip_status"]
+    assert abs(red["primal"] - base["primal"]) <= 1e-6
+    assert red["gpu_builds"] >= 1 and red["gpu_prop_calls"] > 10
+
+
+@needs_driver
+@pytest.mark.gpu
 def test_tree_search_is_reproducible():
     """the device logs the changes of a round in the order its atomics land; the plugin replays them sorted, so two runs
     of the same search visit the same nodes"""
