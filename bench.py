@@ -80,7 +80,27 @@ class ClockSampler:
         self.index = index
         self.thread = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self):
+        """NVML directly (nvidia_ml_py): a sample every 2 ms -- a timed region of 10 ms is over before one nvidia-smi
+        process has started"""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        while not self.stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            mask = int(get_reasons(h))
+            self.rows.append([str(sm), str(mx), ""] + [("Active" if mask & b else "Not Active") for b, _ in bits])
+            self.stop.wait(0.002)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
