@@ -558,7 +558,7 @@ __device__ __forceinline__ void loadTile(const DevProblem& p, int t, int lane, T
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const DevProblem p)
 {
-   if( p.ctrl->skipsweep )
+   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
       return;
    static_assert(TPL == 8 && TILE == 256, "the tile layout is wired into the vector loads");
    // per warp: the sums of the rows that end in the current tile, in row order (at most one row per nonzero)
@@ -909,7 +909,7 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, const unsigned* s
 template <int CH, int MINB>
 __global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const DevProblem p)
 {
-   if( p.ctrl->skipsweep )
+   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
       return;
    sellSweep<CH, false>(p, nullptr, SELL_THREADS);
 }
@@ -1035,9 +1035,14 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
-   const int gw = (blockIdx.x * NT + threadIdx.x) >> 5;
+   // warp-major numbering: warp w of block b is warp w * gridDim + b.  The slices do not divide evenly among the warps
+   // (C3: 6.6 each); with block-major numbering the blocks with the low numbers would hold all the warps that take
+   // one slice more (and of the longest rows), and the other SMs would idle for the last seventh of the kernel
+   const int gw = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;
    const int nw = (gridDim.x * NT) >> 5;
    const int lastword = p.nfreewords - 1;
+   // (taking the slices from the end of the range, longest rows first, so that the extra slice of some warps is a short one,
+   // was measured: 45 instead of 41 us)
    for( int s0 = sbeg + gw; s0 < send; s0 += SELL_NB * nw )
    {
       // ---- one round trip: flags, lengths and offsets of the next four slices of this warp
@@ -1162,7 +1167,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
 template <int NT, int CH, bool MID, bool ALLCOLS = false, bool HD = false, int CHU = 0>
 __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
 {
-   if( p.ctrl->skipsweep )
+   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
       return;
    extern __shared__ __align__(128) unsigned char s_raw[];
    const unsigned tabbytes = (unsigned)p.nfreewords * 4u;
@@ -1197,7 +1202,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
 // ---- block-per-row for rows longer than STREAM_MAXLEN (and empty rows) ---------------------------------------------
 __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProblem p)
 {
-   if( p.ctrl->skipsweep )
+   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
       return;
    __shared__ LeanAcc s_lean[LONG_THREADS / 32];
 
