@@ -222,6 +222,11 @@ static const SellBitsVariant g_sellBitsKernels[] = {
    {sweep_sell_bits_kernel<1024, 2, true, true, false, 0>, 1024, true},     // 5: unit slices like all others
    {sweep_sell_bits_kernel<1024, 2, true, true, false, 2>, 1024, true},     // 6
    {sweep_sell_bits_kernel<1024, 2, true, true, false, 3>, 1024, true},     // 7
+   {sweep_sell_bits_kernel<768, 2, true, true, false, 6>, 768, true},       // 8
+   {sweep_sell_bits_kernel<768, 3, true, true, false, 6>, 768, true},       // 9
+   {sweep_sell_bits_kernel<896, 2, true, true, false, 4>, 896, true},       // 10
+   {sweep_sell_bits_kernel<896, 2, true, true, false, 6>, 896, true},       // 11
+   {sweep_sell_bits_kernel<768, 2, true, true, false, 8>, 768, true},       // 12
 };
 constexpr int NSELLBITSVARIANTS = sizeof(g_sellBitsKernels) / sizeof(g_sellBitsKernels[0]);
 
