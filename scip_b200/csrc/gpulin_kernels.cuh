@@ -1095,12 +1095,16 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
          for( int c = 0; c < maxlen[i]; c += CH )
          {
             double a[CH];
+            int sg[CH];      // UNIT: the sign bit of the coefficient (+1 / -1), in the position of a double's high word
             int cj[CH];
             double2 b[CH];
 #pragma unroll
             for( int k = 0; k < CH; ++k )
             {
-               a[k] = UNIT ? unitCoef(cjn[k]) : an[k];
+               if( UNIT )
+                  sg[k] = (cjn[k] << 1) & (int)0x80000000u;
+               else
+                  a[k] = an[k];
                cj[k] = cjn[k] & COL_MASK;
             }
             if( c + CH < maxlen[i] )
@@ -1131,7 +1135,31 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
             {
                if( c + k < len[i] )
                {
-                  if( MID && HD )
+                  if( UNIT && MID && !HD )
+                  {
+                     // a = +1 / -1: a * mid is mid with the sign flipped, |a| * hw is hw -- the same values as midElem
+                     // computes with a = unitCoef(), without the two multiplications
+                     const double m = __hiloint2double(__double2hiint(b[k].x) ^ sg[k], __double2loint(b[k].x));
+                     macc.M += m;
+                     macc.Mabs += fabs(b[k].x);
+                     macc.H += b[k].y;
+                     macc.hmax = fmaxf(macc.hmax, __double2float_ru(b[k].y));
+                  }
+                  else if( UNIT )
+                  {
+                     const double au = __hiloint2double(0x3ff00000 | sg[k], 0);
+                     if( MID )
+                     {
+                        const double m = au * b[k].x;
+                        macc.M += m;
+                        macc.Mabs += fabs(m);
+                        macc.H += b[k].y;
+                        hmaxd = b[k].y > hmaxd ? b[k].y : hmaxd;
+                     }
+                     else
+                        leanElem(lacc, au, b[k].x, b[k].y);
+                  }
+                  else if( MID && HD )
                   {
                      const double m = a[k] * b[k].x;
                      const double hh = fabs(a[k]) * b[k].y;
