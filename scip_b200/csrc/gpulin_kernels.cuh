@@ -1003,10 +1003,15 @@ __device__ __forceinline__ void gatherUnless(unsigned skip, const double2* addr,
        : "+d"(b.x), "+d"(b.y) : "r"(skip), "l"(addr));
 }
 
-// coefficient of a nonzero of a unit row (+1 or -1), from the sign flag of its column word
-__device__ __forceinline__ double unitCoef(int colword)
+// coefficient of a nonzero of a unit row (+1 or -1) from its sign word: bit 30 of the column word (COL_NEGCOEF) moved to
+// bit 31, the position of the sign in the high word of a double
+__device__ __forceinline__ int unitSign(int colword)
 {
-   return __hiloint2double(0x3ff00000 | ((colword << 1) & (int)0x80000000u), 0);
+   return (colword << 1) & (int)0x80000000u;
+}
+__device__ __forceinline__ double unitCoef(int signword)
+{
+   return __hiloint2double(0x3ff00000 | signword, 0);
 }
 
 // one chunk of CH nonzeros of a row of a SELL slice; UNIT: the column words only (the values are not read)
@@ -1102,7 +1107,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
             for( int k = 0; k < CH; ++k )
             {
                if( UNIT )
-                  sg[k] = (cjn[k] << 1) & (int)0x80000000u;
+                  sg[k] = unitSign(cjn[k]);
                else
                   a[k] = an[k];
                cj[k] = cjn[k] & COL_MASK;
@@ -1147,7 +1152,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
                   }
                   else if( UNIT )
                   {
-                     const double au = __hiloint2double(0x3ff00000 | sg[k], 0);
+                     const double au = unitCoef(sg[k]);
                      if( MID )
                      {
                         const double m = au * b[k].x;
