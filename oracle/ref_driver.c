@@ -226,6 +226,12 @@ static SCIP_DECL_PROPEXEC(propExecDump)
 
 /** variables in .lpb (creation) order; SCIPgetOrigVars is sorted by variable type instead */
 static SCIP_VAR** g_lpbvars = NULL;
+/* --reprop (see propExecReprop) */
+static int g_reprop = 0;
+static int g_repropdone = 0;
+static int g_nfix = 0;
+static int* g_fixvar = NULL;      /* index into g_lpbvars */
+static double* g_fixval = NULL;
 
 static SCIP_RETCODE buildFromLpb(SCIP* scip, const LPB* p)
 {
@@ -238,10 +244,26 @@ static SCIP_RETCODE buildFromLpb(SCIP* scip, const LPB* p)
    for( i = 0; i < p->ncols; ++i )
    {
       SCIP_VARTYPE vt = SCIP_VARTYPE_CONTINUOUS;
+      double lb = p->lb[i];
+      double ub = p->ub[i];
       if( p->vartype[i] )
-         vt = (p->lb[i] == 0.0 && p->ub[i] == 1.0) ? SCIP_VARTYPE_BINARY : SCIP_VARTYPE_INTEGER;
+         vt = (lb == 0.0 && ub == 1.0) ? SCIP_VARTYPE_BINARY : SCIP_VARTYPE_INTEGER;
+      if( g_reprop > 0 && p->vartype[i] && lb == ub && (lb == 0.0 || lb == 1.0) )
+      {
+         /* --reprop: a fixed binary is created free; its fixing is applied as a probing bound change in every cycle */
+         if( g_fixvar == NULL )
+         {
+            g_fixvar = (int*)malloc(sizeof(int) * (size_t)(p->ncols + 1));
+            g_fixval = (double*)malloc(sizeof(double) * (size_t)(p->ncols + 1));
+         }
+         g_fixvar[g_nfix] = (int)i;
+         g_fixval[g_nfix++] = lb;
+         lb = 0.0;
+         ub = 1.0;
+         vt = SCIP_VARTYPE_BINARY;
+      }
       snprintf(name, sizeof(name), "x%lld", (long long)i);
-      SCIP_CALL( SCIPcreateVarBasic(scip, &vars[i], name, p->lb[i], p->ub[i], 0.0, vt) );
+      SCIP_CALL( SCIPcreateVarBasic(scip, &vars[i], name, lb, ub, 0.0, vt) );
       SCIP_CALL( SCIPaddVar(scip, vars[i]) );
    }
    {
@@ -360,6 +382,76 @@ static SCIP_DECL_PROPEXEC(propExecProbe)
    return SCIP_OKAY;
 }
 
+/* --reprop K (with --lpb): the root propagation of the instance, K times inside ONE solve.  Transforming and freeing a
+ * model of 10M nonzeros costs the reference 30 s per solve around 6 s of propagation; here the binaries the instance fixes
+ * (lb == ub) are created free, the root node is propagated (nothing to find), and then K times: SCIPstartProbing, the
+ * instance's fixings as probing bound changes, SCIPpropagateProbing to the fixpoint -- propagationRound (solve.c:437) ->
+ * consPropLinear -> propagateCons -> tightenBounds, the same path on the same rows and bounds -- SCIPendProbing.  One
+ * REPROP line per cycle: SCIPconshdlrGetPropTime(linear) spent in it, wall time of SCIPpropagateProbing, reductions. */
+static double* g_reproplb = NULL; /* local bounds at the fixpoint of the last cycle, .lpb order */
+static double* g_repropub = NULL;
+static int g_repropcutoff = 0;
+static SCIP_Longint g_repropdomreds = 0;
+static double g_reproptime = 0.0;
+
+static SCIP_DECL_PROPEXEC(propExecReprop)
+{
+   SCIP_CONSHDLR* linhdlr = SCIPfindConshdlr(scip, "linear");
+   int norig = SCIPgetNOrigVars(scip);
+   int rep;
+   int i;
+
+   (void)prop;
+   (void)proptiming;
+   *result = SCIP_DIDNOTRUN;
+   if( g_repropdone || SCIPgetDepth(scip) != 0 || SCIPinProbing(scip) )
+      return SCIP_OKAY;
+   g_repropdone = 1;
+   g_reproplb = (double*)malloc(8 * (size_t)norig + 8);
+   g_repropub = (double*)malloc(8 * (size_t)norig + 8);
+   for( rep = 0; rep < g_reprop; ++rep )
+   {
+      SCIP_Bool cutoff = FALSE;
+      SCIP_Longint ndom = 0;
+      const double p0 = SCIPconshdlrGetPropTime(linhdlr);
+      const SCIP_Longint c0 = SCIPconshdlrGetNPropCalls(linhdlr);
+      double t0, t1, t2;
+
+      t0 = wallclock();
+      SCIP_CALL( SCIPstartProbing(scip) );
+      for( i = 0; i < g_nfix; ++i )
+      {
+         SCIP_VAR* tv = SCIPvarGetTransVar(g_lpbvars[g_fixvar[i]]);
+         if( g_fixval[i] < 0.5 )
+            SCIP_CALL( SCIPchgVarUbProbing(scip, tv, g_fixval[i]) );
+         else
+            SCIP_CALL( SCIPchgVarLbProbing(scip, tv, g_fixval[i]) );
+      }
+      t1 = wallclock();
+      SCIP_CALL( SCIPpropagateProbing(scip, -1, &cutoff, &ndom) );
+      t2 = wallclock();
+      g_reproptime = SCIPconshdlrGetPropTime(linhdlr) - p0;
+      g_repropcutoff = cutoff ? 1 : 0;
+      g_repropdomreds = ndom;
+      if( rep + 1 == g_reprop )
+      {
+         for( i = 0; i < norig; ++i )
+         {
+            SCIP_VAR* tv = SCIPvarGetTransVar(g_lpbvars[i]);
+            g_reproplb[i] = SCIPvarGetLbLocal(tv);
+            g_repropub[i] = SCIPvarGetUbLocal(tv);
+         }
+      }
+      SCIP_CALL( SCIPendProbing(scip) );
+      printf("REPROP {\"prop_time_s\": %.9g, \"propagate_wall_s\": %.9g, \"fixings_wall_s\": %.9g, \"backtrack_wall_s\": %.9g, "
+         "\"prop_calls\": %lld, \"domreds\": %lld, \"cutoff\": %d, \"fixings\": %d}\n", g_reproptime, t2 - t1, t1 - t0,
+         wallclock() - t2, (long long)(SCIPconshdlrGetNPropCalls(linhdlr) - c0), (long long)ndom, g_repropcutoff, g_nfix);
+      fflush(stdout);
+   }
+   *result = SCIP_DIDNOTFIND;
+   return SCIP_OKAY;
+}
+
 static SCIP_RETCODE run(int argc, char** argv)
 {
    SCIP* scip = NULL;
@@ -373,8 +465,11 @@ static SCIP_RETCODE run(int argc, char** argv)
    const char* redfile = NULL;
    double boundstreps = -1.0;
    int quiet = 1;
+   int repeat = 1;
+   int rep;
    int i;
    double t0, t1, tbuild;
+   double ttrans = 0.0, tpre = 0.0;
    int infeasible;
    FILE* f;
 
@@ -388,9 +483,11 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--verbose") == 0 ) quiet = 0;
       else if( strcmp(argv[i], "--probe") == 0 && i + 1 < argc ) g_nprobe = atoi(argv[++i]);
       else if( strcmp(argv[i], "--redundant") == 0 && i + 1 < argc ) redfile = argv[++i];
+      else if( strcmp(argv[i], "--repeat") == 0 && i + 1 < argc ) repeat = atoi(argv[++i]);
+      else if( strcmp(argv[i], "--reprop") == 0 && i + 1 < argc ) g_reprop = atoi(argv[++i]);
       else
       {
-         fprintf(stderr, "usage: ref_driver (--read FILE | --lpb FILE) [--out OUT.lpr] [--dump-lpb OUT.lpb] [--boundstreps X] [--verbose]\n");
+         fprintf(stderr, "usage: ref_driver (--read FILE | --lpb FILE) [--out OUT.lpr] [--dump-lpb OUT.lpb] [--boundstreps X] [--repeat K] [--verbose]\n");
          return SCIP_ERROR;
       }
    }
@@ -407,6 +504,17 @@ static SCIP_RETCODE run(int argc, char** argv)
       SCIP_PROP* probeprop = NULL;
       SCIP_CALL( SCIPincludePropBasic(scip, &probeprop, "refprobe", "times the reference's probing cycle at the propagated root",
             -1000, 1, TRUE, SCIP_PROPTIMING_BEFORELP, propExecProbe, NULL) );
+   }
+   if( g_reprop > 0 )
+   {
+      SCIP_PROP* repprop = NULL;
+      if( lpbfile == NULL || repeat > 1 )
+      {
+         fprintf(stderr, "ref_driver: --reprop needs --lpb and excludes --repeat\n");
+         return SCIP_ERROR;
+      }
+      SCIP_CALL( SCIPincludePropBasic(scip, &repprop, "refreprop", "repeats the root propagation of the instance in probing mode",
+            -1000, 1, TRUE, SCIP_PROPTIMING_BEFORELP, propExecReprop, NULL) );
    }
    memset(&propdata, 0, sizeof(propdata));
    propdata.dumpfile = dumpfile;
@@ -435,11 +543,32 @@ static SCIP_RETCODE run(int argc, char** argv)
    propdata.origvars = (SCIP_VAR**)malloc(sizeof(SCIP_VAR*) * (size_t)(propdata.norigvars + 1));
    memcpy(propdata.origvars, g_lpbvars != NULL ? g_lpbvars : SCIPgetOrigVars(scip), sizeof(SCIP_VAR*) * (size_t)propdata.norigvars);
 
-   t0 = wallclock();
-   SCIP_CALL( SCIPsolve(scip) );
-   t1 = wallclock();
+   /* --repeat K: the model is built once and solved K times (SCIPfreeTransform in between; the statistics of a solve
+    * start from zero, misc/resetstat); one REPEAT line per solve but the last, whose results follow as usual */
+   for( rep = 0; ; ++rep )
+   {
+      t0 = wallclock();
+      SCIP_CALL( SCIPtransformProb(scip) );
+      ttrans = wallclock() - t0;
+      SCIP_CALL( SCIPpresolve(scip) );
+      tpre = wallclock() - t0 - ttrans;
+      SCIP_CALL( SCIPsolve(scip) );
+      t1 = wallclock();
+      if( !quiet )
+         fprintf(stderr, "ref_driver: transform %.3f s, presolve stage %.3f s, solve stage %.3f s\n", ttrans, tpre, t1 - t0 - ttrans - tpre);
+      if( rep + 1 >= repeat )
+         break;
+      printf("REPEAT {\"prop_time_s\": %.9g, \"solve_time_s\": %.9g, \"prop_calls\": %lld, \"domreds\": %lld}\n",
+         SCIPconshdlrGetPropTime(SCIPfindConshdlr(scip, "linear")), t1 - t0,
+         (long long)SCIPconshdlrGetNPropCalls(SCIPfindConshdlr(scip, "linear")),
+         (long long)SCIPconshdlrGetNDomredsFound(SCIPfindConshdlr(scip, "linear")));
+      fflush(stdout);
+      SCIP_CALL( SCIPfreeTransform(scip) );
+   }
 
    infeasible = (SCIPgetStatus(scip) == SCIP_STATUS_INFEASIBLE);
+   if( g_reprop > 0 && g_repropdone )
+      infeasible = g_repropcutoff;
    linhdlr = SCIPfindConshdlr(scip, "linear");
 
    printf("{\"status\": \"%s\", \"ncols\": %d, \"nrows\": %d, \"prop_calls\": %lld, \"domreds\": %lld, "
@@ -470,12 +599,16 @@ static SCIP_RETCODE run(int argc, char** argv)
       {
          SCIP_VAR* tv = SCIPvarGetTransVar(propdata.origvars[i]);
          double b = (tv != NULL) ? SCIPvarGetLbGlobal(tv) : SCIPvarGetLbGlobal(propdata.origvars[i]);
+         if( g_reprop > 0 && g_reproplb != NULL )
+            b = g_reproplb[i];
          fwrite(&b, 8, 1, f);
       }
       for( i = 0; i < propdata.norigvars; ++i )
       {
          SCIP_VAR* tv = SCIPvarGetTransVar(propdata.origvars[i]);
          double b = (tv != NULL) ? SCIPvarGetUbGlobal(tv) : SCIPvarGetUbGlobal(propdata.origvars[i]);
+         if( g_reprop > 0 && g_repropub != NULL )
+            b = g_repropub[i];
          fwrite(&b, 8, 1, f);
       }
       fclose(f);
@@ -505,6 +638,7 @@ static SCIP_RETCODE run(int argc, char** argv)
    free(propdata.origvars);
    free(g_probidx2orig);
    free(g_lpbvars);
+   free(g_fixvar); free(g_fixval); free(g_reproplb); free(g_repropub);
    SCIP_CALL( SCIPfree(&scip) );
    return SCIP_OKAY;
 }

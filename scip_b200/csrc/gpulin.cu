@@ -64,7 +64,6 @@ struct gpulin
    int64_t     nstreamelems = 0;
    int         maxlen = 0;
    DevProblem  p{};
-   int         sellvariant = 3;
    int         nsellblocks = 0;
    int         nstreamblocks = 0;
    int         nlongblocks = 0;
@@ -190,45 +189,21 @@ static void destroyGraph(gpulin* h)
    h->graph = nullptr;
 }
 
-// instances of the thread-per-row sweep: {nonzeros per thread and chunk, minimal resident blocks per SM};
-// GPULIN_SELL_VARIANT selects one for experiments
-typedef void (*SellKernel)(const DevProblem);
-static const SellKernel g_sellKernels[] = {
-   sweep_sell_kernel<4, 2>,   // 0
-   sweep_sell_kernel<4, 3>,   // 1
-   sweep_sell_kernel<2, 3>,   // 2
-   sweep_sell_kernel<2, 4>,   // 3
-   sweep_sell_kernel<8, 2>,   // 4
-   sweep_sell_kernel<8, 1>,   // 5
-};
-constexpr int NSELLVARIANTS = sizeof(g_sellKernels) / sizeof(g_sellKernels[0]);
-
-// dynamic shared memory of sweep_sell_bits_kernel: bit table, rings, mbarriers + descriptors
+// dynamic shared memory of sweep_sell_bits_kernel: bit table, mbarrier
 static size_t sellBitsSmem(int nfreewords)
 {
    return (((size_t)nfreewords * 4 + 127) & ~(size_t)127) + SB_AUX_BYTES;
 }
 
-// instances of the bit-table sweep: {threads per block, nonzeros per thread and chunk, midpoint form, table covers all
-// columns}; the first two are the product (chosen by nfreecols >= ncols), GPULIN_SELLBITS_VARIANT selects one for experiments
-typedef void (*SellBitsKernel)(const DevProblem);
-struct SellBitsVariant { SellBitsKernel kernel; int threads; bool allcols; };
-static const SellBitsVariant g_sellBitsKernels[] = {
-   {sweep_sell_bits_kernel<1024, 2, true, false, false, 4>, 1024, false},   // 0
-   {sweep_sell_bits_kernel<1024, 2, true, true, false, 4>, 1024, true},     // 1
-   {sweep_sell_bits_kernel<1024, 2, false, false>, 1024, false},  // 2: lb/ub form (leanElem), unit slices like all others
-   {sweep_sell_bits_kernel<768, 3, true, true>, 768, true},       // 3
-   {sweep_sell_bits_kernel<768, 4, true, false>, 768, false},     // 4
-   {sweep_sell_bits_kernel<1024, 2, true, true, false, 0>, 1024, true},     // 5: unit slices like all others
-   {sweep_sell_bits_kernel<1024, 2, true, true, false, 2>, 1024, true},     // 6
-   {sweep_sell_bits_kernel<1024, 2, true, true, false, 3>, 1024, true},     // 7
-   {sweep_sell_bits_kernel<768, 2, true, true, false, 6>, 768, true},       // 8
-   {sweep_sell_bits_kernel<768, 3, true, true, false, 6>, 768, true},       // 9
-   {sweep_sell_bits_kernel<896, 2, true, true, false, 4>, 896, true},       // 10
-   {sweep_sell_bits_kernel<896, 2, true, true, false, 6>, 896, true},       // 11
-   {sweep_sell_bits_kernel<768, 2, true, true, false, 8>, 768, true},       // 12
+// the thread-per-row sweep: the gather variant (small instances), and the two instances of the bit-table sweep
+// (1024 threads, two nonzeros per thread and chunk, four in the unit slices; the table covers a prefix of / all columns)
+typedef void (*SweepKernel)(const DevProblem);
+static const SweepKernel g_sellKernel = sweep_sell_kernel<2, 4>;
+static const SweepKernel g_sellBitsKernels[2] = {
+   sweep_sell_bits_kernel<1024, 2, false, 4>,
+   sweep_sell_bits_kernel<1024, 2, true, 4>,
 };
-constexpr int NSELLBITSVARIANTS = sizeof(g_sellBitsKernels) / sizeof(g_sellBitsKernels[0]);
+constexpr int SELLBITS_THREADS = 1024;
 
 constexpr int64_t SMALLCALL_MAXCOLS = 256;      // gpulin_propagate after at most this many updated columns starts in one block
 
@@ -268,10 +243,9 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
       else if( h->nstreamblocks > 0 )
          sweep_stream_kernel<<<h->nstreamblocks, SWEEP_THREADS, 0, h->stream>>>(h->p);
       if( h->nsellbitsblocks > 0 )
-         g_sellBitsKernels[h->sellbitsvariant].kernel<<<h->nsellbitsblocks, g_sellBitsKernels[h->sellbitsvariant].threads,
-            sellBitsSmem(h->p.nfreewords), h->stream>>>(h->p);
+         g_sellBitsKernels[h->sellbitsvariant]<<<h->nsellbitsblocks, SELLBITS_THREADS, sellBitsSmem(h->p.nfreewords), h->stream>>>(h->p);
       else if( h->nsellblocks > 0 )
-         g_sellKernels[h->sellvariant]<<<h->nsellblocks, SELL_THREADS, 0, h->stream>>>(h->p);
+         g_sellKernel<<<h->nsellblocks, SELL_THREADS, 0, h->stream>>>(h->p);
       for( int i = 0; i < side; ++i )
          CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
       if( h->nexactblocks > 0 )
@@ -391,6 +365,10 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
          return fail(GPULIN_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
    }
    CU(cudaSetDevice(device));
+   gpulin_numerics defnum;
+   gpulin_default_numerics(&defnum);
+   if( num == nullptr )
+      num = &defnum;
 
    gpulin* h = new gpulin();
    h->shared = new SharedMatrix();
@@ -601,10 +579,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRYCU(cudaMemset(d_tileflag, 0, (size_t)h->ntiles + 64));
    {
       // rows with a coefficient below hugeval / infinity always take the exact rules (see ROWLEN_EXACT)
-      gpulin_numerics dn;
-      gpulin_default_numerics(&dn);
-      const gpulin_numerics* nn = (num != nullptr) ? num : &dn;
-      const double tiny = nn->hugeval / nn->infinity;
+      const double tiny = num->hugeval / num->infinity;
       std::vector<int> flagged(plen);
       for( int64_t i = 0; i < nrows; ++i )
       {
@@ -681,10 +656,6 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.ctrl = d_ctrl;
    p.log = nullptr;
    p.peers = nullptr;
-   gpulin_numerics defnum;
-   gpulin_default_numerics(&defnum);
-   if( num == nullptr )
-      num = &defnum;
    p.num.inf = num->infinity;
    p.num.eps = num->epsilon;
    p.num.sumeps = num->sumepsilon;
@@ -705,54 +676,34 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       int occ = 0;
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_stream_kernel, SWEEP_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
-      const char* oe = getenv("GPULIN_STREAM_OCC");      // experiment: blocks per SM of the persistent grid
-      if( oe != nullptr && atoi(oe) > 0 )
-         occ = atoi(oe);
       const int wpb = SWEEP_THREADS / 32;
       // at least two tiles per warp, never more blocks than stay resident
       const int64_t need = ((int64_t)h->ntiles + 2 * wpb - 1) / (2 * wpb);
       h->nstreamblocks = (int)std::min<int64_t>(need, (int64_t)h->nsm * occ);
       int occs = 0;
-      const char* ve = getenv("GPULIN_SELL_VARIANT");
-      if( ve != nullptr && atoi(ve) >= 0 && atoi(ve) < NSELLVARIANTS )
-         h->sellvariant = atoi(ve);
-      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, g_sellKernels[h->sellvariant], SELL_THREADS, 0) != cudaSuccess || occs < 1 )
+      if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, g_sellKernel, SELL_THREADS, 0) != cudaSuccess || occs < 1 )
          occs = 1;
-      const char* oes = getenv("GPULIN_SELL_OCC");
-      if( oes != nullptr && atoi(oes) > 0 )
-         occs = atoi(oes);
       const int64_t needs = ((int64_t)nslices + (SELL_THREADS / 32) - 1) / (SELL_THREADS / 32);
       h->nsellblocks = (int)std::min<int64_t>(needs, (int64_t)h->nsm * occs);
       // the shared-memory bit-table variant: one block of 1024 threads per SM; worth its prologue (the table is staged
-      // by every block) once there is more than a handful of slices per block; GPULIN_SELLBITS=0 disables it
-      const char* be = getenv("GPULIN_SELLBITS");
-      const bool allcols = h->p.nfreecols >= h->p.ncols;
-      h->sellbitsvariant = allcols ? 1 : 0;
-      const char* bv = getenv("GPULIN_SELLBITS_VARIANT");
-      if( bv != nullptr && atoi(bv) >= 0 && atoi(bv) < NSELLBITSVARIANTS && (allcols || !g_sellBitsKernels[atoi(bv)].allcols) )
-         h->sellbitsvariant = atoi(bv);
-      if( h->nsellblocks > 0 && !(be != nullptr && atoi(be) == 0) && nslices >= h->nsm * 32
-         && cudaFuncSetAttribute(g_sellBitsKernels[h->sellbitsvariant].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      // by every block) once there is more than a handful of slices per block
+      h->sellbitsvariant = h->p.nfreecols >= h->p.ncols ? 1 : 0;
+      if( h->nsellblocks > 0 && nslices >= h->nsm * 32
+         && cudaFuncSetAttribute(g_sellBitsKernels[h->sellbitsvariant], cudaFuncAttributeMaxDynamicSharedMemorySize,
                (int)sellBitsSmem(SELLBITS_MAXWORDS)) == cudaSuccess )
          h->nsellbitsblocks = h->nsm;
-      if( getenv("GPULIN_VERBOSE") != nullptr )
-         fprintf(stderr, "gpulin: %d SELL rows in %d blocks (%d per SM); stream sweep %d rows, %d tiles, %d blocks x %d threads "
-            "(%d per SM); %d long rows\n", h->nsell, h->nsellblocks, occs, h->nstream, h->ntiles, h->nstreamblocks, SWEEP_THREADS,
-            occ, h->nlong);
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_long_kernel, LONG_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nlongblocks = (int)std::min<int64_t>(h->nlong, (int64_t)h->nsm * occ);
-      // two resident blocks per SM with 128 registers, or three with 80 (GPULIN_EXACT_OCC=3; spills)
-      h->exactkernel = (getenv("GPULIN_EXACT_OCC") != nullptr && atoi(getenv("GPULIN_EXACT_OCC")) == 3) ? exact_rows_kernel<3> : exact_rows_kernel<2>;
+      // two resident blocks per SM with 128 registers
+      h->exactkernel = exact_rows_kernel<2>;
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->exactkernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
-      // the sparse-rounds kernel: one block per SM (all must be co-resident: grid syncs); GPULIN_SPARSE=0 disables it
+      // the sparse-rounds kernel: one block per SM (all must be co-resident: grid syncs)
       int coop = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-      const char* se = getenv("GPULIN_SPARSE");
-      if( coop && !(se != nullptr && atoi(se) == 0)
-         && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sparse_rounds_kernel<true>, SPARSE_THREADS, 0) == cudaSuccess && occ >= 1 )
+      if( coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sparse_rounds_kernel<true>, SPARSE_THREADS, 0) == cudaSuccess && occ >= 1 )
          h->nsparseblocks = h->nsm;
    }
 
@@ -1129,7 +1080,7 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
       base->proberescap = nprobes;
    }
    ProbeResult* d_res = (ProbeResult*)base->d_proberes;
-   const bool general = getenv("GPULIN_PROBE_GENERAL") != nullptr;     // experiments: every probe through the general loop
+   const bool general = false;
    if( nprobes > 0 && !general )
    {
       CU(cudaMemcpy(base->d_probevar, var, sizeof(int) * (size_t)nprobes, cudaMemcpyHostToDevice));
@@ -1199,7 +1150,7 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    h->nrows = src->nrows; h->ncols = src->ncols; h->nnz = src->nnz; h->nstored = src->nstored;
    h->nsell = src->nsell; h->nstream = src->nstream; h->nlong = src->nlong; h->ntiles = src->ntiles;
    h->nstreamelems = src->nstreamelems; h->maxlen = src->maxlen;
-   h->sellvariant = src->sellvariant; h->nsellblocks = src->nsellblocks; h->nstreamblocks = src->nstreamblocks;
+   h->nsellblocks = src->nsellblocks; h->nstreamblocks = src->nstreamblocks;
    h->nlongblocks = src->nlongblocks; h->napplyblocks = src->napplyblocks; h->nexactblocks = src->nexactblocks; h->exactkernel = src->exactkernel;
    h->nsparseblocks = src->nsparseblocks;
    h->nsm = src->nsm; h->hostloop = src->hostloop; h->perm = src->perm;

@@ -138,46 +138,50 @@ __device__ __forceinline__ void dd_add_dd(double& hi, double& lo, double bhi, do
 }
 
 // ---- per-row activity state --------------------------------------------------------------------------------
-// The eight counters of infinite / huge contributions (cons_linear.c:187-266) are kept as 4-bit fields that
-// saturate at 2: every rule of the path only asks "0, 1 or more" (canTightenBounds :5234, getMinActivity
-// :2373-2392, residual counters :2726-2805).
+// The eight counters of infinite / huge contributions (cons_linear.c:187-266) are kept as 8-bit fields of one 64-bit
+// word that saturate at 127.  The infinity counters are only ever asked "0, 1 or more" (canTightenBounds :5234,
+// getMinActivity :2373-2392, residual counters :2726-2805); the huge counters enter the relaxed activities of the row
+// verdict as count * hugeval (:2386, :2481), so they keep their true value (a row with more than 127 contributions of
+// 1e15 or more each has an activity beyond 1e17 whichever count is used).
 enum CntField { MINPOSINF = 0, MINNEGINF = 1, MINPOSHUGE = 2, MINNEGHUGE = 3,
                 MAXPOSINF = 4, MAXNEGINF = 5, MAXPOSHUGE = 6, MAXNEGHUGE = 7 };
+typedef unsigned long long Cnt;
+constexpr unsigned CNT_SAT = 127u;
 
-__device__ __forceinline__ unsigned cntGet(unsigned cnt, int f) { return (cnt >> (4 * f)) & 0xFu; }
-__device__ __forceinline__ void cntInc(unsigned& cnt, int f)
+__device__ __forceinline__ unsigned cntGet(Cnt cnt, int f) { return (unsigned)(cnt >> (8 * f)) & 0xFFu; }
+__device__ __forceinline__ void cntInc(Cnt& cnt, int f)
 {
-   if( cntGet(cnt, f) < 2u )
-      cnt += 1u << (4 * f);
+   if( cntGet(cnt, f) < CNT_SAT )
+      cnt += 1ull << (8 * f);
 }
-__device__ __forceinline__ unsigned cntDec(unsigned cnt, int f) { return cnt - (1u << (4 * f)); }
-__device__ __forceinline__ unsigned cntMerge(unsigned a, unsigned b)
+__device__ __forceinline__ Cnt cntDec(Cnt cnt, int f) { return cnt - (1ull << (8 * f)); }
+__device__ __forceinline__ Cnt cntMerge(Cnt a, Cnt b)
 {
-   unsigned x = a + b;                                       // fields 0..4
-   unsigned ge2 = ((x >> 1) | (x >> 2)) & 0x11111111u;       // 1 where field >= 2
-   return (ge2 << 1) | (x & 0x11111111u & ~ge2);
+   const Cnt x = a + b;                                      // fields 0..254: no carry between the bytes
+   const Cnt ge = x & 0x8080808080808080ull;                 // bit 7 where a field is >= 128
+   return (x | (ge - (ge >> 7))) & 0x7f7f7f7f7f7f7f7full;    // ... those become 127
 }
-__device__ __forceinline__ unsigned cntMinSum(unsigned c) { return cntGet(c, 0) + cntGet(c, 1) + cntGet(c, 2) + cntGet(c, 3); }
-__device__ __forceinline__ unsigned cntMaxSum(unsigned c) { return cntGet(c, 4) + cntGet(c, 5) + cntGet(c, 6) + cntGet(c, 7); }
+__device__ __forceinline__ unsigned cntMinSum(Cnt c) { return cntGet(c, 0) + cntGet(c, 1) + cntGet(c, 2) + cntGet(c, 3); }
+__device__ __forceinline__ unsigned cntMaxSum(Cnt c) { return cntGet(c, 4) + cntGet(c, 5) + cntGet(c, 6) + cntGet(c, 7); }
 
 struct RowAcc
 {
    double   minhi, minlo;   // finite part of the minimal activity (double-double)
    double   maxhi, maxlo;   // finite part of the maximal activity
    double   maxdelta;       // max_i |a_i| (ub_i - lb_i), infinity if a variable is unbounded (:1542-1599)
-   unsigned cnt;
+   Cnt      cnt;
 };
 
 __device__ __forceinline__ void accInit(RowAcc& r)
 {
    r.minhi = r.minlo = r.maxhi = r.maxlo = 0.0;
    r.maxdelta = 0.0;
-   r.cnt = 0u;
+   r.cnt = 0ull;
 }
 
 // one bound of one term enters one activity: consdataUpdateActivities with oldbound = 0 (:1773-1948)
 __device__ __forceinline__ void addContributionSlow(const Num& n, double a, double bound, double& hi, double& lo,
-   unsigned& cnt, int fposinf, int fneginf, int fposhuge, int fneghuge)
+   Cnt& cnt, int fposinf, int fneginf, int fposhuge, int fneghuge)
 {
    if( isInf(n, fabs(bound)) )
       cntInc(cnt, bound > 0.0 ? fposinf : fneginf);
@@ -555,7 +559,7 @@ __device__ __forceinline__ void candidates(const Num& n, const Sink& s, const Ro
    double minres, maxres;
    bool mintight, maxtight, minsettoinf, maxsettoinf;
    {
-      unsigned c = r.cnt;
+      Cnt c = r.cnt;
       double delta = 0.0;
       if( isInf(n, minactbound) ) c = cntDec(c, MINPOSINF);
       else if( isInf(n, -minactbound) ) c = cntDec(c, MINNEGINF);
@@ -566,7 +570,7 @@ __device__ __forceinline__ void candidates(const Num& n, const Sink& s, const Ro
          cntGet(c, MINNEGHUGE), delta, false, minres, mintight, minsettoinf);
    }
    {
-      unsigned c = r.cnt;
+      Cnt c = r.cnt;
       double delta = 0.0;
       if( isInf(n, -maxactbound) ) c = cntDec(c, MAXNEGINF);
       else if( isInf(n, maxactbound) ) c = cntDec(c, MAXPOSINF);

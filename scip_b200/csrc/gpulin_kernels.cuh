@@ -388,7 +388,8 @@ __device__ __forceinline__ bool rowClearlyQuiet(const Num& n, const LeanAcc& r, 
    const double cabs = __hiloint2double(r.cabshi + 1, 0);
    if( !(cabs < n.huge) )
       return false;
-   const double E = (double)(len * len + 8) * 2.3e-16 * cabs;
+   const double dl = (double)len;      // (in double: len * len overflows an int from 46341 nonzeros on)
+   const double E = (dl * dl + 8.0) * 2.3e-16 * cabs;
    // verdict: FeasGT(minact,rhs) needs (minact-rhs)/max(1,|minact|,|rhs|) > feastol, impossible if minact-rhs <= feastol/4
    if( (r.minact - rhs) + E > 0.25 * n.feastol || (lhs - r.maxact) + E > 0.25 * n.feastol )
       return false;
@@ -800,9 +801,8 @@ __device__ __forceinline__ void loadChunk(const DevProblem& p, long long base, i
    }
 }
 
-// BITS: the bounds of a column whose bit is set in the shared-memory table s_free are (0,1) -- no gather
-template <int CH, bool BITS>
-__device__ __forceinline__ void sellSweep(const DevProblem& p, const unsigned* s_free, int nblockthreads)
+template <int CH>
+__device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads)
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
@@ -871,15 +871,7 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, const unsigned* s
             {
                if( c + k < len[i] )
                {
-                  const int j = cj[k] & COL_MASK;
-                  if( BITS )
-                  {
-                     b[k] = make_double2(0.0, 1.0);
-                     if( j >= p.nfreecols || ((s_free[j >> 5] >> (j & 31)) & 1u) == 0u )
-                        b[k] = p.bnd[j];
-                  }
-                  else
-                     b[k] = p.bnd[j];
+                  b[k] = p.bnd[cj[k] & COL_MASK];
                }
             }
 #pragma unroll
@@ -911,7 +903,7 @@ __global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const De
 {
    if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
       return;
-   sellSweep<CH, false>(p, nullptr, SELL_THREADS);
+   sellSweep<CH>(p, SELL_THREADS);
 }
 
 // ---- the SELL sweep with a shared-memory bit table -------------------------------------------------------------------
@@ -1009,11 +1001,6 @@ __device__ __forceinline__ int unitSign(int colword)
 {
    return (colword << 1) & (int)0x80000000u;
 }
-__device__ __forceinline__ double unitCoef(int signword)
-{
-   return __hiloint2double(0x3ff00000 | signword, 0);
-}
-
 // one chunk of CH nonzeros of a row of a SELL slice; UNIT: the column words only (the values are not read)
 template <int CH, bool UNIT>
 __device__ __forceinline__ void loadChunkBits(const DevProblem& p, long long base, int c, int len, double (&a)[CH], int (&cj)[CH])
@@ -1030,11 +1017,10 @@ __device__ __forceinline__ void loadChunkBits(const DevProblem& p, long long bas
    }
 }
 
-// the slices [sbeg, send) of the SELL bin, thread per row
-// MID: sums in midpoint / half-width form from bndf (else leanElem from bnd)
-//      ALLCOLS: the table covers every column (no range checks);  HD: the maximal half width is kept as a double
+// the slices [sbeg, send) of the SELL bin, thread per row; sums in midpoint / half-width form from bndf
+//      ALLCOLS: the table covers every column (no range checks)
 //      UNIT: every coefficient of these slices is +1 or -1 (rows [0, nsellunit)): 4 instead of 12 bytes per nonzero
-template <int NT, int CH, bool MID, bool ALLCOLS, bool HD, bool UNIT>
+template <int NT, int CH, bool ALLCOLS, bool UNIT>
 __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigned* s_free, unsigned tabbar, bool& tabready,
    int sbeg, int send, unsigned& nnzdone)
 {
@@ -1093,10 +1079,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
          if( act )
             sd = p.sides[row];
          MidAcc macc;
-         LeanAcc lacc;
          midInit(macc);
-         leanInit(lacc);
-         double hmaxd = 0.0;
          for( int c = 0; c < maxlen[i]; c += CH )
          {
             double a[CH];
@@ -1123,16 +1106,8 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
                {
                   const unsigned w = s_free[ALLCOLS ? cj[k] >> 5 : min(cj[k] >> 5, lastword)];
                   const unsigned fr = (ALLCOLS || cj[k] < p.nfreecols) ? (w >> (cj[k] & 31)) & 1u : 0u;
-                  if( MID )
-                  {
-                     b[k] = make_double2(0.5, 0.5);
-                     gatherUnless(fr, p.bndf + cj[k], b[k]);
-                  }
-                  else
-                  {
-                     b[k] = make_double2(0.0, 1.0);
-                     gatherUnless(fr, p.bnd + cj[k], b[k]);
-                  }
+                  b[k] = make_double2(0.5, 0.5);
+                  gatherUnless(fr, p.bndf + cj[k], b[k]);
                }
             }
 #pragma unroll
@@ -1140,43 +1115,18 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
             {
                if( c + k < len[i] )
                {
-                  if( UNIT && MID && !HD )
+                  if( UNIT )
                   {
                      // a = +1 / -1: a * mid is mid with the sign flipped, |a| * hw is hw -- the same values as midElem
-                     // computes with a = unitCoef(), without the two multiplications
+                     // would compute with a = +1 / -1, without the two multiplications
                      const double m = __hiloint2double(__double2hiint(b[k].x) ^ sg[k], __double2loint(b[k].x));
                      macc.M += m;
                      macc.Mabs += fabs(b[k].x);
                      macc.H += b[k].y;
                      macc.hmax = fmaxf(macc.hmax, __double2float_ru(b[k].y));
                   }
-                  else if( UNIT )
-                  {
-                     const double au = unitCoef(sg[k]);
-                     if( MID )
-                     {
-                        const double m = au * b[k].x;
-                        macc.M += m;
-                        macc.Mabs += fabs(m);
-                        macc.H += b[k].y;
-                        hmaxd = b[k].y > hmaxd ? b[k].y : hmaxd;
-                     }
-                     else
-                        leanElem(lacc, au, b[k].x, b[k].y);
-                  }
-                  else if( MID && HD )
-                  {
-                     const double m = a[k] * b[k].x;
-                     const double hh = fabs(a[k]) * b[k].y;
-                     macc.M += m;
-                     macc.Mabs += fabs(m);
-                     macc.H += hh;
-                     hmaxd = hh > hmaxd ? hh : hmaxd;
-                  }
-                  else if( MID )
-                     midElem(macc, a[k], b[k].x, b[k].y);
                   else
-                     leanElem(lacc, a[k], b[k].x, b[k].y);
+                     midElem(macc, a[k], b[k].x, b[k].y);
                }
             }
          }
@@ -1185,9 +1135,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
          bool handoff = false;
          if( act )
          {
-            if( HD )
-               macc.hmax = __double2float_ru(hmaxd);
-            handoff = ((exactm >> i) & 1u) != 0u || !rowClearlyQuiet(n, MID ? midToLean(macc) : lacc, len[i], sd.x, sd.y);
+            handoff = ((exactm >> i) & 1u) != 0u || !rowClearlyQuiet(n, midToLean(macc), len[i], sd.x, sd.y);
             p.dirty[row] = ROW_CLEAN;
             nnzdone += (unsigned)len[i];
          }
@@ -1196,8 +1144,8 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
    }
 }
 
-// CHU: nonzeros per thread and chunk in the unit slices (0: they take the general path)
-template <int NT, int CH, bool MID, bool ALLCOLS = false, bool HD = false, int CHU = 0>
+// CHU: nonzeros per thread and chunk in the unit slices
+template <int NT, int CH, bool ALLCOLS, int CHU>
 __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
 {
    if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
@@ -1219,12 +1167,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
    const int lane = threadIdx.x & 31;
    const int gw = (blockIdx.x * NT + threadIdx.x) >> 5;
    const int nslices = (p.nsell + 31) >> 5;
-   const int nunitslices = (CHU > 0 && MID) ? p.nsellunit >> 5 : 0;
+   const int nunitslices = p.nsellunit >> 5;
    unsigned nnzdone = 0;
    bool tabready = false;
-   if( CHU > 0 && MID )
-      sellBitsRange<NT, (CHU > 0 ? CHU : 1), MID, ALLCOLS, HD, true>(p, s_free, tabbar, tabready, 0, nunitslices, nnzdone);
-   sellBitsRange<NT, CH, MID, ALLCOLS, HD, false>(p, s_free, tabbar, tabready, nunitslices, nslices, nnzdone);
+   sellBitsRange<NT, CHU, ALLCOLS, true>(p, s_free, tabbar, tabready, 0, nunitslices, nnzdone);
+   sellBitsRange<NT, CH, ALLCOLS, false>(p, s_free, tabbar, tabready, nunitslices, nslices, nnzdone);
    if( !tabready && threadIdx.x < 32 )
       mbarWait(tabbar, 0u);         // the block must not retire under the copies it issued
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);

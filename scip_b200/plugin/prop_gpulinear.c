@@ -96,6 +96,8 @@ struct SCIP_PropData
    int64_t               nnz;
    int64_t               logcap;
    int                   nlinconss;          /**< active constraints of all row sources when the device copy was built */
+   SCIP_CONS*            sourcetail[5];      /**< last constraint in the array of every row source at build time (new constraints
+                                              *   are appended, a deletion moves the last one: part of the staleness check) */
    int                   nrowsof[5];         /**< rows per source: linear, knapsack, setppc, logicor, varbound */
    SCIP_Bool             allrows;            /**< parameter: also read knapsack / setppc / logicor / varbound rows */
    SCIP_Bool             delredundant;       /**< parameter: SCIPdelConsLocal for rows the device proves redundant */
@@ -160,6 +162,16 @@ void freeDeviceCopy(
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->ub, propdata->ncols);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->colptr, propdata->ncols + 1);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->redrows, propdata->nrows);
+   if( propdata->rowcons != NULL )
+   {
+      /* the rows' constraints were captured at build time (they cannot be freed under the device copy) */
+      int r;
+      for( r = 0; r < propdata->nrows; ++r )
+      {
+         if( propdata->rowcons[r] != NULL && SCIPreleaseCons(scip, &propdata->rowcons[r]) != SCIP_OKAY )
+            SCIPwarningMessage(scip, "prop_gpulinear: could not release the constraint of row %d\n", r);
+      }
+   }
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->rowcons, propdata->nrows);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->lhs, propdata->nrows);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->rhs, propdata->nrows);
@@ -193,18 +205,47 @@ static
 int countSourceConss(
    SCIP*                 scip,
    SCIP_Bool             allrows,
-   SCIP_Bool             stable
+   SCIP_Bool             stable,
+   SCIP_CONS**           tails               /**< NROWSOURCES entries: last constraint of every source's array, or NULL */
    )
 {
    int n = 0;
    int s;
-   for( s = 0; s < (allrows ? NROWSOURCES : 1); ++s )
+   for( s = 0; s < NROWSOURCES; ++s )
    {
-      SCIP_CONSHDLR* conshdlr = SCIPfindConshdlr(scip, rowsourcenames[s]);
+      SCIP_CONSHDLR* conshdlr = (allrows || s == 0) ? SCIPfindConshdlr(scip, rowsourcenames[s]) : NULL;
+      int ns = 0;
       if( conshdlr != NULL )
-         n += stable ? SCIPconshdlrGetNConss(conshdlr) : SCIPconshdlrGetNActiveConss(conshdlr);
+         ns = stable ? SCIPconshdlrGetNConss(conshdlr) : SCIPconshdlrGetNActiveConss(conshdlr);
+      n += ns;
+      if( tails != NULL )
+         tails[s] = ns > 0 ? SCIPconshdlrGetConss(conshdlr)[ns - 1] : NULL;
    }
    return n;
+}
+
+/** the device copy is stale if the number of source constraints or of variables changed, or -- one constraint created
+ *  and another one freed leave the number alone -- if the last constraint of a source's array is a different one (new
+ *  constraints are appended, cons.c: conshdlrAddCons; a deletion moves the last constraint into the gap) */
+static
+SCIP_Bool deviceCopyIsStale(
+   SCIP*                 scip,
+   SCIP_PROPDATA*        propdata,
+   int*                  nsourceconss
+   )
+{
+   SCIP_CONS* tails[NROWSOURCES];
+   int s;
+
+   *nsourceconss = countSourceConss(scip, propdata->allrows, propdata->stablecopy, tails);
+   if( propdata->gpu == NULL || propdata->nlinconss != *nsourceconss || propdata->ncols != SCIPgetNVars(scip) )
+      return TRUE;
+   for( s = 0; s < NROWSOURCES; ++s )
+   {
+      if( tails[s] != propdata->sourcetail[s] )
+         return TRUE;
+   }
+   return FALSE;
 }
 
 /** the row  lhs <= sum vals[i] vars[i] <= rhs  of a constraint of source `src`, rewritten to active variables; the
@@ -377,7 +418,7 @@ SCIP_RETCODE buildDeviceCopy(
    freeDeviceCopy(scip, propdata);
 
    nsources = propdata->allrows ? NROWSOURCES : 1;
-   propdata->nlinconss = countSourceConss(scip, propdata->allrows, propdata->stablecopy);
+   propdata->nlinconss = countSourceConss(scip, propdata->allrows, propdata->stablecopy, propdata->sourcetail);
    propdata->nskipped = 0;
    ++propdata->nbuilds;
    if( propdata->nlinconss == 0 )
@@ -411,7 +452,7 @@ SCIP_RETCODE buildDeviceCopy(
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lb, ncols) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->ub, ncols) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colptr, ncols + 1) );
-         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowcons, nrows) );
+         SCIP_CALL( SCIPallocClearBlockMemoryArray(scip, &propdata->rowcons, nrows) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lhs, nrows) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rhs, nrows) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->rowptr, nrows + 1) );
@@ -462,6 +503,7 @@ SCIP_RETCODE buildDeviceCopy(
             if( pass == 1 )
             {
                propdata->rowcons[nrows] = conss[c];
+               SCIP_CALL( SCIPcaptureCons(scip, conss[c]) );
                propdata->rowptr[nrows] = k;
                propdata->lhs[nrows] = lhs;
                propdata->rhs[nrows] = rhs;
@@ -703,13 +745,11 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
    propdata = SCIPpropGetData(prop);
    assert(propdata != NULL);
 
-   nsourceconss = countSourceConss(scip, propdata->allrows, propdata->stablecopy);
-   if( nsourceconss == 0 )
-      return SCIP_OKAY;
-
-   /* staleness: rebuild when the number of constraints of the row sources (see countSourceConss) or of variables changed */
-   if( propdata->gpu == NULL || propdata->nlinconss != nsourceconss || propdata->ncols != SCIPgetNVars(scip) )
+   /* staleness: rebuild when the constraints of the row sources (see countSourceConss) or the variables changed */
+   if( deviceCopyIsStale(scip, propdata, &nsourceconss) )
    {
+      if( nsourceconss == 0 )
+         return SCIP_OKAY;
       SCIP_CALL( buildDeviceCopy(scip, propdata) );
       if( propdata->gpu == NULL )
          return SCIP_OKAY;

@@ -42,6 +42,10 @@ def main():
         "syn_mixedknap_300": synth.mixed_knapsack(300, 3000, 30000, seed=13, dense_range=(300, 900), eq_frac=0.3),
         "syn_mixedknap_300_infeas": synth.mixed_knapsack(300, 3000, 30000, seed=14, dense_range=(300, 900),
                                                          infeasible=True),
+        # numerics: cancellation after an unreliable activity update, three and more huge contributions
+        "syn_edge_cancel": synth.edge_cancellation(),
+        "syn_edge_huge": synth.edge_huge(),
+        "syn_edge_huge_infeas": synth.edge_huge(infeasible=True),
     }
     for name, prob in synth_probs.items():
         path = os.path.join("/tmp", name + ".gen.lpb")

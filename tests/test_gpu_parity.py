@@ -339,3 +339,57 @@ def test_row_partition_with_min_merge_equals_single_device(gpulin, nparts):
     finally:
         for lp in parts:
             lp.close()
+
+
+# ---- BASELINE.json configs at their full size (the oracle needs 7 s for C3 and 14 s for C4 on one host core) -------------
+
+def test_c3_full_size(gpulin):
+    """BASELINE configs[2]: set cover 1M x 1M, 10M nonzeros, seed 1 -- every bound against the oracle"""
+    prob = synth.setcover(1_000_000, 1_000_000, 10_000_000, seed=1)
+    got, want = gpu_vs_oracle(gpulin, prob, what="c3 full size")
+    assert got["status"] == gpulin.FIXPOINT and got["nchanges"] > 200_000
+
+
+def test_c4_full_size(gpulin):
+    """BASELINE configs[3]: mixed knapsack / general integer 200k x 2M, 50M nonzeros, 1 % dense rows, seed 2"""
+    prob = synth.mixed_knapsack(200_000, 2_000_000, 50_000_000, seed=2)
+    with gpulin.LinearPropagator(prob) as lp:
+        lay = lp.layout()
+    assert lay["rows_stream"] > 150_000 and lay["rows_block"] > 1000
+    got, want = gpu_vs_oracle(gpulin, prob, what="c4 full size")
+    assert got["status"] == gpulin.FIXPOINT and got["nchanges"] > 500_000
+
+
+def test_row_longer_than_65536_nonzeros(gpulin):
+    """the error bound of the interval filter is computed in double (an int n*n overflows from 46341 nonzeros on): a row
+    of 70k nonzeros that is quiet, one that tightens, and one that sits within rounding distance of the gate"""
+    rng = np.random.default_rng(17)
+    ncols = 90_000
+    n = 70_000
+    rows, lhs, rhs = [], [], []
+    for kind in range(3):
+        cols = rng.permutation(ncols)[:n].astype(np.int32)
+        vals = rng.integers(1, 10, size=n).astype(np.float64)
+        rows.append((cols, vals))
+        tot = float(vals.sum()) * 5.0            # maximal activity for x in [0, 5]
+        lhs.append(-INF)
+        rhs.append({0: tot + 100.0,              # quiet: slack above every |a| (ub - lb)
+                    1: 0.5 * tot,                # tightens many bounds
+                    2: tot - 45.0 + 1e-9}[kind]) # maxdelta = 45 vs slack 45 + 1e-9: on the gate
+    rowptr = np.cumsum([0] + [len(c) for c, _ in rows]).astype(np.int64)
+    prob = dict(rowptr=rowptr, colidx=np.concatenate([c for c, _ in rows]), vals=np.concatenate([v for _, v in rows]),
+                lhs=np.array(lhs), rhs=np.array(rhs), lb=np.zeros(ncols), ub=np.full(ncols, 5.0),
+                vartype=(rng.random(ncols) < 0.5).astype(np.uint8))
+    for bs in (0.05, 1e-9):
+        got, _ = gpu_vs_oracle(gpulin, prob, maxrounds=200, what=f"70k-nonzero rows bs={bs}", boundstreps=bs)
+    assert got["nchanges"] > 10_000
+
+
+def test_cancellation_and_huge_counts_follow_the_reference(gpulin):
+    """SURVEY 8a row a7 (activities that cancel by twelve orders of magnitude once a variable is fixed) and rows with three
+    and more huge contributions (the verdict uses count * hugeval): the generators behind the fixtures syn_edge_*"""
+    for name, prob, cutoff in (("cancel", synth.edge_cancellation(), False), ("huge", synth.edge_huge(), False),
+                               ("huge infeasible", synth.edge_huge(infeasible=True), True)):
+        for bs in (0.05, 1e-9):
+            got, _ = gpu_vs_oracle(gpulin, prob, maxrounds=100, what=f"{name} bs={bs}", boundstreps=bs)
+            assert (got["status"] == gpulin.CUTOFF) == cutoff, name
