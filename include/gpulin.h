@@ -153,6 +153,17 @@ int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n
  *  device time [ms] (%globaltimer stamps taken by the kernels), nonzeros swept, bound changes accepted */
 int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n);
 
+/** measurement aid: the kernel starts of the last gpulin_propagate call (the first 256), time ordered: ids[i] names the
+ *  kernel (1 begin, 2 thread-per-row sweep, 3 tile sweep, 4 block-per-row sweep, 5 exact rules, 6 / 7 exchange push start /
+ *  end, 8 / 9 exchange merge start / all peers arrived, 10 apply, 11 sparse rounds), us[i] = microseconds since the call
+ *  began on the device (%globaltimer).  Works inside the CUDA-graph loop, where a profiler sees no launches */
+int gpulin_get_trace(gpulin_t* h, int32_t* ids, double* us, int32_t maxn, int32_t* n);
+
+/** several GPUs: per round of the last call (up to maxn) the device time [ms] from the start of the round to the start of
+ *  its exchange (sweeps + exact rules of this rank's share; -1: the round had no exchange -- it ran redundantly on every
+ *  rank) and how long the merge then waited for the slowest peer */
+int gpulin_get_exchange_stats(gpulin_t* h, double* before_ms, double* wait_ms, int32_t maxn, int32_t* n);
+
 /** redundancy feedback -- replaces the verdict at the end of propagateCons (cons_linear.c:7743-7753: a row whose activity
  *  bounds lie inside its sides, GE(minactivity, lhs) and LE(maxactivity, rhs), is deleted locally with SCIPdelConsLocal):
  *  the rows (caller's numbering, ascending) that are redundant for the bounds on the device, e.g. after gpulin_propagate.
@@ -213,18 +224,26 @@ int gpulin_round_sweep(gpulin_t* h);
  *  ranks).  If nchanges or cutoff is non-NULL the call synchronises and returns the round's change count / verdict */
 int gpulin_round_apply(gpulin_t* h, int dense, int64_t* nchanges, int32_t* cutoff);
 
-/* ---- rows sharded over the GPUs of ONE node, candidates exchanged through peer memory (NVLink) ------------------
- * One process per GPU.  Every rank creates its handle on its own row block, exports three CUDA IPC handles, the host
- * language all-gathers them, every rank connects.  From then on gpulin_set_bounds / gpulin_propagate are COLLECTIVE
- * calls (same bounds, same maxrounds on every rank): the exact kernel commits every candidate into the key vector of
- * every rank with system-scope atomics over NVLink, two device-side barriers per round keep the ranks in step, and the
- * whole fixpoint loop stays on the device -- no NCCL call and no host round trip per round. */
+/* ---- several GPUs of ONE node: dense rounds are shared, the exchange goes through peer memory (NVLink) -----------------
+ * Every rank creates its handle on the WHOLE problem (the matrix is 0.25 - 0.9 GB of 180) and holds the same bounds.  In a
+ * dense round a rank sweeps its share of the rows only; the columns its candidates touched travel once, packed, into an
+ * inbox on every other rank (stores through peer memory from inside the round's kernels -- no NCCL call, no host round
+ * trip), every rank merges what it received with atomicMin and applies the same changes; rounds with few marked rows run
+ * on every rank redundantly without any exchange.  gpulin_set_bounds / gpulin_update_bounds / gpulin_propagate become
+ * COLLECTIVE calls: the same arguments on every rank, results identical on every rank.  The counterpart in the reference
+ * is the min/max merge of bounds of syncstore.c:921. */
 
-/** writes this rank's IPC handles (*nbytes bytes; call with out = NULL to query the size) */
-int gpulin_peer_handles(gpulin_t* h, void* out, int64_t* nbytes);
+/** one process per GPU: allocates this rank's inbox for `nranks` ranks and writes its CUDA IPC handle (*nbytes bytes;
+ *  call with out = NULL to query the size); the host language all-gathers the handles */
+int gpulin_peer_handles(gpulin_t* h, int nranks, void* out, int64_t* nbytes);
 
-/** opens the other ranks' buffers; allhandles = the nranks handle blobs in rank order */
+/** opens the other ranks' inboxes; allhandles = the nranks handle blobs in rank order */
 int gpulin_peer_connect(gpulin_t* h, int rank, int nranks, const void* allhandles);
+
+/** one process, n handles of the same problem on n different devices (the SCIP plugin: SCIP is single threaded, one
+ *  process -- prop.c:646): handle i becomes rank i; peer access between the devices is enabled.  Drive the group with
+ *  gpulin_set_bounds + gpulin_propagate_async on every handle, then gpulin_propagate_wait on every handle */
+int gpulin_group_connect(gpulin_t** handles, int n);
 
 #ifdef __cplusplus
 }

@@ -103,11 +103,13 @@ struct gpulin
    cudaGraphExec_t gexec = nullptr;
    cudaGraphConditionalHandle handle = 0;
    bool        hostloop = false;
-   int         npeers = 1;          // > 1 after gpulin_peer_connect: candidates are committed on every rank
+   int         npeers = 1;          // > 1 after gpulin_peer_connect / gpulin_group_connect: dense rounds are shared with the peers
    int         peerrank = 0;
-   unsigned*   d_sync = nullptr;    // this rank's barrier words (exported)
    PeerTable*  d_peers = nullptr;
-   void*       peerptr[MAX_PEERS][3] = {};   // opened IPC pointers of the other ranks
+   unsigned char* d_inbox = nullptr; // this rank's inbox (exported to the peers)
+   int         inboxranks = 0;      // ... sized for this many ranks
+   void*       peerptr[MAX_PEERS] = {};   // opened IPC pointers of the other ranks' inboxes (multi-process connection)
+   int         npushblocks = 0;
    bool        havebounds = false;
    bool        pending = false;     // gpulin_propagate_async was called, gpulin_propagate_wait not yet
    bool        lightfetch = false;  // (unused: every call fetches only the head of the control block now)
@@ -208,13 +210,26 @@ constexpr int SELLBITS_THREADS = 1024;
 constexpr int64_t SMALLCALL_MAXCOLS = 256;      // gpulin_propagate after at most this many updated columns starts in one block
 
 // one propagation round on h->stream
+// the changed-column bits of the exact kernel become the change list; with peers this is the one exchange of a dense
+// round: the listed columns go out to every peer, theirs are merged into the local keys
+static int launchCollect(gpulin* h)
+{
+   if( h->npeers > 1 )
+   {
+      collect_kernel<true><<<h->npushblocks, 256, 0, h->stream>>>(h->p);
+      peer_merge_kernel<<<h->npushblocks, 256, 0, h->stream>>>(h->p);
+   }
+   else
+      collect_kernel<false><<<h->npushblocks, 256, 0, h->stream>>>(h->p);
+   CU(cudaGetLastError());
+   return GPULIN_OK;
+}
+
 template <int MODE, bool GRAPH>
-static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
+static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = true)
 {
    if( sweep )
    {
-      if( MODE == APPLY_PEERS )
-         lists_to_work_kernel<<<std::min(h->napplyblocks, 64), APPLY_THREADS, 0, h->stream>>>(h->p);
       // the three bins are independent: the smaller ones run on side streams beside the largest
       const int nkinds = (h->nsellblocks > 0) + (h->nstreamblocks > 0) + (h->nlongblocks > 0);
       int side = 0;
@@ -250,21 +265,12 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply)
          CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
       if( h->nexactblocks > 0 )
          h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
+      if( collect )
+         OK(launchCollect(h));
    }
    if( apply )
    {
-      if( MODE == APPLY_PEERS )
-         peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);      // every rank's candidates have arrived
-      if( MODE == APPLY_PEERS )
-      {
-         // the bits every rank raised on this rank become the change list; then the same list-driven apply as on one GPU
-         peer_collect_kernel<<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p);
-         apply_kernel<APPLY_LIST, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
-      }
-      else
-         apply_kernel<MODE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
-      if( MODE == APPLY_PEERS )
-         peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);      // nobody commits into keys that are still being read
+      apply_kernel<MODE, GRAPH><<<h->napplyblocks, APPLY_THREADS, 0, h->stream>>>(h->p, h->handle);
       if( MODE == APPLY_LIST && sweep && h->nsparseblocks > 0 )
       {
          // rounds with few marked rows are run by one persistent cooperative kernel (returns at once otherwise)
@@ -296,18 +302,6 @@ static int buildGraph(gpulin* h)
       CU(cudaGraphAddKernelNode(&beginNode, h->graph, nullptr, 0, &kp));
    }
    cudaGraphNode_t afterBegin = beginNode;
-   if( h->npeers > 1 )
-   {
-      // all ranks have their bounds in place before anybody commits a candidate
-      cudaKernelNodeParams kp;
-      memset(&kp, 0, sizeof(kp));
-      void* args[1] = {(void*)&h->p};
-      kp.func = (void*)peer_barrier_kernel;
-      kp.gridDim = dim3(1);
-      kp.blockDim = dim3(1);
-      kp.kernelParams = args;
-      CU(cudaGraphAddKernelNode(&afterBegin, h->graph, &beginNode, 1, &kp));
-   }
    cudaGraphNodeParams cp = {};
    cp.type = cudaGraphNodeTypeConditional;
    cp.conditional.handle = h->handle;
@@ -318,12 +312,23 @@ static int buildGraph(gpulin* h)
    cudaGraph_t body = cp.conditional.phGraph_out[0];
 
    CU(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-   const int lrc = (h->npeers > 1 ? launchRoundKernels<APPLY_PEERS, true>(h, true, true) : launchRoundKernels<APPLY_LIST, true>(h, true, true));
+   const int lrc = launchRoundKernels<APPLY_LIST, true>(h, true, true);
    cudaGraph_t captured = nullptr;
    CU(cudaStreamEndCapture(h->stream, &captured));
    OK(lrc);
    CU(cudaGraphInstantiate(&h->gexec, h->graph, 0));
    return GPULIN_OK;
+}
+
+// the share of rank `rank` of `nranks` in a dense round: every nranks-th SELL slice (the kernels interleave), an equal
+// number of tiles of the stream, every nranks-th block-per-row row
+static void setShare(gpulin* h, int rank, int nranks)
+{
+   DevProblem& p = h->p;
+   p.st0 = (int)((long long)h->ntiles * rank / nranks);
+   p.st1 = (int)((long long)h->ntiles * (rank + 1) / nranks);
+   p.nranks = nranks;
+   p.rank = rank;
 }
 
 extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* rowptr,
@@ -569,7 +574,6 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &d_colbeg, (size_t)ncols + 2, true));
    TRY(devAlloc(h, &d_colrows, (size_t)nnz + 1, true));
    TRY(devAlloc(h, &d_ctrl, 1));
-   TRY(devAlloc(h, &h->d_sync, 64));
    TRY(devAlloc(h, &h->d_peers, 1));
    TRY(devAlloc(h, &h->d_tmplb, (size_t)ncols + 1));
    TRY(devAlloc(h, &h->d_tmpub, (size_t)ncols + 1));
@@ -604,7 +608,6 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRYCU(cudaMemset(d_dirty, 0, (size_t)nrows + 64));
    TRYCU(cudaMemset(d_colbits, 0, sizeof(unsigned) * ((size_t)ncols / 32 + 2)));
    TRYCU(cudaMemset(d_ctrl, 0, sizeof(Ctrl)));
-   TRYCU(cudaMemset(h->d_sync, 0, 64 * sizeof(unsigned)));
    TRYCU(cudaMemset(d_cand, 0, sizeof(long long) * (2 * (size_t)ncols + 2)));
    TRYCU(cudaMallocHost((void**)&h->h_ctrl, sizeof(Ctrl)));
    TRYCU(cudaMallocHost((void**)&h->h_params, 4 * sizeof(int)));
@@ -656,6 +659,19 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.ctrl = d_ctrl;
    p.log = nullptr;
    p.peers = nullptr;
+   setShare(h, 0, 1);
+   {
+      // expected marks per row >= 1: marking every row is cheaper than walking the columns (see apply_kernel) -- where a
+      // spurious mark is cheap: the filter of the thread-per-row rows costs ~3 ps per nonzero and finishes almost every
+      // row it did not have to look at, a longer row that the filter cannot finish costs a pass of the exact rules (and
+      // the marking rule spares most rows of a knapsack-type matrix: an upper bound that moves down does not concern
+      // a <= row with positive coefficients).  So only for matrices whose nonzeros are in short rows
+      long long sellnnz = 0;
+      for( int i = 0; i < h->nsell; ++i )
+         sellnnz += plen[(size_t)i];
+      const double thr = nnz > 0 ? std::ceil((double)nrows * (double)ncols / (double)nnz) : 4e9;
+      p.markall_min = (sellnnz >= (nnz / 10) * 9) ? (unsigned)std::min(thr, 4e9) : 0xffffffffu;
+   }
    p.num.inf = num->infinity;
    p.num.eps = num->epsilon;
    p.num.sumeps = num->sumepsilon;
@@ -700,6 +716,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->exactkernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
+      h->npushblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols / 32 + 255) / 256, (int64_t)h->nsm * 4));
       // the sparse-rounds kernel: one block per SM (all must be co-resident: grid syncs)
       int coop = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
@@ -740,12 +757,10 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    destroyGraph(h);
    for( int r = 0; r < MAX_PEERS; ++r )
    {
-      for( int k = 0; k < 3; ++k )
-      {
-         if( h->peerptr[r][k] != nullptr )
-            cudaIpcCloseMemHandle(h->peerptr[r][k]);
-      }
+      if( h->peerptr[r] != nullptr )
+         cudaIpcCloseMemHandle(h->peerptr[r]);
    }
+   cudaFree(h->d_inbox);
    for( int i = 0; i < h->nalloc; ++i )
       cudaFree(h->d_all[i]);
    if( h->shared != nullptr && --h->shared->refs == 0 )
@@ -909,7 +924,7 @@ extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
    CU(cudaSetDevice(h->device));
    h->lastmaxrounds = maxrounds;
    ++h->version;
-   h->smallcall = h->smallcols >= 0 && h->smallcols <= SMALLCALL_MAXCOLS && h->npeers <= 1 && !h->hostloop && h->smallcalls;
+   h->smallcall = h->smallcols >= 0 && h->smallcols <= SMALLCALL_MAXCOLS && !h->hostloop && h->smallcalls;
    h->smallcols = -1;
    h->h_params[0] = maxrounds;
    h->h_params[1] = (int)h->logcap;
@@ -929,11 +944,9 @@ extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
    else
    {
       begin_kernel<<<1, 1, 0, h->stream>>>(h->p.ctrl);
-      if( h->npeers > 1 )
-         peer_barrier_kernel<<<1, 1, 0, h->stream>>>(h->p);
       for( ;; )
       {
-         OK((h->npeers > 1 ? launchRoundKernels<APPLY_PEERS, false>(h, true, true) : launchRoundKernels<APPLY_LIST, false>(h, true, true)));
+         OK((launchRoundKernels<APPLY_LIST, false>(h, true, true)));
          int cont = 0;
          CU(cudaMemcpyAsync(&h->h_ctrl->cont, &h->p.ctrl->cont, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
          CU(cudaStreamSynchronize(h->stream));
@@ -990,7 +1003,7 @@ extern "C" int gpulin_propagate_wait(gpulin_t* h, gpulin_result* res)
    if( res != nullptr )
       *res = h->last;
    if( c->peererror )
-      return fail(GPULIN_ERR_STATE, "a peer rank did not reach the round barrier within 5 s");
+      return fail(GPULIN_ERR_STATE, "a peer rank did not deliver its candidates within 5 s");
    return GPULIN_OK;
 }
 
@@ -1153,6 +1166,7 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    h->nsellblocks = src->nsellblocks; h->nstreamblocks = src->nstreamblocks;
    h->nlongblocks = src->nlongblocks; h->napplyblocks = src->napplyblocks; h->nexactblocks = src->nexactblocks; h->exactkernel = src->exactkernel;
    h->nsparseblocks = src->nsparseblocks;
+   h->npushblocks = src->npushblocks;
    h->nsm = src->nsm; h->hostloop = src->hostloop; h->perm = src->perm;
    h->p = src->p;
    DevProblem& p = h->p;
@@ -1173,7 +1187,6 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    TRY(devAlloc(h, &d_colbits, (size_t)h->ncols / 32 + 2));
    TRY(devAlloc(h, &d_chglist, (size_t)h->ncols + 1));
    TRY(devAlloc(h, &d_ctrl, 1));
-   TRY(devAlloc(h, &h->d_sync, 64));
    TRY(devAlloc(h, &h->d_peers, 1));
    TRY(devAlloc(h, &h->d_tmplb, (size_t)h->ncols + 1));
    TRY(devAlloc(h, &h->d_tmpub, (size_t)h->ncols + 1));
@@ -1181,7 +1194,6 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    TRYCU(cudaMemset(d_tileflag, 0, (size_t)h->ntiles + 64));
    TRYCU(cudaMemset(d_colbits, 0, sizeof(unsigned) * ((size_t)h->ncols / 32 + 2)));
    TRYCU(cudaMemset(d_ctrl, 0, sizeof(Ctrl)));
-   TRYCU(cudaMemset(h->d_sync, 0, 64 * sizeof(unsigned)));
    TRYCU(cudaMemset(d_cand, 0, sizeof(long long) * (2 * (size_t)h->ncols + 2)));
    TRYCU(cudaMallocHost((void**)&h->h_ctrl, sizeof(Ctrl)));
    TRYCU(cudaMallocHost((void**)&h->h_params, 4 * sizeof(int)));
@@ -1351,6 +1363,59 @@ extern "C" int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int
    return GPULIN_OK;
 }
 
+extern "C" int gpulin_get_exchange_stats(gpulin_t* h, double* before_ms, double* wait_ms, int32_t maxn, int32_t* n)
+{
+   if( h == nullptr || n == nullptr )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( !h->histfetched )
+   {
+      CU(cudaSetDevice(h->device));
+      CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      h->histfetched = true;
+   }
+   const Ctrl* c = h->h_ctrl;
+   const int m = std::min(std::min(h->lastrounds, (int)MAX_HIST), (int)maxn);
+   unsigned long long prev = c->t_start;
+   for( int i = 0; i < m; ++i )
+   {
+      const bool has = h->npeers > 1 && c->hist_push[i] != 0;
+      if( before_ms != nullptr )
+         before_ms[i] = has ? 1e-6 * (double)(c->hist_push[i] - prev) : -1.0;
+      if( wait_ms != nullptr )
+         wait_ms[i] = has ? 1e-6 * (double)c->hist_wait[i] : 0.0;
+      prev = c->hist_time[i];
+   }
+   *n = m;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_trace(gpulin_t* h, int32_t* ids, double* us, int32_t maxn, int32_t* n)
+{
+   if( h == nullptr || n == nullptr || (maxn > 0 && (ids == nullptr || us == nullptr)) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( !h->histfetched )
+   {
+      CU(cudaSetDevice(h->device));
+      CU(cudaMemcpyAsync(h->h_ctrl, h->p.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      h->histfetched = true;
+   }
+   const Ctrl* c = h->h_ctrl;
+   const int m = std::min(std::min((int)c->ntrace, (int)MAX_TRACE), (int)maxn);
+   const unsigned long long mask = 0x00ffffffffffffffull;
+   // (the stamps are appended by atomics in launch order, but kernels on side streams may interleave: sort by time)
+   std::vector<unsigned long long> ev(c->trace, c->trace + m);
+   std::sort(ev.begin(), ev.end(), [&](unsigned long long a, unsigned long long b) { return (a & mask) < (b & mask); });
+   for( int i = 0; i < m; ++i )
+   {
+      ids[i] = (int32_t)(ev[(size_t)i] >> 56);
+      us[i] = 1e-3 * (double)((ev[(size_t)i] & mask) - (c->t_start & mask));
+   }
+   *n = m;
+   return GPULIN_OK;
+}
+
 extern "C" int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats)
 {
    if( h == nullptr || stats == nullptr )
@@ -1374,18 +1439,14 @@ extern "C" int gpulin_get_call_stats(gpulin_t* h, int64_t* stats, int32_t nstats
    int64_t sparse = 0;
    if( h->lastsmall && !h->lastresumed )
       launches = 1;                                      // probe_kernel ran every round
-   else if( h->npeers > 1 )
-   {
-      dense = rounds;
-      launches = 2 + rounds * (1 + nkinds + 1 + 1 + 1 + 1 + 1);   // begin, barrier; lists, sweeps, exact, barrier, collect, apply, barrier
-   }
    else
    {
       sparse = c->nsparse;
       dense = rounds - sparse - (h->lastresumed ? (int64_t)h->smallrounds : 0);
       if( dense < 0 )
          dense = 0;
-      launches = (h->lastresumed ? 1 : 0) + 1 + dense * (nkinds + 2 + (h->nsparseblocks > 0 ? 1 : 0));
+      // begin; per dense round: sweeps, exact, collect, [merge with peers], apply, sparse rounds
+      launches = (h->lastresumed ? 1 : 0) + 1 + dense * (nkinds + 3 + (h->npeers > 1 ? 1 : 0) + (h->nsparseblocks > 0 ? 1 : 0));
    }
    const int64_t v[5] = {launches, dense, sparse, h->lastsmall ? 1 : 0, h->lastresumed ? 1 : 0};
    for( int i = 0; i < nstats && i < 5; ++i )
@@ -1523,11 +1584,12 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    CU(cudaEventRecord(h->evprof[0], h->stream));
    const int keepexact = h->nexactblocks;
    h->nexactblocks = 0;                               // launchRoundKernels skips the exact kernel ...
-   OK((launchRoundKernels<APPLY_LIST, false>(h, true, false)));
+   OK((launchRoundKernels<APPLY_LIST, false>(h, true, false, false)));
    h->nexactblocks = keepexact;
    CU(cudaEventRecord(h->evprof[1], h->stream));
    h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);   // ... which is timed on its own
    CU(cudaEventRecord(h->evprof[2], h->stream));
+   OK(launchCollect(h));                              // (counted with the apply stage)
    OK((launchRoundKernels<APPLY_LIST, false>(h, false, true)));
    CU(cudaEventRecord(h->evprof[3], h->stream));
    CU(cudaEventSynchronize(h->evprof[3]));
@@ -1541,20 +1603,69 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    return GPULIN_OK;
 }
 
-// ---- rows sharded over the GPUs of one node, candidates exchanged through peer memory -------------------------------
+// ---- dense rounds shared by the GPUs of one node (the matrix and the bounds are replicated) -------------------------------
 
-extern "C" int gpulin_peer_handles(gpulin_t* h, void* out, int64_t* nbytes)
+static int allocInbox(gpulin* h, int nranks)
 {
-   if( h == nullptr || nbytes == nullptr )
-      return fail(GPULIN_ERR_ARG, "invalid argument");
-   *nbytes = 3 * (int64_t)sizeof(cudaIpcMemHandle_t);
+   if( h->d_inbox != nullptr && h->inboxranks >= nranks )
+      return GPULIN_OK;
+   if( h->npeers > 1 )
+      return fail(GPULIN_ERR_STATE, "the handle is already connected");
+   CU(cudaSetDevice(h->device));
+   cudaFree(h->d_inbox);
+   h->d_inbox = nullptr;
+   const long long cap = (h->ncols + 3) & ~3LL;
+   const size_t bytes = peerBoxBytes(nranks, cap);
+   cudaError_t e = cudaMalloc((void**)&h->d_inbox, bytes);
+   if( e != cudaSuccess )
+      return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the peer inbox (%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+   CU(cudaMemset(h->d_inbox, 0, PEER_HDR_BYTES));
+   h->inboxranks = nranks;
+   h->devbytes += bytes;
+   return GPULIN_OK;
+}
+
+// boxes[r]: the inbox of rank r as this device addresses it
+static int wirePeers(gpulin* h, int rank, int nranks, unsigned char* const* boxes)
+{
+   PeerTable t;
+   memset(&t, 0, sizeof(t));
+   t.n = nranks;
+   t.rank = rank;
+   t.cap = (h->ncols + 3) & ~3LL;
+   for( int r = 0; r < nranks; ++r )
+      t.box[r] = boxes[r];
+   CU(cudaSetDevice(h->device));
+   CU(cudaStreamSynchronize(h->stream));
+   CU(cudaMemcpy(h->d_peers, &t, sizeof(t), cudaMemcpyHostToDevice));
+   h->p.peers = h->d_peers;
+   h->npeers = nranks;
+   h->peerrank = rank;
+   setShare(h, rank, nranks);
+   h->npushblocks = (int)std::max<int64_t>(1, std::min<int64_t>((std::max(h->ncols / 32, h->nrows / 16) + 255) / 256, (int64_t)h->nsm * 4));
+   // the grids of the sweeps follow the share
+   {
+      const int wpb = SWEEP_THREADS / 32;
+      const int64_t mytiles = h->p.st1 - h->p.st0;
+      const int64_t need = (mytiles + 2 * wpb - 1) / (2 * wpb);
+      h->nstreamblocks = (int)std::min<int64_t>(need, (int64_t)h->nstreamblocks);
+      const int64_t nlongmine = (h->nlong - rank + nranks - 1) / nranks;
+      h->nlongblocks = (int)std::min<int64_t>(std::max<int64_t>(nlongmine, h->nlong > 0 ? 1 : 0), (int64_t)h->nlongblocks);
+   }
+   if( !h->hostloop )
+      OK(buildGraph(h));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_peer_handles(gpulin_t* h, int nranks, void* out, int64_t* nbytes)
+{
+   if( h == nullptr || nbytes == nullptr || nranks < 1 || nranks > MAX_PEERS )
+      return fail(GPULIN_ERR_ARG, "invalid argument (at most %d ranks)", MAX_PEERS);
+   *nbytes = (int64_t)sizeof(cudaIpcMemHandle_t);
    if( out == nullptr )
       return GPULIN_OK;
-   CU(cudaSetDevice(h->device));
-   cudaIpcMemHandle_t* hd = (cudaIpcMemHandle_t*)out;
-   CU(cudaIpcGetMemHandle(&hd[0], h->p.cand));
-   CU(cudaIpcGetMemHandle(&hd[1], h->p.colbits));
-   CU(cudaIpcGetMemHandle(&hd[2], h->d_sync));
+   OK(allocInbox(h, nranks));
+   CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out, h->d_inbox));
    return GPULIN_OK;
 }
 
@@ -1564,39 +1675,74 @@ extern "C" int gpulin_peer_connect(gpulin_t* h, int rank, int nranks, const void
       return fail(GPULIN_ERR_ARG, "invalid argument (at most %d ranks)", MAX_PEERS);
    if( h->npeers > 1 )
       return fail(GPULIN_ERR_STATE, "gpulin_peer_connect called twice");
+   if( h->d_inbox == nullptr || h->inboxranks < nranks )
+      return fail(GPULIN_ERR_STATE, "gpulin_peer_connect before gpulin_peer_handles for %d ranks", nranks);
+   if( nranks == 1 )
+      return GPULIN_OK;
    CU(cudaSetDevice(h->device));
-   CU(cudaStreamSynchronize(h->stream));
    const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)allhandles;
-   PeerTable t;
-   memset(&t, 0, sizeof(t));
-   t.n = nranks;
-   t.rank = rank;
+   unsigned char* boxes[MAX_PEERS] = {nullptr};
    for( int r = 0; r < nranks; ++r )
    {
       if( r == rank )
       {
-         t.cand[r] = h->p.cand;
-         t.colbits[r] = h->p.colbits;
-         t.sync[r] = h->d_sync;
+         boxes[r] = h->d_inbox;
          continue;
       }
-      for( int k = 0; k < 3; ++k )
-      {
-         cudaError_t e = cudaIpcOpenMemHandle(&h->peerptr[r][k], hd[3 * r + k], cudaIpcMemLazyEnablePeerAccess);
-         if( e != cudaSuccess )
-            return fail(GPULIN_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s (peer access between the GPUs is required)",
-               r, cudaGetErrorString(e));
-      }
-      t.cand[r] = (long long*)h->peerptr[r][0];
-      t.colbits[r] = (unsigned*)h->peerptr[r][1];
-      t.sync[r] = (unsigned*)h->peerptr[r][2];
+      cudaError_t e = cudaIpcOpenMemHandle(&h->peerptr[r], hd[r], cudaIpcMemLazyEnablePeerAccess);
+      if( e != cudaSuccess )
+         return fail(GPULIN_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s (peer access between the GPUs is required)",
+            r, cudaGetErrorString(e));
+      boxes[r] = (unsigned char*)h->peerptr[r];
    }
-   CU(cudaMemcpy(h->d_peers, &t, sizeof(t), cudaMemcpyHostToDevice));
-   h->p.peers = h->d_peers;
-   h->npeers = nranks;
-   h->peerrank = rank;
-   if( !h->hostloop )
-      OK(buildGraph(h));
+   return wirePeers(h, rank, nranks, boxes);
+}
+
+// one process, n handles of the same problem on n different devices (the SCIP plugin: SCIP is one process)
+extern "C" int gpulin_group_connect(gpulin_t** hs, int n)
+{
+   if( hs == nullptr || n < 1 || n > MAX_PEERS )
+      return fail(GPULIN_ERR_ARG, "invalid argument (at most %d handles)", MAX_PEERS);
+   for( int i = 0; i < n; ++i )
+   {
+      if( hs[i] == nullptr || hs[i]->npeers > 1 )
+         return fail(GPULIN_ERR_ARG, "handle %d is NULL or already connected", i);
+      if( hs[i]->nrows != hs[0]->nrows || hs[i]->ncols != hs[0]->ncols || hs[i]->nnz != hs[0]->nnz )
+         return fail(GPULIN_ERR_ARG, "handle %d holds a different problem", i);
+      for( int k = 0; k < i; ++k )
+      {
+         if( hs[k]->device == hs[i]->device )
+            return fail(GPULIN_ERR_ARG, "handles %d and %d are on the same device", k, i);
+      }
+   }
+   if( n == 1 )
+      return GPULIN_OK;
+   unsigned char* boxes[MAX_PEERS] = {nullptr};
+   for( int i = 0; i < n; ++i )
+   {
+      OK(allocInbox(hs[i], n));
+      boxes[i] = hs[i]->d_inbox;
+   }
+   for( int i = 0; i < n; ++i )
+   {
+      CU(cudaSetDevice(hs[i]->device));
+      for( int k = 0; k < n; ++k )
+      {
+         if( k == i )
+            continue;
+         int can = 0;
+         CU(cudaDeviceCanAccessPeer(&can, hs[i]->device, hs[k]->device));
+         if( !can )
+            return fail(GPULIN_ERR_CUDA, "device %d cannot access the memory of device %d", hs[i]->device, hs[k]->device);
+         cudaError_t e = cudaDeviceEnablePeerAccess(hs[k]->device, 0);
+         if( e == cudaErrorPeerAccessAlreadyEnabled )
+            (void)cudaGetLastError();
+         else if( e != cudaSuccess )
+            return fail(GPULIN_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", hs[i]->device, hs[k]->device, cudaGetErrorString(e));
+      }
+   }
+   for( int i = 0; i < n; ++i )
+      OK(wirePeers(hs[i], i, n, boxes));
    return GPULIN_OK;
 }
 

@@ -406,19 +406,48 @@ __device__ __forceinline__ bool rowRedundant(const Num& n, const RowAcc& a, doub
 // ---- is merged with atomicMin on its int64 key.  Candidate layout per column j (one 16-byte pair):
 // ----    cand[2j]   = ~d2key(lb)   (bitwise NOT reverses the order: a larger lower bound is a smaller key)
 // ----    cand[2j+1] =  d2key(ub)
-// ---- so both sides tighten by MIN -- one ncclMin all-reduce over the whole vector merges the ranks' candidates.
-// Rows sharded over several GPUs of one node: every rank keeps the full key vector, and a candidate is committed into
-// the key vectors of ALL ranks through peer memory (NVLink P2P atomics, system scope) -- the exchange of the round is
-// fused into the kernel that produces the candidates, no collective follows.
+// ---- so both sides tighten by MIN -- the ranks' candidates merge with one MIN per key (atomicMin of the packed
+// ---- exchange, or one ncclMin all-reduce over the whole vector).
+// Several GPUs of one node (see gpulin_kernels.cuh, "dense rounds sharded over the GPUs of a node"): every rank commits
+// into its OWN key vector; after the exact kernel of a dense round the touched columns travel once, packed, into the
+// inbox of every other rank (peer memory over NVLink), and every rank merges what it received with atomicMin.
 constexpr int MAX_PEERS = 8;
+// An inbox holds, per parity of the exchange number and per source rank, one 8-byte header word and `cap` entries of 32
+// bytes.  Everything is written with plain stores through peer memory and validates itself -- no fence, no flag that has
+// to be ordered behind the data (the scheme of NCCL's low-latency protocols):
+//    header = exchange number << 32 | verdict << 31 | number of entries        (one 8-byte store: atomic)
+//    entry  = { column, exchange number, ~key(lb) } { key(ub), exchange number, 0 }      (two 16-byte stores; the reader
+//             spins until both halves carry the number it waits for)
+struct PeerEntry
+{
+   uint4 a;     // x = column, y = exchange number, (z, w) = ~key(lb)
+   uint4 b;     // (x, y) = key(ub), z = exchange number, w = 0
+};
+struct PeerHeader
+{
+   unsigned long long word;
+   unsigned long long nnz;       // nonzeros the source swept in this round (statistics only: not validated)
+};
+constexpr size_t PEER_HDR_BYTES = 2 * MAX_PEERS * sizeof(PeerHeader);
 struct PeerTable
 {
-   int        n;                   // ranks
-   int        rank;                // this rank
-   long long* cand[MAX_PEERS];     // key vector of every rank ([rank] = the local one)
-   unsigned*  colbits[MAX_PEERS];  // changed-column bits of every rank
-   unsigned*  sync[MAX_PEERS];     // [0] barrier arrivals, [1] epoch of the last cutoff
+   int            n;                  // ranks
+   int            rank;               // this rank
+   long long      cap;                // entries per (parity, source): the number of columns
+   unsigned char* box[MAX_PEERS];     // inbox of every rank ([rank] = the local one): headers | entries
 };
+__host__ __device__ __forceinline__ size_t peerBoxBytes(int nranks, long long cap)
+{
+   return PEER_HDR_BYTES + 2 * (size_t)nranks * (size_t)cap * sizeof(PeerEntry);
+}
+__device__ __forceinline__ PeerHeader* peerHeader(unsigned char* box, int parity, int src)
+{
+   return reinterpret_cast<PeerHeader*>(box) + parity * MAX_PEERS + src;
+}
+__device__ __forceinline__ PeerEntry* peerEntries(const PeerTable& t, unsigned char* box, int parity, int src)
+{
+   return reinterpret_cast<PeerEntry*>(box + PEER_HDR_BYTES) + ((size_t)parity * t.n + src) * (size_t)t.cap;
+}
 
 struct Sink
 {
@@ -426,35 +455,27 @@ struct Sink
    unsigned*        colbits;   // one bit per column: "a key moved this round"
    int*             chglist;   // the columns whose bit was raised this round, in no particular order
    unsigned*        nchgcols;  // length of chglist
-   const PeerTable* peers;     // NULL: single GPU
+   bool             listed;    // small rounds: the first candidate that reaches a column appends it to chglist (bit test with
+                               // an answer, list counter: two dependent round trips).  Dense rounds: the bit goes up with a
+                               // reduction that nobody waits for, and collect_kernel turns the bits into the list afterwards
 };
 
-// returns false if a candidate at least as good is already in place (a plain load first: in a round in which many rows
-// propose bounds for the same column only the first few have to pay for an atomic; a stale value only costs an atomic)
+// a reduction: nobody waits for its answer (a candidate that gets here beats the round-start bound, so its column changes
+// this round whichever candidate wins)
 __device__ __forceinline__ bool commitKey(const Sink& s, size_t idx, long long key)
 {
-   if( key >= __ldcg(&s.cand[idx]) )
-      return false;
-   if( s.peers == nullptr )
-      atomicMin(&s.cand[idx], key);
-   else
-   {
-      for( int r = 0; r < s.peers->n; ++r )
-         atomicMin_system(&s.peers->cand[r][idx], key);
-   }
+   atomicMin(&s.cand[idx], key);
    return true;
 }
 
 // the first candidate of a round that reaches a column puts it on the list the apply kernel works through.  Split in
 // two so that a thread can have the bit tests of several columns in flight before it looks at the first answer.
-// With peers there is no list: the bit is raised on every rank and the apply kernel scans the bits.
 __device__ __forceinline__ bool raiseColumnBit(const Sink& s, int j)
 {
    const unsigned bit = 1u << (j & 31);
-   if( s.peers != nullptr )
+   if( !s.listed )
    {
-      for( int r = 0; r < s.peers->n; ++r )
-         atomicOr_system(&s.peers->colbits[r][j >> 5], bit);
+      atomicOr(&s.colbits[j >> 5], bit);
       return false;
    }
    return (atomicOr(&s.colbits[j >> 5], bit) & bit) == 0u;

@@ -27,6 +27,9 @@ namespace gpl {
 constexpr int SWEEP_THREADS = 128;
 constexpr int LONG_THREADS = 512;
 constexpr int MAX_HIST = 1024;        // rounds with recorded per-round statistics
+constexpr int MAX_TRACE = 256;        // kernel starts with a recorded time stamp per call
+enum TraceId { TR_BEGIN = 1, TR_SWEEP_SELL, TR_SWEEP_STREAM, TR_SWEEP_LONG, TR_EXACT, TR_PUSH, TR_PUSH_END, TR_MERGE,
+               TR_MERGE_READY, TR_APPLY, TR_SPARSE, TR_SPARSE_END };
 constexpr int TILE = 256;             // nonzeros per tile of the CSR stream = 32 lanes x TPL
 constexpr int TPL = 8;                // nonzeros per lane and tile
 constexpr int STREAM_MAXLEN = 4096;   // longer rows (and empty rows) are swept block-per-row
@@ -48,8 +51,9 @@ struct Ctrl
    int                cutoff;       // set by any kernel that proves infeasibility
    unsigned int       ticket;       // apply kernel: blocks finished
    unsigned int       nchgcols;     // columns on the change list of the running round
-   unsigned int       epoch;        // peer barriers passed so far (never reset)
-   int                peererror;    // a peer barrier timed out
+   unsigned int       epoch;        // exchanges with the peer ranks done so far (never reset; the same number on every rank)
+   int                peererror;    // a peer rank did not deliver its candidates in time
+   unsigned int       pushticket;   // peer_push_kernel: blocks finished
    unsigned long long logcount;     // entries produced
    unsigned long long round_nchg;   // accepted bound changes of the running round
    unsigned long long total_nchg;
@@ -61,12 +65,14 @@ struct Ctrl
    unsigned int       resume;       // the next begin_kernel continues the call small_rounds started (round count, totals, log)
    unsigned int       nsparse;      // rounds done by sparse_rounds_kernel in this call (statistics)
    unsigned int       poisoned;     // probing worker: its state is not "node + change log" any more (see probe_kernel)
-   unsigned int       listsvalid;   // an apply step of this call has run: every marked row is on mark list mb (or a count overflowed)
-   unsigned int       skipsweep;    // the running round takes its rows from the mark list (lists_to_work_kernel): no filter sweep
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
    unsigned long long hist_time[MAX_HIST];   // %globaltimer at the end of each round
    unsigned long long hist_nnz[MAX_HIST];
    unsigned long long hist_nchg[MAX_HIST];
+   unsigned int       ntrace;                // kernel-start stamps of the call (the first MAX_TRACE): (id << 56) | %globaltimer
+   unsigned long long trace[MAX_TRACE];
+   unsigned long long hist_push[MAX_HIST];   // several GPUs: %globaltimer when the exchange of the round started (0: none) ...
+   unsigned long long hist_wait[MAX_HIST];   // ... and how long the merge waited for the slowest peer [ns]
 };
 
 struct ChangeRec      // == gpulin_change
@@ -118,7 +124,14 @@ struct DevProblem
    const int*          colrows;
    Ctrl*               ctrl;
    ChangeRec*          log;
-   const PeerTable*    peers;      // NULL: single GPU; else candidates go to every rank's key vector (see Sink)
+   const PeerTable*    peers;      // NULL: single GPU
+   // the share of this rank in a dense round (single GPU: everything): every nranks-th SELL slice of the unit class and
+   // of the others (rank, rank + nranks, ...: neighbouring slices hold rows of the same length and the same kind, so the
+   // ranks get equal work in the filter AND in the exact rules), tiles [st0,st1) of the stream, every nranks-th
+   // block-per-row row
+   int                 st0, st1;
+   int                 nranks, rank;
+   unsigned            markall_min; // an apply step with at least this many changed columns marks ALL rows (see apply_kernel)
    Num                 num;
 };
 
@@ -128,7 +141,15 @@ __device__ __forceinline__ unsigned long long globaltimer()
    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
    return t;
 }
+__device__ __forceinline__ void traceStamp(Ctrl* c, int id)
+{
+   const unsigned i = atomicAdd(&c->ntrace, 1u);
+   if( i < (unsigned)MAX_TRACE )
+      c->trace[i] = ((unsigned long long)id << 56) | (globaltimer() & 0x00ffffffffffffffull);
+}
+#define TRACE_KERNEL_START(c, id) do { if( blockIdx.x == 0 && threadIdx.x == 0 ) traceStamp((c), (id)); } while( 0 )
 
+// time stamp of a kernel start / phase (called by one thread)
 // streaming loads of the matrix: read once per round, evict-first, 16 bytes per request
 __device__ __forceinline__ double2 ldStream2(const double* p)
 {
@@ -191,7 +212,7 @@ struct CandQueue
 // from the activity pass -- the slack test of the first 256 nonzeros needs no load at all, only the few nonzeros that
 // pass it are fetched again (from L1)
 constexpr int ALPHA_SLOTS = 8;
-template <bool ALPHA>
+template <bool ALPHA, bool LISTED>
 __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo& ri, long long base, int stride,
    int first, int step, int len, bool& cutoff, CandQueue& queue, const double (&alpha)[ALPHA_SLOTS])
 {
@@ -204,7 +225,7 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
    s.colbits = p.colbits;
    s.chglist = p.chglist;
    s.nchgcols = &p.ctrl->nchgcols;
-   s.peers = p.peers;
+   s.listed = LISTED;
    int cnt = 0;                        // positions in the queue (warp-uniform)
    int kb = first - lane;              // warp-uniform
    for( ;; )
@@ -405,7 +426,7 @@ __device__ __forceinline__ bool rowClearlyQuiet(const Num& n, const LeanAcc& r, 
 
 // gates, candidate pass and verdict of one row whose exact activities are known (elements first, first+step, ... of
 // the calling thread)
-template <bool ALPHA>
+template <bool ALPHA, bool LISTED>
 __device__ __forceinline__ void rowTighten(const DevProblem& p, const RowAcc& acc, double lhs, double rhs, long long base,
    int stride, int first, int step, int len, CandQueue& queue, const double (&alpha)[ALPHA_SLOTS])
 {
@@ -415,7 +436,7 @@ __device__ __forceinline__ void rowTighten(const DevProblem& p, const RowAcc& ac
    ri.rhs = rhs;
    bool cutoff = false;
    if( rowGates(p.num, ri, len, cutoff) )
-      rowCandidates<ALPHA>(p, ri, base, stride, first, step, len, cutoff, queue, alpha);
+      rowCandidates<ALPHA, LISTED>(p, ri, base, stride, first, step, len, cutoff, queue, alpha);
    if( cutoff || rowInfeasible(p.num, ri.acc, lhs, rhs) )
       p.ctrl->cutoff = 1;
 }
@@ -559,8 +580,7 @@ __device__ __forceinline__ void loadTile(const DevProblem& p, int t, int lane, T
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const DevProblem p)
 {
-   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
-      return;
+   TRACE_KERNEL_START(p.ctrl, TR_SWEEP_STREAM);
    static_assert(TPL == 8 && TILE == 256, "the tile layout is wired into the vector loads");
    // per warp: the sums of the rows that end in the current tile, in row order (at most one row per nonzero)
    __shared__ LeanAcc s_tot[SWEEP_THREADS / 32][TILE];
@@ -569,10 +589,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_stream_kernel(const De
    LeanAcc* tot = s_tot[threadIdx.x >> 5];
    const int gw = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
    const int nw = (gridDim.x * SWEEP_THREADS) >> 5;
-   // contiguous tile range of this warp
-   const int per = (p.ntiles + nw - 1) / nw;
-   const int t0 = gw * per;
-   const int t1 = min(p.ntiles, t0 + per);
+   // contiguous tile range of this warp inside the tiles [st0, st1) of this rank (a row belongs to the warp -- and the
+   // rank -- in whose range it ends: the look-back below reads what lies in front of the range)
+   const int per = (p.st1 - p.st0 + nw - 1) / nw;
+   const int t0 = p.st0 + gw * per;
+   const int t1 = min(p.st1, t0 + per);
    if( t0 >= t1 )
       return;
 
@@ -802,15 +823,15 @@ __device__ __forceinline__ void loadChunk(const DevProblem& p, long long base, i
 }
 
 template <int CH>
-__device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads)
+__device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads, int sbeg, int send, unsigned& nnzdone)
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
    const int gw = (blockIdx.x * nblockthreads + threadIdx.x) >> 5;
    const int nw = (gridDim.x * nblockthreads) >> 5;
-   const int nslices = (p.nsell + 31) >> 5;
-   unsigned nnzdone = 0;
-   for( int s0 = gw; s0 < nslices; s0 += SELL_NB * nw )
+   // this rank's slices of [sbeg, send): sbeg + rank, sbeg + rank + nranks, ... = slice number q of the share
+   const int nq = (send - sbeg - p.rank + p.nranks - 1) / p.nranks;
+   for( int q0 = gw; q0 < nq; q0 += SELL_NB * nw )
    {
       // ---- one round trip: flags, lengths and offsets of the next four slices of this warp
       int len[SELL_NB];
@@ -821,12 +842,13 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
       {
-         const int slice = s0 + i * nw;
+         const int q = q0 + i * nw;
+         const int slice = sbeg + p.rank + q * p.nranks;
          const int row = slice * 32 + lane;
-         const bool valid = slice < nslices && row < p.nsell;
+         const bool valid = q < nq && row < p.nsell;
          const unsigned char f = valid ? p.dirty[row] : ROW_CLEAN;
          const int lw = valid ? p.rowlen[row] : 0;
-         base[i] = (slice < nslices ? p.sell_off[slice] : 0) + lane;
+         base[i] = (q < nq ? p.sell_off[slice] : 0) + lane;
          const bool act = f == ROW_MARKED;
          len[i] = act ? (lw & ~ROWLEN_EXACT) : 0;
          if( act )
@@ -844,7 +866,7 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
       {
-         const int row = (s0 + i * nw) * 32 + lane;
+         const int row = (sbeg + p.rank + (q0 + i * nw) * p.nranks) * 32 + lane;
          const bool act = ((actm >> i) & 1u) != 0u;
          double2 sd = make_double2(0.0, 0.0);
          if( act )
@@ -893,17 +915,18 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads
          pushRow(p, handoff, row, lane, 0, 0);
       }
    }
-   nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
-   if( lane == 0 )
-      addRoundNnz(p, (unsigned long long)nnzdone, gw);
 }
 
 template <int CH, int MINB>
 __global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const DevProblem p)
 {
-   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
-      return;
-   sellSweep<CH>(p, SELL_THREADS);
+   TRACE_KERNEL_START(p.ctrl, TR_SWEEP_SELL);
+   unsigned nnzdone = 0;
+   sellSweep<CH>(p, SELL_THREADS, 0, p.nsellunit >> 5, nnzdone);
+   sellSweep<CH>(p, SELL_THREADS, p.nsellunit >> 5, (p.nsell + 31) >> 5, nnzdone);
+   nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
+   if( (threadIdx.x & 31) == 0 )
+      addRoundNnz(p, (unsigned long long)nnzdone, (blockIdx.x * SELL_THREADS + threadIdx.x) >> 5);
 }
 
 // ---- the SELL sweep with a shared-memory bit table -------------------------------------------------------------------
@@ -1034,7 +1057,9 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
    const int lastword = p.nfreewords - 1;
    // (taking the slices from the end of the range, longest rows first, so that the extra slice of some warps is a short one,
    // was measured: 45 instead of 41 us)
-   for( int s0 = sbeg + gw; s0 < send; s0 += SELL_NB * nw )
+   // this rank's slices of [sbeg, send): sbeg + rank, sbeg + rank + nranks, ... = slice number q of the share
+   const int nq = (send - sbeg - p.rank + p.nranks - 1) / p.nranks;
+   for( int q0 = gw; q0 < nq; q0 += SELL_NB * nw )
    {
       // ---- one round trip: flags, lengths and offsets of the next four slices of this warp
       int len[SELL_NB];
@@ -1045,12 +1070,13 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
       {
-         const int slice = s0 + i * nw;
+         const int q = q0 + i * nw;
+         const int slice = sbeg + p.rank + q * p.nranks;
          const int row = slice * 32 + lane;
-         const bool valid = slice < send && row < p.nsell;
+         const bool valid = q < nq && row < p.nsell;
          const unsigned char f = valid ? p.dirty[row] : ROW_CLEAN;
          const int lw = valid ? p.rowlen[row] : 0;
-         base[i] = (slice < send ? p.sell_off[slice] : 0) + lane;
+         base[i] = (q < nq ? p.sell_off[slice] : 0) + lane;
          const bool act = f == ROW_MARKED;
          len[i] = act ? (lw & ~ROWLEN_EXACT) : 0;
          if( act )
@@ -1073,7 +1099,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
       {
-         const int row = (s0 + i * nw) * 32 + lane;
+         const int row = (sbeg + p.rank + (q0 + i * nw) * p.nranks) * 32 + lane;
          const bool act = ((actm >> i) & 1u) != 0u;
          double2 sd = make_double2(0.0, 0.0);
          if( act )
@@ -1148,8 +1174,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
 template <int NT, int CH, bool ALLCOLS, int CHU>
 __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
 {
-   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
-      return;
+   TRACE_KERNEL_START(p.ctrl, TR_SWEEP_SELL);
    extern __shared__ __align__(128) unsigned char s_raw[];
    const unsigned tabbytes = (unsigned)p.nfreewords * 4u;
    const unsigned* s_free = reinterpret_cast<const unsigned*>(s_raw);
@@ -1166,12 +1191,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
 
    const int lane = threadIdx.x & 31;
    const int gw = (blockIdx.x * NT + threadIdx.x) >> 5;
-   const int nslices = (p.nsell + 31) >> 5;
-   const int nunitslices = p.nsellunit >> 5;
    unsigned nnzdone = 0;
    bool tabready = false;
-   sellBitsRange<NT, CHU, ALLCOLS, true>(p, s_free, tabbar, tabready, 0, nunitslices, nnzdone);
-   sellBitsRange<NT, CH, ALLCOLS, false>(p, s_free, tabbar, tabready, nunitslices, nslices, nnzdone);
+   sellBitsRange<NT, CHU, ALLCOLS, true>(p, s_free, tabbar, tabready, 0, p.nsellunit >> 5, nnzdone);
+   sellBitsRange<NT, CH, ALLCOLS, false>(p, s_free, tabbar, tabready, p.nsellunit >> 5, (p.nsell + 31) >> 5, nnzdone);
    if( !tabready && threadIdx.x < 32 )
       mbarWait(tabbar, 0u);         // the block must not retire under the copies it issued
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
@@ -1182,8 +1205,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
 // ---- block-per-row for rows longer than STREAM_MAXLEN (and empty rows) ---------------------------------------------
 __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProblem p)
 {
-   if( p.peers != nullptr && p.ctrl->skipsweep )      // (only set with peers: no dependent load in front of a single-GPU sweep)
-      return;
+   TRACE_KERNEL_START(p.ctrl, TR_SWEEP_LONG);
    __shared__ LeanAcc s_lean[LONG_THREADS / 32];
 
    const int lane = threadIdx.x & 31;
@@ -1192,7 +1214,7 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
    const int row0 = p.nsx;
    const int nrows = p.nrows - row0;
 
-   for( int r = blockIdx.x; r < nrows; r += gridDim.x )
+   for( int r = p.rank + p.nranks * (int)blockIdx.x; r < nrows; r += p.nranks * (int)gridDim.x )
    {
       const int row = row0 + r;
       __syncthreads();                  // previous row done with the shared state and its flag
@@ -1352,7 +1374,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
                sk.colbits = p.colbits;
                sk.chglist = p.chglist;
                sk.nchgcols = &p.ctrl->nchgcols;
-               sk.peers = p.peers;
+               sk.listed = SPARSE;
                static_assert(EXACT_Q == 4, "the slot selection below is written for four slots");
                unsigned pass = 0u;
 #pragma unroll
@@ -1410,7 +1432,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
             alpha[q] = 0.0;
          accumulateExact<true>(p, acc, beg, 1, lane, 32, len, alpha);
          accWarpReduce(acc, lane);
-         rowTighten<true>(p, acc, sd.x, sd.y, beg, 1, lane, 32, len, s_queue[warp], alpha);
+         rowTighten<true, SPARSE>(p, acc, sd.x, sd.y, beg, 1, lane, 32, len, s_queue[warp], alpha);
       }
    }
 
@@ -1445,7 +1467,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
 #pragma unroll 1
       for( int w = 1; w < nblockthreads / 32; ++w )
          accMerge(acc, s_acc[w]);
-      rowTighten<false>(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, nblockthreads, len, s_queue[warp], noalpha);
+      rowTighten<false, SPARSE>(p, acc, sd.x, sd.y, beg, 1, threadIdx.x, nblockthreads, len, s_queue[warp], noalpha);
    }
    if( SPARSE && nnzdone != 0 )
       addRoundNnz(p, nnzdone, gtid >> 5);
@@ -1457,6 +1479,7 @@ __global__ void __launch_bounds__(EXACT_THREADS, MINB) exact_rows_kernel(const D
    __shared__ RowAcc s_acc[EXACT_THREADS / 32];
    __shared__ CandQueue s_queue[EXACT_THREADS / 32];
 
+   TRACE_KERNEL_START(p.ctrl, TR_EXACT);
    const unsigned n0 = p.ctrl->nexact[0];
    const unsigned n1 = p.ctrl->nexact[1];
    const unsigned n2 = p.ctrl->nexact[2];
@@ -1590,17 +1613,35 @@ __device__ __forceinline__ void markRowRange(const DevProblem& p, long long qbeg
             }
          }
       }
+      // the flag goes up with an atomic on its word: exactly one of the columns that race for a row notes it, so the
+      // lists hold no row twice and their lengths are the same on every rank of a node (the ranks decide by them
+      // whether the next round is a small one, and must decide alike); the atomics of a trip are in flight together
+      bool won[4];
 #pragma unroll
       for( int t = 0; t < 4; ++t )
       {
+         won[t] = false;
          if( fl[t] != ROW_MARKED )
          {
-            p.dirty[r[t]] = ROW_MARKED;
+            if( listfull && r[t] < p.nsell )
+               p.dirty[r[t]] = ROW_MARKED;            // (nobody reads the lists of this round any more)
+            else
+            {
+               unsigned* word = reinterpret_cast<unsigned*>(p.dirty + (r[t] & ~3));
+               const int shift = 8 * (r[t] & 3);
+               won[t] = ((atomicOr(word, (unsigned)ROW_MARKED << shift) >> shift) & 0xffu) != ROW_MARKED;
+            }
+         }
+      }
+#pragma unroll
+      for( int t = 0; t < 4; ++t )
+      {
+         if( won[t] )
+         {
             if( r[t] >= p.nsell && r[t] < p.nsx )
                p.tileflag[(rb[t] - p.streambase) >> 8] = 1;
             if( listfull )
                continue;
-            // note the row for a sparse round (two columns racing for the same row may both note it: harmless)
             const int bin = r[t] < p.nsell ? 0 : (r[t] < p.nsx ? 1 : 2);
             const unsigned wb = p.ctrl->mb ^ 1u;
             const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
@@ -1647,6 +1688,8 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
       c->hist_time[r] = globaltimer();
       c->hist_nnz[r] = nnz;
       c->hist_nchg[r] = nchg;
+      if( r + 1 < MAX_HIST )
+         c->hist_push[r + 1] = 0;       // (set by the exchange of that round, if it has one)
    }
    c->total_nchg += nchg;
    c->total_nnz += nnz;
@@ -1658,7 +1701,6 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
    c->nmark[c->mb][0] = c->nmark[c->mb][1] = c->nmark[c->mb][2] = 0;
    c->mb ^= 1u;
    c->round = r + 1;
-   c->listsvalid = 1;
    int cont = 0;
    if( c->cutoff )
       c->status = 1;
@@ -1794,7 +1836,7 @@ __device__ __forceinline__ void logChangesBuffered(const DevProblem& p, WarpLog&
 // column; returns the number of bound changes this thread accepted
 template <int G>
 __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlist, int gtid, int nthreads, int round, int logcap,
-   ChangeRec* warplogbuf = nullptr)
+   ChangeRec* warplogbuf = nullptr, bool markall = false)
 {
    WarpLog wlog;
    wlog.buf = warplogbuf;
@@ -1865,7 +1907,7 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
       }
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
-      if( valid )
+      if( valid && !markall )
          markRowRange(p, q0, q1, gl, G, which, listfull);
    }
    if( wlog.buf != nullptr )
@@ -1876,12 +1918,9 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
 // DENSE = false: the columns on the change list of this round -- cost proportional to the changes (single GPU);
 //                eight lanes per column: one accepts the bounds, all mark the rows of the column;
 // DENSE = true : every column compares its (all-reduced) candidate keys with its bounds (rows sharded over ranks:
-//                a key may have been moved by another rank)
-//         PEERS: the changed-column bits (raised on every rank by every rank's exact kernel) are scanned, a word per
-//                thread; all ranks hold the same keys and bits, so they all accept the same changes
+//                a key may have been moved by another rank: the host-driven NCCL rounds)
 constexpr int APPLY_LIST = 0;
 constexpr int APPLY_DENSE = 1;
-constexpr int APPLY_PEERS = 2;
 
 template <int MODE, bool GRAPH>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
@@ -1893,6 +1932,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
    __syncthreads();
 
    Ctrl* c = p.ctrl;
+   TRACE_KERNEL_START(c, TR_APPLY);
    const int lane = threadIdx.x & 31;
    const int round = c->round;
    const int logcap = c->logcap;
@@ -1900,34 +1940,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
    int mychg = 0;
    const int nthreads = gridDim.x * APPLY_THREADS;
    const int gtid = blockIdx.x * APPLY_THREADS + threadIdx.x;
-   if( MODE == APPLY_PEERS )
-   {
-      const int nwords = (p.ncols + 31) >> 5;
-      for( int w = gtid; w < nwords; w += nthreads )
-      {
-         unsigned bits = p.colbits[w];
-         if( bits == 0u )
-            continue;
-         p.colbits[w] = 0u;
-         while( bits != 0u )
-         {
-            const int j = 32 * w + __ffs(bits) - 1;
-            bits &= bits - 1u;
-            bool lbchg;
-            bool ubchg;
-            double2 nb;
-            const int nc = applyColumn(p, j, nb, lbchg, ubchg);
-            if( nc > 0 )
-            {
-               markColumnRows(p, j, 0, 1, (lbchg ? COLROW_LB : 0) | (ubchg ? COLROW_UB : 0));
-               if( logcap > 0 )
-                  logChanges(p, j, round, logcap, nc, lbchg, ubchg, nb);
-            }
-            mychg += nc;
-         }
-      }
-   }
-   else if( MODE == APPLY_DENSE )
+   if( MODE == APPLY_DENSE )
    {
       // the local list only serves to lower the bits again
       for( unsigned i = gtid; i < nlist; i += nthreads )
@@ -1951,7 +1964,28 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
       }
    }
    else
-      mychg += applyListPhase<APPLY_G>(p, nlist, gtid, nthreads, round, logcap, s_log[MODE == APPLY_LIST ? threadIdx.x >> 5 : 0]);
+   {
+      // Many changed columns (one mark per row and more to expect): walking the rows of every changed column costs more than
+      // the filter sweep of the rows that would have stayed unmarked -- ALL rows are marked instead (a row whose bounds did
+      // not move is finished by the filter, or reproduces candidates that are in place already: the result is the same).
+      // The decision depends on the length of the change list alone, so every rank of a node takes it alike.
+      const bool markall = nlist >= p.markall_min;
+      mychg += applyListPhase<APPLY_G>(p, nlist, gtid, nthreads, round, logcap, s_log[MODE == APPLY_LIST ? threadIdx.x >> 5 : 0], markall);
+      if( markall )
+      {
+         uint4* d = reinterpret_cast<uint4*>(p.dirty);
+         const unsigned one = 0x01010101u * ROW_MARKED;
+         const int nq = p.nrows >> 4;
+         for( int i = gtid; i < nq; i += nthreads )
+            d[i] = make_uint4(one, one, one, one);
+         for( int r = (nq << 4) + gtid; r < p.nrows; r += nthreads )
+            p.dirty[r] = ROW_MARKED;
+         for( int t = gtid; t < p.ntiles; t += nthreads )
+            p.tileflag[t] = 1;
+         if( gtid == 0 )
+            atomicMax(&c->nmark[c->mb ^ 1u][0], (unsigned)MARKCAP + 1u);      // the lists are not complete: a dense round follows
+      }
+   }
    mychg = __reduce_add_sync(0xffffffffu, mychg);
    if( lane == 0 && mychg != 0 )
       atomicAdd(&s_nchg, mychg);
@@ -1970,50 +2004,54 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
    }
 }
 
-// ---- rows sharded over peers, a round with few marked rows: the rows on the mark list go straight to the work lists of
-// ---- the exact kernel and the filter sweeps of this round return at once (the cooperative sparse-rounds kernel is not
-// ---- used with peers: every round needs its two barriers over the ranks).  The decision is local to the rank.
-__global__ void __launch_bounds__(APPLY_THREADS) lists_to_work_kernel(const DevProblem p)
+// ---- dense rounds: the changed-column bits become the change list -- and travel to the other GPUs of the node -----------
+// In a dense round the exact kernel commits with reductions only (atomicMin on the key, atomicOr on the column's bit:
+// nobody waits for an answer).  collect_kernel turns the bits into the change list of the apply step: a word per thread,
+// one atomic on the list counter per warp.
+//
+// PEERS -- dense rounds sharded over the GPUs of a node.  Every rank holds the WHOLE matrix (0.25 - 0.9 GB of 180) and
+// identical bounds, sweeps only its share of the rows (DevProblem::rank ... st1) and commits the candidates of those rows
+// into its own key vector.  Then
+//   collect_kernel<true>  stores every column it lists, (column, ~key(lb), key(ub)), into the inbox of every other rank
+//                         through peer memory (NVLink; plain stores that validate themselves, see PeerEntry: no fence,
+//                         no atomics), the last block to finish adds the header (count, verdict);
+//   peer_merge_kernel     waits for the headers of all other ranks, merges their entries into the local keys with
+//                         atomicMin and puts columns on the change list that are not there yet.
+// After the merge all ranks hold the same keys and the same set of changed columns; the list-driven apply step and the
+// small rounds that follow (sparse_rounds_kernel) run on every rank redundantly -- deterministic, so the ranks stay
+// identical and need no further exchange until the next dense round.  One exchange per dense round, volume proportional
+// to the changed columns; its counterpart in the reference is the min/max merge of syncstore.c:921.
+// The inboxes are double buffered by the parity of the exchange number: a rank can be at most one exchange ahead of
+// the slowest rank (it needs everybody's entries of exchange e before it can send those of e + 1).
+__device__ __forceinline__ void storeV4(void* addr, const uint4& v)
 {
-   Ctrl* c = p.ctrl;
-   const unsigned mb = c->mb;
-   const unsigned n0 = c->nmark[mb][0];
-   const unsigned n1 = c->nmark[mb][1];
-   const unsigned n2 = c->nmark[mb][2];
-   const bool sparse = c->listsvalid != 0 && n0 <= 16384u && n1 <= 4096u && n2 <= 64u;
-   if( !sparse )
-   {
-      if( blockIdx.x == 0 && threadIdx.x == 0 )
-         c->skipsweep = 0;
-      return;
-   }
-   if( blockIdx.x == 0 && threadIdx.x == 0 )
-      c->skipsweep = 1;
-   const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
-   const unsigned total = n0 + n1 + n2;
-   unsigned long long nnzdone = 0;
-   for( unsigned i = blockIdx.x * APPLY_THREADS + threadIdx.x; i < total; i += gridDim.x * APPLY_THREADS )
-   {
-      const int bin = i < n0 ? 0 : (i < n0 + n1 ? 1 : 2);
-      const int row = bin == 0 ? ml[i] : (bin == 1 ? ml[MARKCAP + (i - n0)] : ml[2 * MARKCAP + (i - n0 - n1)]);
-      if( !claimRow(p, row) )
-         continue;
-      nnzdone += (unsigned long long)(p.rowlen[row] & ~ROWLEN_EXACT);
-      const unsigned pos = atomicAdd(&c->nexact[bin], 1u);
-      p.xlist[(bin == 0 ? 0 : (bin == 1 ? p.nsell : p.nsx)) + pos] = row;
-   }
-   addRoundNnz(p, nnzdone, (int)(blockIdx.x * APPLY_THREADS + threadIdx.x) >> 5);
+   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 loadV4Volatile(const void* addr)
+{
+   uint4 v;
+   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr) : "memory");
+   return v;
 }
 
-// ---- rows sharded over peers: the changed-column bits (raised on every rank by every rank's exact kernel) become the
-// ---- change list, so that the list-driven apply step (4 lanes per column) serves this mode as well: a word per thread,
-// ---- one atomic on the list counter per warp
-__global__ void __launch_bounds__(APPLY_THREADS) peer_collect_kernel(const DevProblem p)
+template <bool PEERS>
+__global__ void __launch_bounds__(256) collect_kernel(const DevProblem p)
 {
+   Ctrl* c = p.ctrl;
+   TRACE_KERNEL_START(c, TR_PUSH);
    const int lane = threadIdx.x & 31;
    const int nwords = (p.ncols + 31) >> 5;
-   const int nthreads = gridDim.x * APPLY_THREADS;
-   const int gtid = blockIdx.x * APPLY_THREADS + threadIdx.x;
+   const int nthreads = gridDim.x * blockDim.x;
+   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+   const unsigned epoch = c->epoch + 1u;          // (PEERS: the last block to finish stores it)
+   const int parity = (int)(epoch & 1u);
+   if( PEERS && gtid == 0 && c->round < MAX_HIST )
+   {
+      c->hist_push[c->round] = globaltimer();
+      c->hist_wait[c->round] = 0;
+   }
+   __shared__ int s_stage[256 / 32][1024];       // per warp: the columns of its 32 words, in list order
+   int* stage = s_stage[threadIdx.x >> 5];
    for( int w0 = gtid - lane; w0 < nwords; w0 += nthreads )      // warp-uniform trip count
    {
       const int w = w0 + lane;
@@ -2032,13 +2070,175 @@ __global__ void __launch_bounds__(APPLY_THREADS) peer_collect_kernel(const DevPr
          continue;
       unsigned base = 0u;
       if( lane == 31 )
-         base = atomicAdd(&p.ctrl->nchgcols, (unsigned)total);
-      base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - mine);
+         base = atomicAdd(&c->nchgcols, (unsigned)total);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      // the columns are staged in list order, so that the stores below -- to the list, and through NVLink to the peers --
+      // are contiguous over the lanes of the warp (scattered 16-byte stores cost a link packet each)
+      int pos = incl - mine;
       while( bits != 0u )
       {
-         p.chglist[base++] = 32 * w + __ffs(bits) - 1;
+         stage[pos++] = 32 * w + __ffs(bits) - 1;
          bits &= bits - 1u;
       }
+      __syncwarp();
+      for( int i = lane; i < total; i += 32 )
+      {
+         const int j = stage[i];
+         p.chglist[base + i] = j;
+         if( PEERS )
+         {
+            const PeerTable& t = *p.peers;
+            const longlong2 k = reinterpret_cast<const longlong2*>(p.cand)[j];
+            PeerEntry e;
+            e.a = make_uint4((unsigned)j, epoch, (unsigned)(unsigned long long)k.x, (unsigned)((unsigned long long)k.x >> 32));
+            e.b = make_uint4((unsigned)(unsigned long long)k.y, (unsigned)((unsigned long long)k.y >> 32), epoch, 0u);
+            for( int r = 0; r < t.n; ++r )
+            {
+               if( r == t.rank )
+                  continue;
+               PeerEntry* dst = peerEntries(t, t.box[r], parity, t.rank) + base + i;
+               storeV4(&dst->a, e.a);
+               storeV4(&dst->b, e.b);
+            }
+         }
+      }
+      __syncwarp();
+   }
+   if( !PEERS )
+      return;
+   // the marks of this round are spent on every rank: the rows of the other ranks' shares were swept there
+   {
+      uint4* d = reinterpret_cast<uint4*>(p.dirty);
+      const int nq = (p.nrows + 15) >> 4;
+      for( int i = gtid; i < nq; i += nthreads )
+         d[i] = make_uint4(0u, 0u, 0u, 0u);
+      uint4* f = reinterpret_cast<uint4*>(p.tileflag);
+      const int nf = (p.ntiles + 15) >> 4;
+      for( int i = gtid; i < nf; i += nthreads )
+         f[i] = make_uint4(0u, 0u, 0u, 0u);
+   }
+   __threadfence();
+   __syncthreads();
+   __shared__ bool s_last;
+   if( threadIdx.x == 0 )
+      s_last = atomicAdd(&c->pushticket, 1u) == gridDim.x - 1;
+   __syncthreads();
+   if( !s_last )
+      return;
+   __threadfence();
+   const PeerTable& t = *p.peers;
+   const unsigned n = *reinterpret_cast<volatile unsigned*>(&c->nchgcols);
+   if( (int)threadIdx.x < t.n && (int)threadIdx.x != t.rank )
+   {
+      unsigned long long nnz = 0;
+      for( int i = 0; i < NNZ_SLOTS; ++i )
+         nnz += c->round_nnz[i];
+      PeerHeader* h = peerHeader(t.box[threadIdx.x], parity, t.rank);
+      *reinterpret_cast<volatile unsigned long long*>(&h->nnz) = nnz;
+      *reinterpret_cast<volatile unsigned long long*>(&h->word) =
+         ((unsigned long long)epoch << 32) | (c->cutoff ? 0x80000000ull : 0ull) | (unsigned long long)n;
+   }
+   __syncthreads();
+   if( threadIdx.x == 0 )
+   {
+      c->pushticket = 0;
+      c->epoch = epoch;
+      traceStamp(c, TR_PUSH_END);
+   }
+}
+
+__global__ void __launch_bounds__(256) peer_merge_kernel(const DevProblem p)
+{
+   const PeerTable& t = *p.peers;
+   Ctrl* c = p.ctrl;
+   const unsigned epoch = c->epoch;
+   const int parity = (int)(epoch & 1u);
+   __shared__ unsigned s_count[MAX_PEERS];
+   __shared__ int s_fail;
+   TRACE_KERNEL_START(c, TR_MERGE);
+   if( threadIdx.x == 0 )
+      s_fail = 0;
+   __syncthreads();
+   if( (int)threadIdx.x < t.n )
+   {
+      unsigned cnt = 0u;
+      if( (int)threadIdx.x != t.rank )
+      {
+         PeerHeader* h = peerHeader(t.box[t.rank], parity, threadIdx.x);
+         const unsigned long long tstart = globaltimer();
+         unsigned long long word;
+         for( ;; )
+         {
+            word = *reinterpret_cast<volatile unsigned long long*>(&h->word);
+            if( (unsigned)(word >> 32) == epoch )
+               break;
+            if( globaltimer() - tstart > 5000000000ull )     // 5 s: a peer is gone -- give up instead of hanging the GPU
+            {
+               s_fail = 1;
+               break;
+            }
+         }
+         if( blockIdx.x == 0 && c->round < MAX_HIST )
+            atomicMax(&c->hist_wait[c->round], globaltimer() - tstart);
+         if( !s_fail )
+         {
+            cnt = (unsigned)word & 0x7fffffffu;
+            if( (word & 0x80000000ull) != 0ull )
+               c->cutoff = 1;
+            if( blockIdx.x == 0 )
+               addRoundNnz(p, *reinterpret_cast<volatile unsigned long long*>(&h->nnz), threadIdx.x);
+         }
+      }
+      s_count[threadIdx.x] = cnt;
+   }
+   __syncthreads();
+   TRACE_KERNEL_START(c, TR_MERGE_READY);
+   Sink s;
+   s.cand = p.cand;
+   s.colbits = p.colbits;
+   s.chglist = p.chglist;
+   s.nchgcols = &p.ctrl->nchgcols;
+   s.listed = true;
+   const int nthreads = gridDim.x * blockDim.x;
+   for( int r = 0; r < t.n && !s_fail; ++r )
+   {
+      if( r == t.rank )
+         continue;
+      const PeerEntry* ent = peerEntries(t, t.box[t.rank], parity, r);
+      const unsigned n = s_count[r];
+      for( unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads )
+      {
+         // the entry may still be on its way: both halves carry the exchange number once they have landed
+         uint4 a = loadV4Volatile(&ent[i].a);
+         uint4 b = loadV4Volatile(&ent[i].b);
+         if( a.y != epoch || b.z != epoch )
+         {
+            const unsigned long long tstart = globaltimer();
+            do
+            {
+               a = loadV4Volatile(&ent[i].a);
+               b = loadV4Volatile(&ent[i].b);
+            } while( (a.y != epoch || b.z != epoch) && globaltimer() - tstart < 5000000000ull );
+            if( a.y != epoch || b.z != epoch )
+            {
+               s_fail = 1;
+               break;
+            }
+         }
+         const int j = (int)a.x;
+         const long long kl = (long long)(((unsigned long long)a.w << 32) | a.z);
+         const long long ku = (long long)(((unsigned long long)b.y << 32) | b.x);
+         atomicMin(&p.cand[2 * (size_t)j], kl);
+         atomicMin(&p.cand[2 * (size_t)j + 1], ku);
+         const bool first = raiseColumnBit(s, j);
+         listChangedColumn(s, j, first);
+      }
+   }
+   __syncthreads();
+   if( s_fail && threadIdx.x == 0 )
+   {
+      c->peererror = 1;
+      c->cutoff = 1;
    }
 }
 
@@ -2063,6 +2263,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const Dev
    const int lane = threadIdx.x & 31;
    const int gtid = blockIdx.x * SPARSE_THREADS + threadIdx.x;
    const int nthreads = gridDim.x * SPARSE_THREADS;
+   TRACE_KERNEL_START(c, TR_SPARSE);
 
    for( ;; )
    {
@@ -2320,43 +2521,6 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_list_kernel(const DevP
    }
 }
 
-// ---- barrier over the ranks of a node through peer memory (one thread per rank) -----------------------------------
-// Every rank adds 1 to the arrival word of every rank and spins on its own word.  Two barriers per round: after the
-// exact kernel (all candidates of all ranks are in every key vector) and after the apply kernel (nobody commits into a
-// key vector that is still being read).  The cutoff verdict travels as "epoch of the last cutoff".
-__global__ void peer_barrier_kernel(const DevProblem p)
-{
-   const PeerTable* t = p.peers;
-   Ctrl* c = p.ctrl;
-   if( t == nullptr )
-      return;
-   __threadfence_system();
-   const unsigned epoch = ++c->epoch;
-   if( c->cutoff )
-   {
-      for( int r = 0; r < t->n; ++r )
-         atomicMax_system(&t->sync[r][1], epoch);
-      __threadfence_system();
-   }
-   for( int r = 0; r < t->n; ++r )
-      atomicAdd_system(&t->sync[r][0], 1u);
-   const unsigned target = (unsigned)t->n * epoch;
-   volatile unsigned* mine = t->sync[t->rank];
-   const unsigned long long tstart = globaltimer();
-   while( mine[0] < target )
-   {
-      if( globaltimer() - tstart > 5000000000ull )     // 5 s: a peer is gone -- give up instead of hanging the GPU
-      {
-         c->peererror = 1;
-         c->cutoff = 1;
-         break;
-      }
-   }
-   __threadfence_system();
-   if( mine[1] == epoch )
-      c->cutoff = 1;
-}
-
 // ---- bound (re)initialisation ----------------------------------------------------------------------------------
 __global__ void set_bounds_kernel(const DevProblem p, const double* lb, const double* ub)
 {
@@ -2496,8 +2660,6 @@ __global__ void begin_kernel(Ctrl* c)
       c->resume = 0;
       c->cont = 1;
       c->status = 0;
-      c->listsvalid = 0;
-      c->skipsweep = 0;
       c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
       c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
       return;
@@ -2512,15 +2674,16 @@ __global__ void begin_kernel(Ctrl* c)
    c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
    c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
    c->nsparse = 0;
-   c->listsvalid = 0;
-   c->skipsweep = 0;
    c->logcount = 0;
    c->round_nchg = 0;
    for( int i = 0; i < NNZ_SLOTS; ++i )
       c->round_nnz[i] = 0;
    c->total_nchg = 0;
    c->total_nnz = 0;
+   c->hist_push[0] = 0;
+   c->ntrace = 0;
    c->t_start = globaltimer();
+   traceStamp(c, TR_BEGIN);
 }
 
 // multi-GPU: the verdict travels in the two spare keys behind the candidate vector (MIN all-reduce)

@@ -67,7 +67,10 @@ _SIGNATURES = {
     "gpulin_set_stream": (ctypes.c_int, [_P, _P]),
     "gpulin_sync": (ctypes.c_int, [_P]),
     "gpulin_exchange_buffer": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)]),
-    "gpulin_peer_handles": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_peer_handles": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_group_connect": (ctypes.c_int, [_P, ctypes.c_int]),
+    "gpulin_get_trace": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+    "gpulin_get_exchange_stats": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_peer_connect": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "gpulin_get_keys": (ctypes.c_int, [_P, _P]),
     "gpulin_set_keys": (ctypes.c_int, [_P, _P]),
@@ -254,6 +257,25 @@ class LinearPropagator:
                                                 ctypes.byref(n)))
         return ms[:n.value], nnz[:n.value], nchg[:n.value]
 
+    TRACE_NAMES = {1: "begin", 2: "sweep_sell", 3: "sweep_stream", 4: "sweep_long", 5: "exact", 6: "push", 7: "push_end",
+                   8: "merge", 9: "merge_ready", 10: "apply", 11: "sparse", 12: "sparse_end"}
+
+    def trace(self, maxn: int = 256):
+        """[(kernel name, microseconds since the device-side start of the last call)] in time order"""
+        ids = np.zeros(maxn, dtype=np.int32)
+        us = np.zeros(maxn, dtype=np.float64)
+        n = ctypes.c_int32(0)
+        _check(self._lib.gpulin_get_trace(self._h, ids.ctypes.data, us.ctypes.data, maxn, ctypes.byref(n)))
+        return [(self.TRACE_NAMES.get(int(i), str(int(i))), float(t)) for i, t in zip(ids[:n.value], us[:n.value])]
+
+    def exchange_stats(self, maxn: int = 1024):
+        """several GPUs: per round (ms from the round's start to its exchange or -1, ms the merge waited for the peers)"""
+        before = np.zeros(maxn)
+        wait = np.zeros(maxn)
+        n = ctypes.c_int32(0)
+        _check(self._lib.gpulin_get_exchange_stats(self._h, before.ctypes.data, wait.ctypes.data, maxn, ctypes.byref(n)))
+        return before[:n.value], wait[:n.value]
+
     def set_change_log(self, capacity: int):
         _check(self._lib.gpulin_set_change_log(self._h, int(capacity)))
 
@@ -324,11 +346,11 @@ class LinearPropagator:
         assert keys.shape == (2 * self.ncols + 2,)
         _check(self._lib.gpulin_set_keys(self._h, keys.ctypes.data))
 
-    def peer_handles(self) -> bytes:
+    def peer_handles(self, nranks: int) -> bytes:
         n = ctypes.c_int64(0)
-        _check(self._lib.gpulin_peer_handles(self._h, None, ctypes.byref(n)))
+        _check(self._lib.gpulin_peer_handles(self._h, int(nranks), None, ctypes.byref(n)))
         buf = ctypes.create_string_buffer(n.value)
-        _check(self._lib.gpulin_peer_handles(self._h, buf, ctypes.byref(n)))
+        _check(self._lib.gpulin_peer_handles(self._h, int(nranks), buf, ctypes.byref(n)))
         return buf.raw
 
     def peer_connect(self, rank: int, handles):

@@ -373,9 +373,9 @@ def test_row_longer_than_65536_nonzeros(gpulin):
         rows.append((cols, vals))
         tot = float(vals.sum()) * 5.0            # maximal activity for x in [0, 5]
         lhs.append(-INF)
-        rhs.append({0: tot + 100.0,              # quiet: slack above every |a| (ub - lb)
-                    1: 0.5 * tot,                # tightens many bounds
-                    2: tot - 45.0 + 1e-9}[kind]) # maxdelta = 45 vs slack 45 + 1e-9: on the gate
+        rhs.append({0: tot + 100.0,              # quiet: the maximal activity stays below the side
+                    1: 20.0,                     # tightens every variable with a coefficient of 5 and more
+                    2: 45.0 + 5e-10}[kind])      # maxdelta = 45 vs slack 45 + 5e-10: on the gate (eps = 1e-9)
     rowptr = np.cumsum([0] + [len(c) for c, _ in rows]).astype(np.int64)
     prob = dict(rowptr=rowptr, colidx=np.concatenate([c for c, _ in rows]), vals=np.concatenate([v for _, v in rows]),
                 lhs=np.array(lhs), rhs=np.array(rhs), lb=np.zeros(ncols), ub=np.full(ncols, 5.0),

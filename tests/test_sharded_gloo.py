@@ -38,6 +38,13 @@ class OracleEngine:
         self.keys = torch.from_numpy(keys)
         return self.keys
 
+    # the packed exchange of the product's multi-GPU round (sharded.ReplicatedPropagator)
+    def get_keys(self):
+        return sharded.encode_keys(self.lb, self.ub)
+
+    def set_keys(self, keys):
+        self.keys = torch.from_numpy(np.ascontiguousarray(keys))
+
     def round_apply(self):
         nlb, nub, cutoff = sharded.decode_keys(self.keys.numpy())
         cross = nlb > nub
@@ -57,7 +64,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, probs, out):
+def _worker(rank, world, port, probs, out, packed=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -66,7 +73,8 @@ def _worker(rank, world, port, probs, out):
             cuts = sharded.partition_rows(prob["rowptr"], world)
             eng = OracleEngine(prob, (int(cuts[rank]), int(cuts[rank + 1])), **numerics)
             eng.set_bounds(prob["lb"], prob["ub"])
-            res = sharded.ShardedPropagator(eng).propagate(maxrounds=500)
+            driver = sharded.ReplicatedPropagator if packed else sharded.ShardedPropagator
+            res = driver(eng).propagate(maxrounds=500)
             lb, ub = eng.get_bounds()
             out[(name, rank)] = (res, lb, ub)
     finally:
@@ -92,8 +100,28 @@ def test_partition_rows_balances_nonzeros():
         assert nnz.max() - nnz.min() <= 2 * np.diff(prob["rowptr"]).max()
 
 
+def test_packed_exchange_equals_the_dense_min():
+    # pack_changes / merge_changes (the host mirror of peer_push_kernel / peer_merge_kernel): merging the packets of two
+    # ranks into either rank's keys == the elementwise MIN of the two key vectors
+    rng = np.random.default_rng(1)
+    lb, ub = rng.normal(size=50), rng.normal(size=50) + 5.0
+    base = sharded.encode_keys(lb, ub)
+    a, b = base.copy(), base.copy()
+    ia, ib = rng.integers(0, 100, size=30), rng.integers(0, 100, size=30)
+    a[ia] -= rng.integers(1, 1000, size=30)
+    b[ib] -= rng.integers(1, 1000, size=30)
+    want = np.minimum(a, b)
+    for mine, other in ((a, b), (b, a)):
+        got = mine.copy()
+        cols, pairs = sharded.pack_changes(base, other)
+        assert len(cols) <= 30
+        sharded.merge_changes(got, cols, pairs)
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.timeout(300)
-def test_two_ranks_reach_the_single_process_fixpoint():
+@pytest.mark.parametrize("packed", [False, True])
+def test_two_ranks_reach_the_single_process_fixpoint(packed):
     probs = {
         "bell5": (load_golden("bell5", "1e-9")[0], dict(boundstreps=1e-9)),
         "egout": (load_golden("egout", "1e-9")[0], dict(boundstreps=1e-9)),
@@ -105,7 +133,7 @@ def test_two_ranks_reach_the_single_process_fixpoint():
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, port, probs, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, probs, out, packed), nprocs=world, join=True)
         out = dict(out)
     for name, (prob, numerics) in probs.items():
         want = oracle.propagate(prob, **numerics)
