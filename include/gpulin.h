@@ -107,6 +107,16 @@ int gpulin_set_bounds(gpulin_t* h, const double* lb, const double* ub);
 /** same, bounds already on the device of this handle */
 int gpulin_set_bounds_device(gpulin_t* h, const double* d_lb, const double* d_ub);
 
+/** bounds as 2 bits per column against resident reference bounds.  At a node of a MIP almost every column sits at its
+ *  global bounds or is fixed to one of them: 2 bits of information instead of 16 bytes over PCIe.
+ *  gpulin_set_reference_bounds uploads the reference (e.g. SCIPvarGetLbGlobal/UbGlobal, pub_var.h:853,865) once;
+ *  gpulin_set_bounds_packed then takes codes[(ncols + 15) / 16] words, column j in bits 2 (j % 16) .. of word j / 16:
+ *  0 = reference bounds, 1 = fixed to the reference lower bound, 2 = fixed to the reference upper bound, 3 = explicit: the
+ *  bounds follow in (idx, lb, ub)[nexplicit].  Marks every row, like gpulin_set_bounds */
+int gpulin_set_reference_bounds(gpulin_t* h, const double* lb, const double* ub);
+int gpulin_set_bounds_packed(gpulin_t* h, const uint32_t* codes, int64_t nexplicit, const int32_t* idx, const double* lb,
+   const double* ub);
+
 /** overwrites n bounds (tightened or relaxed: branching, backtracking) and marks only the rows of those
  *  columns -- the counterpart of eventExecLinear's SCIPmarkConsPropagate (cons_linear.c:17229) */
 int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, const double* lb, const double* ub);
@@ -148,6 +158,10 @@ int gpulin_set_change_log(gpulin_t* h, int64_t capacity);
 /** copies up to maxn log entries of the last gpulin_propagate call; *n gets the number of entries that
  *  were produced (if *n > capacity the log overflowed and only the first `capacity` are valid) */
 int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n);
+
+/** the same log as 12-byte records { uint32 column | is_upper << 31, new bound as 2 x uint32 (low, high word) }; the round
+ *  of an entry follows from its position: the log is round ordered, gpulin_get_round_stats gives the counts per round */
+int gpulin_get_changes_packed(gpulin_t* h, void* out, int64_t maxn, int64_t* n);
 
 /** per-round statistics of the last gpulin_propagate call (up to maxn rounds; any output array may be NULL):
  *  device time [ms] (%globaltimer stamps taken by the kernels), nonzeros swept, bound changes accepted */

@@ -93,6 +93,10 @@ struct gpulin
    double*     d_updlb = nullptr;
    double*     d_updub = nullptr;
    int64_t     updcap = 0;
+   double2*    d_ref = nullptr;     // reference bounds of gpulin_set_bounds_packed (allocated on first use)
+   unsigned*   d_codes = nullptr;   // ... and the staged codes, 2 bits per column
+   unsigned*   d_packlog = nullptr; // staging of gpulin_get_changes_packed (12 bytes per entry)
+   int64_t     packlogcap = 0;
    cudaStream_t stream = nullptr;
    bool        ownstream = true;
    cudaStream_t aux[2] = {nullptr, nullptr};     // the medium / long sweeps run beside the short sweep
@@ -781,6 +785,9 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    cudaFree(h->d_updidx);
    cudaFree(h->d_updlb);
    cudaFree(h->d_updub);
+   cudaFree(h->d_ref);
+   cudaFree(h->d_codes);
+   cudaFree(h->d_packlog);
    for( int i = 0; i < 2; ++i )
    {
       if( h->aux[i] != nullptr )
@@ -849,6 +856,105 @@ extern "C" int gpulin_set_bounds(gpulin_t* h, const double* lb, const double* ub
    return gpulin_set_bounds_device(h, h->d_tmplb, h->d_tmpub);
 }
 
+static int growUpdateStaging(gpulin* h, int64_t n)
+{
+   if( n <= h->updcap )
+      return GPULIN_OK;
+   CU(cudaStreamSynchronize(h->stream));
+   cudaFree(h->d_updidx);
+   cudaFree(h->d_updlb);
+   cudaFree(h->d_updub);
+   h->d_updidx = nullptr;
+   h->d_updlb = nullptr;
+   h->d_updub = nullptr;
+   h->updcap = 0;
+   const int64_t cap = std::max<int64_t>(n, 1024);
+   if( cudaMalloc((void**)&h->d_updidx, sizeof(int) * (size_t)cap) != cudaSuccess
+      || cudaMalloc((void**)&h->d_updlb, sizeof(double) * (size_t)cap) != cudaSuccess
+      || cudaMalloc((void**)&h->d_updub, sizeof(double) * (size_t)cap) != cudaSuccess )
+      return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the bound-update staging failed");
+   h->updcap = cap;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_set_reference_bounds(gpulin_t* h, const double* lb, const double* ub)
+{
+   if( h == nullptr || lb == nullptr || ub == nullptr )
+      return fail(GPULIN_ERR_ARG, "NULL argument");
+   CU(cudaSetDevice(h->device));
+   if( h->d_ref == nullptr )
+   {
+      if( cudaMalloc((void**)&h->d_ref, sizeof(double2) * ((size_t)h->ncols + 1)) != cudaSuccess
+         || cudaMalloc((void**)&h->d_codes, sizeof(unsigned) * ((size_t)h->ncols / 16 + 2)) != cudaSuccess )
+         return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the reference bounds failed");
+   }
+   CU(cudaMemcpyAsync(h->d_tmplb, lb, sizeof(double) * (size_t)h->ncols, cudaMemcpyHostToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->d_tmpub, ub, sizeof(double) * (size_t)h->ncols, cudaMemcpyHostToDevice, h->stream));
+   set_reference_kernel<<<gridFor(h, h->ncols), 256, 0, h->stream>>>((int)h->ncols, h->d_tmplb, h->d_tmpub, h->d_ref);
+   CU(cudaGetLastError());
+   CU(cudaStreamSynchronize(h->stream));     // (the host arrays may be pageable and temporary)
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_set_bounds_packed(gpulin_t* h, const uint32_t* codes, int64_t nexplicit, const int32_t* idx,
+   const double* lb, const double* ub)
+{
+   if( h == nullptr || codes == nullptr || nexplicit < 0 || (nexplicit > 0 && (idx == nullptr || lb == nullptr || ub == nullptr)) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( h->d_ref == nullptr )
+      return fail(GPULIN_ERR_STATE, "gpulin_set_bounds_packed before gpulin_set_reference_bounds");
+   for( int64_t i = 0; i < nexplicit; ++i )
+   {
+      if( idx[i] < 0 || idx[i] >= h->ncols )
+         return fail(GPULIN_ERR_ARG, "column index %d out of range", idx[i]);
+   }
+   CU(cudaSetDevice(h->device));
+   const size_t nwords = ((size_t)h->ncols + 15) / 16;
+   CU(cudaMemcpyAsync(h->d_codes, codes, sizeof(unsigned) * nwords, cudaMemcpyHostToDevice, h->stream));
+   set_bounds_packed_kernel<<<gridFor(h, std::max(h->ncols, h->nrows)), 256, 0, h->stream>>>(h->p, h->d_ref, h->d_codes);
+   if( nexplicit > 0 )
+   {
+      OK(growUpdateStaging(h, nexplicit));
+      CU(cudaMemcpyAsync(h->d_updidx, idx, sizeof(int) * (size_t)nexplicit, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_updlb, lb, sizeof(double) * (size_t)nexplicit, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_updub, ub, sizeof(double) * (size_t)nexplicit, cudaMemcpyHostToDevice, h->stream));
+      update_explicit_kernel<<<gridFor(h, nexplicit), 256, 0, h->stream>>>(h->p, nexplicit, h->d_updidx, h->d_updlb, h->d_updub);
+   }
+   CU(cudaGetLastError());
+   h->smallcols = -1;
+   ++h->version;
+   h->havebounds = true;
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_changes_packed(gpulin_t* h, void* out, int64_t maxn, int64_t* n)
+{
+   if( h == nullptr || n == nullptr || maxn < 0 || (maxn > 0 && out == nullptr) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   CU(cudaSetDevice(h->device));
+   const int64_t produced = (int64_t)h->h_ctrl->logcount;
+   *n = produced;
+   const int64_t m = std::min(std::min(produced, h->logcap), maxn);
+   if( m <= 0 )
+      return GPULIN_OK;
+   if( m > h->packlogcap )
+   {
+      CU(cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_packlog);
+      h->d_packlog = nullptr;
+      h->packlogcap = 0;
+      const int64_t cap = std::max<int64_t>(h->logcap, m);
+      if( cudaMalloc((void**)&h->d_packlog, 12 * (size_t)cap) != cudaSuccess )
+         return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the packed change log failed");
+      h->packlogcap = cap;
+   }
+   pack_log_kernel<<<gridFor(h, m), 256, 0, h->stream>>>(h->d_log, m, h->d_packlog);
+   CU(cudaGetLastError());
+   CU(cudaMemcpyAsync(out, h->d_packlog, 12 * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}
+
 extern "C" int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, const double* lb, const double* ub)
 {
    if( h == nullptr || n < 0 || (n > 0 && (idx == nullptr || lb == nullptr || ub == nullptr)) )
@@ -881,23 +987,7 @@ extern "C" int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, 
          h->smallcols += n;
       return GPULIN_OK;
    }
-   if( n > h->updcap )
-   {
-      CU(cudaStreamSynchronize(h->stream));
-      cudaFree(h->d_updidx);
-      cudaFree(h->d_updlb);
-      cudaFree(h->d_updub);
-      h->d_updidx = nullptr;
-      h->d_updlb = nullptr;
-      h->d_updub = nullptr;
-      h->updcap = 0;
-      const int64_t cap = std::max<int64_t>(n, 1024);
-      if( cudaMalloc((void**)&h->d_updidx, sizeof(int) * (size_t)cap) != cudaSuccess
-         || cudaMalloc((void**)&h->d_updlb, sizeof(double) * (size_t)cap) != cudaSuccess
-         || cudaMalloc((void**)&h->d_updub, sizeof(double) * (size_t)cap) != cudaSuccess )
-         return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the bound-update staging failed");
-      h->updcap = cap;
-   }
+   OK(growUpdateStaging(h, n));
    CU(cudaMemcpyAsync(h->d_updidx, idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
    CU(cudaMemcpyAsync(h->d_updlb, lb, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
    CU(cudaMemcpyAsync(h->d_updub, ub, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));

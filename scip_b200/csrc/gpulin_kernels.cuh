@@ -2551,6 +2551,77 @@ __global__ void set_bounds_kernel(const DevProblem p, const double* lb, const do
       p.tileflag[t] = 1;
 }
 
+// ---- bounds as 2 bits per column against resident reference bounds (gpulin_set_bounds_packed): at a node of a MIP almost
+// ---- every column sits at its reference (global) bounds or is fixed to one of them -- 2 bits of information, not 16 bytes
+constexpr unsigned BND_REF = 0u;        // the reference bounds
+constexpr unsigned BND_FIXLB = 1u;      // fixed to the reference lower bound
+constexpr unsigned BND_FIXUB = 2u;      // fixed to the reference upper bound
+constexpr unsigned BND_EXPLICIT = 3u;   // on the explicit list (scattered by update_explicit_kernel afterwards)
+__global__ void set_bounds_packed_kernel(const DevProblem p, const double2* ref, const unsigned* codes)
+{
+   const int stride = gridDim.x * blockDim.x;          // a multiple of 32: a warp owns the 32 columns of one word of freebits
+   const int nallwords = max(p.nfreewords, (p.ncols + 31) / 32);
+   for( int j0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < nallwords * 32; j0 += stride )
+   {
+      const int j = j0 + (threadIdx.x & 31);
+      bool fr = false;
+      if( j < p.ncols )
+      {
+         const unsigned code = (codes[j >> 4] >> (2 * (j & 15))) & 3u;
+         const double2 r = ref[j];
+         const double l = (code == BND_FIXUB ? r.y : r.x) + 0.0;
+         const double u = (code == BND_FIXLB ? r.x : r.y) + 0.0;
+         const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
+         reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+         p.bndf[j] = midHalfWidth(l, u);
+         fr = isFree01(l, u);
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, fr);
+      if( (threadIdx.x & 31) == 0 )
+         p.freebits[j0 >> 5] = word;
+   }
+   for( int w = blockIdx.x * blockDim.x + threadIdx.x; w < (p.ncols + 31) / 32; w += stride )
+      p.colbits[w] = 0u;
+   for( int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nrows; r += stride )
+      p.dirty[r] = ROW_MARKED;
+   for( int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.ntiles; t += stride )
+      p.tileflag[t] = 1;
+}
+__global__ void set_reference_kernel(int ncols, const double* lb, const double* ub, double2* ref)
+{
+   const int stride = gridDim.x * blockDim.x;
+   for( int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += stride )
+      ref[j] = make_double2(lb[j] + 0.0, ub[j] + 0.0);
+}
+// the explicit entries of a packed bound vector (every row is marked already)
+__global__ void update_explicit_kernel(const DevProblem p, long long nupd, const int* idx, const double* lb, const double* ub)
+{
+   const long long stride = (long long)gridDim.x * blockDim.x;
+   for( long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nupd; i += stride )
+   {
+      const int j = idx[i];
+      const double l = lb[i] + 0.0;
+      const double u = ub[i] + 0.0;
+      const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
+      reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
+      noteBounds(p, j, l, u);
+   }
+}
+// the change log as 12-byte records: { column | is_upper << 31, new bound (2 x 32 bits) }; the round of an entry follows
+// from its position (the log is round ordered, the per-round counts come with gpulin_get_round_stats)
+__global__ void pack_log_kernel(const ChangeRec* log, long long n, unsigned* out)
+{
+   const long long stride = (long long)gridDim.x * blockDim.x;
+   for( long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride )
+   {
+      const ChangeRec r = log[i];
+      const unsigned long long b = (unsigned long long)__double_as_longlong(r.newbound);
+      out[3 * i] = (unsigned)r.var | (r.is_upper ? 0x80000000u : 0u);
+      out[3 * i + 1] = (unsigned)b;
+      out[3 * i + 2] = (unsigned)(b >> 32);
+   }
+}
+
 __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const int* idx, const double* lb, const double* ub)
 {
    const long long stride = (long long)gridDim.x * blockDim.x;

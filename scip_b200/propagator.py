@@ -69,6 +69,9 @@ _SIGNATURES = {
     "gpulin_exchange_buffer": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_peer_handles": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_group_connect": (ctypes.c_int, [_P, ctypes.c_int]),
+    "gpulin_set_reference_bounds": (ctypes.c_int, [_P, _P, _P]),
+    "gpulin_set_bounds_packed": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P]),
+    "gpulin_get_changes_packed": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_get_trace": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_get_exchange_stats": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_peer_connect": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
@@ -188,6 +191,54 @@ class LinearPropagator:
     def get_bounds_ptr(self, lb_ptr: int, ub_ptr: int, on_device: bool):
         fn = self._lib.gpulin_get_bounds_device if on_device else self._lib.gpulin_get_bounds
         _check(fn(self._h, lb_ptr, ub_ptr))
+
+    def set_reference_bounds(self, lb, ub):
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        assert lb.shape == (self.ncols,) and ub.shape == (self.ncols,)
+        _check(self._lib.gpulin_set_reference_bounds(self._h, lb.ctypes.data, ub.ctypes.data))
+        self._ref = (lb + 0.0, ub + 0.0)
+
+    def pack_bounds(self, lb, ub):
+        """(codes[uint32], idx, lb, ub of the explicit entries) of bounds against the reference bounds"""
+        rl, ru = self._ref
+        lb = np.asarray(lb, dtype=np.float64) + 0.0
+        ub = np.asarray(ub, dtype=np.float64) + 0.0
+        code = np.full(self.ncols, 3, dtype=np.uint32)
+        code[(lb == rl) & (ub == rl)] = 1
+        code[(lb == ru) & (ub == ru)] = 2
+        code[(lb == rl) & (ub == ru)] = 0
+        idx = np.flatnonzero(code == 3).astype(np.int32)
+        pad = (-self.ncols) % 16
+        c = np.concatenate([code, np.zeros(pad, dtype=np.uint32)]).reshape(-1, 16)
+        words = (c << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+        return np.ascontiguousarray(words), idx, np.ascontiguousarray(lb[idx]), np.ascontiguousarray(ub[idx])
+
+    def set_bounds_packed(self, words, idx, lb, ub):
+        _check(self._lib.gpulin_set_bounds_packed(self._h, words.ctypes.data, len(idx), idx.ctypes.data if len(idx) else None,
+                                                  lb.ctypes.data if len(idx) else None, ub.ctypes.data if len(idx) else None))
+        _check(self._lib.gpulin_sync(self._h))
+
+    def set_bounds_packed_ptr(self, words_ptr: int, nexplicit: int = 0, idx_ptr=None, lb_ptr=None, ub_ptr=None):
+        """raw pointers (pinned host memory: asynchronous copies)"""
+        _check(self._lib.gpulin_set_bounds_packed(self._h, words_ptr, int(nexplicit), idx_ptr, lb_ptr, ub_ptr))
+
+    def changes_packed(self, maxn: int):
+        """the change log as (var, is_upper, newbound) arrays + number of entries produced"""
+        buf = np.empty(3 * max(maxn, 1), dtype=np.uint32)
+        n = ctypes.c_int64(0)
+        _check(self._lib.gpulin_get_changes_packed(self._h, buf.ctypes.data, maxn, ctypes.byref(n)))
+        m = min(n.value, maxn)
+        rec = buf[:3 * m].reshape(m, 3)
+        var = (rec[:, 0] & 0x7FFFFFFF).astype(np.int32)
+        upper = (rec[:, 0] >> 31).astype(np.int32)
+        val = (rec[:, 1].astype(np.uint64) | (rec[:, 2].astype(np.uint64) << np.uint64(32))).view(np.float64)
+        return var, upper, val, n.value
+
+    def changes_packed_ptr(self, out_ptr: int, maxn: int) -> int:
+        n = ctypes.c_int64(0)
+        _check(self._lib.gpulin_get_changes_packed(self._h, out_ptr, maxn, ctypes.byref(n)))
+        return n.value
 
     def update_bounds(self, idx, lb, ub):
         idx = np.ascontiguousarray(idx, dtype=np.int32)

@@ -393,3 +393,43 @@ def test_cancellation_and_huge_counts_follow_the_reference(gpulin):
         for bs in (0.05, 1e-9):
             got, _ = gpu_vs_oracle(gpulin, prob, maxrounds=100, what=f"{name} bs={bs}", boundstreps=bs)
             assert (got["status"] == gpulin.CUTOFF) == cutoff, name
+
+
+def test_packed_bounds_and_packed_change_log(gpulin):
+    """gpulin_set_bounds_packed (2 bits per column against resident reference bounds + an explicit list) gives the state
+    gpulin_set_bounds gives; gpulin_get_changes_packed returns the log of gpulin_get_changes in 12-byte records"""
+    prob = synth.mixed_knapsack(1500, 15_000, 300_000, seed=41, dense_range=(1200, 2500))
+    rng = np.random.default_rng(5)
+    n = len(prob["lb"])
+    lb, ub = prob["lb"].copy(), prob["ub"].copy()
+    fin = (np.abs(lb) < 1e19) & (np.abs(ub) < 1e19)
+    u = rng.random(n)
+    tolb = fin & (u < 0.03)
+    toub = fin & (u >= 0.03) & (u < 0.05)
+    shrink = fin & (u >= 0.05) & (u < 0.07) & (ub - lb >= 2.0)
+    ub[tolb] = lb[tolb]
+    lb[toub] = ub[toub]
+    ub[shrink] = np.floor(0.5 * (lb[shrink] + ub[shrink]))
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.set_change_log(200_000)
+        lp.set_bounds(lb, ub)
+        a = lp.propagate()
+        alb, aub = lp.get_bounds()
+        log, nlog = lp.changes(200_000)
+        lp.set_reference_bounds(prob["lb"], prob["ub"])
+        words, idx, elb, eub = lp.pack_bounds(lb, ub)
+        assert len(words) == (n + 15) // 16 and 0 < len(idx) <= int(shrink.sum()) + 1
+        lp.set_bounds_packed(words, idx, elb, eub)
+        b = lp.propagate()
+        blb, bub = lp.get_bounds()
+        var, upper, val, npk = lp.changes_packed(200_000)
+    want = oracle.propagate(prob, lb=lb, ub=ub)
+    assert a["status"] == b["status"] == want["status"]
+    if want["status"] != oracle.STATUS_CUTOFF:
+        assert (a["nrounds"], a["nchanges"]) == (b["nrounds"], b["nchanges"]) == (want["nrounds"], want["nchanges"])
+        assert np.array_equal(alb, blb) and np.array_equal(aub, bub)
+        assert_bounds_match(blb, bub, want["lb"], want["ub"], prob["vartype"], what="packed bounds")
+        assert npk == nlog == b["nchanges"]
+        # same entries (the order inside a round is whatever the atomics made it: compare as sets per round)
+        key = lambda v, up, x: sorted(zip(v.tolist(), up.tolist(), x.tolist()))  # noqa: E731
+        assert key(var, upper, val) == key(log["var"], log["is_upper"], log["newbound"])
