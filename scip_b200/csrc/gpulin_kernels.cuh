@@ -1671,18 +1671,29 @@ __device__ __forceinline__ void markColumnRows(const DevProblem& p, int j, int f
    markColumnRows(p, j, first, step, which, listfull);
 }
 
-// loop control (propagateDomains, solve.c:766-787), run by one thread after the last column was applied
+// loop control (propagateDomains, solve.c:766-787), run by ONE WARP after the last column was applied (all 32 lanes call
+// it): the lanes add up the spread counters of swept nonzeros, lane 0 does the rest -- every load is issued before the
+// first store, so that the step costs two memory round trips instead of one per field
 template <bool GRAPH>
 __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle handle)
 {
-   const unsigned long long nchg = c->round_nchg;
-   const int r = c->round;
-   unsigned long long nnz = 0;
-   for( int i = 0; i < NNZ_SLOTS; ++i )
-   {
-      nnz += c->round_nnz[i];
-      c->round_nnz[i] = 0;
-   }
+   static_assert(NNZ_SLOTS == 64, "two slots per lane");
+   const int lane = threadIdx.x & 31;
+   unsigned long long nnz = __ldcg(&c->round_nnz[lane]) + __ldcg(&c->round_nnz[lane + 32]);
+   const unsigned long long nchg = __ldcg(&c->round_nchg);
+   const int r = __ldcg(&c->round);
+   const int cutoff = __ldcg(&c->cutoff);
+   const int maxrounds = __ldcg(&c->maxrounds);
+   const unsigned mb = __ldcg(&c->mb);
+   const unsigned long long tnchg = __ldcg(&c->total_nchg);
+   const unsigned long long tnnz = __ldcg(&c->total_nnz);
+   c->round_nnz[lane] = 0;
+   c->round_nnz[lane + 32] = 0;
+#pragma unroll
+   for( int m = 16; m >= 1; m >>= 1 )
+      nnz += __shfl_xor_sync(0xffffffffu, nnz, m);
+   if( lane != 0 )
+      return;
    if( r < MAX_HIST )
    {
       c->hist_time[r] = globaltimer();
@@ -1691,22 +1702,22 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
       if( r + 1 < MAX_HIST )
          c->hist_push[r + 1] = 0;       // (set by the exchange of that round, if it has one)
    }
-   c->total_nchg += nchg;
-   c->total_nnz += nnz;
+   c->total_nchg = tnchg + nchg;
+   c->total_nnz = tnnz + nnz;
    c->round_nchg = 0;
    c->ticket = 0;
    c->nchgcols = 0;
    c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
    // the list this apply step filled becomes the one a sparse round reads; the other one is empty again
-   c->nmark[c->mb][0] = c->nmark[c->mb][1] = c->nmark[c->mb][2] = 0;
-   c->mb ^= 1u;
+   c->nmark[mb][0] = c->nmark[mb][1] = c->nmark[mb][2] = 0;
+   c->mb = mb ^ 1u;
    c->round = r + 1;
    int cont = 0;
-   if( c->cutoff )
+   if( cutoff )
       c->status = 1;
    else if( nchg == 0 )
       c->status = 0;
-   else if( c->maxrounds > 0 && r + 1 >= c->maxrounds )
+   else if( maxrounds > 0 && r + 1 >= maxrounds )
       c->status = 2;
    else
       cont = 1;
@@ -1836,7 +1847,7 @@ __device__ __forceinline__ void logChangesBuffered(const DevProblem& p, WarpLog&
 // column; returns the number of bound changes this thread accepted
 template <int G>
 __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlist, int gtid, int nthreads, int round, int logcap,
-   ChangeRec* warplogbuf = nullptr, bool markall = false)
+   ChangeRec* warplogbuf = nullptr)
 {
    WarpLog wlog;
    wlog.buf = warplogbuf;
@@ -1907,7 +1918,7 @@ __device__ __forceinline__ int applyListPhase(const DevProblem& p, unsigned nlis
       }
       // every candidate that reached the column beat the round-start bound, so the column changes (a crossing pair
       // clamped back to its old value is the one exception): the group marks without waiting for the verdict
-      if( valid && !markall )
+      if( valid )
          markRowRange(p, q0, q1, gl, G, which, listfull);
    }
    if( wlog.buf != nullptr )
@@ -1970,7 +1981,32 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
       // not move is finished by the filter, or reproduces candidates that are in place already: the result is the same).
       // The decision depends on the length of the change list alone, so every rank of a node takes it alike.
       const bool markall = nlist >= p.markall_min;
-      mychg += applyListPhase<APPLY_G>(p, nlist, gtid, nthreads, round, logcap, s_log[MODE == APPLY_LIST ? threadIdx.x >> 5 : 0], markall);
+      if( !markall )
+         mychg += applyListPhase<APPLY_G>(p, nlist, gtid, nthreads, round, logcap, s_log[MODE == APPLY_LIST ? threadIdx.x >> 5 : 0]);
+      else
+      {
+         // a thread per column: accept the bounds, log the changes
+         WarpLog wlog;
+         wlog.buf = s_log[MODE == APPLY_LIST ? threadIdx.x >> 5 : 0];
+         wlog.n = 0;
+         const unsigned trips = (nlist + nthreads - 1) / nthreads;       // uniform
+         for( unsigned it = 0; it < trips; ++it )
+         {
+            const unsigned i = it * nthreads + gtid;
+            const int j = i < nlist ? p.chglist[i] : -1;
+            bool lbchg = false;
+            bool ubchg = false;
+            double2 nb = make_double2(0.0, 0.0);
+            if( j >= 0 )
+            {
+               mychg += applyColumn(p, j, nb, lbchg, ubchg);
+               atomicAnd(&p.colbits[j >> 5], ~(1u << (j & 31)));
+            }
+            if( logcap > 0 )
+               logChangesBuffered(p, wlog, j, round, logcap, lbchg, ubchg, nb);
+         }
+         flushWarpLog(p, wlog, logcap);
+      }
       if( markall )
       {
          uint4* d = reinterpret_cast<uint4*>(p.dirty);
@@ -1990,17 +2026,19 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p
    if( lane == 0 && mychg != 0 )
       atomicAdd(&s_nchg, mychg);
    __syncthreads();
+   __shared__ bool s_last;
    if( threadIdx.x == 0 )
    {
       if( s_nchg != 0 )
          atomicAdd(&c->round_nchg, (unsigned long long)s_nchg);
       __threadfence();
-      const unsigned t = atomicAdd(&c->ticket, 1u);
-      if( t == gridDim.x - 1 )
-      {
-         __threadfence();
-         controlStep<GRAPH>(c, handle);
-      }
+      s_last = atomicAdd(&c->ticket, 1u) == gridDim.x - 1;
+   }
+   __syncthreads();
+   if( s_last && threadIdx.x < 32 )
+   {
+      __threadfence();
+      controlStep<GRAPH>(c, handle);
    }
 }
 
@@ -2293,16 +2331,22 @@ __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const Dev
       if( lane == 0 && mychg != 0 )
          atomicAdd(&s_nchg, mychg);
       __syncthreads();
-      if( threadIdx.x == 0 && s_nchg != 0 )
-         atomicAdd(&c->round_nchg, (unsigned long long)s_nchg);
-      __threadfence();
-      grid.sync();
-
-      // ---- loop control
-      if( gtid == 0 )
+      // ---- loop control: by the block that finishes the apply phase last, in front of the second grid sync
+      __shared__ bool s_last;
+      if( threadIdx.x == 0 )
       {
+         if( s_nchg != 0 )
+            atomicAdd(&c->round_nchg, (unsigned long long)s_nchg);
+         __threadfence();
+         s_last = atomicAdd(&c->ticket, 1u) == gridDim.x - 1;
+      }
+      __syncthreads();
+      if( s_last && threadIdx.x < 32 )
+      {
+         __threadfence();
          controlStep<GRAPH>(c, handle);
-         ++c->nsparse;
+         if( threadIdx.x == 0 )
+            ++c->nsparse;
          __threadfence();
       }
       grid.sync();
@@ -2438,8 +2482,10 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
          atomicAdd(&s_nchg, mychg);
       __syncthreads();
       if( tid == 0 )
-      {
          c->round_nchg = (unsigned long long)s_nchg;
+      if( tid < 32 )
+      {
+         __syncwarp();
          controlStep<false>(c, 0);
       }
       __syncthreads();
