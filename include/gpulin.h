@@ -146,6 +146,15 @@ int gpulin_reset_from(gpulin_t* h, gpulin_t* base);
 int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
    const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges);
 
+/** the same, and what every probe implied: probe i's accepted bound changes in round order are chg[chgbeg[i] .. chgbeg[i+1])
+ *  (chgbeg has nprobes + 1 entries) -- the proplbs / propubs that SCIPapplyProbingVar returns per candidate
+ *  (prop_probing.c:1203-1303), in sparse form; the bounds at the probe's fixpoint are the node's bounds overwritten by
+ *  these entries in order.  *nchg = entries produced; if they exceed maxchg the call fails with GPULIN_ERR_ARG and *nchg
+ *  says how many are needed */
+int gpulin_probe_batch_changes(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
+   const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges, int64_t* chgbeg, gpulin_change* chg,
+   int64_t maxchg, int64_t* nchg);
+
 /** copies the current bounds to host memory */
 int gpulin_get_bounds(gpulin_t* h, double* lb, double* ub);
 

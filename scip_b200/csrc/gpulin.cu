@@ -124,6 +124,9 @@ struct gpulin
    double*     d_probelb = nullptr;
    double*     d_probeub = nullptr;
    int64_t     proberescap = 0;
+   ChangeRec*  d_probelog = nullptr;   // change logs of the probes of a batch (gpulin_probe_batch_changes) + the cursor behind them
+   unsigned long long* d_probecursor = nullptr;
+   int64_t     probelogcap = 0;
    uint64_t    version = 1;         // counts the calls that can change this handle's bounds (workers compare it)
    uint64_t    syncedversion = 0;   // probing worker: version of the base handle it last took the bounds from
    int64_t     smallcols = -1;      // columns updated since the last clean fixpoint (< 0: the marks are not all on the list)
@@ -749,6 +752,8 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    for( gpulin* w : h->workers )
       gpulin_destroy(w);
    h->workers.clear();
+   cudaFree(h->d_probelog);
+   cudaFree(h->d_probecursor);
    cudaFree(h->d_proberes);
    cudaFree(h->d_probevar);
    cudaFree(h->d_probelb);
@@ -1130,8 +1135,9 @@ extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
 // BASELINE config 5 / SCIPapplyProbingVar (prop_probing.c:1254-1279): probe i starts from the bounds of `base` (the
 // node), sets variable var[i] to [lb[i], ub[i]] and propagates to its fixpoint.  nworkers clones of the base handle keep
 // that many probes in flight on their own streams; a worker returns to the node by undoing its change log.
-extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
-   const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges)
+static int probeBatchImpl(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
+   const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges, bool wantlog, int64_t* chgbeg,
+   gpulin_change* chg, int64_t maxchg, int64_t* nchg)
 {
    if( base == nullptr || nworkers < 1 || nprobes < 0 || (nprobes > 0 && (var == nullptr || lb == nullptr || ub == nullptr)) )
       return fail(GPULIN_ERR_ARG, "invalid argument");
@@ -1184,6 +1190,21 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
    }
    ProbeResult* d_res = (ProbeResult*)base->d_proberes;
    const bool general = false;
+   if( wantlog )
+   {
+      const int64_t want = std::max<int64_t>(maxchg, 1);
+      if( want > base->probelogcap )
+      {
+         cudaFree(base->d_probelog);
+         base->d_probelog = nullptr;
+         base->probelogcap = 0;
+         CU(cudaMalloc((void**)&base->d_probelog, sizeof(ChangeRec) * (size_t)want));
+         base->probelogcap = want;
+      }
+      if( base->d_probecursor == nullptr )
+         CU(cudaMalloc((void**)&base->d_probecursor, sizeof(unsigned long long)));
+      CU(cudaMemset(base->d_probecursor, 0, sizeof(unsigned long long)));
+   }
    if( nprobes > 0 && !general )
    {
       CU(cudaMemcpy(base->d_probevar, var, sizeof(int) * (size_t)nprobes, cudaMemcpyHostToDevice));
@@ -1201,7 +1222,8 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
          w->syncedversion = base->version;
       }
       probe_list_kernel<<<1, PROBE_THREADS, 0, w->stream>>>(w->p, base->p, w->lastvar, base->d_probevar, base->d_probelb,
-         base->d_probeub, wi, nworkers, (int)nprobes, maxrounds, (int)w->logcap, d_res);
+         base->d_probeub, wi, nworkers, (int)nprobes, maxrounds, (int)w->logcap, d_res, wantlog ? base->d_probelog : nullptr,
+         base->d_probecursor, wantlog ? base->probelogcap : 0);
       w->lastvar = var[wi + ((nprobes - 1 - wi) / nworkers) * nworkers];
    }
    CU(cudaGetLastError());
@@ -1210,6 +1232,19 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
    std::vector<ProbeResult> res((size_t)nprobes);
    if( nprobes > 0 && !general )
       CU(cudaMemcpy(res.data(), d_res, sizeof(ProbeResult) * (size_t)nprobes, cudaMemcpyDeviceToHost));
+   // ---- the change logs: device order -> probe order
+   std::vector<ChangeRec> devlog;
+   std::vector<std::vector<ChangeRec>> rerunlog;
+   if( wantlog && nprobes > 0 )
+   {
+      unsigned long long used = 0;
+      CU(cudaMemcpy(&used, base->d_probecursor, sizeof(used), cudaMemcpyDeviceToHost));
+      used = std::min<unsigned long long>(used, (unsigned long long)base->probelogcap);
+      devlog.resize((size_t)used);
+      if( used > 0 )
+         CU(cudaMemcpy(devlog.data(), base->d_probelog, sizeof(ChangeRec) * (size_t)used, cudaMemcpyDeviceToHost));
+      rerunlog.resize((size_t)nprobes);
+   }
    // ---- probes that outgrew the block are rerun through the general loop on worker 0
    for( int64_t i = 0; i < nprobes; ++i )
    {
@@ -1227,6 +1262,16 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
       res[(size_t)i].status = r.status;
       res[(size_t)i].nrounds = r.nrounds;
       res[(size_t)i].nchanges = r.nchanges;
+      if( wantlog )
+      {
+         int64_t nl = 0;
+         std::vector<ChangeRec>& rl = rerunlog[(size_t)i];
+         rl.resize((size_t)std::min<int64_t>(r.nchanges, w->logcap));
+         static_assert(sizeof(gpulin_change) == sizeof(ChangeRec), "change record layout");
+         OK(gpulin_get_changes(w, (gpulin_change*)rl.data(), (int64_t)rl.size(), &nl));
+         res[(size_t)i].logoff = -2;       // in rerunlog
+         res[(size_t)i].nlog = (long long)std::min<int64_t>(nl, (int64_t)rl.size());
+      }
    }
    for( int64_t i = 0; i < nprobes; ++i )
    {
@@ -1234,7 +1279,48 @@ extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes,
       if( nrounds != nullptr ) nrounds[i] = res[(size_t)i].nrounds;
       if( nchanges != nullptr ) nchanges[i] = res[(size_t)i].nchanges;
    }
+   if( wantlog )
+   {
+      int64_t pos = 0;
+      bool fits = true;
+      for( int64_t i = 0; i < nprobes; ++i )
+      {
+         const ProbeResult& pr = res[(size_t)i];
+         chgbeg[i] = pos;
+         const ChangeRec* src = nullptr;
+         if( pr.logoff == -2 )
+            src = rerunlog[(size_t)i].data();
+         else if( pr.logoff >= 0 && (size_t)(pr.logoff + pr.nlog) <= devlog.size() )
+            src = devlog.data() + pr.logoff;
+         else if( pr.nlog > 0 )
+            fits = false;                   // the device buffer was too small for this probe
+         if( pos + pr.nlog <= maxchg && src != nullptr && fits )
+            memcpy((void*)(chg + pos), src, sizeof(ChangeRec) * (size_t)pr.nlog);
+         else if( pr.nlog > 0 )
+            fits = false;
+         pos += pr.nlog;
+      }
+      chgbeg[nprobes] = pos;
+      *nchg = pos;
+      if( !fits )
+         return fail(GPULIN_ERR_ARG, "the change buffer holds %lld entries, the batch produced %lld", (long long)maxchg, (long long)pos);
+   }
    return GPULIN_OK;
+}
+
+extern "C" int gpulin_probe_batch(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
+   const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges)
+{
+   return probeBatchImpl(base, nworkers, nprobes, var, lb, ub, maxrounds, status, nrounds, nchanges, false, nullptr, nullptr, 0, nullptr);
+}
+
+extern "C" int gpulin_probe_batch_changes(gpulin_t* base, int nworkers, int64_t nprobes, const int32_t* var, const double* lb,
+   const double* ub, int maxrounds, int32_t* status, int32_t* nrounds, int64_t* nchanges, int64_t* chgbeg, gpulin_change* chg,
+   int64_t maxchg, int64_t* nchg)
+{
+   if( chgbeg == nullptr || nchg == nullptr || maxchg < 0 || (maxchg > 0 && chg == nullptr) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   return probeBatchImpl(base, nworkers, nprobes, var, lb, ub, maxrounds, status, nrounds, nchanges, true, chgbeg, chg, maxchg, nchg);
 }
 
 // a second set of bound vectors on the same matrix: shares the read-only arrays, owns everything a round writes
@@ -1243,8 +1329,6 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    if( src == nullptr || out == nullptr )
       return fail(GPULIN_ERR_ARG, "invalid argument");
    *out = nullptr;
-   if( src->npeers > 1 )
-      return fail(GPULIN_ERR_STATE, "a handle connected to peers cannot be cloned");
    CU(cudaSetDevice(src->device));
    gpulin* h = new gpulin();
    h->shared = src->shared;
@@ -1315,6 +1399,10 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    p.ctrl = d_ctrl;
    p.log = nullptr;
    p.peers = nullptr;
+   // (the clone of a handle that shares its dense rounds with peers works alone: it takes every row itself)
+   h->npeers = 1;
+   h->peerrank = 0;
+   setShare(h, 0, 1);
    if( !h->hostloop )
    {
       rc = buildGraph(h);

@@ -2372,13 +2372,16 @@ struct ProbeResult
    int       status;
    int       nrounds;
    long long nchanges;
+   long long logoff;     // position of the probe's change log in the output of the batch (-1: it did not fit, or none was asked for)
+   long long nlog;       // its length
 };
 
 // The same kernel serves small incremental calls on any handle (j < 0, keepmarks): the rows gpulin_update_bounds marked
 // since the last fixpoint are on mark list mb^1; if the cascade outgrows the block the marks stay and the general loop
 // continues the call (Ctrl::resume).
 __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem& base, int restorevar, int j, double l, double u,
-   int maxrounds, int logcap, int keepmarks, ProbeResult* out, RowAcc* s_acc, CandQueue* s_queue, int& s_nchg)
+   int maxrounds, int logcap, int keepmarks, ProbeResult* out, RowAcc* s_acc, CandQueue* s_queue, int& s_nchg,
+   ChangeRec* outlog = nullptr, unsigned long long* outcursor = nullptr, long long outcap = 0)
 {
    Ctrl* c = p.ctrl;
    const int tid = threadIdx.x;
@@ -2391,6 +2394,8 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
          out->status = GPULIN_PROBE_OVERFLOW;
          out->nrounds = 0;
          out->nchanges = 0;
+         out->logoff = -1;
+         out->nlog = 0;
       }
       return;
    }
@@ -2528,6 +2533,23 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
             p.dirty[ml[2 * MARKCAP + i]] = ROW_CLEAN;
       }
       __syncthreads();
+      // ---- the bounds the probe implied (SCIPapplyProbingVar hands them out as proplbs / propubs, prop_probing.c:1203-1303):
+      // ---- its change log goes to the output of the batch, one reservation per probe
+      long long logoff = -1;
+      const unsigned long long nl = min(c->logcount, (unsigned long long)c->logcap);
+      if( outlog != nullptr )
+      {
+         __shared__ long long s_off;
+         if( tid == 0 )
+            s_off = (long long)atomicAdd(outcursor, nl);
+         __syncthreads();
+         if( s_off + (long long)nl <= outcap )
+         {
+            logoff = s_off;
+            for( unsigned long long i = tid; i < nl; i += PROBE_THREADS )
+               outlog[logoff + (long long)i] = p.log[i];
+         }
+      }
       if( tid == 0 )
       {
          c->nmark[mb][0] = c->nmark[mb][1] = c->nmark[mb][2] = 0;
@@ -2536,6 +2558,8 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
          out->status = overflow ? GPULIN_PROBE_OVERFLOW : c->status;
          out->nrounds = c->round;
          out->nchanges = (long long)c->total_nchg;
+         out->logoff = logoff;
+         out->nlog = (long long)nl;
       }
    }
 }
@@ -2553,7 +2577,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_kernel(const DevProble
 // batch instead of one per probe (the host's launch rate was what bounded a batch)
 __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_list_kernel(const DevProblem p, const DevProblem base, int restorevar,
    const int* vars, const double* lbs, const double* ubs, int first, int stride, int n, int maxrounds, int logcap,
-   ProbeResult* out)
+   ProbeResult* out, ChangeRec* outlog, unsigned long long* outcursor, long long outcap)
 {
    __shared__ RowAcc s_acc[PROBE_THREADS / 32];
    __shared__ CandQueue s_queue[PROBE_THREADS / 32];
@@ -2561,7 +2585,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_list_kernel(const DevP
    for( int i = first; i < n; i += stride )
    {
       const int j = vars[i];
-      probeBody(p, base, restorevar, j, lbs[i], ubs[i], maxrounds, logcap, 0, out + i, s_acc, s_queue, s_nchg);
+      probeBody(p, base, restorevar, j, lbs[i], ubs[i], maxrounds, logcap, 0, out + i, s_acc, s_queue, s_nchg, outlog, outcursor, outcap);
       restorevar = j;
       __syncthreads();
    }

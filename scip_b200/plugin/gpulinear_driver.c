@@ -117,6 +117,18 @@ static SCIP_DECL_PROPEXEC(propExecProbecheck)
    SCIP_Bool* cutbatch;
    SCIP_Longint* ndom;
    SCIP_Longint* nchg;
+   SCIP_Real* probelb;        /* local bounds after SCIP's own probing cycle, n x nvars */
+   SCIP_Real* probeub;
+   SCIP_Real* nodelb;
+   SCIP_Real* nodeub;
+   int* chgbeg;
+   SCIP_VAR** chgvars;
+   SCIP_BOUNDTYPE* chgtypes;
+   SCIP_Real* chgbounds;
+   int nchgs = 0;
+   int maxchgs;
+   int nboundmismatch = 0;
+   int v;
    SCIP_Bool nodecutoff = FALSE;
    int nvars = SCIPgetNVars(scip);
    int n = 0;
@@ -161,6 +173,15 @@ static SCIP_DECL_PROPEXEC(propExecProbecheck)
       }
       ++n;
    }
+   maxchgs = 64 * (n + 1) + 4 * nvars;
+   SCIP_CALL( SCIPallocBufferArray(scip, &probelb, (n + 1) * nvars) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &probeub, (n + 1) * nvars) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &nodelb, nvars) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &nodeub, nvars) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &chgbeg, n + 1) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &chgvars, maxchgs) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &chgtypes, maxchgs) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &chgbounds, maxchgs) );
    t0 = wallclock();
    for( i = 0; i < n; ++i )
    {
@@ -170,6 +191,11 @@ static SCIP_DECL_PROPEXEC(propExecProbecheck)
       if( pub[i] < SCIPvarGetUbLocal(pv[i]) )
          SCIP_CALL( SCIPchgVarUbProbing(scip, pv[i], pub[i]) );
       SCIP_CALL( SCIPpropagateProbing(scip, -1, &cutscip[i], &ndom[i]) );
+      for( v = 0; v < nvars; ++v )
+      {
+         probelb[i * nvars + v] = SCIPvarGetLbLocal(vars[v]);
+         probeub[i * nvars + v] = SCIPvarGetUbLocal(vars[v]);
+      }
       SCIP_CALL( SCIPendProbing(scip) );
       ncutscip += cutscip[i] ? 1 : 0;
    }
@@ -186,10 +212,56 @@ static SCIP_DECL_PROPEXEC(propExecProbecheck)
          if( cutbatch[i] != cutscip[i] )
             ++nmismatch;
       }
+      /* the implied bounds of every probe (SCIPapplyProbingVar's proplbs / propubs): the node's bounds overwritten by the
+       * probe's bound changes must be the bounds SCIP's own probing cycle ended with */
+      SCIP_CALL( SCIPprobeBatchBoundsGpulinear(scip, n, pv, plb, pub, &nodecutoff, cutbatch, chgbeg, chgvars, chgtypes,
+            chgbounds, maxchgs, &nchgs) );
+      for( v = 0; v < nvars; ++v )
+      {
+         nodelb[v] = SCIPvarGetLbLocal(vars[v]);
+         nodeub[v] = SCIPvarGetUbLocal(vars[v]);
+      }
+      for( i = 0; i < n && nchgs <= maxchgs; ++i )
+      {
+         int e;
+         if( cutbatch[i] || cutscip[i] )
+            continue;
+         for( v = 0; v < nvars; ++v )
+         {
+            probelb[n * nvars + v] = nodelb[v];
+            probeub[n * nvars + v] = nodeub[v];
+         }
+         v = SCIPvarGetProbindex(pv[i]);
+         probelb[n * nvars + v] = MAX(nodelb[v], plb[i]);
+         probeub[n * nvars + v] = MIN(nodeub[v], pub[i]);
+         for( e = chgbeg[i]; e < chgbeg[i + 1]; ++e )
+         {
+            v = SCIPvarGetProbindex(chgvars[e]);
+            if( chgtypes[e] == SCIP_BOUNDTYPE_UPPER )
+               probeub[n * nvars + v] = chgbounds[e];
+            else
+               probelb[n * nvars + v] = chgbounds[e];
+         }
+         for( v = 0; v < nvars; ++v )
+         {
+            if( !SCIPisFeasEQ(scip, probelb[n * nvars + v], probelb[i * nvars + v])
+               || !SCIPisFeasEQ(scip, probeub[n * nvars + v], probeub[i * nvars + v]) )
+               ++nboundmismatch;
+         }
+      }
    }
    printf("PROBEBATCH {\"probes\": %d, \"cutoffs_scip\": %d, \"cutoffs_batch\": %d, \"mismatches\": %d, \"node_cutoff\": %d, "
-      "\"probes_with_changes\": %d, \"scip_probing_s\": %.9g, \"batch_s\": %.9g}\n", n, ncutscip, ncutbatch, nmismatch,
-      (int)nodecutoff, nactive, t1 - t0, t2 - t1);
+      "\"probes_with_changes\": %d, \"implied_bound_changes\": %d, \"implied_bound_mismatches\": %d, "
+      "\"scip_probing_s\": %.9g, \"batch_s\": %.9g}\n", n, ncutscip, ncutbatch, nmismatch,
+      (int)nodecutoff, nactive, nchgs, nboundmismatch, t1 - t0, t2 - t1);
+   SCIPfreeBufferArray(scip, &chgbounds);
+   SCIPfreeBufferArray(scip, &chgtypes);
+   SCIPfreeBufferArray(scip, &chgvars);
+   SCIPfreeBufferArray(scip, &chgbeg);
+   SCIPfreeBufferArray(scip, &nodeub);
+   SCIPfreeBufferArray(scip, &nodelb);
+   SCIPfreeBufferArray(scip, &probeub);
+   SCIPfreeBufferArray(scip, &probelb);
    SCIPfreeBufferArray(scip, &nchg);
    SCIPfreeBufferArray(scip, &ndom);
    SCIPfreeBufferArray(scip, &cutbatch);
@@ -219,6 +291,7 @@ static SCIP_RETCODE run(int argc, char** argv)
    int presolve = 0;
    int activeonly = 0;
    int delredundant = 0;
+   int ndevices = 1;
    int rowsof[5] = {-1, -1, -1, -1, -1};
    char pname[128];
    double t0, t1;
@@ -237,6 +310,7 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--presolve") == 0 ) presolve = 1;
       else if( strcmp(argv[i], "--active-rows-only") == 0 ) activeonly = 1;
       else if( strcmp(argv[i], "--del-redundant") == 0 ) delredundant = 1;
+      else if( strcmp(argv[i], "--ndevices") == 0 && i + 1 < argc ) ndevices = atoi(argv[++i]);
       else if( strcmp(argv[i], "--probe-batch") == 0 && i + 1 < argc ) g_nprobecheck = atoi(argv[++i]);
       else
       {
@@ -293,6 +367,8 @@ static SCIP_RETCODE run(int argc, char** argv)
          SCIP_CALL( SCIPsetBoolParam(scip, "propagating/gpulinear/stablecopy", FALSE) );
       if( delredundant )
          SCIP_CALL( SCIPsetBoolParam(scip, "propagating/gpulinear/delredundant", TRUE) );
+      if( ndevices > 1 )
+         SCIP_CALL( SCIPsetIntParam(scip, "propagating/gpulinear/ndevices", ndevices) );
    }
 
    if( readfile != NULL )

@@ -78,6 +78,9 @@
 struct SCIP_PropData
 {
    gpulin_t*             gpu;                /**< device copy of the linear rows, or NULL */
+   gpulin_t*             peergpu[7];         /**< ndevices > 1: the copies on the other devices (gpulin_group_connect) */
+   int                   npeergpus;          /**< copies in peergpu[] */
+   int                   ndevices;           /**< parameter: devices that share the dense rounds (device, device + 1, ...) */
    SCIP_VAR**            vars;               /**< column -> variable (by probindex at build time) */
    SCIP_CONS**           rowcons;            /**< row -> linear constraint */
    SCIP_Real*            lb;                 /**< host bound buffers */
@@ -133,6 +136,11 @@ void freeDeviceCopy(
    SCIP_PROPDATA*        propdata
    )
 {
+   while( propdata->npeergpus > 0 )
+   {
+      gpulin_destroy(propdata->peergpu[--propdata->npeergpus]);
+      propdata->peergpu[propdata->npeergpus] = NULL;
+   }
    if( propdata->gpu != NULL )
    {
       gpulin_destroy(propdata->gpu);
@@ -550,6 +558,15 @@ SCIP_RETCODE buildDeviceCopy(
 
    rc = gpulin_create(propdata->device, nrows, ncols, propdata->nnz, propdata->rowptr, propdata->colidx, propdata->vals,
       propdata->lhs, propdata->rhs, vartype, &num, &propdata->gpu);
+   /* several devices: SCIP is one process and calls PROPEXEC on one thread (prop.c:646-716), so the copies on the other
+    * devices are driven from here -- the same problem on every device, connected in-process */
+   while( rc == GPULIN_OK && propdata->npeergpus + 1 < propdata->ndevices )
+   {
+      rc = gpulin_create(propdata->device + propdata->npeergpus + 1, nrows, ncols, propdata->nnz, propdata->rowptr,
+         propdata->colidx, propdata->vals, propdata->lhs, propdata->rhs, vartype, &num, &propdata->peergpu[propdata->npeergpus]);
+      if( rc == GPULIN_OK )
+         ++propdata->npeergpus;
+   }
    SCIPfreeBufferArray(scip, &fill);
    SCIPfreeBufferArray(scip, &vartype);
    SCIPfreeBufferArray(scip, &rowvals);
@@ -557,6 +574,9 @@ SCIP_RETCODE buildDeviceCopy(
    if( rc != GPULIN_OK )
    {
       SCIPerrorMessage("prop_gpulinear: gpulin_create failed (%d): %s\n", rc, gpulin_last_error());
+      while( propdata->npeergpus > 0 )
+         gpulin_destroy(propdata->peergpu[--propdata->npeergpus]);
+      gpulin_destroy(propdata->gpu);
       propdata->gpu = NULL;
       return SCIP_ERROR;
    }
@@ -564,10 +584,26 @@ SCIP_RETCODE buildDeviceCopy(
    propdata->logcap = (int64_t)DEFAULT_LOGCAPFAC * ncols + 1024;
    SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->changes, propdata->logcap) );
    rc = gpulin_set_change_log(propdata->gpu, propdata->logcap);
+   /* (the same log on every device: the devices must take every decision alike, also "the log is full") */
+   for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
+      rc = gpulin_set_change_log(propdata->peergpu[j], propdata->logcap);
    if( rc != GPULIN_OK )
    {
       SCIPerrorMessage("prop_gpulinear: gpulin_set_change_log failed (%d): %s\n", rc, gpulin_last_error());
       return SCIP_ERROR;
+   }
+   if( propdata->npeergpus > 0 )
+   {
+      gpulin_t* group[8];
+      group[0] = propdata->gpu;
+      for( j = 0; j < propdata->npeergpus; ++j )
+         group[j + 1] = propdata->peergpu[j];
+      rc = gpulin_group_connect(group, propdata->npeergpus + 1);
+      if( rc != GPULIN_OK )
+      {
+         SCIPerrorMessage("prop_gpulinear: gpulin_group_connect failed (%d): %s\n", rc, gpulin_last_error());
+         return SCIP_ERROR;
+      }
    }
 
    /* from now on every bound change of a column is noted (cf. consCatchAllEvents, cons_linear.c:717) */
@@ -770,6 +806,8 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
       propdata->fullsync = FALSE;
       ++propdata->nfullsyncs;
       rc = gpulin_set_bounds(propdata->gpu, propdata->lb, propdata->ub);
+      for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
+         rc = gpulin_set_bounds(propdata->peergpu[j], propdata->lb, propdata->ub);
    }
    else
    {
@@ -785,9 +823,31 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
       propdata->ntouched = 0;
       propdata->nupdates += n;
       rc = gpulin_update_bounds(propdata->gpu, n, propdata->updidx, propdata->lb, propdata->ub);
+      for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
+         rc = gpulin_update_bounds(propdata->peergpu[j], n, propdata->updidx, propdata->lb, propdata->ub);
    }
-   if( rc == GPULIN_OK )
+   if( rc == GPULIN_OK && propdata->npeergpus == 0 )
       rc = gpulin_propagate(propdata->gpu, propdata->maxrounds < 0 ? 0 : propdata->maxrounds, &res);
+   else if( rc == GPULIN_OK )
+   {
+      /* a collective call: enqueued on every device, then awaited on every device (the devices exchange their candidates
+       * among themselves); every device ends with the same bounds, the results are taken from the first */
+      gpulin_result peerres;
+      rc = gpulin_propagate_async(propdata->gpu, propdata->maxrounds < 0 ? 0 : propdata->maxrounds);
+      for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
+         rc = gpulin_propagate_async(propdata->peergpu[j], propdata->maxrounds < 0 ? 0 : propdata->maxrounds);
+      if( rc == GPULIN_OK )
+         rc = gpulin_propagate_wait(propdata->gpu, &res);
+      for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
+      {
+         rc = gpulin_propagate_wait(propdata->peergpu[j], &peerres);
+         if( rc == GPULIN_OK && (peerres.status != res.status || peerres.nrounds != res.nrounds || peerres.nchanges != res.nchanges) )
+         {
+            SCIPerrorMessage("prop_gpulinear: device %d disagrees with device %d\n", propdata->device + j + 1, propdata->device);
+            return SCIP_ERROR;
+         }
+      }
+   }
    if( rc != GPULIN_OK )
    {
       SCIPerrorMessage("prop_gpulinear: device propagation failed (%d): %s\n", rc, gpulin_last_error());
@@ -1031,6 +1091,9 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/stablecopy",
          "keep one device copy of all existing global rows across the tree (FALSE: of the rows active at the node of the build, rebuilt whenever that number changes)",
          &propdata->stablecopy, FALSE, DEFAULT_STABLECOPY, NULL, NULL) );
+   SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/ndevices",
+         "number of CUDA devices (device, device + 1, ...) that share the dense propagation rounds",
+         &propdata->ndevices, TRUE, 1, 1, 8, NULL, NULL) );
    SCIP_CALL( SCIPaddIntParam(scip, "propagating/" PROP_NAME "/device",
          "CUDA device ordinal",
          &propdata->device, TRUE, DEFAULT_DEVICE, 0, 1023, NULL, NULL) );
@@ -1070,6 +1133,51 @@ SCIP_Longint SCIPgetNBuildsGpulinear(
 }
 
 /** a batch of independent probes on the current node, see prop_gpulinear.h */
+/** the node first: device copy up to date, node bounds on the device, node fixpoint replayed into SCIP; a second pass
+ *  takes the values SCIP adjusted during the replay back to the device; then the columns of the probed variables */
+static
+SCIP_RETCODE prepareProbeBatch(
+   SCIP*                 scip,
+   SCIP_PROP*            prop,
+   SCIP_PROPDATA*        propdata,
+   int                   nprobes,
+   SCIP_VAR**            vars,
+   SCIP_Bool*            nodecutoff,
+   int32_t*              cols
+   )
+{
+   SCIP_RESULT result;
+   int iter;
+   int i;
+
+   if( nodecutoff != NULL )
+      *nodecutoff = FALSE;
+   for( iter = 0; iter < 4; ++iter )
+   {
+      SCIP_CALL( propExecGpulinear(scip, prop, SCIP_PROPTIMING_BEFORELP, &result) );
+      if( result == SCIP_CUTOFF )
+      {
+         if( nodecutoff != NULL )
+            *nodecutoff = TRUE;
+         return SCIP_OKAY;
+      }
+      if( result != SCIP_REDUCEDDOM && propdata->ntouched == 0 && !propdata->fullsync )
+         break;
+   }
+   if( propdata->gpu == NULL )
+      return SCIP_OKAY;
+   for( i = 0; i < nprobes; ++i )
+   {
+      cols[i] = SCIPvarGetProbindex(vars[i]);
+      if( cols[i] < 0 || cols[i] >= propdata->ncols || propdata->vars[cols[i]] != vars[i] )
+      {
+         SCIPerrorMessage("prop_gpulinear: probe %d: <%s> is not an active problem variable\n", i, SCIPvarGetName(vars[i]));
+         return SCIP_INVALIDDATA;
+      }
+   }
+   return SCIP_OKAY;
+}
+
 SCIP_RETCODE SCIPprobeBatchGpulinear(
    SCIP*                 scip,               /**< SCIP data structure */
    int                   nprobes,            /**< number of probes */
@@ -1084,12 +1192,12 @@ SCIP_RETCODE SCIPprobeBatchGpulinear(
 {
    SCIP_PROP* prop = SCIPfindProp(scip, PROP_NAME);
    SCIP_PROPDATA* propdata;
-   SCIP_RESULT result;
+   SCIP_Bool nodecut = FALSE;
+   SCIP_RETCODE retcode;
    int32_t* cols;
    int32_t* status;
    int32_t* rounds;
    int64_t* nchanges;
-   int iter;
    int rc;
    int i;
 
@@ -1100,23 +1208,6 @@ SCIP_RETCODE SCIPprobeBatchGpulinear(
    }
    propdata = SCIPpropGetData(prop);
    assert(propdata != NULL);
-   if( nodecutoff != NULL )
-      *nodecutoff = FALSE;
-
-   /* the node first: device copy up to date, node bounds on the device, node fixpoint replayed into SCIP; a second
-    * pass takes the values SCIP adjusted during the replay back to the device */
-   for( iter = 0; iter < 4; ++iter )
-   {
-      SCIP_CALL( propExecGpulinear(scip, prop, SCIP_PROPTIMING_BEFORELP, &result) );
-      if( result == SCIP_CUTOFF )
-      {
-         if( nodecutoff != NULL )
-            *nodecutoff = TRUE;
-         return SCIP_OKAY;
-      }
-      if( result != SCIP_REDUCEDDOM && propdata->ntouched == 0 && !propdata->fullsync )
-         break;
-   }
    for( i = 0; i < nprobes; ++i )
    {
       if( cutoff != NULL )
@@ -1126,27 +1217,20 @@ SCIP_RETCODE SCIPprobeBatchGpulinear(
       if( nchgbds != NULL )
          nchgbds[i] = 0;
    }
-   if( propdata->gpu == NULL || nprobes == 0 )
-      return SCIP_OKAY;
-
-   SCIP_CALL( SCIPallocBufferArray(scip, &cols, nprobes) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &cols, nprobes + 1) );
+   retcode = prepareProbeBatch(scip, prop, propdata, nprobes, vars, &nodecut, cols);
+   if( nodecutoff != NULL )
+      *nodecutoff = nodecut;
+   if( retcode != SCIP_OKAY || nodecut || propdata->gpu == NULL || nprobes == 0 )
+   {
+      SCIPfreeBufferArray(scip, &cols);
+      return retcode;
+   }
    SCIP_CALL( SCIPallocBufferArray(scip, &status, nprobes) );
    SCIP_CALL( SCIPallocBufferArray(scip, &rounds, nprobes) );
    SCIP_CALL( SCIPallocBufferArray(scip, &nchanges, nprobes) );
-   rc = GPULIN_OK;
-   for( i = 0; i < nprobes; ++i )
-   {
-      cols[i] = SCIPvarGetProbindex(vars[i]);
-      if( cols[i] < 0 || cols[i] >= propdata->ncols || propdata->vars[cols[i]] != vars[i] )
-      {
-         SCIPerrorMessage("SCIPprobeBatchGpulinear: probe %d: <%s> is not an active problem variable\n", i, SCIPvarGetName(vars[i]));
-         rc = GPULIN_ERR_ARG;
-         break;
-      }
-   }
-   if( rc == GPULIN_OK )
-      rc = gpulin_probe_batch(propdata->gpu, 32, nprobes, cols, lbs, ubs, propdata->maxrounds < 0 ? 0 : propdata->maxrounds,
-         status, rounds, nchanges);
+   rc = gpulin_probe_batch(propdata->gpu, 32, nprobes, cols, lbs, ubs, propdata->maxrounds < 0 ? 0 : propdata->maxrounds,
+      status, rounds, nchanges);
    if( rc == GPULIN_OK )
    {
       for( i = 0; i < nprobes; ++i )
@@ -1166,6 +1250,95 @@ SCIP_RETCODE SCIPprobeBatchGpulinear(
    if( rc != GPULIN_OK )
    {
       SCIPerrorMessage("SCIPprobeBatchGpulinear failed (%d): %s\n", rc, gpulin_last_error());
+      return SCIP_ERROR;
+   }
+   return SCIP_OKAY;
+}
+
+SCIP_RETCODE SCIPprobeBatchBoundsGpulinear(
+   SCIP*                 scip,               /**< SCIP data structure */
+   int                   nprobes,            /**< number of probes */
+   SCIP_VAR**            vars,               /**< active problem variable of each probe */
+   SCIP_Real*            lbs,                /**< lower bound of the variable in its probe */
+   SCIP_Real*            ubs,                /**< upper bound of the variable in its probe */
+   SCIP_Bool*            nodecutoff,         /**< the node itself is infeasible: no probe was run */
+   SCIP_Bool*            cutoff,             /**< per probe: the probe is infeasible */
+   int*                  chgbeg,             /**< per probe: first entry of its bound changes (nprobes + 1 entries) */
+   SCIP_VAR**            chgvars,            /**< variable of every bound change */
+   SCIP_BOUNDTYPE*       chgtypes,           /**< bound type of every bound change */
+   SCIP_Real*            chgbounds,          /**< new bound of every bound change */
+   int                   maxchgs,            /**< capacity of the three arrays */
+   int*                  nchgs               /**< bound changes produced */
+   )
+{
+   SCIP_PROP* prop = SCIPfindProp(scip, PROP_NAME);
+   SCIP_PROPDATA* propdata;
+   SCIP_Bool nodecut = FALSE;
+   SCIP_RETCODE retcode;
+   gpulin_change* chg;
+   int32_t* cols;
+   int32_t* status;
+   int64_t* beg;
+   int64_t nchg = 0;
+   int rc;
+   int i;
+
+   if( prop == NULL )
+   {
+      SCIPerrorMessage("prop_gpulinear is not included\n");
+      return SCIP_PLUGINNOTFOUND;
+   }
+   if( chgbeg == NULL || nchgs == NULL || maxchgs < 0 )
+      return SCIP_INVALIDDATA;
+   propdata = SCIPpropGetData(prop);
+   assert(propdata != NULL);
+   *nchgs = 0;
+   for( i = 0; i <= nprobes; ++i )
+      chgbeg[i] = 0;
+   for( i = 0; i < nprobes && cutoff != NULL; ++i )
+      cutoff[i] = FALSE;
+   SCIP_CALL( SCIPallocBufferArray(scip, &cols, nprobes + 1) );
+   retcode = prepareProbeBatch(scip, prop, propdata, nprobes, vars, &nodecut, cols);
+   if( nodecutoff != NULL )
+      *nodecutoff = nodecut;
+   if( retcode != SCIP_OKAY || nodecut || propdata->gpu == NULL || nprobes == 0 )
+   {
+      SCIPfreeBufferArray(scip, &cols);
+      return retcode;
+   }
+   SCIP_CALL( SCIPallocBufferArray(scip, &status, nprobes) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &beg, nprobes + 1) );
+   SCIP_CALL( SCIPallocBufferArray(scip, &chg, maxchgs + 1) );
+   rc = gpulin_probe_batch_changes(propdata->gpu, 32, nprobes, cols, lbs, ubs, propdata->maxrounds < 0 ? 0 : propdata->maxrounds,
+      status, NULL, NULL, beg, chg, maxchgs, &nchg);
+   if( rc == GPULIN_OK || (rc == GPULIN_ERR_ARG && nchg > maxchgs) )
+   {
+      for( i = 0; i < nprobes; ++i )
+      {
+         if( cutoff != NULL )
+            cutoff[i] = (status[i] == GPULIN_CUTOFF);
+         chgbeg[i] = (int)beg[i];
+      }
+      chgbeg[nprobes] = (int)beg[nprobes];
+      *nchgs = (int)nchg;
+      if( rc == GPULIN_OK )
+      {
+         for( i = 0; i < (int)nchg; ++i )
+         {
+            chgvars[i] = propdata->vars[chg[i].var];
+            chgtypes[i] = chg[i].is_upper ? SCIP_BOUNDTYPE_UPPER : SCIP_BOUNDTYPE_LOWER;
+            chgbounds[i] = chg[i].newbound;
+         }
+      }
+      rc = GPULIN_OK;
+   }
+   SCIPfreeBufferArray(scip, &chg);
+   SCIPfreeBufferArray(scip, &beg);
+   SCIPfreeBufferArray(scip, &status);
+   SCIPfreeBufferArray(scip, &cols);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("SCIPprobeBatchBoundsGpulinear failed (%d): %s\n", rc, gpulin_last_error());
       return SCIP_ERROR;
    }
    return SCIP_OKAY;

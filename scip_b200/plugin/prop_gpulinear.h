@@ -14,6 +14,7 @@
 #include "scip/type_retcode.h"
 #include "scip/type_scip.h"
 #include "scip/type_var.h"
+#include "scip/type_lp.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -54,6 +55,28 @@ SCIP_RETCODE SCIPprobeBatchGpulinear(
    SCIP_Bool*            cutoff,             /**< per probe: the probe is infeasible */
    int*                  nrounds,            /**< per probe: propagation rounds */
    SCIP_Longint*         nchgbds             /**< per probe: bound changes found */
+   );
+
+/** the same batch, and what every probe implied -- the proplbs / propubs that SCIPapplyProbingVar (prop_probing.c:1203-1303)
+ *  returns per candidate, in sparse form: the bound changes of probe i are the entries chgbeg[i] .. chgbeg[i+1] - 1 of
+ *  (chgvars, chgtypes, chgbounds), in the order they were found (a variable may appear more than once: the last entry is
+ *  its bound at the probe's fixpoint; the probed variable itself is not listed unless propagation tightened it further).
+ *  chgbeg needs nprobes + 1 entries.  If the batch produced more than maxchgs entries, *nchgs says how many are needed and
+ *  only chgbeg is valid. */
+SCIP_RETCODE SCIPprobeBatchBoundsGpulinear(
+   SCIP*                 scip,               /**< SCIP data structure */
+   int                   nprobes,            /**< number of probes */
+   SCIP_VAR**            vars,               /**< active problem variable of each probe */
+   SCIP_Real*            lbs,                /**< lower bound of the variable in its probe */
+   SCIP_Real*            ubs,                /**< upper bound of the variable in its probe */
+   SCIP_Bool*            nodecutoff,         /**< the node itself is infeasible: no probe was run */
+   SCIP_Bool*            cutoff,             /**< per probe: the probe is infeasible */
+   int*                  chgbeg,             /**< per probe: first entry of its bound changes (nprobes + 1 entries) */
+   SCIP_VAR**            chgvars,            /**< variable of every bound change */
+   SCIP_BOUNDTYPE*       chgtypes,           /**< bound type of every bound change */
+   SCIP_Real*            chgbounds,          /**< new bound of every bound change */
+   int                   maxchgs,            /**< capacity of the three arrays */
+   int*                  nchgs               /**< bound changes produced */
    );
 
 #ifdef __cplusplus

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "gpulin_clone": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "gpulin_reset_from": (ctypes.c_int, [_P, _P]),
     "gpulin_probe_batch": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, _P, _P, _P, ctypes.c_int, _P, _P, _P]),
+    "gpulin_probe_batch_changes": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, _P, _P, _P, ctypes.c_int, _P, _P, _P, _P, _P,
+                                                  ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_get_bounds": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_get_bounds_device": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_set_change_log": (ctypes.c_int, [_P, ctypes.c_int64]),
@@ -298,6 +300,25 @@ class LinearPropagator:
         _check(self._lib.gpulin_probe_batch(self._h, int(nworkers), n, var.ctypes.data, lb.ctypes.data, ub.ctypes.data,
                                             int(maxrounds), status.ctypes.data, nrounds.ctypes.data, nchanges.ctypes.data))
         return dict(status=status, nrounds=nrounds, nchanges=nchanges)
+
+    def probe_batch_changes(self, var, lb, ub, nworkers: int = 32, maxrounds: int = 0, maxchg: int = 1 << 20) -> dict:
+        """like probe_batch, plus what every probe implied: ``changes[chgbeg[i]:chgbeg[i+1]]`` are probe i's accepted
+        bound changes in round order (the sparse form of SCIPapplyProbingVar's proplbs / propubs)"""
+        var = np.ascontiguousarray(var, dtype=np.int32)
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        n = len(var)
+        status = np.zeros(n, dtype=np.int32)
+        nrounds = np.zeros(n, dtype=np.int32)
+        nchanges = np.zeros(n, dtype=np.int64)
+        chgbeg = np.zeros(n + 1, dtype=np.int64)
+        chg = np.zeros(max(maxchg, 1), dtype=CHANGE_DTYPE)
+        nchg = ctypes.c_int64(0)
+        _check(self._lib.gpulin_probe_batch_changes(self._h, int(nworkers), n, var.ctypes.data, lb.ctypes.data, ub.ctypes.data,
+                                                    int(maxrounds), status.ctypes.data, nrounds.ctypes.data,
+                                                    nchanges.ctypes.data, chgbeg.ctypes.data, chg.ctypes.data, int(maxchg),
+                                                    ctypes.byref(nchg)))
+        return dict(status=status, nrounds=nrounds, nchanges=nchanges, chgbeg=chgbeg, changes=chg[:nchg.value])
 
     def round_stats(self, maxn: int = 1024):
         ms = np.zeros(maxn, dtype=np.float64)

@@ -161,3 +161,42 @@ def test_batched_probing_entry_matches_scip_probing(name):
     info = json.loads(lines[0][len("PROBEBATCH "):])
     assert info["probes"] > 0 and info["node_cutoff"] == 0
     assert info["mismatches"] == 0 and info["cutoffs_batch"] == info["cutoffs_scip"], info
+    # SCIPprobeBatchBoundsGpulinear: the implied bounds of every probe (what SCIPapplyProbingVar returns as proplbs /
+    # propubs, prop_probing.c:1203-1303) are the bounds SCIP's own probing cycle ends with
+    assert info["implied_bound_mismatches"] == 0, info
+    assert info["probes_with_changes"] == 0 or info["implied_bound_changes"] > 0, info
+
+
+def _ngpus():
+    try:
+        from scip_b200 import propagator
+        return propagator.load_library().gpulin_device_count()
+    except Exception:
+        return 0
+
+
+@needs_driver
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("name", ["bell5", "dcmulti", "egout", "p0548", "syn_mixedknap_300", "syn_setcover_2k_infeas"])
+def test_plugin_with_two_devices_reaches_the_reference_fixpoint(tmp_path, name):
+    """propagating/gpulinear/ndevices = 2: SCIP (one process, one thread) drives a copy of the rows on each of two GPUs
+    through SCIP_DECL_PROPEXEC; the devices share the dense rounds (gpulin_group_connect) -- same fixpoint as the reference"""
+    prob, ref = load_golden(name, "1e-9")
+    out = str(tmp_path / "o.lpr")
+    info = run_driver("--lpb", os.path.join(GOLDEN, name + ".lpb"), "--boundstreps", "1e-9", "--ndevices", "2", "--out", out)
+    got = oracle.read_lpr(out)
+    assert got["infeasible"] == ref["infeasible"], name
+    assert info["gpu_prop_calls"] >= 1
+    if not ref["infeasible"]:
+        assert_bounds_match(got["lb"] + 0.0, got["ub"] + 0.0, ref["lb"] + 0.0, ref["ub"] + 0.0, prob["vartype"], what=name)
+
+
+@needs_driver
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_plugin_with_two_devices_in_tree_search():
+    one = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve")
+    two = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", "--ndevices", "2")
+    assert two["scip_status"] == one["scip_status"] and abs(two["primal"] - one["primal"]) <= 1e-6
+    assert (two["nodes"], two["gpu_prop_calls"], two["gpu_domreds"]) == (one["nodes"], one["gpu_prop_calls"], one["gpu_domreds"])
