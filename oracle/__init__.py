@@ -85,8 +85,12 @@ def _problem(prob):
     return p, keep
 
 
-def propagate(prob, lb=None, ub=None, maxrounds: int = 0, **numerics):
+def propagate(prob, lb=None, ub=None, maxrounds: int = 0, rangedrow: bool = False, sortlb=None, sortub=None, tie=None,
+              **numerics):
     """Jacobi fixpoint of the C restatement.  ``prob`` is a dict with rowptr/colidx/vals/lhs/rhs/vartype (+lb/ub).
+    ``rangedrow``: with the gcd rule for ranged rows (rangedRowPropagation, cons_linear.c:5715-6696), which walks a row in
+    the reference's sorted order: ``sortlb`` / ``sortub`` = the global bounds the reference sorted by (default: the
+    bounds on entry), ``tie`` = SCIPvarGetProbindex of every column (default: the column index).
     Returns dict(status, lb, ub, nrounds, nchanges)."""
     p, keep = _problem(prob)
     num = _numerics(**numerics)
@@ -94,6 +98,20 @@ def propagate(prob, lb=None, ub=None, maxrounds: int = 0, **numerics):
     ub = np.array(prob["ub"] if ub is None else ub, dtype=np.float64, copy=True)
     nrounds = ctypes.c_int(0)
     nchg = ctypes.c_int64(0)
+    if rangedrow:
+        slb = None if sortlb is None else np.ascontiguousarray(sortlb, dtype=np.float64)
+        sub = None if sortub is None else np.ascontiguousarray(sortub, dtype=np.float64)
+        tb = None if tie is None else np.ascontiguousarray(tie, dtype=np.int32)
+        fn = _lib().oracle_propagate_ranged
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.POINTER(_Problem), ctypes.POINTER(_Numerics), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p, ctypes.c_void_p,
+                       ctypes.c_void_p]
+        st = fn(ctypes.byref(p), ctypes.byref(num), lb.ctypes.data, ub.ctypes.data, int(maxrounds), ctypes.byref(nrounds),
+                ctypes.byref(nchg), None if slb is None else slb.ctypes.data, None if sub is None else sub.ctypes.data,
+                None if tb is None else tb.ctypes.data)
+        del keep
+        return dict(status=int(st), lb=lb, ub=ub, nrounds=nrounds.value, nchanges=nchg.value)
     st = _lib().oracle_propagate(ctypes.byref(p), ctypes.byref(num), lb.ctypes.data, ub.ctypes.data, int(maxrounds),
                                  ctypes.byref(nrounds), ctypes.byref(nchg))
     del keep
@@ -158,7 +176,8 @@ def read_lpr(path):
                 solve_time_s=solvetime)
 
 
-def run_reference(path, boundstreps=None, dump_lpb=None, out_lpr=None, is_lpb=None, timeout=3600):
+def run_reference(path, boundstreps=None, dump_lpb=None, out_lpr=None, is_lpb=None, timeout=3600, rangedrow=False,
+                  dump_tie=None):
     """run the compiled reference on ``path`` (an .lpb, or any file a reference reader accepts); returns the
     parsed JSON summary (+ bounds if ``out_lpr`` is given)"""
     if not have_reference():
@@ -172,6 +191,10 @@ def run_reference(path, boundstreps=None, dump_lpb=None, out_lpr=None, is_lpb=No
         cmd += ["--dump-lpb", dump_lpb]
     if out_lpr:
         cmd += ["--out", out_lpr]
+    if rangedrow:
+        cmd += ["--rangedrow"]
+    if dump_tie:
+        cmd += ["--dump-tie", dump_tie]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=timeout).stdout
     res = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
     if out_lpr:

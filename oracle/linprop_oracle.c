@@ -16,6 +16,8 @@
  *   SCIPnodeAddBoundinfer (last drop)  tree.c:2020-2059
  *   tolerance predicates               set.c:6824-6976, 7133-7150, 7254-7372, 7433-7455, 7711-7753; misc.c:11162
  *   double-double sum                  dbldblarith.h:154-187
+ *   rangedRowPropagation (gcd rule)    cons_linear.c:5715-6696  (optional: oracle_propagate_ranged)
+ *   consdataCompVarProp (row order)    cons_linear.c:3191-3257  (the gcd rule walks the row in this order)
  *
  * Deliberate differences from the reference's control flow:
  *   - rounds are synchronous (Jacobi): every candidate of a round is judged against the round-start bounds and
@@ -503,7 +505,386 @@ static int tightenVarBounds(const ORACLE_NUMERICS* n, const ROWACT* ra, double a
    return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * ranged-row propagation: rangedRowPropagation, cons_linear.c:5715-6696, with constraints/linear/rangedrowartcons = FALSE
+ * (the branches that ADD constraints, :6286-6306, :6565-6600, :6603-6688, are not part of the bound propagation path).
+ *
+ * The rule walks the nonzeros of the row in storage order, and by the time it runs the reference has sorted the row
+ * (tightenBounds :7041 -> consdataSort :3337 -> consdataCompVarProp :3191): binaries first by decreasing |a|, then the
+ * other integers by decreasing |a (ub_global - lb_global)|, then the continuous variables; ties by SCIPvarGetProbindex.
+ * RANGED holds that order for every row with two finite sides and at least three nonzeros.
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct
+{
+   const int64_t* ord;       /* nnz: ord[rowptr[r] + v] = position (into colidx / vals) of the v-th nonzero of row r in sorted order */
+} RANGED;
+
+static double epsFloor(const ORACLE_NUMERICS* n, double x) { return floor(x + n->epsilon); }       /* SCIPfloor, def.h:197 */
+static double epsCeil(const ORACLE_NUMERICS* n, double x) { return ceil(x - n->epsilon); }         /* SCIPceil,  def.h:198 */
+static int epsIsInt(const ORACLE_NUMERICS* n, double x) { return x - epsFloor(n, x) <= n->epsilon; } /* SCIPisIntegral, def.h:203 */
+
+static long long calcGcd(long long a, long long b)      /* SCIPcalcGreComDiv (misc.c:9197): the value, by Euclid */
+{
+   while( b != 0 )
+   {
+      long long t = a % b;
+      a = b;
+      b = t;
+   }
+   return a;
+}
+
+/* comparator context (qsort has no user pointer in C99) */
+static const ORACLE_PROBLEM* g_sortprob = NULL;
+static const double* g_sortglb = NULL;
+static const double* g_sortgub = NULL;
+static const int32_t* g_sorttie = NULL;
+
+static int isBinaryCol(int64_t j)
+{
+   /* SCIPvarIsBinary (var.c:23801): binary type, or integral with global bounds inside [0,1] */
+   return g_sortprob->vartype[j] != 0 && g_sortglb[j] >= 0.0 && g_sortgub[j] <= 1.0;
+}
+
+static int compVarProp(const void* x, const void* y)     /* consdataCompVarProp, cons_linear.c:3191-3257 */
+{
+   const int64_t k1 = *(const int64_t*)x;
+   const int64_t k2 = *(const int64_t*)y;
+   const int64_t j1 = g_sortprob->colidx[k1];
+   const int64_t j2 = g_sortprob->colidx[k2];
+   const int b1 = isBinaryCol(j1);
+   const int b2 = isBinaryCol(j2);
+   const long long t1 = g_sorttie != NULL ? g_sorttie[j1] : j1;
+   const long long t2 = g_sorttie != NULL ? g_sorttie[j2] : j2;
+   if( b1 != b2 )
+      return b1 ? -1 : +1;
+   if( b1 )
+   {
+      const double a1 = fabs(g_sortprob->vals[k1]);
+      const double a2 = fabs(g_sortprob->vals[k2]);
+      if( a1 - a2 > 1e-9 )
+         return -1;
+      if( a2 - a1 > 1e-9 )
+         return +1;
+      return t1 < t2 ? -1 : (t1 > t2 ? +1 : 0);
+   }
+   else
+   {
+      const int i1 = g_sortprob->vartype[j1] != 0;
+      const int i2 = g_sortprob->vartype[j2] != 0;
+      if( i1 != i2 )
+         return i1 ? -1 : +1;          /* integer type before continuous */
+      if( !i1 )
+         return t1 < t2 ? -1 : (t1 > t2 ? +1 : 0);
+      else
+      {
+         const double c1 = fabs(g_sortprob->vals[k1] * (g_sortgub[j1] - g_sortglb[j1]));
+         const double c2 = fabs(g_sortprob->vals[k2] * (g_sortgub[j2] - g_sortglb[j2]));
+         if( c1 - c2 > 1e-9 )
+            return -1;
+         if( c2 - c1 > 1e-9 )
+            return +1;
+         return t1 < t2 ? -1 : (t1 > t2 ? +1 : 0);
+      }
+   }
+}
+
+static int isRangedRow(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, int64_t r)
+{
+   return p->rowptr[r + 1] - p->rowptr[r] >= 3 && !isInf(n, -p->lhs[r]) && !isInf(n, p->rhs[r]);
+}
+
+/* one row; candidates are merged into newlb / newub (judged against the round-start bounds lb / ub); returns 1 on cutoff */
+static int rangedRowPropagation(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const RANGED* rr, const double* lb,
+   const double* ub, int64_t r, double* newlb, double* newub)
+{
+   const int64_t beg = p->rowptr[r];
+   const int nvars = (int)(p->rowptr[r + 1] - beg);
+   const int64_t* ord = rr->ord + beg;
+   const double feastol = n->feastol;
+   double fixedact = 0.0;
+   double lhs, rhs;
+   double minactinfvars = 0.0;
+   double maxactinfvars = 0.0;
+   long long gcd;
+   int* infcheck;         /* positions v (sorted order) of the second group */
+   int ninfcheckvars = 0;
+   int nfixedconsvars = 0;
+   int nunfixedvars;
+   int ncontvars = 0;
+   int gcdisone = 1;
+   int possiblegcd = 1;
+   int cutoff = 0;
+   int v;
+
+#define RR_COL(v_)   (p->colidx[ord[v_]])
+#define RR_VAL(v_)   (p->vals[ord[v_]])
+#define RR_FIXED(v_) (isEQ(n, lb[RR_COL(v_)], ub[RR_COL(v_)]))
+#define RR_INT(v_)   (p->vartype[RR_COL(v_)] != 0)
+#define RR_SECOND(v_) (!RR_INT(v_) || !epsIsInt(n, RR_VAL(v_)) || isEQ(n, fabs(RR_VAL(v_)), 1.0))
+
+   if( !isRangedRow(p, n, r) )      /* :5771-5776 */
+      return 0;
+
+   /* fixed activity (:5805-5816), summed from the last nonzero to the first like the reference */
+   for( v = nvars - 1; v >= 0; --v )
+   {
+      if( RR_FIXED(v) )
+      {
+         fixedact += lb[RR_COL(v)] * RR_VAL(v);
+         ++nfixedconsvars;
+      }
+   }
+   if( isHuge(n, fabs(fixedact)) )     /* :5819 */
+      return 0;
+   lhs = p->lhs[r] - fixedact;
+   rhs = p->rhs[r] - fixedact;
+   nunfixedvars = nvars - nfixedconsvars;
+   infcheck = (int*)malloc(sizeof(int) * (size_t)(nvars + 1));
+
+   /* partition (:5851-5893): everything in front of the first unfixed integer variable with an integral coefficient of
+    * absolute value > 1 goes to the second group */
+   v = -1;
+   do
+   {
+      ++v;
+      while( v < nvars && RR_SECOND(v) )
+      {
+         if( !RR_FIXED(v) )
+         {
+            if( !RR_INT(v) )
+               ++ncontvars;
+            gcdisone = gcdisone && isEQ(n, fabs(RR_VAL(v)), 1.0);
+            possiblegcd = 0;
+            infcheck[ninfcheckvars++] = v;
+         }
+         ++v;
+      }
+   }
+   while( v < nvars && RR_FIXED(v) );
+
+   if( v == nvars || ncontvars + 2 > nunfixedvars )      /* :5889, :5893 */
+      goto TERMINATE;
+
+   gcd = (long long)(fabs(RR_VAL(v)) + feastol);
+   /* the rest (:5907-5957): gcd over the first group, what does not share a divisor joins the second */
+   for( ; v < nvars; ++v )
+   {
+      if( RR_FIXED(v) )
+         continue;
+      if( RR_SECOND(v) )
+      {
+         if( !RR_INT(v) )
+            ++ncontvars;
+         gcdisone = gcdisone && isEQ(n, fabs(RR_VAL(v)), 1.0);
+         possiblegcd = 0;
+         infcheck[ninfcheckvars++] = v;
+      }
+      else
+      {
+         const long long gcdtmp = calcGcd(gcd, (long long)(fabs(RR_VAL(v)) + feastol));
+         if( gcdtmp == 1 )
+            infcheck[ninfcheckvars++] = v;
+         else
+            gcd = gcdtmp;
+      }
+   }
+   if( ninfcheckvars == 0 )      /* :5962 */
+      goto TERMINATE;
+
+   /* activities of the second group (:5973-6018), last to first */
+   for( v = ninfcheckvars - 1; v >= 0; --v )
+   {
+      const double l = lb[RR_COL(infcheck[v])];
+      const double u = ub[RR_COL(infcheck[v])];
+      const double a = RR_VAL(infcheck[v]);
+      int mininvalid = 0;
+      int maxinvalid = 0;
+      if( isInf(n, -l) )
+      {
+         if( a < 0.0 ) maxinvalid = 1; else mininvalid = 1;
+      }
+      else
+      {
+         if( a < 0.0 ) maxactinfvars += a * l; else minactinfvars += a * l;
+      }
+      if( isInf(n, u) )
+      {
+         if( a > 0.0 ) maxinvalid = 1; else mininvalid = 1;
+      }
+      else
+      {
+         if( a > 0.0 ) maxactinfvars += a * u; else minactinfvars += a * u;
+      }
+      if( isHuge(n, -minactinfvars) )
+         mininvalid = 1;
+      if( isHuge(n, maxactinfvars) )
+         maxinvalid = 1;
+      if( mininvalid || maxinvalid )
+         goto TERMINATE;
+   }
+
+   /* no multiple of the gcd between the sides (:6036-6047) */
+   if( !epsIsInt(n, (lhs - maxactinfvars) / (double)gcd)
+      && isGT(n, epsCeil(n, (lhs - maxactinfvars) / (double)gcd) * (double)gcd, rhs - minactinfvars) )
+      cutoff = 1;
+   else if( ncontvars == 0 )
+   {
+      long long gcdinfvars = -1;
+      if( possiblegcd )
+      {
+         v = ninfcheckvars - 1;
+         gcdinfvars = (long long)(fabs(RR_VAL(infcheck[v])) + feastol);
+         for( ; v >= 0 && gcdinfvars >= 2; --v )
+            gcdinfvars = calcGcd(gcdinfvars, (long long)(fabs(RR_VAL(infcheck[v])) + feastol));
+      }
+      else if( gcdisone )
+         gcdinfvars = 1;
+
+      if( gcdinfvars >= 1 )
+      {
+         double value;
+         double value2;
+         double minvalue = 0.0;
+         double maxvalue = 0.0;
+         int haveminvalue = 0;
+         int nsols = 0;
+         long long guard = 0;
+
+         /* the values the second group can take, from below (:6072-6099) */
+         value = epsCeil(n, minactinfvars - feastol);
+         while( isLE(n, value, maxactinfvars) && ++guard < 100000000LL )
+         {
+            value2 = value + (double)gcd * epsCeil(n, (lhs - value) / (double)gcd);
+            if( !isGE(n, value2, lhs) )
+               value2 += (double)gcd;
+            if( isLE(n, value2, rhs) )
+            {
+               ++nsols;
+               if( nsols == 3 )
+                  break;
+               if( !haveminvalue )
+               {
+                  minvalue = value;
+                  haveminvalue = 1;
+               }
+               maxvalue = value;
+            }
+            value += (double)gcdinfvars;
+         }
+         /* more than two: the last one from above (:6103-6130) */
+         if( nsols == 3 )
+         {
+            guard = 0;
+            value = epsFloor(n, maxactinfvars + feastol);
+            while( isGE(n, value, minactinfvars) && ++guard < 100000000LL )
+            {
+               value2 = value + (double)gcd * epsFloor(n, (rhs - value) / (double)gcd);
+               if( !isLE(n, value2, rhs) )
+                  value2 -= (double)gcd;
+               if( isGE(n, value2, lhs) )
+               {
+                  maxvalue = value;
+                  break;
+               }
+               value -= (double)gcdinfvars;
+            }
+         }
+
+         if( nsols == 0 )        /* :6136 */
+            cutoff = 1;
+         else
+         {
+            /* the single variable that can be bounded: the only one of the second group (:6156, :6323), or the only
+             * unfixed one outside it (:6188, :6385) */
+            int target = -1;
+            int insecond = 0;
+            if( ninfcheckvars == 1 )
+            {
+               target = infcheck[0];
+               insecond = 1;
+            }
+            else if( ninfcheckvars == nunfixedvars - 1 )
+            {
+               int w = 0;
+               for( v = 0; v < nvars; ++v )
+               {
+                  if( RR_FIXED(v) )
+                     continue;
+                  if( w < ninfcheckvars && infcheck[w] == v )
+                  {
+                     ++w;
+                     continue;
+                  }
+                  target = v;
+                  break;
+               }
+            }
+            if( target >= 0 )
+            {
+               const int64_t j = RR_COL(target);
+               const double a = RR_VAL(target);
+               const int integral = p->vartype[j] != 0;
+               double nlb, nub;
+               if( nsols == 1 )
+               {
+                  /* SCIPinferVarFixCons (scip_var.c:6896): lower bound, then upper bound, both forced */
+                  double fix;
+                  if( insecond )
+                     fix = maxvalue / a;                                                      /* :6172 */
+                  else
+                     fix = a < 0.0 ? epsFloor(n, (lhs - maxvalue) / a) : epsCeil(n, (lhs - maxvalue) / a);   /* :6224-6231 */
+                  inferLb(n, integral, fix, lb[j], ub[j], 1, &newlb[j], &cutoff);
+                  if( !cutoff )
+                     inferUb(n, integral, fix, lb[j], ub[j], 1, &newub[j], &cutoff);
+               }
+               else
+               {
+                  if( insecond )
+                  {
+                     nlb = a < 0.0 ? maxvalue / a : minvalue / a;            /* :6332-6341 */
+                     nub = a < 0.0 ? minvalue / a : maxvalue / a;
+                  }
+                  else if( a < 0.0 )
+                  {
+                     nlb = epsFloor(n, (rhs - minvalue) / a);                /* :6424-6427 */
+                     nub = epsFloor(n, (lhs - maxvalue) / a);
+                  }
+                  else
+                  {
+                     nlb = epsCeil(n, (lhs - maxvalue) / a);                 /* :6431-6432 */
+                     nub = epsCeil(n, (rhs - minvalue) / a);
+                  }
+                  if( nlb > lb[j] )
+                     inferLb(n, integral, nlb, lb[j], ub[j], 1, &newlb[j], &cutoff);
+                  if( !cutoff && nub < ub[j] )
+                     inferUb(n, integral, nub, lb[j], ub[j], 1, &newub[j], &cutoff);
+               }
+            }
+         }
+      }
+   }
+
+ TERMINATE:
+   free(infcheck);
+   return cutoff;
+#undef RR_COL
+#undef RR_VAL
+#undef RR_FIXED
+#undef RR_INT
+#undef RR_SECOND
+}
+
+static int sweepImpl(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const RANGED* rr, const double* lb, const double* ub,
+   double* newlb, double* newub, int64_t rowbegin, int64_t rowend);
+
 int oracle_sweep(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const double* lb, const double* ub,
+   double* newlb, double* newub, int64_t rowbegin, int64_t rowend)
+{
+   return sweepImpl(p, n, NULL, lb, ub, newlb, newub, rowbegin, rowend);
+}
+
+static int sweepImpl(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const RANGED* rr, const double* lb, const double* ub,
    double* newlb, double* newub, int64_t rowbegin, int64_t rowend)
 {
    int64_t r;
@@ -555,6 +936,10 @@ int oracle_sweep(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const double
             return 1;
       }
 
+      /* ranged rows (propagateCons :7699-7712; tightenbounds is on) */
+      if( rr != NULL && rangedRowPropagation(p, n, rr, lb, ub, r, newlb, newub) )
+         return 1;
+
       /* row verdict: cons_linear.c:7715-7742 (goodrelax = TRUE) */
       getMinActivity(n, ra.minact, ra.minposinf, ra.minneginf, ra.minposhuge, ra.minneghuge, 0.0, 1, &minact, &t1, &s1);
       getMaxActivity(n, ra.maxact, ra.maxposinf, ra.maxneginf, ra.maxposhuge, ra.maxneghuge, 0.0, 1, &maxact, &t2, &s2);
@@ -593,8 +978,55 @@ int64_t oracle_redundant_rows(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n,
    return count;
 }
 
+static int propagateImpl(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const RANGED* rr, double* lb, double* ub,
+   int maxrounds, int* nrounds, int64_t* nchanges);
+
 int oracle_propagate(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, double* lb, double* ub, int maxrounds,
    int* nrounds, int64_t* nchanges)
+{
+   return propagateImpl(p, n, NULL, lb, ub, maxrounds, nrounds, nchanges);
+}
+
+/* the sorted order of every ranged row (see RANGED); sortlb / sortub: the global bounds the reference sorts by, tie: the
+ * SCIPvarGetProbindex of every column or NULL (the column index) */
+int64_t oracle_ranged_order(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const double* sortlb, const double* sortub,
+   const int32_t* tie, int64_t* ord)
+{
+   int64_t r;
+   int64_t k;
+   int64_t nranged = 0;
+   for( k = 0; k < p->nnz; ++k )
+      ord[k] = k;
+   g_sortprob = p;
+   g_sortglb = sortlb;
+   g_sortgub = sortub;
+   g_sorttie = tie;
+   for( r = 0; r < p->nrows; ++r )
+   {
+      if( isRangedRow(p, n, r) )
+      {
+         qsort(ord + p->rowptr[r], (size_t)(p->rowptr[r + 1] - p->rowptr[r]), sizeof(int64_t), compVarProp);
+         ++nranged;
+      }
+   }
+   return nranged;
+}
+
+int oracle_propagate_ranged(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, double* lb, double* ub, int maxrounds,
+   int* nrounds, int64_t* nchanges, const double* sortlb, const double* sortub, const int32_t* tie)
+{
+   RANGED rr;
+   int64_t* ord = (int64_t*)malloc(sizeof(int64_t) * (size_t)(p->nnz + 1));
+   int status;
+   oracle_ranged_order(p, n, sortlb != NULL ? sortlb : lb, sortub != NULL ? sortub : ub, tie, ord);
+   rr.ord = ord;
+   status = propagateImpl(p, n, &rr, lb, ub, maxrounds, nrounds, nchanges);
+   free(ord);
+   return status;
+}
+
+static int propagateImpl(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, const RANGED* rr, double* lb, double* ub,
+   int maxrounds, int* nrounds, int64_t* nchanges)
 {
    double* newlb = (double*)malloc(sizeof(double) * (size_t)(p->ncols + 1));
    double* newub = (double*)malloc(sizeof(double) * (size_t)(p->ncols + 1));
@@ -618,7 +1050,7 @@ int oracle_propagate(const ORACLE_PROBLEM* p, const ORACLE_NUMERICS* n, double* 
       memcpy(newlb, lb, sizeof(double) * (size_t)p->ncols);
       memcpy(newub, ub, sizeof(double) * (size_t)p->ncols);
       ++round;
-      cutoff = oracle_sweep(p, n, lb, ub, newlb, newub, 0, p->nrows);
+      cutoff = sweepImpl(p, n, rr, lb, ub, newlb, newub, 0, p->nrows);
       if( cutoff )
       {
          status = ORACLE_STATUS_CUTOFF;

@@ -60,6 +60,35 @@ int oracle_propagate(
    int64_t*               nchanges    /* out: number of accepted bound changes (per variable and round) */
    );
 
+/** the same with ranged-row propagation switched on (rangedRowPropagation, cons_linear.c:5715-6696, with
+ *  constraints/linear/rangedrowartcons = FALSE): after the bound tightening of a row with two finite sides and at least
+ *  three nonzeros the gcd rule runs on it.  The rule walks the row in the order the reference has sorted it in
+ *  (consdataCompVarProp, cons_linear.c:3191): sortlb / sortub = the global bounds at that time (NULL: lb / ub on entry),
+ *  tie = SCIPvarGetProbindex of every column (NULL: the column index) */
+int oracle_propagate_ranged(
+   const ORACLE_PROBLEM*  prob,
+   const ORACLE_NUMERICS* num,
+   double*                lb,
+   double*                ub,
+   int                    maxrounds,
+   int*                   nrounds,
+   int64_t*               nchanges,
+   const double*          sortlb,
+   const double*          sortub,
+   const int32_t*         tie
+   );
+
+/** the order itself: ord[rowptr[r] + v] = position of the v-th nonzero of row r in the reference's sorted order (identity
+ *  for rows the ranged-row rule does not look at); returns the number of ranged rows */
+int64_t oracle_ranged_order(
+   const ORACLE_PROBLEM*  prob,
+   const ORACLE_NUMERICS* num,
+   const double*          sortlb,
+   const double*          sortub,
+   const int32_t*         tie,
+   int64_t*               ord        /* nnz, out */
+   );
+
 /** one synchronous sweep over rows [rowbegin,rowend): reads lb/ub, writes improved bounds into newlb/newub
  *  (which must hold copies of lb/ub on entry); returns 1 if a cutoff was detected, else 0 */
 int oracle_sweep(

@@ -125,6 +125,11 @@ static int lpb_read(const char* fn, LPB* p)
 /** index of a transformed variable in original-variable order (stored in a side table keyed by probindex) */
 static int* g_probidx2orig = NULL;
 
+/* --dump-tie FILE: SCIPvarGetProbindex of every variable (.lpb order) at the first root propagation -- the last key by
+ * which the reference sorts the nonzeros of a row (consdataCompVarProp, cons_linear.c:3191), which the ranged-row rule walks */
+static const char* g_tiefile = NULL;
+static int32_t* g_tie = NULL;
+
 /** dump the linear rows as seen at the first propagation call */
 static SCIP_RETCODE dumpProblem(SCIP* scip, SCIP_PROPDATA* propdata)
 {
@@ -139,6 +144,8 @@ static SCIP_RETCODE dumpProblem(SCIP* scip, SCIP_PROPDATA* propdata)
 
    ntransvars = SCIPgetNVars(scip);
    g_probidx2orig = (int*)malloc(sizeof(int) * (size_t)(ntransvars + 1));
+   if( g_tiefile != NULL )
+      g_tie = (int32_t*)malloc(sizeof(int32_t) * (size_t)(propdata->norigvars + 1));
    for( i = 0; i < ntransvars; ++i )
       g_probidx2orig[i] = -1;
 
@@ -156,6 +163,8 @@ static SCIP_RETCODE dumpProblem(SCIP* scip, SCIP_PROPDATA* propdata)
          return SCIP_ERROR;
       }
       g_probidx2orig[pi] = i;
+      if( g_tiefile != NULL )
+         g_tie[i] = pi;
       p.lb[i] = SCIPvarGetLbLocal(tv);
       p.ub[i] = SCIPvarGetUbLocal(tv);
       p.vartype[i] = SCIPvarIsIntegral(tv) ? 1 : 0;
@@ -466,6 +475,7 @@ static SCIP_RETCODE run(int argc, char** argv)
    double boundstreps = -1.0;
    int quiet = 1;
    int repeat = 1;
+   int rangedrow = 0;
    int rep;
    int i;
    double t0, t1, tbuild;
@@ -484,6 +494,8 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--probe") == 0 && i + 1 < argc ) g_nprobe = atoi(argv[++i]);
       else if( strcmp(argv[i], "--redundant") == 0 && i + 1 < argc ) redfile = argv[++i];
       else if( strcmp(argv[i], "--repeat") == 0 && i + 1 < argc ) repeat = atoi(argv[++i]);
+      else if( strcmp(argv[i], "--rangedrow") == 0 ) rangedrow = 1;
+      else if( strcmp(argv[i], "--dump-tie") == 0 && i + 1 < argc ) g_tiefile = argv[++i];
       else if( strcmp(argv[i], "--reprop") == 0 && i + 1 < argc ) g_reprop = atoi(argv[++i]);
       else
       {
@@ -521,6 +533,12 @@ static SCIP_RETCODE run(int argc, char** argv)
    SCIP_CALL( SCIPincludePropBasic(scip, &prop, "refdump", "dumps linear rows at the first root propagation call",
          100000000, 1, FALSE, SCIP_PROPTIMING_BEFORELP, propExecDump, &propdata) );
    SCIP_CALL( applyParitySettings(scip, boundstreps, quiet) );
+   if( rangedrow )
+   {
+      /* the gcd rule on, its branches that ADD constraints off (they change the model, not the bounds) */
+      SCIP_CALL( SCIPsetBoolParam(scip, "constraints/linear/rangedrowpropagation", TRUE) );
+      SCIP_CALL( SCIPsetBoolParam(scip, "constraints/linear/rangedrowartcons", FALSE) );
+   }
 
    t0 = wallclock();
    if( readfile != NULL )
@@ -635,6 +653,15 @@ static SCIP_RETCODE run(int argc, char** argv)
       fclose(f);
    }
 
+   if( g_tiefile != NULL && g_tie != NULL )
+   {
+      f = fopen(g_tiefile, "wb");
+      if( f == NULL )
+         return SCIP_ERROR;
+      fwrite(g_tie, sizeof(int32_t), (size_t)propdata.norigvars, f);
+      fclose(f);
+   }
+   free(g_tie);
    free(propdata.origvars);
    free(g_probidx2orig);
    free(g_lpbvars);

@@ -301,3 +301,80 @@ def edge_huge(infeasible=False):
     lhs = [-INF, -4.5e15 if not infeasible else -3.5e15, -INF]
     rhs = [3.5e15 if not infeasible else 2.5e15, INF, 6.0]
     return _from_rows(rows, lhs, rhs, lb, ub, vt)
+
+
+def ranged_rows(nrows=400, ncols=600, seed=31, infeasible=False):
+    """equations and ranged rows with a divisibility structure -- what the reference's ranged-row propagation looks at
+    (rangedRowPropagation, cons_linear.c:5715-6696): integer variables whose coefficients share a divisor g >= 2, beside
+    one variable (or a few) with a coefficient of 1 or one that is coprime to g.  Row kinds: (A) g-group + one odd
+    variable, equation; (B) the same with sides a little apart; (C) one variable with coefficient g beside several +1 / -1
+    variables; (D) with a continuous variable (only the infeasibility test applies); (E) plain inequalities that couple the
+    variables.  A feasible point is planted; ``infeasible`` adds the reference's own example 12 x1 + 9 x2 - x3 = 0 with
+    x3 in [1, 2]."""
+    rng = np.random.default_rng(seed)
+    kind = rng.random(ncols)
+    vartype = (kind < 0.85).astype(np.uint8)
+    isbin = kind < 0.25
+    ub = np.where(isbin, 1.0, np.where(vartype != 0, rng.integers(3, 61, size=ncols).astype(np.float64), 10.0))
+    lb = np.zeros(ncols)
+    xstar = np.where(vartype != 0, np.floor(rng.random(ncols) * (ub + 1.0)), np.round(rng.random(ncols) * ub, 3))
+    xstar = np.minimum(xstar, ub)
+    fixed = rng.random(ncols) < 0.04
+    lb = np.where(fixed, xstar, lb)
+    ub = np.where(fixed, xstar, ub)
+    ints = np.flatnonzero((vartype != 0) & ~isbin)
+    bins = np.flatnonzero(isbin)
+    conts = np.flatnonzero(vartype == 0)
+    rows, lhs, rhs = [], [], []
+    for r in range(nrows):
+        t = rng.random()
+        g = int(rng.choice([2, 3, 4, 5, 6, 10, 12]))
+        if t < 0.35 or t >= 0.9:            # (A) / (D)
+            k = int(rng.integers(2, 7))
+            cols = rng.choice(ints, size=k + 1, replace=False)
+            coefs = [float(g * int(rng.integers(1, 6)) * (1 if rng.random() < 0.7 else -1)) for _ in range(k)]
+            odd = [1.0, -1.0, float(g + 1), float(2 * g - 1)][int(rng.integers(0, 4))]
+            row = list(zip(cols[:k].tolist(), coefs)) + [(int(cols[k]), odd)]
+            if t >= 0.9 and len(conts) > 0:
+                row.append((int(rng.choice(conts)), float(rng.integers(1, 4))))
+            act = sum(a * xstar[j] for j, a in row)
+            rows.append(row)
+            lhs.append(act)
+            rhs.append(act)
+        elif t < 0.55:                      # (B)
+            k = int(rng.integers(2, 6))
+            cols = rng.choice(ints, size=k + 1, replace=False)
+            row = [(int(cols[i]), float(g * int(rng.integers(1, 5)))) for i in range(k)] + [(int(cols[k]), 1.0)]
+            act = sum(a * xstar[j] for j, a in row)
+            rows.append(row)
+            lhs.append(act - float(rng.integers(0, max(g - 1, 1))))
+            rhs.append(act + float(rng.integers(0, max(g - 1, 1))))
+        elif t < 0.75:                      # (C)
+            k = int(rng.integers(2, 6))
+            z = int(rng.choice(ints))
+            others = rng.choice(bins, size=k, replace=False)
+            row = [(z, float(g * (1 if rng.random() < 0.8 else -1)))] + [(int(j), 1.0 if rng.random() < 0.6 else -1.0) for j in others]
+            act = sum(a * xstar[j] for j, a in row)
+            rows.append(row)
+            lhs.append(act)
+            rhs.append(act + float(rng.integers(0, 2)))
+        else:                               # (E)
+            k = int(rng.integers(3, 9))
+            cols = rng.choice(ncols, size=k, replace=False)
+            row = [(int(j), float(rng.integers(1, 9)) * (1 if rng.random() < 0.8 else -1)) for j in cols]
+            act = sum(a * xstar[j] for j, a in row)
+            rows.append(row)
+            lhs.append(-INF)
+            rhs.append(act + float(rng.integers(0, 6)))
+    if infeasible:
+        # three fresh integer columns: only the divisibility argument sees that the row has no solution
+        x1, x2, x3 = ncols, ncols + 1, ncols + 2
+        lb = np.concatenate([lb, [-INF, -INF, 1.0]])
+        ub = np.concatenate([ub, [INF, INF, 2.0]])
+        vartype = np.concatenate([vartype, np.ones(3, dtype=np.uint8)])
+        rows.append([(x1, 12.0), (x2, 9.0), (x3, -1.0)])
+        lhs.append(0.0)
+        rhs.append(0.0)
+    prob = _from_rows(rows, lhs, rhs, lb, ub, vartype)
+    prob["name"] = f"ranged_rows_{nrows}x{ncols}_s{seed}"
+    return prob

@@ -16,9 +16,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names():
+def _manifest():
     with open(os.path.join(GOLDEN, "manifest.json")) as f:
-        return sorted(json.load(f))
+        return json.load(f)
+
+
+def golden_names():
+    """fixtures of the parity protocol proper (ranged-row propagation off on both sides)"""
+    return sorted(n for n, e in _manifest().items() if not e["1e-9"].get("rangedrow"))
+
+
+def golden_ranged_names():
+    """fixtures the reference produced with constraints/linear/rangedrowpropagation = TRUE (rangedrowartcons = FALSE)"""
+    return sorted(n for n, e in _manifest().items() if e["1e-9"].get("rangedrow"))
+
+
+def load_golden_tie(name):
+    """SCIPvarGetProbindex of every column of a ranged-row fixture: the last sort key of the row order its rule walks"""
+    return np.fromfile(os.path.join(GOLDEN, name + ".tie"), dtype=np.int32)
 
 
 def load_golden(name, bs):

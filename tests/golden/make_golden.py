@@ -47,6 +47,16 @@ def main():
         "syn_edge_huge": synth.edge_huge(),
         "syn_edge_huge_infeas": synth.edge_huge(infeasible=True),
     }
+    # ranged-row (gcd) propagation, rangedRowPropagation cons_linear.c:5715-6696: these instances are run with
+    # constraints/linear/rangedrowpropagation = TRUE (and rangedrowartcons = FALSE: the rule's branches that add constraints
+    # are not bound propagation); <name>.tie = SCIPvarGetProbindex of every column, the last sort key of the row order
+    # the rule walks (consdataCompVarProp :3191)
+    ranged_probs = {
+        "syn_ranged_400": synth.ranged_rows(400, 600, seed=31),
+        "syn_ranged_400b": synth.ranged_rows(400, 600, seed=33),
+        "syn_ranged_infeas": synth.ranged_rows(200, 300, seed=34, infeasible=True),
+    }
+    synth_probs.update(ranged_probs)
     for name, prob in synth_probs.items():
         path = os.path.join("/tmp", name + ".gen.lpb")
         write_lpb(path, prob)
@@ -54,11 +64,15 @@ def main():
     for name, path, is_lpb in jobs:
         entry = {}
         for bs in ("1e-9", "0.05"):
+            ranged = name in ranged_probs
             res = oracle.run_reference(path, boundstreps=float(bs), is_lpb=is_lpb,
                                        dump_lpb=os.path.join(HERE, name + ".lpb"),
-                                       out_lpr=os.path.join(HERE, f"{name}.bs{bs}.lpr"))
+                                       out_lpr=os.path.join(HERE, f"{name}.bs{bs}.lpr"), rangedrow=ranged,
+                                       dump_tie=os.path.join(HERE, name + ".tie") if ranged else None)
             entry[bs] = dict(infeasible=bool(res["infeasible"]), prop_calls=int(res["prop_calls"]),
                              domreds=int(res["domreds"]))
+            if ranged:
+                entry[bs]["rangedrow"] = True
         manifest[name] = entry
         print(name, entry)
     with open(os.path.join(HERE, "manifest.json"), "w") as f:

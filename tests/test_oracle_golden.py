@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import assert_bounds_match, golden_names, load_golden, load_golden_redundant
+from conftest import assert_bounds_match, golden_names, golden_ranged_names, load_golden, load_golden_redundant, load_golden_tie
 
 NAMES = golden_names()
 
@@ -79,3 +79,21 @@ def test_oracle_redundant_rows_are_the_rows_the_reference_deletes(name):
     deleted = load_golden_redundant(name)
     assert deleted.shape == (len(prob["lhs"]),)
     assert np.array_equal(oracle.redundant_rows(prob, ref["lb"], ref["ub"], boundstreps=1e-9), deleted)
+
+
+@pytest.mark.parametrize("name", golden_ranged_names())
+@pytest.mark.parametrize("bs", ["1e-9", "0.05"])
+def test_oracle_ranged_row_propagation_matches_the_reference(name, bs):
+    # rangedRowPropagation (cons_linear.c:5715-6696; the gcd rule for equations and ranged rows) switched on in the
+    # reference; the restatement walks every row in the reference's sorted order (consdataCompVarProp :3191)
+    prob, ref = load_golden(name, bs)
+    res = oracle.propagate(prob, boundstreps=float(bs), maxrounds=1000, rangedrow=True, tie=load_golden_tie(name))
+    assert (res["status"] == oracle.STATUS_CUTOFF) == ref["infeasible"]
+    if not ref["infeasible"]:
+        if bs == "1e-9":
+            assert_bounds_match(res["lb"], res["ub"], ref["lb"] + 0.0, ref["ub"] + 0.0, prob["vartype"], what=name)
+        # the rule finds something the activity argument does not
+        plain = oracle.propagate(prob, boundstreps=float(bs), maxrounds=1000)
+        assert ((plain["lb"] != res["lb"]) | (plain["ub"] != res["ub"])).sum() > 0
+    else:
+        assert oracle.propagate(prob, boundstreps=float(bs), maxrounds=1000)["status"] == oracle.STATUS_FIXPOINT
