@@ -117,6 +117,15 @@ int gpulin_set_reference_bounds(gpulin_t* h, const double* lb, const double* ub)
 int gpulin_set_bounds_packed(gpulin_t* h, const uint32_t* codes, int64_t nexplicit, const int32_t* idx, const double* lb,
    const double* ub);
 
+/** ranged-row propagation on (enable != 0) or off (the default): the gcd rule for equations and ranged rows with at least
+ *  three nonzeros -- rangedRowPropagation, cons_linear.c:5715-6696 (constraints/linear/rangedrowpropagation), without its
+ *  branches that add constraints (constraints/linear/rangedrowartcons = FALSE) -- runs on every marked ranged row beside the
+ *  activity rules.  The rule depends on the order in which it walks a row, and the reference has sorted the row by then
+ *  (consdataCompVarProp, cons_linear.c:3191-3257): glb / gub = the global bounds the reference sorts by
+ *  (SCIPvarGetLbGlobal / UbGlobal), tie = SCIPvarGetProbindex of every column (NULL: the column index).  Call it before
+ *  the handle is connected to peers or cloned */
+int gpulin_set_rangedrow(gpulin_t* h, int enable, const double* glb, const double* gub, const int32_t* tie);
+
 /** overwrites n bounds (tightened or relaxed: branching, backtracking) and marks only the rows of those
  *  columns -- the counterpart of eventExecLinear's SCIPmarkConsPropagate (cons_linear.c:17229) */
 int gpulin_update_bounds(gpulin_t* h, int64_t n, const int32_t* idx, const double* lb, const double* ub);

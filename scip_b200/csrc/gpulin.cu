@@ -48,7 +48,7 @@ static int fail(int code, const char* fmt, ...)
 // the read-only device arrays of the matrix, shared by a handle and its clones (gpulin_clone)
 struct SharedMatrix
 {
-   void*  ptrs[16] = {nullptr};
+   void*  ptrs[64] = {nullptr};
    int    n = 0;
    int    refs = 1;
    size_t bytes = 0;
@@ -93,6 +93,14 @@ struct gpulin
    double*     d_updlb = nullptr;
    double*     d_updub = nullptr;
    int64_t     updcap = 0;
+   // ranged-row propagation (gpulin_set_rangedrow): host copy of the rows with two finite sides and >= 3 nonzeros
+   std::vector<int> rr_row;             // permuted row id
+   std::vector<long long> rr_ptr;
+   std::vector<int> rr_col;
+   std::vector<double> rr_val;
+   std::vector<unsigned char> h_vartype;
+   void*       d_rr[6] = {nullptr};     // device arrays of RangedRows (beg, row, cols, vals, idx, scratch)
+   int         nrangedblocks = 0;
    double2*    d_ref = nullptr;     // reference bounds of gpulin_set_bounds_packed (allocated on first use)
    unsigned*   d_codes = nullptr;   // ... and the staged codes, 2 bits per column
    unsigned*   d_packlog = nullptr; // staging of gpulin_get_changes_packed (12 bytes per entry)
@@ -237,6 +245,9 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = 
 {
    if( sweep )
    {
+      // ranged rows first: the gcd rule looks at the marks the sweeps are about to lower
+      if( h->p.rr.n > 0 && MODE == APPLY_LIST )
+         rangedrow_kernel<<<h->nrangedblocks, RANGED_THREADS, 0, h->stream>>>(h->p);
       // the three bins are independent: the smaller ones run on side streams beside the largest
       const int nkinds = (h->nsellblocks > 0) + (h->nstreamblocks > 0) + (h->nlongblocks > 0);
       int side = 0;
@@ -505,6 +516,24 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    for( int64_t i = 0; i < nrows; ++i )
       sides[(size_t)i] = make_double2(lhs[perm[(size_t)i]], rhs[perm[(size_t)i]]);
 
+   // ---- rows the ranged-row rule looks at (rangedRowPropagation :5771-5776): kept on the host until gpulin_set_rangedrow
+   h->rr_ptr.assign(1, 0);
+   for( int64_t i = 0; i < nrows; ++i )
+   {
+      const int64_t r = perm[(size_t)i];
+      if( plen[(size_t)i] >= 3 && lhs[r] > -num->infinity && rhs[r] < num->infinity )
+      {
+         h->rr_row.push_back((int)i);
+         for( int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k )
+         {
+            h->rr_col.push_back(colidx[k]);
+            h->rr_val.push_back(vals[k]);
+         }
+         h->rr_ptr.push_back((long long)h->rr_col.size());
+      }
+   }
+   h->h_vartype.assign(vartype, vartype + ncols);
+
    // ---- tiles of the stream: row-end bit per nonzero, first unfinished row per tile ----------------------------------
    std::vector<unsigned char> endmask((size_t)h->ntiles * 32 + 32, 0);
    std::vector<int> tile_row0((size_t)h->ntiles + 2, nsx);
@@ -666,6 +695,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.ctrl = d_ctrl;
    p.log = nullptr;
    p.peers = nullptr;
+   memset(&p.rr, 0, sizeof(p.rr));
    setShare(h, 0, 1);
    {
       // expected marks per row >= 1: marking every row is cheaper than walking the columns (see apply_kernel) -- where a
@@ -790,6 +820,7 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    cudaFree(h->d_updidx);
    cudaFree(h->d_updlb);
    cudaFree(h->d_updub);
+   cudaFree(h->d_rr[5]);
    cudaFree(h->d_ref);
    cudaFree(h->d_codes);
    cudaFree(h->d_packlog);
@@ -957,6 +988,112 @@ extern "C" int gpulin_get_changes_packed(gpulin_t* h, void* out, int64_t maxn, i
    CU(cudaGetLastError());
    CU(cudaMemcpyAsync(out, h->d_packlog, 12 * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
    CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}
+
+// ranged-row propagation on / off.  On: every ranged row is copied in the order the reference walks it -- the order of
+// consdataCompVarProp (cons_linear.c:3191-3257): binaries by decreasing |a|, the other integers by decreasing
+// |a (ub_global - lb_global)|, continuous variables; ties by SCIPvarGetProbindex (`tie`, NULL: the column index)
+extern "C" int gpulin_set_rangedrow(gpulin_t* h, int enable, const double* glb, const double* gub, const int32_t* tie)
+{
+   if( h == nullptr || (enable && (glb == nullptr || gub == nullptr)) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( h->npeers > 1 && (h->p.rr.n > 0) != (enable != 0 && !h->rr_row.empty()) )
+      return fail(GPULIN_ERR_STATE, "gpulin_set_rangedrow must be called before the handle is connected to peers");
+   CU(cudaSetDevice(h->device));
+   CU(cudaStreamSynchronize(h->stream));
+   // (the row copies belong to the shared matrix -- clones use them; arrays of an earlier call stay until it goes --,
+   // the scratch words to this handle)
+   cudaFree(h->d_rr[5]);
+   for( int i = 0; i < 6; ++i )
+      h->d_rr[i] = nullptr;
+   memset(&h->p.rr, 0, sizeof(h->p.rr));
+   const int n = (int)h->rr_row.size();
+   if( enable && n > 0 && h->shared->n + 5 > 64 )
+      return fail(GPULIN_ERR_STATE, "gpulin_set_rangedrow called too often on this matrix");
+   if( enable && n > 0 )
+   {
+      const size_t nnzr = h->rr_col.size();
+      std::vector<int> scols(nnzr);
+      std::vector<double> svals(nnzr);
+      std::vector<int> order;
+      int maxlen = 0;
+      auto isbin = [&](int j) { return h->h_vartype[(size_t)j] != 0 && glb[j] >= 0.0 && gub[j] <= 1.0; };
+      auto tiekey = [&](int j) { return tie != nullptr ? (long long)tie[j] : (long long)j; };
+      for( int i = 0; i < n; ++i )
+      {
+         const long long b = h->rr_ptr[(size_t)i];
+         const int len = (int)(h->rr_ptr[(size_t)i + 1] - b);
+         maxlen = std::max(maxlen, len);
+         order.resize((size_t)len);
+         std::iota(order.begin(), order.end(), 0);
+         const int* c = h->rr_col.data() + b;
+         const double* a = h->rr_val.data() + b;
+         std::sort(order.begin(), order.end(), [&](int x, int y) {
+            const int j1 = c[x];
+            const int j2 = c[y];
+            const bool b1 = isbin(j1);
+            const bool b2 = isbin(j2);
+            if( b1 != b2 )
+               return b1;
+            if( b1 )
+            {
+               const double a1 = std::fabs(a[x]);
+               const double a2 = std::fabs(a[y]);
+               if( a1 - a2 > 1e-9 ) return true;
+               if( a2 - a1 > 1e-9 ) return false;
+               return tiekey(j1) < tiekey(j2);
+            }
+            const bool i1 = h->h_vartype[(size_t)j1] != 0;
+            const bool i2 = h->h_vartype[(size_t)j2] != 0;
+            if( i1 != i2 )
+               return i1;
+            if( !i1 )
+               return tiekey(j1) < tiekey(j2);
+            const double c1 = std::fabs(a[x] * (gub[j1] - glb[j1]));
+            const double c2 = std::fabs(a[y] * (gub[j2] - glb[j2]));
+            if( c1 - c2 > 1e-9 ) return true;
+            if( c2 - c1 > 1e-9 ) return false;
+            return tiekey(j1) < tiekey(j2);
+         });
+         for( int v = 0; v < len; ++v )
+         {
+            const int j = c[order[(size_t)v]];
+            scols[(size_t)(b + v)] = j | (h->h_vartype[(size_t)j] != 0 ? (int)0x80000000u : 0);
+            svals[(size_t)(b + v)] = a[order[(size_t)v]];
+         }
+      }
+      std::vector<int> idx((size_t)h->nrows + 1, -1);
+      for( int i = 0; i < n; ++i )
+         idx[(size_t)h->rr_row[(size_t)i]] = i;
+      const int scratchwords = (maxlen + 31) / 32 + 1;
+      const size_t nwarps = (size_t)h->nsm * 64;      // more warps than any grid that runs the rule has
+      size_t bytes[6] = {sizeof(long long) * ((size_t)n + 1), sizeof(int) * (size_t)n, sizeof(int) * nnzr, sizeof(double) * nnzr,
+         sizeof(int) * ((size_t)h->nrows + 1), sizeof(unsigned) * nwarps * (size_t)scratchwords};
+      const void* src[6] = {h->rr_ptr.data(), h->rr_row.data(), scols.data(), svals.data(), idx.data(), nullptr};
+      for( int i = 0; i < 6; ++i )
+      {
+         if( cudaMalloc(&h->d_rr[i], std::max<size_t>(bytes[i], 16)) != cudaSuccess )
+            return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the ranged rows failed");
+         if( src[i] != nullptr )
+            CU(cudaMemcpy(h->d_rr[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+         if( i < 5 )
+            h->shared->ptrs[h->shared->n++] = h->d_rr[i];
+      }
+      RangedRows& R = h->p.rr;
+      R.n = n;
+      R.beg = (const long long*)h->d_rr[0];
+      R.row = (const int*)h->d_rr[1];
+      R.cols = (const int*)h->d_rr[2];
+      R.vals = (const double*)h->d_rr[3];
+      R.idx = (const int*)h->d_rr[4];
+      R.scratch = (unsigned*)h->d_rr[5];
+      R.scratchwords = scratchwords;
+      h->nrangedblocks = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n * 32 + RANGED_THREADS - 1) / RANGED_THREADS, (int64_t)h->nsm * 8));
+   }
+   // kernel parameters are baked into the graph
+   if( !h->hostloop )
+      OK(buildGraph(h));
    return GPULIN_OK;
 }
 
@@ -1399,6 +1536,18 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    p.ctrl = d_ctrl;
    p.log = nullptr;
    p.peers = nullptr;
+   h->nrangedblocks = src->nrangedblocks;
+   if( p.rr.n > 0 )
+   {
+      // the ranged rows are shared, the scratch words of the rule are not
+      const size_t words = (size_t)h->nsm * 64 * (size_t)p.rr.scratchwords;
+      if( cudaMalloc(&h->d_rr[5], sizeof(unsigned) * words) != cudaSuccess )
+      {
+         gpulin_destroy(h);
+         return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the ranged-row scratch failed");
+      }
+      p.rr.scratch = (unsigned*)h->d_rr[5];
+   }
    // (the clone of a handle that shares its dense rounds with peers works alone: it takes every row itself)
    h->npeers = 1;
    h->peerrank = 0;

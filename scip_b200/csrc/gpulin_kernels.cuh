@@ -21,6 +21,7 @@
 #pragma once
 
 #include "gpulin_device.cuh"
+#include "gpulin_ranged.cuh"
 
 namespace gpl {
 
@@ -132,6 +133,7 @@ struct DevProblem
    int                 st0, st1;
    int                 nranks, rank;
    unsigned            markall_min; // an apply step with at least this many changed columns marks ALL rows (see apply_kernel)
+   RangedRows          rr;          // ranged-row propagation (gpulin_set_rangedrow); rr.n == 0: off
    Num                 num;
 };
 
@@ -1473,6 +1475,55 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
       addRoundNnz(p, nnzdone, gtid >> 5);
 }
 
+// ---- ranged-row propagation (gpulin_ranged.cuh) for the rows marked for propagation, a warp per row ---------------------
+// Dense rounds: rangedrow_kernel runs in front of the filter sweeps (which lower the marks); with several GPUs a rank takes
+// every nranks-th ranged row.  Small rounds: the marked rows are on the mark lists; rangedListPhase runs in front of the
+// exact rules (which claim the rows).
+constexpr int RANGED_THREADS = 256;
+__global__ void __launch_bounds__(RANGED_THREADS) rangedrow_kernel(const DevProblem p)
+{
+   const RangedRows& R = p.rr;
+   const int gw = (blockIdx.x * RANGED_THREADS + threadIdx.x) >> 5;
+   const int nw = (gridDim.x * RANGED_THREADS) >> 5;
+   Sink s;
+   s.cand = p.cand;
+   s.colbits = p.colbits;
+   s.chglist = p.chglist;
+   s.nchgcols = &p.ctrl->nchgcols;
+   s.listed = false;
+   unsigned* scratch = R.scratch + (size_t)gw * R.scratchwords;
+   for( int i = p.rank + p.nranks * gw; i < R.n; i += p.nranks * nw )
+   {
+      if( p.dirty[R.row[i]] != ROW_MARKED )
+         continue;
+      rangedRowWarp(p.num, s, R, p.bnd, p.sides, i, scratch, &p.ctrl->cutoff);
+   }
+}
+
+// the ranged rows among the rows on the mark lists (all bins); gw / nw: this warp and the number of warps at work
+__device__ __forceinline__ void rangedListPhase(const DevProblem& p, const int* ml, unsigned n0, unsigned n1, unsigned n2,
+   int gw, int nw)
+{
+   const RangedRows& R = p.rr;
+   if( R.n == 0 )
+      return;
+   Sink s;
+   s.cand = p.cand;
+   s.colbits = p.colbits;
+   s.chglist = p.chglist;
+   s.nchgcols = &p.ctrl->nchgcols;
+   s.listed = true;
+   unsigned* scratch = R.scratch + (size_t)gw * R.scratchwords;
+   const unsigned total = n0 + n1 + n2;
+   for( unsigned i = gw; i < total; i += nw )
+   {
+      const int row = i < n0 ? ml[i] : (i < n0 + n1 ? ml[MARKCAP + (i - n0)] : ml[2 * MARKCAP + (i - n0 - n1)]);
+      const int rr = R.idx[row];
+      if( rr >= 0 )
+         rangedRowWarp(p.num, s, R, p.bnd, p.sides, rr, scratch, &p.ctrl->cutoff);
+   }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(EXACT_THREADS, MINB) exact_rows_kernel(const DevProblem p)
 {
@@ -2317,8 +2368,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS) sparse_rounds_kernel(const Dev
       if( threadIdx.x == 0 )
          s_nchg = 0;
 
-      // ---- the exact rules for the marked rows
+      // ---- the exact rules for the marked rows (ranged rows: the gcd rule first, it does not claim the row)
       const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
+      rangedListPhase(p, ml, n0, n1, n2, gtid >> 5, nthreads >> 5);
       exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, s_queue, SPARSE_THREADS);
       __threadfence();
       grid.sync();
@@ -2479,6 +2531,7 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
       if( tid == 0 )
          s_nchg = 0;
       const int* ml = p.marklist + (size_t)mb * 3 * MARKCAP;
+      rangedListPhase(p, ml, n0, n1, n2, tid >> 5, PROBE_THREADS >> 5);
       exactPhase<true>(p, ml, n0, ml + MARKCAP, n1, ml + 2 * MARKCAP, n2, s_acc, s_queue, PROBE_THREADS);
       __syncthreads();
       int mychg = applyListPhase<SPARSE_G>(p, c->nchgcols, tid, PROBE_THREADS, c->round, c->logcap);

@@ -292,6 +292,7 @@ static SCIP_RETCODE run(int argc, char** argv)
    int activeonly = 0;
    int delredundant = 0;
    int ndevices = 1;
+   int rangedrow = 0;
    int rowsof[5] = {-1, -1, -1, -1, -1};
    char pname[128];
    double t0, t1;
@@ -311,6 +312,7 @@ static SCIP_RETCODE run(int argc, char** argv)
       else if( strcmp(argv[i], "--active-rows-only") == 0 ) activeonly = 1;
       else if( strcmp(argv[i], "--del-redundant") == 0 ) delredundant = 1;
       else if( strcmp(argv[i], "--ndevices") == 0 && i + 1 < argc ) ndevices = atoi(argv[++i]);
+      else if( strcmp(argv[i], "--rangedrow") == 0 ) rangedrow = 1;
       else if( strcmp(argv[i], "--probe-batch") == 0 && i + 1 < argc ) g_nprobecheck = atoi(argv[++i]);
       else
       {
@@ -344,7 +346,9 @@ static SCIP_RETCODE run(int argc, char** argv)
    if( !solve )
       SCIP_CALL( SCIPsetLongintParam(scip, "limits/nodes", 1LL) );
    SCIP_CALL( SCIPsetBoolParam(scip, "conflict/enable", solve ? TRUE : FALSE) );
-   SCIP_CALL( SCIPsetBoolParam(scip, "constraints/linear/rangedrowpropagation", FALSE) );
+   /* --rangedrow: the gcd rule on -- in cons_linear with --cpu, else on the device; never its artificial constraints */
+   SCIP_CALL( SCIPsetBoolParam(scip, "constraints/linear/rangedrowpropagation", (usecpu && rangedrow) ? TRUE : FALSE) );
+   SCIP_CALL( SCIPsetBoolParam(scip, "constraints/linear/rangedrowartcons", FALSE) );
    SCIP_CALL( SCIPsetIntParam(scip, "timing/clocktype", 2) );
    if( SCIPgetParam(scip, "misc/usesymmetry") != NULL )
       SCIP_CALL( SCIPsetIntParam(scip, "misc/usesymmetry", 0) );
@@ -369,6 +373,8 @@ static SCIP_RETCODE run(int argc, char** argv)
          SCIP_CALL( SCIPsetBoolParam(scip, "propagating/gpulinear/delredundant", TRUE) );
       if( ndevices > 1 )
          SCIP_CALL( SCIPsetIntParam(scip, "propagating/gpulinear/ndevices", ndevices) );
+      if( rangedrow )
+         SCIP_CALL( SCIPsetBoolParam(scip, "propagating/gpulinear/rangedrow", TRUE) );
    }
 
    if( readfile != NULL )

@@ -104,6 +104,7 @@ struct SCIP_PropData
    int                   nrowsof[5];         /**< rows per source: linear, knapsack, setppc, logicor, varbound */
    SCIP_Bool             allrows;            /**< parameter: also read knapsack / setppc / logicor / varbound rows */
    SCIP_Bool             delredundant;       /**< parameter: SCIPdelConsLocal for rows the device proves redundant */
+   SCIP_Bool             rangedrow;          /**< parameter: ranged-row (gcd) propagation on the device (constraints/linear/rangedrowpropagation) */
    SCIP_Longint          ndelconss;          /**< constraints deleted locally on the device's verdict */
    int32_t*              redrows;            /**< buffer for gpulin_get_redundant_rows */
    SCIP_Bool             deterministic;      /**< parameter: sort the change log inside every round before the replay */
@@ -566,6 +567,19 @@ SCIP_RETCODE buildDeviceCopy(
          propdata->colidx, propdata->vals, propdata->lhs, propdata->rhs, vartype, &num, &propdata->peergpu[propdata->npeergpus]);
       if( rc == GPULIN_OK )
          ++propdata->npeergpus;
+   }
+   /* ranged-row propagation (rangedRowPropagation, cons_linear.c:5715-6696): the device walks a ranged row in the order
+    * cons_linear sorts it in (consdataCompVarProp :3191) -- by the global bounds; a column is its variable's probindex */
+   if( rc == GPULIN_OK && propdata->rangedrow )
+   {
+      for( j = 0; j < ncols; ++j )
+      {
+         propdata->lb[j] = SCIPvarGetLbGlobal(probvars[j]);
+         propdata->ub[j] = SCIPvarGetUbGlobal(probvars[j]);
+      }
+      rc = gpulin_set_rangedrow(propdata->gpu, 1, propdata->lb, propdata->ub, NULL);
+      for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
+         rc = gpulin_set_rangedrow(propdata->peergpu[j], 1, propdata->lb, propdata->ub, NULL);
    }
    SCIPfreeBufferArray(scip, &fill);
    SCIPfreeBufferArray(scip, &vartype);
@@ -1082,6 +1096,9 @@ SCIP_RETCODE SCIPincludePropGpulinear(
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/allrows",
          "also propagate the linear rows behind knapsack, setppc, logicor and varbound constraints (cf. matrix.c)",
          &propdata->allrows, FALSE, DEFAULT_ALLROWS, NULL, NULL) );
+   SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/rangedrow",
+         "should the device run the ranged-row (gcd) propagation of equations and ranged rows as well (the counterpart of constraints/linear/rangedrowpropagation, without artificial constraints)?",
+         &propdata->rangedrow, FALSE, FALSE, NULL, NULL) );
    SCIP_CALL( SCIPaddBoolParam(scip, "propagating/" PROP_NAME "/delredundant",
          "delete rows locally that the device finds redundant for the node's bounds (the end of propagateCons; cons_linear does this itself for its own rows)",
          &propdata->delredundant, FALSE, DEFAULT_DELREDUNDANT, NULL, NULL) );

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "gpulin_set_reference_bounds": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_set_bounds_packed": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P]),
     "gpulin_get_changes_packed": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_set_rangedrow": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P]),
     "gpulin_get_trace": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_get_exchange_stats": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_peer_connect": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
@@ -241,6 +242,17 @@ class LinearPropagator:
         n = ctypes.c_int64(0)
         _check(self._lib.gpulin_get_changes_packed(self._h, out_ptr, maxn, ctypes.byref(n)))
         return n.value
+
+    def set_rangedrow(self, enable: bool, glb=None, gub=None, tie=None):
+        """ranged-row (gcd) propagation on / off; glb / gub: the global bounds the reference sorts its rows by, tie: the
+        SCIPvarGetProbindex of every column (default: the column index)"""
+        if not enable:
+            _check(self._lib.gpulin_set_rangedrow(self._h, 0, None, None, None))
+            return
+        glb = np.ascontiguousarray(glb, dtype=np.float64)
+        gub = np.ascontiguousarray(gub, dtype=np.float64)
+        tb = None if tie is None else np.ascontiguousarray(tie, dtype=np.int32)
+        _check(self._lib.gpulin_set_rangedrow(self._h, 1, glb.ctypes.data, gub.ctypes.data, None if tb is None else tb.ctypes.data))
 
     def update_bounds(self, idx, lb, ub):
         idx = np.ascontiguousarray(idx, dtype=np.int32)
@@ -449,10 +461,14 @@ class LinearPropagator:
         return nchg.value, cutoff.value
 
 
-def propagate(prob, lb=None, ub=None, maxrounds: int = 0, device: int = 0, **numerics) -> dict:
+def propagate(prob, lb=None, ub=None, maxrounds: int = 0, device: int = 0, rangedrow: bool = False, tie=None, **numerics) -> dict:
     """one-shot: build, propagate to the fixpoint, read back; returns dict(status, lb, ub, nrounds, nchanges, ...)"""
     with LinearPropagator(prob, device=device, **numerics) as lp:
-        lp.set_bounds(prob["lb"] if lb is None else lb, prob["ub"] if ub is None else ub)
+        lb = prob["lb"] if lb is None else lb
+        ub = prob["ub"] if ub is None else ub
+        if rangedrow:
+            lp.set_rangedrow(True, lb, ub, tie)
+        lp.set_bounds(lb, ub)
         res = lp.propagate(maxrounds)
         res["lb"], res["ub"] = lp.get_bounds()
     return res

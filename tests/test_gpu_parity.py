@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import assert_bounds_match, golden_names, load_golden, load_golden_redundant
+from conftest import (assert_bounds_match, golden_names, golden_ranged_names, load_golden, load_golden_redundant,
+                      load_golden_tie)
 from scip_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -433,3 +434,56 @@ def test_packed_bounds_and_packed_change_log(gpulin):
         # same entries (the order inside a round is whatever the atomics made it: compare as sets per round)
         key = lambda v, up, x: sorted(zip(v.tolist(), up.tolist(), x.tolist()))  # noqa: E731
         assert key(var, upper, val) == key(log["var"], log["is_upper"], log["newbound"])
+
+
+# ---- ranged-row (gcd) propagation: rangedRowPropagation, cons_linear.c:5715-6696 ------------------------------------------
+
+@pytest.mark.parametrize("name", golden_ranged_names())
+def test_ranged_row_propagation_reaches_the_reference_fixpoint(gpulin, name):
+    """the reference ran with constraints/linear/rangedrowpropagation = TRUE (rangedrowartcons = FALSE)"""
+    prob, ref = load_golden(name, "1e-9")
+    tie = load_golden_tie(name)
+    got = gpulin.propagate(prob, maxrounds=1000, boundstreps=1e-9, rangedrow=True, tie=tie)
+    assert (got["status"] == gpulin.CUTOFF) == ref["infeasible"]
+    if not ref["infeasible"]:
+        assert_bounds_match(got["lb"], got["ub"], ref["lb"] + 0.0, ref["ub"] + 0.0, prob["vartype"], what=name)
+    else:
+        assert gpulin.propagate(prob, maxrounds=1000, boundstreps=1e-9)["status"] == gpulin.FIXPOINT    # only the gcd rule sees it
+    for bs in (1e-9, 0.05):
+        want = oracle.propagate(prob, maxrounds=1000, boundstreps=bs, rangedrow=True, tie=tie)
+        got = gpulin.propagate(prob, maxrounds=1000, boundstreps=bs, rangedrow=True, tie=tie)
+        assert got["status"] == want["status"], (name, bs)
+        if want["status"] != oracle.STATUS_CUTOFF:
+            assert (got["nrounds"], got["nchanges"]) == (want["nrounds"], want["nchanges"]), (name, bs)
+            assert_bounds_match(got["lb"], got["ub"], want["lb"], want["ub"], prob["vartype"], what=f"{name} bs={bs}")
+
+
+@pytest.mark.parametrize("seed", [41, 42, 43, 44])
+def test_ranged_row_propagation_matches_the_oracle_on_larger_instances(gpulin, seed):
+    # dense rounds (the rule in front of the filter sweeps), small rounds and incremental calls (the rule in front of the
+    # exact rules of the listed rows); rows longer than one warp pass
+    prob = synth.ranged_rows(20_000 if seed < 43 else 3000, 30_000 if seed < 43 else 4000, seed=seed, infeasible=(seed == 44))
+    want = oracle.propagate(prob, maxrounds=1000, rangedrow=True)
+    plain = oracle.propagate(prob, maxrounds=1000)
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.set_rangedrow(True, prob["lb"], prob["ub"])
+        lp.set_bounds(prob["lb"], prob["ub"])
+        got = lp.propagate(1000)
+        assert got["status"] == want["status"]
+        if want["status"] == oracle.STATUS_CUTOFF:
+            return
+        assert (got["nrounds"], got["nchanges"]) == (want["nrounds"], want["nchanges"])
+        lb, ub = lp.get_bounds()
+        assert_bounds_match(lb, ub, want["lb"], want["ub"], prob["vartype"], what=f"ranged seed {seed}")
+        assert ((plain["lb"] != want["lb"]) | (plain["ub"] != want["ub"])).sum() > 0
+        # an incremental call: a few integer variables fixed, one block (or the general loop) continues
+        free = np.flatnonzero((ub - lb >= 2.0) & (prob["vartype"] != 0))[:4]
+        lp.update_bounds(free, lb[free], lb[free])
+        r2 = lp.propagate(1000)
+        lb2, ub2 = lb.copy(), ub.copy()
+        ub2[free] = lb[free]
+        w2 = oracle.propagate(prob, lb=lb2, ub=ub2, maxrounds=1000, rangedrow=True, sortlb=prob["lb"], sortub=prob["ub"])
+        assert r2["status"] == w2["status"]
+        if w2["status"] != oracle.STATUS_CUTOFF:
+            glb, gub = lp.get_bounds()
+            assert_bounds_match(glb, gub, w2["lb"], w2["ub"], prob["vartype"], what=f"ranged seed {seed} incremental")

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import GOLDEN, ROOT, assert_bounds_match, golden_names, load_golden
+from conftest import GOLDEN, ROOT, assert_bounds_match, golden_names, golden_ranged_names, load_golden
 
 DRIVER = os.path.join(ROOT, "scip_b200", "plugin", "_build", "gpulinear_driver")
 needs_driver = pytest.mark.skipif(not (os.path.exists(DRIVER) and oracle.have_reference()),
@@ -200,3 +200,26 @@ def test_plugin_with_two_devices_in_tree_search():
     two = run_driver("--lpb", os.path.join(GOLDEN, "enigma.lpb"), "--solve", "--ndevices", "2")
     assert two["scip_status"] == one["scip_status"] and abs(two["primal"] - one["primal"]) <= 1e-6
     assert (two["nodes"], two["gpu_prop_calls"], two["gpu_domreds"]) == (one["nodes"], one["gpu_prop_calls"], one["gpu_domreds"])
+
+
+@needs_driver
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_ranged_names())
+def test_plugin_ranged_row_propagation(tmp_path, name):
+    """propagating/gpulinear/rangedrow: the gcd rule of rangedRowPropagation (cons_linear.c:5715-6696) on the device, rows
+    walked in cons_linear's sorted order -- the fixpoint of the reference run with rangedrowpropagation = TRUE"""
+    prob, ref = load_golden(name, "1e-9")
+    out = str(tmp_path / "o.lpr")
+    info = run_driver("--lpb", os.path.join(GOLDEN, name + ".lpb"), "--boundstreps", "1e-9", "--rangedrow", "--out", out)
+    got = oracle.read_lpr(out)
+    assert got["infeasible"] == ref["infeasible"], name
+    assert info["gpu_prop_calls"] >= 1 and info["linear_domreds"] == 0
+    if not ref["infeasible"]:
+        assert_bounds_match(got["lb"] + 0.0, got["ub"] + 0.0, ref["lb"] + 0.0, ref["ub"] + 0.0, prob["vartype"], what=name)
+    # and the driver's own --cpu --rangedrow run is that reference
+    cpu = str(tmp_path / "c.lpr")
+    run_driver("--lpb", os.path.join(GOLDEN, name + ".lpb"), "--boundstreps", "1e-9", "--rangedrow", "--cpu", "--out", cpu)
+    c = oracle.read_lpr(cpu)
+    assert c["infeasible"] == ref["infeasible"]
+    if not ref["infeasible"]:
+        assert np.array_equal(c["lb"], ref["lb"]) and np.array_equal(c["ub"], ref["ub"])
