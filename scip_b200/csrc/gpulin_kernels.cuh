@@ -1318,21 +1318,22 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
          int row = 0;
          if( valid )
             row = list0[item];
-         if( SPARSE )
-         {
-            int mine = (valid && gl == 0) ? (claimRow(p, row) ? 1 : 0) : 0;
-            mine = __shfl_sync(0xffffffffu, mine, lane & ~(EXACT_G - 1));
-            valid = mine != 0;
-         }
          int len = 0;
          long long base = 0;
          double2 sd = make_double2(0.0, 0.0);
          if( valid )
          {
+            // (the header of the row is on its way while the claim below is answered: the list names real rows)
             len = p.rowlen[row] & ~ROWLEN_EXACT;
             base = p.sell_off[row >> 5] + (row & 31);
             sd = p.sides[row];
-            if( SPARSE && gl == 0 )
+         }
+         if( SPARSE )
+         {
+            int mine = (valid && gl == 0) ? (claimRow(p, row) ? 1 : 0) : 0;
+            mine = __shfl_sync(0xffffffffu, mine, lane & ~(EXACT_G - 1));
+            valid = mine != 0;      // (the loads below do not wait for this: a row that is not ours costs a few loads)
+            if( valid && gl == 0 )
                nnzdone += (unsigned long long)len;
          }
          double a[EXACT_Q];
@@ -1985,7 +1986,7 @@ constexpr int APPLY_LIST = 0;
 constexpr int APPLY_DENSE = 1;
 
 template <int MODE, bool GRAPH>
-__global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
+__global__ void __launch_bounds__(APPLY_THREADS, 4) apply_kernel(const DevProblem p, cudaGraphConditionalHandle handle)
 {
    __shared__ int s_nchg;
    __shared__ ChangeRec s_log[MODE == APPLY_LIST ? APPLY_THREADS / 32 : 1][MODE == APPLY_LIST ? LOGBUF : 1];
@@ -2170,24 +2171,43 @@ __global__ void __launch_bounds__(256) collect_kernel(const DevProblem p)
          bits &= bits - 1u;
       }
       __syncwarp();
-      for( int i = lane; i < total; i += 32 )
+      for( int i0 = 0; i0 < total; i0 += 32 )      // uniform
       {
-         const int j = stage[i];
-         p.chglist[base + i] = j;
+         const int i = i0 + lane;
+         const int j = i < total ? stage[i] : 0;
+         if( i < total )
+            p.chglist[base + i] = j;
          if( PEERS )
          {
             const PeerTable& t = *p.peers;
-            const longlong2 k = reinterpret_cast<const longlong2*>(p.cand)[j];
-            PeerEntry e;
-            e.a = make_uint4((unsigned)j, epoch, (unsigned)(unsigned long long)k.x, (unsigned)((unsigned long long)k.x >> 32));
-            e.b = make_uint4((unsigned)(unsigned long long)k.y, (unsigned)((unsigned long long)k.y >> 32), epoch, 0u);
-            for( int r = 0; r < t.n; ++r )
+            longlong2 k = make_longlong2(0, 0);
+            if( i < total )
+               k = reinterpret_cast<const longlong2*>(p.cand)[j];
+            const uint4 ea = make_uint4((unsigned)j, epoch, (unsigned)(unsigned long long)k.x, (unsigned)((unsigned long long)k.x >> 32));
+            const uint4 eb = make_uint4((unsigned)(unsigned long long)k.y, (unsigned)((unsigned long long)k.y >> 32), epoch, 0u);
+            // the 32 entries of this trip go out as two stores of 512 contiguous bytes per peer: lane L writes the 16-byte
+            // half (L & 1) of entry 16 h + L / 2 (a warp store that touches every other 16 bytes costs a link packet per lane)
+#pragma unroll
+            for( int h = 0; h < 2; ++h )
             {
-               if( r == t.rank )
-                  continue;
-               PeerEntry* dst = peerEntries(t, t.box[r], parity, t.rank) + base + i;
-               storeV4(&dst->a, e.a);
-               storeV4(&dst->b, e.b);
+               const int src = 16 * h + (lane >> 1);
+               uint4 va;
+               uint4 vb;
+               va.x = __shfl_sync(0xffffffffu, ea.x, src); va.y = __shfl_sync(0xffffffffu, ea.y, src);
+               va.z = __shfl_sync(0xffffffffu, ea.z, src); va.w = __shfl_sync(0xffffffffu, ea.w, src);
+               vb.x = __shfl_sync(0xffffffffu, eb.x, src); vb.y = __shfl_sync(0xffffffffu, eb.y, src);
+               vb.z = __shfl_sync(0xffffffffu, eb.z, src); vb.w = __shfl_sync(0xffffffffu, eb.w, src);
+               const uint4 v = (lane & 1) ? vb : va;
+               if( i0 + src < total )
+               {
+                  for( int r = 0; r < t.n; ++r )
+                  {
+                     if( r == t.rank )
+                        continue;
+                     unsigned char* dst = reinterpret_cast<unsigned char*>(peerEntries(t, t.box[r], parity, t.rank) + base + i0 + src);
+                     storeV4(dst + 16 * (lane & 1), v);
+                  }
+               }
             }
          }
       }

@@ -85,6 +85,9 @@ struct SCIP_PropData
    SCIP_CONS**           rowcons;            /**< row -> linear constraint */
    SCIP_Real*            lb;                 /**< host bound buffers */
    SCIP_Real*            ub;
+   SCIP_Real*            reflb;              /**< reference bounds on the device (global bounds at build time): a full bound */
+   SCIP_Real*            refub;              /**<   upload sends 2 bits per column against them (gpulin_set_bounds_packed) */
+   uint32_t*             codes;              /**< the 2-bit codes, 16 columns per word */
    gpulin_change*        changes;            /**< change log buffer */
    int64_t*              rowptr;             /**< host CSR (kept for PROPRESPROP) */
    int32_t*              colidx;
@@ -169,6 +172,9 @@ void freeDeviceCopy(
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->vars, propdata->ncols);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->lb, propdata->ncols);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->ub, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->reflb, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->refub, propdata->ncols);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->codes, (propdata->ncols + 15) / 16);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->colptr, propdata->ncols + 1);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->redrows, propdata->nrows);
    if( propdata->rowcons != NULL )
@@ -460,6 +466,9 @@ SCIP_RETCODE buildDeviceCopy(
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->vars, ncols) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lb, ncols) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->ub, ncols) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->reflb, ncols) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->refub, ncols) );
+         SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->codes, (ncols + 15) / 16) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->colptr, ncols + 1) );
          SCIP_CALL( SCIPallocClearBlockMemoryArray(scip, &propdata->rowcons, nrows) );
          SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->lhs, nrows) );
@@ -618,6 +627,22 @@ SCIP_RETCODE buildDeviceCopy(
          SCIPerrorMessage("prop_gpulinear: gpulin_group_connect failed (%d): %s\n", rc, gpulin_last_error());
          return SCIP_ERROR;
       }
+   }
+
+   /* the reference of the packed bound uploads: the global bounds of now (a column at a node sits at them, or is fixed to
+    * one of them, or -- rarely -- has other local bounds: 2 bits per column + an explicit list instead of 16 bytes) */
+   for( j = 0; j < ncols; ++j )
+   {
+      propdata->reflb[j] = SCIPvarGetLbGlobal(propdata->vars[j]);
+      propdata->refub[j] = SCIPvarGetUbGlobal(propdata->vars[j]);
+   }
+   rc = gpulin_set_reference_bounds(propdata->gpu, propdata->reflb, propdata->refub);
+   for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
+      rc = gpulin_set_reference_bounds(propdata->peergpu[j], propdata->reflb, propdata->refub);
+   if( rc != GPULIN_OK )
+   {
+      SCIPerrorMessage("prop_gpulinear: gpulin_set_reference_bounds failed (%d): %s\n", rc, gpulin_last_error());
+      return SCIP_ERROR;
    }
 
    /* from now on every bound change of a column is noted (cf. consCatchAllEvents, cons_linear.c:717) */
@@ -810,18 +835,36 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
    /* bounds of the current node: everything after a (re)build or a cutoff, else only what changed since the last call */
    if( propdata->fullsync || !propdata->incremental )
    {
+      int nexplicit = 0;
+      memset(propdata->codes, 0, sizeof(uint32_t) * (size_t)((propdata->ncols + 15) / 16));
       for( j = 0; j < propdata->ncols; ++j )
       {
-         propdata->lb[j] = SCIPvarGetLbLocal(propdata->vars[j]);
-         propdata->ub[j] = SCIPvarGetUbLocal(propdata->vars[j]);
+         const SCIP_Real l = SCIPvarGetLbLocal(propdata->vars[j]);
+         const SCIP_Real u = SCIPvarGetUbLocal(propdata->vars[j]);
+         uint32_t code;
+         if( l == propdata->reflb[j] && u == propdata->refub[j] ) /*lint !e777*/
+            code = 0;
+         else if( l == propdata->reflb[j] && u == propdata->reflb[j] ) /*lint !e777*/
+            code = 1;
+         else if( l == propdata->refub[j] && u == propdata->refub[j] ) /*lint !e777*/
+            code = 2;
+         else
+         {
+            code = 3;
+            propdata->updidx[nexplicit] = j;
+            propdata->lb[nexplicit] = l;
+            propdata->ub[nexplicit] = u;
+            ++nexplicit;
+         }
+         propdata->codes[j >> 4] |= code << (2 * (j & 15));
          propdata->istouched[j] = FALSE;
       }
       propdata->ntouched = 0;
       propdata->fullsync = FALSE;
       ++propdata->nfullsyncs;
-      rc = gpulin_set_bounds(propdata->gpu, propdata->lb, propdata->ub);
+      rc = gpulin_set_bounds_packed(propdata->gpu, propdata->codes, nexplicit, propdata->updidx, propdata->lb, propdata->ub);
       for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
-         rc = gpulin_set_bounds(propdata->peergpu[j], propdata->lb, propdata->ub);
+         rc = gpulin_set_bounds_packed(propdata->peergpu[j], propdata->codes, nexplicit, propdata->updidx, propdata->lb, propdata->ub);
    }
    else
    {

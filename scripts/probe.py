@@ -38,7 +38,9 @@ def main():
         for i in range(len(ms)):
             print(f"   round {i}: {ms[i]*1e3:9.1f} us  nnz {nnz[i]:10d}  changes {nchg[i]:8d}  "
                   f"{nnz[i]/max(ms[i],1e-9)/1e6:8.1f} Gnnz/s")
-    print("trace: " + "  ".join(f"{name}@{t:.1f}" for name, t in lp.trace()[:80]))
+    tr = lp.trace()
+    print("trace: " + "  ".join(f"{name}@{t:.1f}" for name, t in tr[:80]))
+    print("stages: " + "  ".join(f"{tr[i][0]}={tr[i + 1][1] - tr[i][1]:.1f}" for i in range(min(len(tr) - 1, 12))))
     print(f"algorithmic bytes/round {abytes/1e6:.1f} MB; first round {abytes/ms[0]/1e6:.1f} GB/s "
           f"= {abytes/ms[0]/1e6/6544.3:.3f} of measured HBM peak")
     lb, ub = lp.get_bounds()
