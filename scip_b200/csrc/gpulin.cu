@@ -231,8 +231,8 @@ static int launchCollect(gpulin* h)
 {
    if( h->npeers > 1 )
    {
-      collect_kernel<true><<<h->npushblocks, 256, 0, h->stream>>>(h->p);
-      peer_merge_kernel<<<h->npushblocks, 256, 0, h->stream>>>(h->p);
+      collect_kernel<true><<<h->npushblocks, 256, COLLECT_SMEM_PEERS, h->stream>>>(h->p);
+      peer_merge_kernel<<<h->nsm * 8, 256, 0, h->stream>>>(h->p);
    }
    else
       collect_kernel<false><<<h->npushblocks, 256, 0, h->stream>>>(h->p);
@@ -1979,6 +1979,7 @@ static int wirePeers(gpulin* h, int rank, int nranks, unsigned char* const* boxe
       const int64_t nlongmine = (h->nlong - rank + nranks - 1) / nranks;
       h->nlongblocks = (int)std::min<int64_t>(std::max<int64_t>(nlongmine, h->nlong > 0 ? 1 : 0), (int64_t)h->nlongblocks);
    }
+   CU(cudaFuncSetAttribute(collect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COLLECT_SMEM_PEERS));
    if( !h->hostloop )
       OK(buildGraph(h));
    return GPULIN_OK;

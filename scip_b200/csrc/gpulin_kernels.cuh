@@ -2124,6 +2124,16 @@ __device__ __forceinline__ uint4 loadV4Volatile(const void* addr)
    return v;
 }
 
+// shared -> global bulk copy through the async proxy (TMA); the destination may be peer memory: the copy engine of the SM
+// writes whole bursts to the link instead of one packet per warp store
+__device__ __forceinline__ void bulkStore(void* dst, unsigned src, unsigned bytes)
+{
+   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+constexpr int COLLECT_WARPS = 256 / 32;
+constexpr int COLLECT_CHUNK = 128;                      // entries a warp stages before it sends them (4 KB)
+constexpr int COLLECT_SMEM_PEERS = COLLECT_WARPS * (1024 * (int)sizeof(int) + COLLECT_CHUNK * (int)sizeof(PeerEntry));
+
 template <bool PEERS>
 __global__ void __launch_bounds__(256) collect_kernel(const DevProblem p)
 {
@@ -2140,8 +2150,11 @@ __global__ void __launch_bounds__(256) collect_kernel(const DevProblem p)
       c->hist_push[c->round] = globaltimer();
       c->hist_wait[c->round] = 0;
    }
-   __shared__ int s_stage[256 / 32][1024];       // per warp: the columns of its 32 words, in list order
-   int* stage = s_stage[threadIdx.x >> 5];
+   // per warp: the columns of its 32 words in list order (and, with peers, the entries of a chunk on their way out)
+   __shared__ int s_stage[PEERS ? 1 : COLLECT_WARPS][PEERS ? 1 : 1024];
+   extern __shared__ __align__(128) unsigned char s_dyn[];
+   int* stage = PEERS ? reinterpret_cast<int*>(s_dyn) + (threadIdx.x >> 5) * 1024 : s_stage[PEERS ? 0 : (threadIdx.x >> 5)];
+   PeerEntry* sent = reinterpret_cast<PeerEntry*>(s_dyn + COLLECT_WARPS * 1024 * sizeof(int)) + (threadIdx.x >> 5) * COLLECT_CHUNK;
    for( int w0 = gtid - lane; w0 < nwords; w0 += nthreads )      // warp-uniform trip count
    {
       const int w = w0 + lane;
@@ -2162,8 +2175,8 @@ __global__ void __launch_bounds__(256) collect_kernel(const DevProblem p)
       if( lane == 31 )
          base = atomicAdd(&c->nchgcols, (unsigned)total);
       base = __shfl_sync(0xffffffffu, base, 31);
-      // the columns are staged in list order, so that the stores below -- to the list, and through NVLink to the peers --
-      // are contiguous over the lanes of the warp (scattered 16-byte stores cost a link packet each)
+      // the columns are staged in list order, so that what follows -- the stores to the list, the entries for the peers --
+      // is contiguous over the lanes of the warp
       int pos = incl - mine;
       while( bits != 0u )
       {
@@ -2171,48 +2184,63 @@ __global__ void __launch_bounds__(256) collect_kernel(const DevProblem p)
          bits &= bits - 1u;
       }
       __syncwarp();
-      for( int i0 = 0; i0 < total; i0 += 32 )      // uniform
+      if( !PEERS )
       {
-         const int i = i0 + lane;
-         const int j = i < total ? stage[i] : 0;
-         if( i < total )
-            p.chglist[base + i] = j;
-         if( PEERS )
+         for( int i = lane; i < total; i += 32 )
+            p.chglist[base + i] = stage[i];
+      }
+      else
+      {
+         const PeerTable& t = *p.peers;
+         for( int c0 = 0; c0 < total; c0 += COLLECT_CHUNK )      // uniform
          {
-            const PeerTable& t = *p.peers;
-            longlong2 k = make_longlong2(0, 0);
-            if( i < total )
-               k = reinterpret_cast<const longlong2*>(p.cand)[j];
-            const uint4 ea = make_uint4((unsigned)j, epoch, (unsigned)(unsigned long long)k.x, (unsigned)((unsigned long long)k.x >> 32));
-            const uint4 eb = make_uint4((unsigned)(unsigned long long)k.y, (unsigned)((unsigned long long)k.y >> 32), epoch, 0u);
-            // the 32 entries of this trip go out as two stores of 512 contiguous bytes per peer: lane L writes the 16-byte
-            // half (L & 1) of entry 16 h + L / 2 (a warp store that touches every other 16 bytes costs a link packet per lane)
+            const int n = min(COLLECT_CHUNK, total - c0);
+            int j[COLLECT_CHUNK / 32];
+            longlong2 k[COLLECT_CHUNK / 32];
 #pragma unroll
-            for( int h = 0; h < 2; ++h )
+            for( int q = 0; q < COLLECT_CHUNK / 32; ++q )
             {
-               const int src = 16 * h + (lane >> 1);
-               uint4 va;
-               uint4 vb;
-               va.x = __shfl_sync(0xffffffffu, ea.x, src); va.y = __shfl_sync(0xffffffffu, ea.y, src);
-               va.z = __shfl_sync(0xffffffffu, ea.z, src); va.w = __shfl_sync(0xffffffffu, ea.w, src);
-               vb.x = __shfl_sync(0xffffffffu, eb.x, src); vb.y = __shfl_sync(0xffffffffu, eb.y, src);
-               vb.z = __shfl_sync(0xffffffffu, eb.z, src); vb.w = __shfl_sync(0xffffffffu, eb.w, src);
-               const uint4 v = (lane & 1) ? vb : va;
-               if( i0 + src < total )
+               const int i = c0 + 32 * q + lane;
+               j[q] = i < total ? stage[i] : -1;
+               if( j[q] >= 0 )
                {
-                  for( int r = 0; r < t.n; ++r )
-                  {
-                     if( r == t.rank )
-                        continue;
-                     unsigned char* dst = reinterpret_cast<unsigned char*>(peerEntries(t, t.box[r], parity, t.rank) + base + i0 + src);
-                     storeV4(dst + 16 * (lane & 1), v);
-                  }
+                  p.chglist[base + i] = j[q];
+                  k[q] = reinterpret_cast<const longlong2*>(p.cand)[j[q]];
                }
             }
+#pragma unroll
+            for( int q = 0; q < COLLECT_CHUNK / 32; ++q )
+            {
+               if( j[q] >= 0 )
+               {
+                  PeerEntry e;
+                  e.a = make_uint4((unsigned)j[q], epoch, (unsigned)(unsigned long long)k[q].x, (unsigned)((unsigned long long)k[q].x >> 32));
+                  e.b = make_uint4((unsigned)(unsigned long long)k[q].y, (unsigned)((unsigned long long)k[q].y >> 32), epoch, 0u);
+                  sent[32 * q + lane] = e;
+               }
+            }
+            // the entries of the chunk leave as one bulk copy per peer (generic-proxy writes to shared memory first become
+            // visible to the async proxy); every rank starts with its right neighbour: eight ranks that all write to rank 0
+            // first, then to rank 1, ... would meet at one port of the switch
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if( lane == 0 )
+            {
+               for( int kk = 1; kk < t.n; ++kk )
+               {
+                  const int r = (t.rank + kk) % t.n;
+                  bulkStore(peerEntries(t, t.box[r], parity, t.rank) + base + c0, smemAddr(sent), (unsigned)n * (unsigned)sizeof(PeerEntry));
+               }
+               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the chunk buffer may be refilled
+            }
+            __syncwarp();
          }
       }
       __syncwarp();
    }
+   if( PEERS && lane == 0 )
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
    if( !PEERS )
       return;
    // the marks of this round are spent on every rank: the rows of the other ranks' shares were swept there
@@ -2315,7 +2343,8 @@ __global__ void __launch_bounds__(256) peer_merge_kernel(const DevProblem p)
          continue;
       const PeerEntry* ent = peerEntries(t, t.box[t.rank], parity, r);
       const unsigned n = s_count[r];
-      for( unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads )
+      // (the blocks start at different places of the list, so that short lists of several sources keep all blocks busy)
+      for( unsigned i = ((blockIdx.x + 37u * (unsigned)r) % gridDim.x) * blockDim.x + threadIdx.x; i < n; i += nthreads )
       {
          // the entry may still be on its way: both halves carry the exchange number once they have landed
          uint4 a = loadV4Volatile(&ent[i].a);
