@@ -212,7 +212,8 @@ int gpulin_get_layout(gpulin_t* h, int64_t* stats, int32_t nstats);
 /** what the last gpulin_propagate call launched: [0] kernel launches, [1] rounds run by the dense kernels (filter sweep(s)
  *  + exact + apply [+ barriers with peers]), [2] rounds run inside the persistent sparse-rounds kernel, [3] 1 if the call
  *  was started by the one-block kernel (few updated bounds since the last fixpoint), [4] 1 if that kernel handed over to
- *  the general loop */
+ *  the general loop, [5] rows whose exact activities came along from the filter sweep and that took the thread-per-row
+ *  phase of the exact kernel (integer rows over integral columns, see gpulin_kernels.cuh: FastAcc) */
 int gpulin_get_call_stats(gpulin_t* h, int64_t* stats, int32_t nstats);
 
 /** algorithmic bytes of one full round: nnz*12 + nrows*20 + ncols*17 */

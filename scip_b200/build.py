@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpulin.so")
 SOURCES = ["gpulin.cu"]
-DEPS = ["gpulin.cu", "gpulin_kernels.cuh", "gpulin_device.cuh", os.path.join("..", "..", "include", "gpulin.h")]
+DEPS = ["gpulin.cu", "gpulin_kernels.cuh", "gpulin_device.cuh", "gpulin_ranged.cuh", os.path.join("..", "..", "include", "gpulin.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

@@ -80,7 +80,7 @@ struct gpulin
    int         nsm = 148;
    std::vector<int> perm;        // permuted row -> caller's row
    // device allocations
-   void*       d_all[32] = {nullptr};
+   void*       d_all[48] = {nullptr};
    int         nalloc = 0;
    size_t      devbytes = 0;
    double*     d_tmplb = nullptr;   // staging for set/get_bounds
@@ -367,7 +367,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    {
       if( rowptr[r + 1] < rowptr[r] )
          return fail(GPULIN_ERR_ARG, "rowptr is not monotone at row %lld", (long long)r);
-      if( rowptr[r + 1] - rowptr[r] >= (1LL << 31) )
+      if( rowptr[r + 1] - rowptr[r] >= (1LL << 29) )
          return fail(GPULIN_ERR_ARG, "row %lld is too long", (long long)r);
    }
    for( int64_t k = 0; k < nnz; ++k )
@@ -492,7 +492,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       off += plen[(size_t)i];
    }
    h->nstored = off;
-   if( h->nstored >= (1LL << 40) || h->nstreamelems / TILE >= (1LL << 31) - 64 || nrows >= (1LL << 30) )
+   if( h->nstored >= (1LL << 40) || sell_off[(size_t)nslices] >= (1LL << 36) || h->nstreamelems / TILE >= (1LL << 31) - 64 || nrows >= (1LL << 30) )
    {
       gpulin_destroy(h);
       return fail(GPULIN_ERR_ARG, "matrix too large");
@@ -579,7 +579,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 
    // ---- upload ---------------------------------------------------------------------------------------------------
    DevProblem& p = h->p;
-   long long* d_sell_off; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
+   long long* d_sell_off; int* d_sell_off32; unsigned char* d_coltype; unsigned char* d_colstate; int* d_flist; FastAcc* d_facc; unsigned* d_fracflag; int* d_rowlen; long long* d_rowbeg; double* d_vals; int* d_cols; double2* d_sides;
    int* d_tile_row0; unsigned char* d_endmask; unsigned char* d_tileflag;
    unsigned* d_freebits; double2* d_bndf;
    int* d_xlist; int* d_marklist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned* d_colbits; int* d_chglist; long long* d_colbeg; int* d_colrows;
@@ -588,6 +588,12 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
 #define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
 #define TRYCU(x) do { if( rc == GPULIN_OK ) { cudaError_t e_ = (x); if( e_ != cudaSuccess ) rc = fail(GPULIN_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while( 0 )
    TRY(devAlloc(h, &d_sell_off, (size_t)nslices + 1, true));
+   TRY(devAlloc(h, &d_sell_off32, (size_t)nslices + 1, true));
+   TRY(devAlloc(h, &d_coltype, (size_t)ncols + 1, true));
+   TRY(devAlloc(h, &d_colstate, (size_t)ncols + 1));
+   TRY(devAlloc(h, &d_flist, (size_t)h->nsell + 1));
+   TRY(devAlloc(h, &d_facc, (size_t)h->nsell + 1));
+   TRY(devAlloc(h, &d_fracflag, 1));
    TRY(devAlloc(h, &d_tile_row0, (size_t)h->ntiles + 2, true));
    TRY(devAlloc(h, &d_endmask, (size_t)h->ntiles * 32 + 32, true));
    TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
@@ -614,6 +620,15 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRY(devAlloc(h, &h->d_tmplb, (size_t)ncols + 1));
    TRY(devAlloc(h, &h->d_tmpub, (size_t)ncols + 1));
    TRYCU(cudaMemcpy(d_sell_off, sell_off.data(), sizeof(long long) * ((size_t)nslices + 1), cudaMemcpyHostToDevice));
+   {
+      std::vector<int> off32((size_t)nslices + 1);
+      for( int sl = 0; sl <= nslices; ++sl )
+         off32[(size_t)sl] = (int)(sell_off[(size_t)sl] >> 5);
+      TRYCU(cudaMemcpy(d_sell_off32, off32.data(), sizeof(int) * ((size_t)nslices + 1), cudaMemcpyHostToDevice));
+   }
+   TRYCU(cudaMemcpy(d_coltype, vartype, (size_t)ncols, cudaMemcpyHostToDevice));
+   TRYCU(cudaMemset(d_colstate, CS_OTHER, (size_t)ncols + 1));
+   TRYCU(cudaMemset(d_fracflag, 0, sizeof(unsigned)));
    TRYCU(cudaMemcpy(d_tile_row0, tile_row0.data(), sizeof(int) * ((size_t)h->ntiles + 1), cudaMemcpyHostToDevice));
    TRYCU(cudaMemcpy(d_endmask, endmask.data(), (size_t)h->ntiles * 32, cudaMemcpyHostToDevice));
    TRYCU(cudaMemset(d_tileflag, 0, (size_t)h->ntiles + 64));
@@ -632,6 +647,12 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
                break;
             }
          }
+         // integer coefficients over columns of integral type: the filter's sums can be exact (see FastAcc)
+         bool allint = true;
+         for( int64_t k = rowptr[r]; k < rowptr[r + 1] && allint; ++k )
+            allint = vartype[colidx[k]] != 0 && std::fabs(vals[k]) <= 1048576.0 && vals[k] == std::rint(vals[k]);
+         if( allint )
+            flagged[(size_t)i] |= ROWLEN_INT;
       }
       TRYCU(cudaMemcpy(d_rowlen, flagged.data(), sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice));
    }
@@ -671,6 +692,12 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    p.ntiles = h->ntiles;
    p.streambase = streambase;
    p.sell_off = d_sell_off;
+   p.sell_off32 = d_sell_off32;
+   p.coltype = d_coltype;
+   p.colstate = d_colstate;
+   p.flist = d_flist;
+   p.facc = d_facc;
+   p.fracflag = d_fracflag;
    p.tile_row0 = d_tile_row0;
    p.endmask = d_endmask;
    p.tileflag = d_tileflag;
@@ -753,6 +780,12 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->exactkernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
+      // the thread-per-row phase of the exact kernel takes the rows that came with their activities when there are more of
+      // them than eight lanes each finish in two trips (GPULIN_FASTMIN overrides the threshold: the tests run the phase on
+      // small instances with it)
+      p.fastmin = 8u * (unsigned)h->nexactblocks * (EXACT_THREADS / 32);
+      if( getenv("GPULIN_FASTMIN") != nullptr )
+         p.fastmin = (unsigned)std::max(0, atoi(getenv("GPULIN_FASTMIN")));
       h->npushblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols / 32 + 255) / 256, (int64_t)h->nsm * 4));
       // the sparse-rounds kernel: one block per SM (all must be co-resident: grid syncs)
       int coop = 0;
@@ -874,6 +907,7 @@ extern "C" int gpulin_set_bounds_device(gpulin_t* h, const double* d_lb, const d
    if( h == nullptr || d_lb == nullptr || d_ub == nullptr )
       return fail(GPULIN_ERR_ARG, "NULL argument");
    CU(cudaSetDevice(h->device));
+   CU(cudaMemsetAsync(h->p.fracflag, 0, sizeof(unsigned), h->stream));
    set_bounds_kernel<<<gridFor(h, std::max(h->ncols, h->nrows)), 256, 0, h->stream>>>(h->p, d_lb, d_ub);
    h->smallcols = -1;
    ++h->version;
@@ -947,6 +981,7 @@ extern "C" int gpulin_set_bounds_packed(gpulin_t* h, const uint32_t* codes, int6
    CU(cudaSetDevice(h->device));
    const size_t nwords = ((size_t)h->ncols + 15) / 16;
    CU(cudaMemcpyAsync(h->d_codes, codes, sizeof(unsigned) * nwords, cudaMemcpyHostToDevice, h->stream));
+   CU(cudaMemsetAsync(h->p.fracflag, 0, sizeof(unsigned), h->stream));
    set_bounds_packed_kernel<<<gridFor(h, std::max(h->ncols, h->nrows)), 256, 0, h->stream>>>(h->p, h->d_ref, h->d_codes);
    if( nexplicit > 0 )
    {
@@ -1259,6 +1294,8 @@ extern "C" int gpulin_reset_from(gpulin_t* h, gpulin_t* base)
    CU(cudaMemcpyAsync(h->p.cand, base->p.cand, sizeof(long long) * 2 * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemcpyAsync(h->p.freebits, base->p.freebits, h->freebytes, cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemcpyAsync(h->p.bndf, base->p.bndf, sizeof(double2) * (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->p.colstate, base->p.colstate, (size_t)h->ncols, cudaMemcpyDeviceToDevice, h->stream));
+   CU(cudaMemcpyAsync(h->p.fracflag, base->p.fracflag, sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream));
    CU(cudaMemsetAsync(h->p.dirty, 0, (size_t)h->nrows, h->stream));
    CU(cudaMemsetAsync(&h->p.ctrl->poisoned, 0, sizeof(unsigned), h->stream));
    CU(cudaMemsetAsync(&h->p.ctrl->nmark[0][0], 0, sizeof(unsigned) * 8, h->stream));
@@ -1483,7 +1520,14 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    DevProblem& p = h->p;
    unsigned char* d_dirty; unsigned char* d_tileflag; int* d_xlist; double2* d_bnd; long long* d_cand; unsigned* d_colbits;
    int* d_chglist; Ctrl* d_ctrl; int* d_marklist; unsigned* d_freebits; double2* d_bndf;
+   unsigned char* d_colstate; int* d_flist; FastAcc* d_facc; unsigned* d_fracflag;
    int rc = GPULIN_OK;
+   TRY(devAlloc(h, &d_colstate, (size_t)h->ncols + 1));
+   TRY(devAlloc(h, &d_flist, (size_t)h->nsell + 1));
+   TRY(devAlloc(h, &d_facc, (size_t)h->nsell + 1));
+   TRY(devAlloc(h, &d_fracflag, 1));
+   TRYCU(cudaMemset(d_colstate, CS_OTHER, (size_t)h->ncols + 1));
+   TRYCU(cudaMemset(d_fracflag, 0, sizeof(unsigned)));
    TRY(devAlloc(h, &d_dirty, (size_t)h->nrows + 64));
    TRY(devAlloc(h, &d_tileflag, (size_t)h->ntiles + 64));
    TRY(devAlloc(h, &d_xlist, (size_t)h->nrows + 1));
@@ -1530,6 +1574,10 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    p.bnd = d_bnd;
    p.freebits = d_freebits;
    p.bndf = d_bndf;
+   p.colstate = d_colstate;
+   p.flist = d_flist;
+   p.facc = d_facc;
+   p.fracflag = d_fracflag;
    p.cand = d_cand;
    p.colbits = d_colbits;
    p.chglist = d_chglist;
@@ -1775,8 +1823,8 @@ extern "C" int gpulin_get_call_stats(gpulin_t* h, int64_t* stats, int32_t nstats
       // begin; per dense round: sweeps, exact, collect, [merge with peers], apply, sparse rounds
       launches = (h->lastresumed ? 1 : 0) + 1 + dense * (nkinds + 3 + (h->npeers > 1 ? 1 : 0) + (h->nsparseblocks > 0 ? 1 : 0));
    }
-   const int64_t v[5] = {launches, dense, sparse, h->lastsmall ? 1 : 0, h->lastresumed ? 1 : 0};
-   for( int i = 0; i < nstats && i < 5; ++i )
+   const int64_t v[6] = {launches, dense, sparse, h->lastsmall ? 1 : 0, h->lastresumed ? 1 : 0, (int64_t)c->nfastrows};
+   for( int i = 0; i < nstats && i < 6; ++i )
       stats[i] = v[i];
    return GPULIN_OK;
 }

@@ -61,11 +61,13 @@ struct Ctrl
    unsigned long long total_nnz;
    unsigned long long t_start;      // %globaltimer at the start of the call
    unsigned int       nexact[4];    // rows the filter sweeps handed to the exact kernel in the running round, per list
+                                    // ([0..2]: xlist per bin, [3]: flist, the short rows whose exact activities came along)
    alignas(16) unsigned int nmark[2][4];  // (16-byte aligned: read as one word) rows marked (per bin) into mark list buffer 0 / 1; marking writes buffer mb^1
    unsigned int       mb;           // the buffer the last apply filled = what a sparse round reads
    unsigned int       resume;       // the next begin_kernel continues the call small_rounds started (round count, totals, log)
    unsigned int       nsparse;      // rounds done by sparse_rounds_kernel in this call (statistics)
    unsigned int       poisoned;     // probing worker: its state is not "node + change log" any more (see probe_kernel)
+   unsigned int       nfastrows;    // rows that took the thread-per-row phase of the exact kernel in this call (statistics)
    unsigned long long round_nnz[NNZ_SLOTS];  // nonzeros swept in the running round (sum over the slots)
    unsigned long long hist_time[MAX_HIST];   // %globaltimer at the end of each round
    unsigned long long hist_nnz[MAX_HIST];
@@ -85,6 +87,32 @@ struct ChangeRec      // == gpulin_change
    int    reserved;
 };
 
+// exact activities that come along with a row the filter sweep hands over (flist / facc).  If every coefficient of a row is
+// an integer, every column is of integral type and every bound of those columns is an integer (ROWLEN_INT, fracflag), all
+// products a * bound are integers; as long as their absolute sum stays below 2^40 EVERY partial sum of the filter's plain
+// fp64 accumulation (in whatever order, also in the midpoint / half-width form: multiples of 1/2) is exact -- and then the
+// double-double accumulation of the exact rules yields the same value with a zero low word (dd_add: s = hi + c is exact, so
+// e = 0).  Such a row skips the activity pass of the exact rules: gates and candidates start from these three numbers.
+struct alignas(32) FastAcc
+{
+   double minact;
+   double maxact;
+   double maxdelta;
+   int    len;        // the header of the row comes along (the sweep has it in registers): one round trip less in the
+   int    off32;      // dependent chain of the phase that takes these rows (fastShortPhase)
+   double lhs;
+   double rhs;
+   double spare[2];
+};
+constexpr int FAST_CABSHI = 0x42700000;        // high word of 2^40: the bound on the absolute sums
+constexpr float FAST_MAXDELTA = 4194304.0f;    // 2^22: below it the fp32 maximum (of multiples of 1/2, rounded up) is exact
+
+// state of a column as the unit slices of the bit-table sweep see it (colstate[], kept by noteBounds)
+constexpr unsigned char CS_FREE = 0;     // (0,1)
+constexpr unsigned char CS_FIX0 = 1;     // (0,0)
+constexpr unsigned char CS_FIX1 = 2;     // (1,1)
+constexpr unsigned char CS_OTHER = 3;    // anything else: the bound pair is gathered
+
 struct DevProblem
 {
    int                 nrows;
@@ -97,9 +125,10 @@ struct DevProblem
    int                 ntiles;     // tiles of the stream (its storage is padded with zero coefficients to a whole tile)
    long long           streambase; // element offset of the first tile of the stream (a multiple of TILE)
    const long long*    sell_off;   // per SELL slice: element offset; element k of row r sits at sell_off[r>>5] + (r&31) + 32 k
+   const int*          sell_off32; // sell_off / 32 (the offsets are multiples of 32)
    // rows (permuted numbering)
    const long long*    rowbeg;     // element offset of the first nonzero
-   const int*          rowlen;     // length | ROWLEN_EXACT
+   const int*          rowlen;     // length | ROWLEN_EXACT | ROWLEN_INT
    const double2*      sides;      // (lhs, rhs)
    unsigned char*      dirty;      // marked for propagation
    const double*       vals;
@@ -109,11 +138,16 @@ struct DevProblem
    const unsigned char* endmask;   // per tile and lane: bit i = nonzero 8*lane+i is the last of its row
    unsigned char*      tileflag;   // a marked row starts in this tile
    int*                xlist;      // rows handed to exact_rows_kernel, one list per bin: [0,nsell) [nsell,nsx) [nsx,nrows)
+   int*                flist;      // rows of the thread-per-row class handed over TOGETHER WITH their exact activities (FastAcc) ...
+   FastAcc*            facc;       // ... which sit at the same position of this array
+   unsigned*           fracflag;   // != 0: a column of integral type has (had) a bound that is not an integer -- no FastAcc
+   const unsigned char* coltype;   // per column: != 0 integral type
    int*                marklist;   // rows marked by the apply step: [buffer 0|1][bin 0..2][MARKCAP]; complete unless a
                                    // count exceeds MARKCAP (the dirty flags are the ground truth, the lists a shortcut)
    // columns
    const double2*      bnd;        // (lb, ub) at round start
    double2*            bndf;       // ((lb+ub)/2, (ub-lb)/2) per column: what sweep_sell_bits_kernel gathers instead of bnd
+   unsigned char*      colstate;   // CS_* per column
    unsigned*           freebits;   // bit per column: bnd == (0,1) exactly; nfreewords words (a multiple of 4) are staged into
    int                 nfreewords; // shared memory by sweep_sell_bits_kernel, they cover the columns [0, nfreecols)
    int                 nfreecols;
@@ -133,6 +167,7 @@ struct DevProblem
    int                 st0, st1;
    int                 nranks, rank;
    unsigned            markall_min; // an apply step with at least this many changed columns marks ALL rows (see apply_kernel)
+   unsigned            fastmin;     // exact_rows_kernel: the rows of flist take the thread-per-row phase if there are more than this
    RangedRows          rr;          // ranged-row propagation (gpulin_set_rangedrow); rr.n == 0: off
    Num                 num;
 };
@@ -330,6 +365,9 @@ __device__ __forceinline__ void rowCandidates(const DevProblem& p, const RowInfo
 // exact pass touches (from L2) only rows that have work.
 constexpr int ROWLEN_EXACT = 0x40000000;   // flag in rowlen[]: the row has a coefficient so small that an infinite
                                            // bound could hide behind a non-huge product -> always the exact rules
+constexpr int ROWLEN_INT = 0x20000000;     // flag in rowlen[]: every coefficient is an integer (|a| <= 2^20) and every column
+                                           // of the row is of integral type -- see FastAcc
+constexpr int ROWLEN_MASK = ~(ROWLEN_EXACT | ROWLEN_INT);
 
 struct LeanAcc
 {
@@ -531,7 +569,7 @@ __device__ __forceinline__ int finishRow(const DevProblem& p, int row, const Lea
       return 0;
    p.dirty[row] = ROW_CLEAN;
    const bool exact = (lenword & ROWLEN_EXACT) != 0;
-   const int len = lenword & ~ROWLEN_EXACT;
+   const int len = lenword & ROWLEN_MASK;
    nnzdone += (unsigned)len;
    return (exact || !rowClearlyQuiet(p.num, tot, len, sd.x, sd.y)) ? 1 : 0;
 }
@@ -548,6 +586,46 @@ __device__ __forceinline__ void pushRow(const DevProblem& p, bool want, int row,
    pos = __shfl_sync(0xffffffffu, pos, 0);
    if( want )
       p.xlist[listoff + pos + __popc(m & ((1u << lane) - 1u))] = row;
+}
+
+// may the sums of the filter stand in for the exact activities of this row?  (see FastAcc)
+__device__ __forceinline__ bool fastAccValid(int lenword, bool intbounds, const LeanAcc& la)
+{
+   return intbounds && (lenword & (ROWLEN_INT | ROWLEN_EXACT)) == ROWLEN_INT && la.cabshi < FAST_CABSHI && la.maxdelta < FAST_MAXDELTA;
+}
+
+// the same for the rows of the thread-per-row class: a row with fast == true goes to flist together with its activities
+// and its header (length, offset of its slice / 32, sides)
+__device__ __forceinline__ void pushShortRow(const DevProblem& p, bool want, bool fast, int row, int lane, const LeanAcc& la,
+   int len, int off32, const double2& sd)
+{
+   const unsigned mg = __ballot_sync(0xffffffffu, want && !fast);
+   const unsigned mf = __ballot_sync(0xffffffffu, want && fast);
+   if( (mg | mf) == 0u )
+      return;
+   unsigned posg = 0u;
+   unsigned posf = 0u;
+   if( lane == 0 )
+   {
+      if( mg != 0u )
+         posg = atomicAdd(&p.ctrl->nexact[0], (unsigned)__popc(mg));
+      if( mf != 0u )
+         posf = atomicAdd(&p.ctrl->nexact[3], (unsigned)__popc(mf));
+   }
+   posg = __shfl_sync(0xffffffffu, posg, 0);
+   posf = __shfl_sync(0xffffffffu, posf, 0);
+   const unsigned below = (1u << lane) - 1u;
+   if( want && !fast )
+      p.xlist[posg + __popc(mg & below)] = row;
+   if( want && fast )
+   {
+      const unsigned q = posf + __popc(mf & below);
+      p.flist[q] = row;
+      double2* dst = reinterpret_cast<double2*>(p.facc + q);
+      dst[0] = make_double2(la.minact, la.maxact);
+      dst[1] = make_double2((double)la.maxdelta, __hiloint2double(off32, len));
+      dst[2] = sd;
+   }
 }
 
 // 32-byte streaming loads (LDG.256): one full sector per lane and request
@@ -825,7 +903,7 @@ __device__ __forceinline__ void loadChunk(const DevProblem& p, long long base, i
 }
 
 template <int CH>
-__device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads, int sbeg, int send, unsigned& nnzdone)
+__device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads, bool intbounds, int sbeg, int send, unsigned& nnzdone)
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
@@ -841,6 +919,7 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads
       long long base[SELL_NB];
       unsigned actm = 0u;
       unsigned exactm = 0u;
+      unsigned intm = 0u;
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
       {
@@ -852,11 +931,13 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads
          const int lw = valid ? p.rowlen[row] : 0;
          base[i] = (q < nq ? p.sell_off[slice] : 0) + lane;
          const bool act = f == ROW_MARKED;
-         len[i] = act ? (lw & ~ROWLEN_EXACT) : 0;
+         len[i] = act ? (lw & ROWLEN_MASK) : 0;
          if( act )
             actm |= 1u << i;
          if( act && (lw & ROWLEN_EXACT) != 0 )
             exactm |= 1u << i;
+         if( act && (lw & ROWLEN_INT) != 0 )
+            intm |= 1u << i;
       }
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
@@ -908,13 +989,16 @@ __device__ __forceinline__ void sellSweep(const DevProblem& p, int nblockthreads
          if( maxlen[i] == 0 && i + 1 < SELL_NB )
             loadChunk<CH>(p, base[i + 1], 0, len[i + 1], an, cjn);
          bool handoff = false;
+         bool fast = false;
          if( act )
          {
-            handoff = ((exactm >> i) & 1u) != 0u || !rowClearlyQuiet(n, acc, len[i], sd.x, sd.y);
+            const bool exact = ((exactm >> i) & 1u) != 0u;
+            handoff = exact || !rowClearlyQuiet(n, acc, len[i], sd.x, sd.y);
+            fast = handoff && fastAccValid(exact ? ROWLEN_EXACT : (((intm >> i) & 1u) != 0u ? ROWLEN_INT : 0), intbounds, acc);
             p.dirty[row] = ROW_CLEAN;
             nnzdone += (unsigned)len[i];
          }
-         pushRow(p, handoff, row, lane, 0, 0);
+         pushShortRow(p, handoff, fast, row, lane, acc, len[i], (int)((base[i] - lane) >> 5), sd);
       }
    }
 }
@@ -924,8 +1008,9 @@ __global__ void __launch_bounds__(SELL_THREADS, MINB) sweep_sell_kernel(const De
 {
    TRACE_KERNEL_START(p.ctrl, TR_SWEEP_SELL);
    unsigned nnzdone = 0;
-   sellSweep<CH>(p, SELL_THREADS, 0, p.nsellunit >> 5, nnzdone);
-   sellSweep<CH>(p, SELL_THREADS, p.nsellunit >> 5, (p.nsell + 31) >> 5, nnzdone);
+   const bool intbounds = *p.fracflag == 0u;
+   sellSweep<CH>(p, SELL_THREADS, intbounds, 0, p.nsellunit >> 5, nnzdone);
+   sellSweep<CH>(p, SELL_THREADS, intbounds, p.nsellunit >> 5, (p.nsell + 31) >> 5, nnzdone);
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
    if( (threadIdx.x & 31) == 0 )
       addRoundNnz(p, (unsigned long long)nnzdone, (blockIdx.x * SELL_THREADS + threadIdx.x) >> 5);
@@ -1047,7 +1132,7 @@ __device__ __forceinline__ void loadChunkBits(const DevProblem& p, long long bas
 //      UNIT: every coefficient of these slices is +1 or -1 (rows [0, nsellunit)): 4 instead of 12 bytes per nonzero
 template <int NT, int CH, bool ALLCOLS, bool UNIT>
 __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigned* s_free, unsigned tabbar, bool& tabready,
-   int sbeg, int send, unsigned& nnzdone)
+   bool intbounds, int sbeg, int send, unsigned& nnzdone)
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
@@ -1069,6 +1154,7 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
       long long base[SELL_NB];
       unsigned actm = 0u;
       unsigned exactm = 0u;
+      unsigned intm = 0u;
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
       {
@@ -1080,11 +1166,13 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
          const int lw = valid ? p.rowlen[row] : 0;
          base[i] = (q < nq ? p.sell_off[slice] : 0) + lane;
          const bool act = f == ROW_MARKED;
-         len[i] = act ? (lw & ~ROWLEN_EXACT) : 0;
+         len[i] = act ? (lw & ROWLEN_MASK) : 0;
          if( act )
             actm |= 1u << i;
          if( act && (lw & ROWLEN_EXACT) != 0 )
             exactm |= 1u << i;
+         if( act && (lw & ROWLEN_INT) != 0 )
+            intm |= 1u << i;
       }
 #pragma unroll
       for( int i = 0; i < SELL_NB; ++i )
@@ -1161,18 +1249,222 @@ __device__ __forceinline__ void sellBitsRange(const DevProblem& p, const unsigne
          if( maxlen[i] == 0 && i + 1 < SELL_NB )
             loadChunkBits<CH, UNIT>(p, base[i + 1], 0, len[i + 1], an, cjn);
          bool handoff = false;
+         bool fast = false;
+         const LeanAcc la = midToLean(macc);
          if( act )
          {
-            handoff = ((exactm >> i) & 1u) != 0u || !rowClearlyQuiet(n, midToLean(macc), len[i], sd.x, sd.y);
+            const bool exact = ((exactm >> i) & 1u) != 0u;
+            handoff = exact || !rowClearlyQuiet(n, la, len[i], sd.x, sd.y);
+            fast = handoff && fastAccValid(exact ? ROWLEN_EXACT : (((intm >> i) & 1u) != 0u ? ROWLEN_INT : 0), intbounds, la);
             p.dirty[row] = ROW_CLEAN;
             nnzdone += (unsigned)len[i];
          }
-         pushRow(p, handoff, row, lane, 0, 0);
+         pushShortRow(p, handoff, fast, row, lane, la, len[i], (int)((base[i] - lane) >> 5), sd);
       }
    }
 }
 
-// CHU: nonzeros per thread and chunk in the unit slices
+// ---- the unit slices (rows [0, nsellunit): every coefficient is +1 or -1) -------------------------------------------------
+// A column whose bit is set in the table has the bounds (0,1): its term is m = +-1/2, h = 1/2.  Such nonzeros are COUNTED
+// (the free columns, and those of them with a negative coefficient, as two 16-bit fields of one register) instead of summed
+// in fp64: three integer instructions, no constants to materialise; the sums of the counted part, (nf - 2 nn)/2 and nf/2,
+// are exact.  A column that is not free is looked up in colstate[] (one byte: eight lookups in flight cost eight
+// registers, eight bound pairs would cost 32): fixed at 0 -- no term at all; fixed at 1 -- counted like the free ones
+// (m = +-1, h = 0); only what is left (general integers, continuous columns) takes the fp64 path with its gather of bndf.
+// Both steps sit behind warp votes: a chunk whose columns are all free never sees the second, a chunk of binaries never
+// the third.
+// Measured (C3, 10M nonzeros, full round): 38.9 us against 40.3 us for the version that summed every nonzero in fp64; chunks
+// of 8 or 16 nonzeros, 768 / 512 threads with more registers, and flags / lengths / offsets fetched a batch ahead were all
+// slower (53 - 104 us: the 64-register budget of a 1024-thread block spills, and a spilled load is waited for at once).
+constexpr int UNIT_NB = 2;           // slices per batch
+
+// FULL: all nonzeros of the chunk exist in every lane (a slice of rows of one length, all marked): no predicates
+template <int UNIT_CH, bool ALLCOLS, bool FULL>
+__device__ __forceinline__ void unitChunk(const DevProblem& p, const unsigned* s_free, const int (&w)[UNIT_CH], int nvalid,
+   unsigned& cntfree, unsigned& cntone, MidAcc& macc)
+{
+   unsigned notfree = 0u;
+#pragma unroll
+   for( int k = 0; k < UNIT_CH; ++k )
+   {
+      const bool there = FULL || k < nvalid;                      // (a word that was not loaded must not index the table)
+      const unsigned wk = there ? (unsigned)w[k] : 0u;
+      const unsigned col = wk & (unsigned)COL_MASK;
+      const unsigned word = s_free[ALLCOLS ? col >> 5 : min(col >> 5, (unsigned)(p.nfreewords - 1))];
+      unsigned fr = (word >> (col & 31u)) & 1u;
+      if( !ALLCOLS && col >= (unsigned)p.nfreecols )
+         fr = 0u;
+      if( !there )
+         fr = 0u;
+      // low half: free columns; high half: free columns with a negative coefficient (COL_NEGCOEF is bit 30 of the word)
+      cntfree += fr * (1u + ((wk >> 14) & 0x10000u));
+      if( there && fr == 0u )
+         notfree |= 1u << k;
+   }
+   if( __any_sync(0xffffffffu, notfree != 0u) )
+   {
+      unsigned code[UNIT_CH];      // (not bytes: a byte array would live in local memory)
+#pragma unroll
+      for( int k = 0; k < UNIT_CH; ++k )
+      {
+         if( (notfree >> k) & 1u )
+            code[k] = p.colstate[w[k] & COL_MASK];
+      }
+      unsigned other = 0u;
+#pragma unroll
+      for( int k = 0; k < UNIT_CH; ++k )
+      {
+         if( (notfree >> k) & 1u )
+         {
+            if( code[k] == CS_FIX1 )
+               cntone += 1u + (((unsigned)w[k] >> 14) & 0x10000u);
+            else if( code[k] != CS_FIX0 )
+               other |= 1u << k;
+         }
+      }
+      if( __any_sync(0xffffffffu, other != 0u) )
+      {
+#pragma unroll
+         for( int k = 0; k < UNIT_CH; ++k )
+         {
+            if( (other >> k) & 1u )
+            {
+               // a = +1 / -1: a * mid is mid with the sign flipped, |a| * hw is hw (the values midElem would compute)
+               const double2 b = p.bndf[w[k] & COL_MASK];
+               const double m = __hiloint2double(__double2hiint(b.x) ^ unitSign(w[k]), __double2loint(b.x));
+               macc.M += m;
+               macc.Mabs += fabs(b.x);
+               macc.H += b.y;
+               macc.hmax = fmaxf(macc.hmax, __double2float_ru(b.y));
+            }
+         }
+      }
+   }
+}
+
+template <int UNIT_CH>
+__device__ __forceinline__ void loadUnitChunk(const DevProblem& p, long long base, int c, int len, int (&w)[UNIT_CH])
+{
+#pragma unroll
+   for( int k = 0; k < UNIT_CH; ++k )
+   {
+      if( c + k < len )
+         w[k] = ldStream(p.cols + base + 32LL * (c + k));
+   }
+}
+
+// flags, length words and offsets of the slices of one batch of a warp
+struct UnitHdr
+{
+   int           lw[UNIT_NB];
+   int           off32[UNIT_NB];
+   unsigned char f[UNIT_NB];
+};
+
+template <int NT, bool ALLCOLS, int UNIT_CH>
+__device__ __forceinline__ void sellUnitRange(const DevProblem& p, const unsigned* s_free, unsigned tabbar, bool& tabready,
+   bool intbounds, int sbeg, int send, unsigned& nnzdone)
+{
+   const Num& n = p.num;
+   const int lane = threadIdx.x & 31;
+   const int gw = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;      // warp-major, see sellBitsRange
+   const int nw = (gridDim.x * NT) >> 5;
+   const int nq = (send - sbeg - p.rank + p.nranks - 1) / p.nranks;
+   auto loadHdr = [&](int q0, UnitHdr& h)
+   {
+#pragma unroll
+      for( int i = 0; i < UNIT_NB; ++i )
+      {
+         const int q = q0 + i * nw;
+         const int slice = sbeg + p.rank + q * p.nranks;
+         const int row = slice * 32 + lane;
+         const bool valid = q < nq && row < p.nsell;
+         h.f[i] = valid ? p.dirty[row] : ROW_CLEAN;
+         h.lw[i] = valid ? p.rowlen[row] : 0;
+         h.off32[i] = q < nq ? p.sell_off32[slice] : 0;
+      }
+   };
+   int wn[UNIT_CH];
+   for( int q0 = gw; q0 < nq; q0 += UNIT_NB * nw )
+   {
+      UnitHdr h;
+      loadHdr(q0, h);
+      int len[UNIT_NB];
+      int maxlen[UNIT_NB];
+      bool uniform[UNIT_NB];
+#pragma unroll
+      for( int i = 0; i < UNIT_NB; ++i )
+      {
+         len[i] = h.f[i] == ROW_MARKED ? (h.lw[i] & ROWLEN_MASK) : 0;
+         maxlen[i] = __reduce_max_sync(0xffffffffu, len[i]);
+         uniform[i] = __reduce_min_sync(0xffffffffu, len[i]) == maxlen[i];
+      }
+      loadUnitChunk<UNIT_CH>(p, 32LL * h.off32[0] + lane, 0, len[0], wn);
+      if( !tabready )
+      {
+         mbarWait(tabbar, 0u);      // the first column words are on their way while the table arrives
+         tabready = true;
+      }
+#pragma unroll
+      for( int i = 0; i < UNIT_NB; ++i )
+      {
+         const int row = (sbeg + p.rank + (q0 + i * nw) * p.nranks) * 32 + lane;
+         const long long base = 32LL * h.off32[i] + lane;
+         const bool act = h.f[i] == ROW_MARKED;
+         double2 sd = make_double2(0.0, 0.0);
+         if( act )
+            sd = p.sides[row];
+         MidAcc macc;
+         midInit(macc);
+         unsigned cntfree = 0u;
+         unsigned cntone = 0u;
+         for( int c = 0; c < maxlen[i]; c += UNIT_CH )
+         {
+            int w[UNIT_CH];
+#pragma unroll
+            for( int k = 0; k < UNIT_CH; ++k )
+               w[k] = wn[k];
+            // the chunk after this one
+            if( c + UNIT_CH < maxlen[i] )
+               loadUnitChunk<UNIT_CH>(p, base, c + UNIT_CH, len[i], wn);
+            else if( i + 1 < UNIT_NB )
+               loadUnitChunk<UNIT_CH>(p, 32LL * h.off32[i + 1 < UNIT_NB ? i + 1 : i] + lane, 0, len[i + 1 < UNIT_NB ? i + 1 : i], wn);
+            if( uniform[i] && c + UNIT_CH <= maxlen[i] )
+               unitChunk<UNIT_CH, ALLCOLS, true>(p, s_free, w, UNIT_CH, cntfree, cntone, macc);
+            else
+               unitChunk<UNIT_CH, ALLCOLS, false>(p, s_free, w, len[i] - c, cntfree, cntone, macc);
+         }
+         if( maxlen[i] == 0 && i + 1 < UNIT_NB )
+            loadUnitChunk<UNIT_CH>(p, 32LL * h.off32[i + 1 < UNIT_NB ? i + 1 : i] + lane, 0, len[i + 1 < UNIT_NB ? i + 1 : i], wn);
+         bool handoff = false;
+         bool fast = false;
+         LeanAcc la;
+         leanInit(la);
+         if( act )
+         {
+            // the counted part: nf free columns (nfn of them with coefficient -1), n1 columns fixed at 1 (n1n with -1)
+            const int nf = (int)(cntfree & 0xffffu);
+            const int nfn = (int)(cntfree >> 16);
+            const int n1 = (int)(cntone & 0xffffu);
+            const int n1n = (int)(cntone >> 16);
+            const double half = 0.5 * (double)nf;
+            macc.M += (half - (double)nfn) + (double)(n1 - 2 * n1n);
+            macc.Mabs += half + (double)n1;
+            macc.H += half;
+            if( nf > 0 )
+               macc.hmax = fmaxf(macc.hmax, 0.5f);
+            la = midToLean(macc);
+            handoff = (h.lw[i] & ROWLEN_EXACT) != 0 || !rowClearlyQuiet(n, la, len[i], sd.x, sd.y);
+            fast = handoff && fastAccValid(h.lw[i], intbounds, la);
+            p.dirty[row] = ROW_CLEAN;
+            nnzdone += (unsigned)len[i];
+         }
+         pushShortRow(p, handoff, fast, row, lane, la, len[i], h.off32[i], sd);
+      }
+   }
+}
+
+// CHU: nonzeros per thread and chunk in the unit slices (sellUnitRange)
 template <int NT, int CH, bool ALLCOLS, int CHU>
 __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem p)
 {
@@ -1195,8 +1487,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_sell_bits_kernel(const DevProblem
    const int gw = (blockIdx.x * NT + threadIdx.x) >> 5;
    unsigned nnzdone = 0;
    bool tabready = false;
-   sellBitsRange<NT, CHU, ALLCOLS, true>(p, s_free, tabbar, tabready, 0, p.nsellunit >> 5, nnzdone);
-   sellBitsRange<NT, CH, ALLCOLS, false>(p, s_free, tabbar, tabready, p.nsellunit >> 5, (p.nsell + 31) >> 5, nnzdone);
+   const bool intbounds = *p.fracflag == 0u;
+   sellUnitRange<NT, ALLCOLS, CHU>(p, s_free, tabbar, tabready, intbounds, 0, p.nsellunit >> 5, nnzdone);
+   sellBitsRange<NT, CH, ALLCOLS, false>(p, s_free, tabbar, tabready, intbounds, p.nsellunit >> 5, (p.nsell + 31) >> 5, nnzdone);
    if( !tabready && threadIdx.x < 32 )
       mbarWait(tabbar, 0u);         // the block must not retire under the copies it issued
    nnzdone = __reduce_add_sync(0xffffffffu, nnzdone);
@@ -1224,7 +1517,7 @@ __global__ void __launch_bounds__(LONG_THREADS) sweep_long_kernel(const DevProbl
          continue;
       int len = p.rowlen[row];
       const bool exact = (len & ROWLEN_EXACT) != 0;
-      len &= ~ROWLEN_EXACT;
+      len &= ROWLEN_MASK;
       const long long beg = p.rowbeg[row];
       const double2 sd = p.sides[row];
 
@@ -1297,7 +1590,7 @@ __device__ __forceinline__ bool claimRow(const DevProblem& p, int row)
 // (marklist) -- in a round with few marked rows the filter pass is skipped and every marked row gets the exact rules
 template <bool SPARSE>
 __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0, unsigned n0, const int* list1, unsigned n1,
-   const int* list2, unsigned n2, RowAcc* s_acc, CandQueue* s_queue, int nblockthreads)
+   const int* list2, unsigned n2, RowAcc* s_acc, CandQueue* s_queue, int nblockthreads, const int* list0b = nullptr, unsigned n0b = 0u)
 {
    const Num& n = p.num;
    const int lane = threadIdx.x & 31;
@@ -1310,21 +1603,23 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
    {
       const int gl = lane & (EXACT_G - 1);
       const int ngroups = nthreads / EXACT_G;
-      const unsigned rounds = (n0 + ngroups - 1) / ngroups;      // warp-uniform trip count
+      // (a second list of short rows: the rows that came with their activities when there are too few of them for the
+      // thread-per-row phase, see exact_rows_kernel)
+      const unsigned rounds = (n0 + n0b + ngroups - 1) / ngroups;      // warp-uniform trip count
       for( unsigned it = 0; it < rounds; ++it )
       {
          const unsigned item = it * ngroups + gtid / EXACT_G;
-         bool valid = item < n0;
+         bool valid = item < n0 + n0b;
          int row = 0;
          if( valid )
-            row = list0[item];
+            row = item < n0 ? list0[item] : list0b[item - n0];
          int len = 0;
          long long base = 0;
          double2 sd = make_double2(0.0, 0.0);
          if( valid )
          {
             // (the header of the row is on its way while the claim below is answered: the list names real rows)
-            len = p.rowlen[row] & ~ROWLEN_EXACT;
+            len = p.rowlen[row] & ROWLEN_MASK;
             base = p.sell_off[row >> 5] + (row & 31);
             sd = p.sides[row];
          }
@@ -1422,7 +1717,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
             if( !mine )
                continue;
          }
-         const int len = p.rowlen[row] & ~ROWLEN_EXACT;
+         const int len = p.rowlen[row] & ROWLEN_MASK;
          const long long beg = p.rowbeg[row];
          const double2 sd = p.sides[row];
          if( SPARSE && lane == 0 )
@@ -1453,7 +1748,7 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
          if( !s_mine )
             continue;
       }
-      const int len = p.rowlen[row] & ~ROWLEN_EXACT;
+      const int len = p.rowlen[row] & ROWLEN_MASK;
       const long long beg = p.rowbeg[row];
       const double2 sd = p.sides[row];
       if( SPARSE && threadIdx.x == 0 )
@@ -1474,6 +1769,192 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
    }
    if( SPARSE && nnzdone != 0 )
       addRoundNnz(p, nnzdone, gtid >> 5);
+}
+
+// ---- short rows that came with their exact activities (flist / facc, see FastAcc): a THREAD per row -------------------
+// No activity pass, no butterfly: gates, then one pass over the nonzeros.  The candidate rules are long and few nonzeros
+// reach them (the slack test), so the nonzeros that do are COMPACTED over the 32 rows of the warp: they collect in a
+// queue in shared memory together with what the rules need to know about their row (FastStash), and the warp runs the
+// rules 32 nonzeros at a time with every lane busy.  The rules are the same functions the eight-lanes-per-row path
+// calls, on the same numbers (see FastAcc), so the candidates are identical.
+constexpr int FAST_CH = 4;            // nonzeros per thread and trip (8 spill: the column words of the next trip must stay in registers)
+constexpr int FAST_QCAP = 64;         // fewer than 32 left over + at most 32 new
+struct FastStash                      // RowInfo of the row of a lane, as far as candidates() reads it
+{
+   double lhs, rhs, minact, maxact, maxdelta, slackR, slackL;
+   unsigned flags;                    // 1: easy, 2: force, 4: rhs finite, 8: lhs finite
+   unsigned spare;
+};
+struct FastCand
+{
+   int    rowlane;
+   int    colword;
+   double a, l, u;
+};
+struct FastShared
+{
+   FastStash st[32];
+   FastCand  q[FAST_QCAP];
+};
+
+__device__ __forceinline__ void fastRunQueue(const Num& n, const Sink& sk, FastShared& sh, int head, int take, int lane, bool& cutoff)
+{
+   __syncwarp();
+   if( lane < take )
+   {
+      const FastCand c = sh.q[head + lane];
+      const FastStash& t = sh.st[c.rowlane];
+      RowInfo ri;
+      accInit(ri.acc);
+      ri.acc.minhi = t.minact;
+      ri.acc.maxhi = t.maxact;
+      ri.acc.maxdelta = t.maxdelta;
+      ri.lhs = t.lhs;
+      ri.rhs = t.rhs;
+      ri.minact = t.minact;
+      ri.maxact = t.maxact;
+      ri.slackR = t.slackR;
+      ri.slackL = t.slackL;
+      ri.easy = (t.flags & 1u) != 0u;
+      ri.force = (t.flags & 2u) != 0u;
+      ri.rhsfin = (t.flags & 4u) != 0u;
+      ri.lhsfin = (t.flags & 8u) != 0u;
+      bool touched = false;
+      candidates(n, sk, ri, c.a, c.colword & COL_MASK, c.colword < 0, c.l, c.u, cutoff, touched);
+      if( touched )
+         raiseColumnBit(sk, c.colword & COL_MASK);
+   }
+   __syncwarp();
+}
+
+__device__ __forceinline__ void fastShortPhase(const DevProblem& p, unsigned nfast, int gtid, int nthreads, FastShared& sh)
+{
+   const Num& n = p.num;
+   const int lane = threadIdx.x & 31;
+   const unsigned below = (1u << lane) - 1u;
+   Sink sk;
+   sk.cand = p.cand;
+   sk.colbits = p.colbits;
+   sk.chglist = p.chglist;
+   sk.nchgcols = &p.ctrl->nchgcols;
+   sk.listed = false;
+   for( unsigned item0 = (unsigned)(gtid - lane); item0 < nfast; item0 += (unsigned)nthreads )      // warp-uniform
+   {
+      const unsigned item = item0 + (unsigned)lane;
+      const bool valid = item < nfast;
+      int len = 0;
+      long long base = 0;
+      bool unit = false;
+      bool go = false;
+      bool cutoff = false;
+      double thr = 0.0;
+      RowInfo ri;
+      accInit(ri.acc);
+      ri.lhs = ri.rhs = 0.0;
+      ri.easy = false;
+      if( valid )
+      {
+         const int row = p.flist[item];
+         const double2 f0 = reinterpret_cast<const double2*>(p.facc + item)[0];
+         const double2 f1 = reinterpret_cast<const double2*>(p.facc + item)[1];
+         const double2 sd = reinterpret_cast<const double2*>(p.facc + item)[2];
+         len = __double2loint(f1.y);
+         base = 32LL * __double2hiint(f1.y) + (row & 31);
+         unit = row < p.nsellunit;
+         ri.acc.minhi = f0.x;
+         ri.acc.maxhi = f0.y;
+         ri.acc.maxdelta = f1.x;
+         ri.lhs = sd.x;
+         ri.rhs = sd.y;
+         go = rowGates(n, ri, len, cutoff);
+         if( go )
+         {
+            thr = slackThreshold(n, ri.force);
+            FastStash t;
+            t.lhs = ri.lhs; t.rhs = ri.rhs; t.minact = ri.acc.minhi; t.maxact = ri.acc.maxhi; t.maxdelta = ri.acc.maxdelta;
+            t.slackR = ri.easy ? ri.slackR : 0.0;
+            t.slackL = ri.easy ? ri.slackL : 0.0;
+            t.flags = (ri.easy ? 1u : 0u) | (ri.force ? 2u : 0u) | (ri.rhsfin ? 4u : 0u) | (ri.lhsfin ? 8u : 0u);
+            t.spare = 0u;
+            sh.st[lane] = t;
+         }
+         if( rowInfeasible(n, ri.acc, ri.lhs, ri.rhs) )
+            cutoff = true;
+      }
+      const int golen = go ? len : 0;
+      const int kmax = __reduce_max_sync(0xffffffffu, golen);
+      int cnt = 0;                       // entries in the queue (warp-uniform)
+      // the column words of a trip are fetched while the bounds of the trip before are gathered
+      int cjn[FAST_CH];
+      // (unconditional loads -- a nonzero that does not exist reads the first one of the row again: with predicated loads the
+      // array would live in local memory, and every load would be waited for at once)
+#pragma unroll
+      for( int q = 0; q < FAST_CH; ++q )
+         cjn[q] = p.cols[base + 32LL * (q < golen ? q : 0)];
+      for( int k0 = 0; k0 < kmax; k0 += FAST_CH )
+      {
+         double a[FAST_CH];
+         int cj[FAST_CH];
+         double2 b[FAST_CH];
+#pragma unroll
+         for( int q = 0; q < FAST_CH; ++q )
+         {
+            cj[q] = cjn[q];
+            if( k0 + q < golen && !unit )
+               a[q] = p.vals[base + 32LL * (k0 + q)];
+         }
+#pragma unroll
+         for( int q = 0; q < FAST_CH; ++q )
+            cjn[q] = p.cols[base + 32LL * (k0 + FAST_CH + q < golen ? k0 + FAST_CH + q : 0)];
+#pragma unroll
+         for( int q = 0; q < FAST_CH; ++q )
+         {
+            if( k0 + q < golen )
+            {
+               b[q] = p.bnd[cj[q] & COL_MASK];
+               if( unit )
+                  a[q] = (cj[q] & COL_NEGCOEF) != 0 ? -1.0 : 1.0;
+            }
+         }
+#pragma unroll
+         for( int q = 0; q < FAST_CH; ++q )
+         {
+            const bool pass = k0 + q < golen && (!ri.easy || passesSlackTest(ri, fabs(a[q]) * (b[q].y - b[q].x), thr));
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if( m == 0u )
+               continue;
+            if( pass )
+            {
+               FastCand c;
+               c.rowlane = lane;
+               c.colword = cj[q];
+               c.a = a[q];
+               c.l = b[q].x;
+               c.u = b[q].y;
+               sh.q[cnt + __popc(m & below)] = c;
+            }
+            cnt += __popc(m);
+            if( cnt >= 32 )
+            {
+               fastRunQueue(n, sk, sh, 0, 32, lane, cutoff);
+               // what is left (fewer than 32 entries) moves to the front
+               const int rest = cnt - 32;
+               FastCand mv;
+               if( lane < rest )
+                  mv = sh.q[32 + lane];
+               __syncwarp();
+               if( lane < rest )
+                  sh.q[lane] = mv;
+               cnt = rest;
+            }
+         }
+      }
+      if( cnt > 0 )
+         fastRunQueue(n, sk, sh, 0, cnt, lane, cutoff);
+      if( cutoff )
+         p.ctrl->cutoff = 1;
+      __syncwarp();                      // the stash is rewritten by the next trip
+   }
 }
 
 // ---- ranged-row propagation (gpulin_ranged.cuh) for the rows marked for propagation, a warp per row ---------------------
@@ -1535,9 +2016,24 @@ __global__ void __launch_bounds__(EXACT_THREADS, MINB) exact_rows_kernel(const D
    const unsigned n0 = p.ctrl->nexact[0];
    const unsigned n1 = p.ctrl->nexact[1];
    const unsigned n2 = p.ctrl->nexact[2];
-   if( (n0 | n1 | n2) == 0u )
+   const unsigned nfast = p.ctrl->nexact[3];
+   if( (n0 | n1 | n2 | nfast) == 0u )
       return;
-   exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, s_queue, EXACT_THREADS);
+   // The thread-per-row phase pays off when it has rows for most of its lanes (32 rows per warp in flight instead of 4);
+   // a few rows are finished sooner by eight lanes each (one trip instead of a loop over the nonzeros): then the rows of
+   // flist simply join the short rows of xlist and their activities are computed like everybody else's.
+   const bool usefast = nfast > p.fastmin;
+   if( usefast )
+   {
+      __shared__ FastShared s_fast[EXACT_THREADS / 32];
+      if( blockIdx.x == 0 && threadIdx.x == 0 )
+         p.ctrl->nfastrows += nfast;
+      fastShortPhase(p, nfast, blockIdx.x * EXACT_THREADS + threadIdx.x, gridDim.x * EXACT_THREADS, s_fast[threadIdx.x >> 5]);
+      if( (n0 | n1 | n2) == 0u )
+         return;
+   }
+   exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, s_queue, EXACT_THREADS, p.flist,
+      usefast ? 0u : nfast);
 }
 
 // ---- redundancy feedback (propagateCons, cons_linear.c:7743-7753): flags[r] = 1 iff row r (permuted numbering) is
@@ -1550,7 +2046,7 @@ __global__ void __launch_bounds__(256) redundant_rows_kernel(const DevProblem p,
    const int nw = (gridDim.x * blockDim.x) >> 5;
    for( int row = gw; row < p.nrows; row += nw )
    {
-      const int len = p.rowlen[row] & ~ROWLEN_EXACT;
+      const int len = p.rowlen[row] & ROWLEN_MASK;
       const bool sell = row < p.nsell;
       const long long base = sell ? p.sell_off[row >> 5] + (row & 31) : p.rowbeg[row];
       const double2 sd = p.sides[row];
@@ -1573,9 +2069,23 @@ __device__ __forceinline__ double2 midHalfWidth(double l, double u)
 {
    return make_double2(0.5 * l + 0.5 * u, 0.5 * u - 0.5 * l);
 }
+__device__ __forceinline__ unsigned char columnState(double l, double u)
+{
+   if( l == 0.0 )
+      return u == 1.0 ? CS_FREE : (u == 0.0 ? CS_FIX0 : CS_OTHER);
+   return (l == 1.0 && u == 1.0) ? CS_FIX1 : CS_OTHER;
+}
+// a bound of a column of integral type that is neither an integer nor infinite switches the FastAcc shortcut off (the flag
+// is sticky until the next gpulin_set_bounds; bounds that come out of the propagation itself are integers: adjustedLb/Ub)
+__device__ __forceinline__ void checkIntegralBounds(const DevProblem& p, int j, double l, double u)
+{
+   if( p.coltype[j] != 0 && (l != rint(l) || u != rint(u)) )
+      *p.fracflag = 1u;
+}
 __device__ __forceinline__ void noteBounds(const DevProblem& p, int j, double l, double u)
 {
    p.bndf[j] = midHalfWidth(l, u);
+   p.colstate[j] = columnState(l, u);
    const unsigned m = 1u << (j & 31);
    if( isFree01(l, u) )
       atomicOr(&p.freebits[j >> 5], m);
@@ -1759,7 +2269,7 @@ __device__ __forceinline__ void controlStep(Ctrl* c, cudaGraphConditionalHandle 
    c->round_nchg = 0;
    c->ticket = 0;
    c->nchgcols = 0;
-   c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
+   c->nexact[0] = c->nexact[1] = c->nexact[2] = c->nexact[3] = 0;
    // the list this apply step filled becomes the one a sparse round reads; the other one is empty again
    c->nmark[mb][0] = c->nmark[mb][1] = c->nmark[mb][2] = 0;
    c->mb = mb ^ 1u;
@@ -2527,8 +3037,9 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
       c->cutoff = 0;
       c->ticket = 0;
       c->nchgcols = 0;
-      c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
+      c->nexact[0] = c->nexact[1] = c->nexact[2] = c->nexact[3] = 0;
       c->nsparse = 0;
+      c->nfastrows = 0;
       c->logcount = 0;
       c->round_nchg = 0;
       for( int i = 0; i < NNZ_SLOTS; ++i )
@@ -2547,6 +3058,7 @@ __device__ __forceinline__ void probeBody(const DevProblem& p, const DevProblem&
          const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
          reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
          noteBounds(p, j, l, u);
+         checkIntegralBounds(p, j, l, u);
       }
    }
    __syncthreads();
@@ -2709,6 +3221,8 @@ __global__ void set_bounds_kernel(const DevProblem p, const double* lb, const do
          const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
          reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
          p.bndf[j] = midHalfWidth(l, u);
+         p.colstate[j] = columnState(l, u);
+         checkIntegralBounds(p, j, l, u);
          fr = isFree01(l, u);
       }
       const unsigned word = __ballot_sync(0xffffffffu, fr);
@@ -2746,6 +3260,8 @@ __global__ void set_bounds_packed_kernel(const DevProblem p, const double2* ref,
          const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
          reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
          p.bndf[j] = midHalfWidth(l, u);
+         p.colstate[j] = columnState(l, u);
+         checkIntegralBounds(p, j, l, u);
          fr = isFree01(l, u);
       }
       const unsigned word = __ballot_sync(0xffffffffu, fr);
@@ -2777,6 +3293,7 @@ __global__ void update_explicit_kernel(const DevProblem p, long long nupd, const
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
       noteBounds(p, j, l, u);
+      checkIntegralBounds(p, j, l, u);
    }
 }
 // the change log as 12-byte records: { column | is_upper << 31, new bound (2 x 32 bits) }; the round of an entry follows
@@ -2805,6 +3322,7 @@ __global__ void update_bounds_kernel(const DevProblem p, long long nupd, const i
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
       noteBounds(p, j, l, u);
+      checkIntegralBounds(p, j, l, u);
       markColumnRows(p, j, 0, 1);
    }
 }
@@ -2839,6 +3357,7 @@ __global__ void update_small_kernel(const DevProblem p, const SmallUpdate su)
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
       noteBounds(p, j, l, u);
+      checkIntegralBounds(p, j, l, u);
    }
    markColumnRows(p, j, lane, 32);
 }
@@ -2853,6 +3372,7 @@ __global__ void update_one_kernel(const DevProblem p, int j, double l, double u)
       const_cast<double2*>(p.bnd)[j] = make_double2(l, u);
       reinterpret_cast<longlong2*>(p.cand)[j] = make_longlong2(~d2key(l), d2key(u));
       noteBounds(p, j, l, u);
+      checkIntegralBounds(p, j, l, u);
    }
    markColumnRows(p, j, threadIdx.x, blockDim.x);
 }
@@ -2913,10 +3433,11 @@ __global__ void begin_kernel(Ctrl* c)
    c->cutoff = 0;
    c->ticket = 0;
    c->nchgcols = 0;
-   c->nexact[0] = c->nexact[1] = c->nexact[2] = 0;
+   c->nexact[0] = c->nexact[1] = c->nexact[2] = c->nexact[3] = 0;
    c->nmark[0][0] = c->nmark[0][1] = c->nmark[0][2] = 0;
    c->nmark[1][0] = c->nmark[1][1] = c->nmark[1][2] = 0;
    c->nsparse = 0;
+   c->nfastrows = 0;
    c->logcount = 0;
    c->round_nchg = 0;
    for( int i = 0; i < NNZ_SLOTS; ++i )

@@ -392,9 +392,9 @@ class LinearPropagator:
 
     def call_stats(self) -> dict:
         """what the last propagate call launched (kernel launches, dense / sparse rounds, one-block call, hand-over)"""
-        st = np.zeros(5, dtype=np.int64)
-        _check(self._lib.gpulin_get_call_stats(self._h, st.ctypes.data, 5))
-        return dict(zip(("launches", "dense_rounds", "sparse_rounds", "small_call", "resumed"), (int(x) for x in st)))
+        st = np.zeros(6, dtype=np.int64)
+        _check(self._lib.gpulin_get_call_stats(self._h, st.ctypes.data, 6))
+        return dict(zip(("launches", "dense_rounds", "sparse_rounds", "small_call", "resumed", "fast_rows"), (int(x) for x in st)))
 
     def algorithmic_bytes(self) -> int:
         b = ctypes.c_int64(0)

@@ -487,3 +487,99 @@ def test_ranged_row_propagation_matches_the_oracle_on_larger_instances(gpulin, s
         if w2["status"] != oracle.STATUS_CUTOFF:
             glb, gub = lp.get_bounds()
             assert_bounds_match(glb, gub, w2["lb"], w2["ub"], prob["vartype"], what=f"ranged seed {seed} incremental")
+
+
+# ---- integer rows over integral columns: the exact kernel takes their activities from the filter sweep (FastAcc) ----------
+def _fast_vs_oracle(gpulin, prob, what, expect_fast, **numerics):
+    """propagates with the thread-per-row phase of the exact kernel forced on (GPULIN_FASTMIN=0 is set by the caller)
+    and compares bounds, verdict, rounds and changes with the oracle; returns the number of rows that took the phase"""
+    want = oracle.propagate(prob, **numerics)
+    with gpulin.LinearPropagator(prob, **numerics) as lp:
+        lp.set_bounds(prob["lb"], prob["ub"])
+        got = lp.propagate(0)
+        lb, ub = lp.get_bounds()
+        fast = lp.call_stats()["fast_rows"]
+    assert got["status"] == want["status"], what
+    if want["status"] != oracle.STATUS_CUTOFF:
+        assert got["nrounds"] == want["nrounds"] and got["nchanges"] == want["nchanges"], what
+        assert_bounds_match(lb, ub, want["lb"], want["ub"], prob["vartype"], what=what)
+    assert (fast > 0) == expect_fast, f"{what}: {fast} rows took the thread-per-row phase"
+    return fast
+
+
+@pytest.mark.parametrize("gen,bs", [("setcover", 1e-9), ("setcover", 0.05), ("setcover_small", 1e-9), ("infeasible", 1e-9),
+                                    ("shortknap", 1e-9), ("shortknap", 0.05), ("unitnet", 1e-9)])
+def test_integer_rows_take_their_activities_from_the_filter(gpulin, monkeypatch, gen, bs):
+    monkeypatch.setenv("GPULIN_FASTMIN", "0")
+    prob = {"setcover": lambda: synth.setcover(200_000, 200_000, 2_000_000, seed=12),       # bit-table sweep, unit + weighted
+            "setcover_small": lambda: synth.setcover(20_000, 20_000, 200_000, seed=13),     # gather variant of the sweep
+            "infeasible": lambda: synth.setcover(50_000, 50_000, 500_000, seed=14, infeasible=True),
+            # short knapsack rows over binaries, general integers and 20 % continuous columns: rows with and without the flag
+            "shortknap": lambda: synth.mixed_knapsack(60_000, 40_000, 900_000, seed=15, dense_frac=0.0, len_range=(3, 30)),
+            "unitnet": lambda: synth.unit_network(100_000, 80_000, 500_000, seed=16)}[gen]()
+    if gen == "infeasible":
+        want = oracle.propagate(prob, boundstreps=bs)
+        got = gpulin.propagate(prob, boundstreps=bs)
+        assert got["status"] == want["status"] == oracle.STATUS_CUTOFF
+    else:
+        _fast_vs_oracle(gpulin, prob, f"{gen} bs={bs}", expect_fast=True, boundstreps=bs)
+
+
+def test_fractional_bounds_of_integer_columns_switch_the_shortcut_off(gpulin, monkeypatch):
+    """a bound of an integral column that is not an integer makes the filter's sums inexact: no row may skip its activity
+    pass then (the flag is sticky until the next gpulin_set_bounds, which looks at every column again)"""
+    monkeypatch.setenv("GPULIN_FASTMIN", "0")
+    prob = synth.setcover(50_000, 50_000, 500_000, seed=17)
+    frac = dict(prob)
+    frac["ub"] = prob["ub"].copy()
+    frac["lb"] = prob["lb"].copy()
+    free = np.flatnonzero((prob["lb"] == 0.0) & (prob["ub"] == 1.0))
+    frac["ub"][free[:200:2]] = 1.5        # (relaxations: the instance stays feasible)
+    frac["lb"][free[1:200:2]] = -0.5
+    want = oracle.propagate(frac)
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.set_bounds(frac["lb"], frac["ub"])
+        got = lp.propagate(0)
+        lb, ub = lp.get_bounds()
+        assert lp.call_stats()["fast_rows"] == 0
+        assert want["status"] == oracle.STATUS_FIXPOINT and want["nchanges"] > 0
+        assert got["status"] == want["status"] and got["nrounds"] == want["nrounds"] and got["nchanges"] == want["nchanges"]
+        assert_bounds_match(lb, ub, want["lb"], want["ub"], prob["vartype"], what="fractional bounds")
+        # integral bounds again on the same handle: the shortcut is back, the result is the oracle's
+        want = oracle.propagate(prob)
+        lp.set_bounds(prob["lb"], prob["ub"])
+        got = lp.propagate(0)
+        lb, ub = lp.get_bounds()
+        assert lp.call_stats()["fast_rows"] > 0
+        assert got["status"] == want["status"] and got["nrounds"] == want["nrounds"] and got["nchanges"] == want["nchanges"]
+        assert_bounds_match(lb, ub, want["lb"], want["ub"], prob["vartype"], what="integral bounds again")
+
+
+def test_rows_whose_sums_could_round_keep_the_double_double_pass(gpulin, monkeypatch):
+    """integer coefficients beyond 2^20, or products whose absolute sum reaches 2^40: the flag / the magnitude test keep
+    such rows on the double-double path; the result is the oracle's either way"""
+    monkeypatch.setenv("GPULIN_FASTMIN", "0")
+    rng = np.random.default_rng(18)
+    nrows, ncols = 4000, 3000
+    rows, lhs, rhs = [], [], []
+    lb = np.zeros(ncols)
+    ub = np.full(ncols, 1e9)
+    ub[: ncols // 2] = rng.integers(1, 50, size=ncols // 2).astype(np.float64)
+    for r in range(nrows):
+        n = int(rng.integers(2, 12))
+        big = r % 2 == 0
+        cols = rng.choice(ncols // 2, size=n, replace=False) + (ncols // 2 if r % 4 == 1 else 0)
+        coef = rng.integers(1, 9, size=n).astype(np.float64) * (float(2 ** 21 + 1) if big else 1.0)
+        x = np.floor(rng.random(n) * np.minimum(ub[cols], 40.0))
+        rows.append(list(zip(cols.tolist(), coef.tolist())))
+        lhs.append(-INF)
+        rhs.append(float((coef * x).sum() + rng.integers(0, 5) * coef.min()))
+    prob = synth._from_rows(rows, np.array(lhs), np.array(rhs), lb, ub, np.ones(ncols, dtype=np.uint8))
+    want = oracle.propagate(prob)
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.set_bounds(prob["lb"], prob["ub"])
+        got = lp.propagate(0)
+        lbg, ubg = lp.get_bounds()
+    assert got["status"] == want["status"] and got["nrounds"] == want["nrounds"] and got["nchanges"] == want["nchanges"]
+    assert_bounds_match(lbg, ubg, want["lb"], want["ub"], prob["vartype"], what="large integer data")
+    assert got["nchanges"] > 0
