@@ -69,6 +69,7 @@ struct gpulin
    int         nlongblocks = 0;
    int         napplyblocks = 0;
    int         nexactblocks = 0;
+   int         nfastblocks = 0;     // grid of fast_rows_kernel (0: no row of the thread-per-row class can take it)
    int         nsparseblocks = 0;   // grid of the persistent sparse-rounds kernel (0: disabled)
    void        (*exactkernel)(const DevProblem) = nullptr;
    unsigned char* d_redflags = nullptr; // gpulin_get_redundant_rows: one flag per row, device / pinned host (allocated on first use)
@@ -109,6 +110,7 @@ struct gpulin
    bool        ownstream = true;
    cudaStream_t aux[2] = {nullptr, nullptr};     // the medium / long sweeps run beside the short sweep
    cudaEvent_t evfork = nullptr, evjoin[2] = {nullptr, nullptr};
+   cudaEvent_t evfork2 = nullptr, evjoin2 = nullptr;   // exact_rows_kernel || fast_rows_kernel
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    cudaEvent_t evprof[4] = {nullptr, nullptr, nullptr, nullptr};
    cudaGraph_t graph = nullptr;
@@ -282,7 +284,19 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = 
       for( int i = 0; i < side; ++i )
          CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
       if( h->nexactblocks > 0 )
+      {
+         // the rows that came with their activities run beside the exact rules of the others
+         if( h->nfastblocks > 0 )
+         {
+            CU(cudaEventRecord(h->evfork2, h->stream));
+            CU(cudaStreamWaitEvent(h->aux[0], h->evfork2, 0));
+            fast_rows_kernel<<<h->nfastblocks, FAST_THREADS, 0, h->aux[0]>>>(h->p);
+            CU(cudaEventRecord(h->evjoin2, h->aux[0]));
+         }
          h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
+         if( h->nfastblocks > 0 )
+            CU(cudaStreamWaitEvent(h->stream, h->evjoin2, 0));
+      }
       if( collect )
          OK(launchCollect(h));
    }
@@ -584,6 +598,7 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    unsigned* d_freebits; double2* d_bndf;
    int* d_xlist; int* d_marklist; unsigned char* d_dirty; double2* d_bnd; long long* d_cand; unsigned* d_colbits; int* d_chglist; long long* d_colbeg; int* d_colrows;
    Ctrl* d_ctrl;
+   std::vector<int> rowflags;      // rowlen words with their flags
    int rc = GPULIN_OK;
 #define TRY(x) do { if( rc == GPULIN_OK ) rc = (x); } while( 0 )
 #define TRYCU(x) do { if( rc == GPULIN_OK ) { cudaError_t e_ = (x); if( e_ != cudaSuccess ) rc = fail(GPULIN_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while( 0 )
@@ -635,7 +650,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    {
       // rows with a coefficient below hugeval / infinity always take the exact rules (see ROWLEN_EXACT)
       const double tiny = num->hugeval / num->infinity;
-      std::vector<int> flagged(plen);
+      std::vector<int>& flagged = rowflags;
+      flagged = plen;
       for( int64_t i = 0; i < nrows; ++i )
       {
          const int64_t r = perm[(size_t)i];
@@ -676,6 +692,8 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
    TRYCU(cudaEventCreateWithFlags(&h->evfork, cudaEventDisableTiming));
    TRYCU(cudaEventCreateWithFlags(&h->evjoin[0], cudaEventDisableTiming));
    TRYCU(cudaEventCreateWithFlags(&h->evjoin[1], cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evfork2, cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evjoin2, cudaEventDisableTiming));
    TRYCU(cudaEventCreate(&h->ev0));
    TRYCU(cudaEventCreate(&h->ev1));
    if( rc != GPULIN_OK )
@@ -729,7 +747,9 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       // spurious mark is cheap: the filter of the thread-per-row rows costs ~3 ps per nonzero and finishes almost every
       // row it did not have to look at, a longer row that the filter cannot finish costs a pass of the exact rules (and
       // the marking rule spares most rows of a knapsack-type matrix: an upper bound that moves down does not concern
-      // a <= row with positive coefficients).  So only for matrices whose nonzeros are in short rows
+      // a <= row with positive coefficients).  So only for matrices whose nonzeros are in short rows.  (Tried on C4, where
+      // the first round changes 677k columns of 25 rows each: marking everything takes 114 us off its apply step and puts
+      // 330 us on the second round, which sweeps and re-examines four times the rows.)
       long long sellnnz = 0;
       for( int i = 0; i < h->nsell; ++i )
          sellnnz += plen[(size_t)i];
@@ -780,10 +800,20 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->exactkernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
-      // the thread-per-row phase of the exact kernel takes the rows that came with their activities when there are more of
-      // them than eight lanes each finish in two trips (GPULIN_FASTMIN overrides the threshold: the tests run the phase on
-      // small instances with it)
-      p.fastmin = 8u * (unsigned)h->nexactblocks * (EXACT_THREADS / 32);
+      // the thread-per-row phase of the exact kernel takes the rows that came with their activities when there are enough of
+      // them: it needs ~36 us whatever their number (up to 32 rows per resident warp), eight lanes per row need ~6.4 us per
+      // trip of 4 rows per warp -- the break-even is at ~22 rows per warp (measured on C3; GPULIN_FASTMIN overrides the
+      // threshold: the tests run the phase on small instances with it)
+      {
+         int occf = 0;
+         if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, fast_rows_kernel, FAST_THREADS, 0) != cudaSuccess || occf < 1 )
+            occf = 1;
+         bool anyint = false;
+         for( int64_t i = 0; i < h->nsell && !anyint; ++i )
+            anyint = (rowflags[(size_t)i] & ROWLEN_INT) != 0;
+         h->nfastblocks = anyint ? (int)std::max<int64_t>(1, std::min<int64_t>((h->nsell + FAST_THREADS - 1) / FAST_THREADS, (int64_t)h->nsm * occf)) : 0;
+      }
+      p.fastmin = 22u * (unsigned)h->nexactblocks * (EXACT_THREADS / 32);
       if( getenv("GPULIN_FASTMIN") != nullptr )
          p.fastmin = (unsigned)std::max(0, atoi(getenv("GPULIN_FASTMIN")));
       h->npushblocks = (int)std::max<int64_t>(1, std::min<int64_t>((ncols / 32 + 255) / 256, (int64_t)h->nsm * 4));
@@ -871,6 +901,10 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    }
    if( h->evfork != nullptr )
       cudaEventDestroy(h->evfork);
+   if( h->evfork2 != nullptr )
+      cudaEventDestroy(h->evfork2);
+   if( h->evjoin2 != nullptr )
+      cudaEventDestroy(h->evjoin2);
    if( h->ev0 != nullptr )
       cudaEventDestroy(h->ev0);
    if( h->ev1 != nullptr )
@@ -1560,6 +1594,8 @@ extern "C" int gpulin_clone(gpulin_t* src, gpulin_t** out)
    TRYCU(cudaEventCreateWithFlags(&h->evfork, cudaEventDisableTiming));
    TRYCU(cudaEventCreateWithFlags(&h->evjoin[0], cudaEventDisableTiming));
    TRYCU(cudaEventCreateWithFlags(&h->evjoin[1], cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evfork2, cudaEventDisableTiming));
+   TRYCU(cudaEventCreateWithFlags(&h->evjoin2, cudaEventDisableTiming));
    TRYCU(cudaEventCreate(&h->ev0));
    TRYCU(cudaEventCreate(&h->ev1));
    if( rc != GPULIN_OK )
@@ -1821,7 +1857,7 @@ extern "C" int gpulin_get_call_stats(gpulin_t* h, int64_t* stats, int32_t nstats
       if( dense < 0 )
          dense = 0;
       // begin; per dense round: sweeps, exact, collect, [merge with peers], apply, sparse rounds
-      launches = (h->lastresumed ? 1 : 0) + 1 + dense * (nkinds + 3 + (h->npeers > 1 ? 1 : 0) + (h->nsparseblocks > 0 ? 1 : 0));
+      launches = (h->lastresumed ? 1 : 0) + 1 + dense * (nkinds + 3 + (h->nfastblocks > 0 ? 1 : 0) + (h->npeers > 1 ? 1 : 0) + (h->nsparseblocks > 0 ? 1 : 0));
    }
    const int64_t v[6] = {launches, dense, sparse, h->lastsmall ? 1 : 0, h->lastresumed ? 1 : 0, (int64_t)c->nfastrows};
    for( int i = 0; i < nstats && i < 6; ++i )
@@ -1962,6 +1998,8 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    OK((launchRoundKernels<APPLY_LIST, false>(h, true, false, false)));
    h->nexactblocks = keepexact;
    CU(cudaEventRecord(h->evprof[1], h->stream));
+   if( h->nfastblocks > 0 )
+      fast_rows_kernel<<<h->nfastblocks, FAST_THREADS, 0, h->stream>>>(h->p);
    h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);   // ... which is timed on its own
    CU(cudaEventRecord(h->evprof[2], h->stream));
    OK(launchCollect(h));                              // (counted with the apply stage)

@@ -2016,24 +2016,28 @@ __global__ void __launch_bounds__(EXACT_THREADS, MINB) exact_rows_kernel(const D
    const unsigned n0 = p.ctrl->nexact[0];
    const unsigned n1 = p.ctrl->nexact[1];
    const unsigned n2 = p.ctrl->nexact[2];
-   const unsigned nfast = p.ctrl->nexact[3];
+   // (the rows of flist -- the short rows that came with their activities -- are finished by fast_rows_kernel when there are
+   // enough of them; otherwise they simply join the short rows of xlist and their activities are computed like everybody
+   // else's: a few rows are finished sooner by eight lanes each, in one trip, than by a loop over their nonzeros)
+   const unsigned nfast = p.ctrl->nexact[3] > p.fastmin ? 0u : p.ctrl->nexact[3];
    if( (n0 | n1 | n2 | nfast) == 0u )
       return;
-   // The thread-per-row phase pays off when it has rows for most of its lanes (32 rows per warp in flight instead of 4);
-   // a few rows are finished sooner by eight lanes each (one trip instead of a loop over the nonzeros): then the rows of
-   // flist simply join the short rows of xlist and their activities are computed like everybody else's.
-   const bool usefast = nfast > p.fastmin;
-   if( usefast )
-   {
-      __shared__ FastShared s_fast[EXACT_THREADS / 32];
-      if( blockIdx.x == 0 && threadIdx.x == 0 )
-         p.ctrl->nfastrows += nfast;
-      fastShortPhase(p, nfast, blockIdx.x * EXACT_THREADS + threadIdx.x, gridDim.x * EXACT_THREADS, s_fast[threadIdx.x >> 5]);
-      if( (n0 | n1 | n2) == 0u )
-         return;
-   }
-   exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, s_queue, EXACT_THREADS, p.flist,
-      usefast ? 0u : nfast);
+   exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, s_queue, EXACT_THREADS, p.flist, nfast);
+}
+
+// runs beside exact_rows_kernel, as its own launch: inside the exact kernel the phase spilled (and slowed the eight-lane path
+// down by a tenth).  Two resident blocks per SM: with three or four (80 / 64 registers) the column words of the next trip
+// are spilled and waited for at once -- 43 / 48 us instead of 36 for the 74k rows of C3's first round.
+constexpr int FAST_THREADS = 256;
+__global__ void __launch_bounds__(FAST_THREADS, 2) fast_rows_kernel(const DevProblem p)
+{
+   __shared__ FastShared s_fast[FAST_THREADS / 32];
+   const unsigned nfast = p.ctrl->nexact[3];
+   if( nfast <= p.fastmin )
+      return;
+   if( blockIdx.x == 0 && threadIdx.x == 0 )
+      p.ctrl->nfastrows += nfast;
+   fastShortPhase(p, nfast, blockIdx.x * FAST_THREADS + threadIdx.x, gridDim.x * FAST_THREADS, s_fast[threadIdx.x >> 5]);
 }
 
 // ---- redundancy feedback (propagateCons, cons_linear.c:7743-7753): flags[r] = 1 iff row r (permuted numbering) is
@@ -2617,6 +2621,8 @@ __global__ void __launch_bounds__(APPLY_THREADS, 4) apply_kernel(const DevProble
 //                         no atomics), the last block to finish adds the header (count, verdict);
 //   peer_merge_kernel     waits for the headers of all other ranks, merges their entries into the local keys with
 //                         atomicMin and puts columns on the change list that are not there yet.
+// (Measured on 8 GPUs, C4's first round, 85k entries per rank: bulk copies 137 us, plain 16-byte stores in 512-byte runs
+// 278 us; letting the receivers PULL the lists from the senders' memory instead took 20 us to list and 300 us to merge.)
 // After the merge all ranks hold the same keys and the same set of changed columns; the list-driven apply step and the
 // small rounds that follow (sparse_rounds_kernel) run on every rank redundantly -- deterministic, so the ranks stay
 // identical and need no further exchange until the next dense round.  One exchange per dense round, volume proportional
@@ -2846,41 +2852,53 @@ __global__ void __launch_bounds__(256) peer_merge_kernel(const DevProblem p)
    s.chglist = p.chglist;
    s.nchgcols = &p.ctrl->nchgcols;
    s.listed = true;
-   const int nthreads = gridDim.x * blockDim.x;
-   for( int r = 0; r < t.n && !s_fail; ++r )
+   // the lists of all sources as one index space (entry i belongs to the source r with off[r] <= i < off[r + 1]): every
+   // thread of the grid has an entry in flight, whatever the number of sources and the lengths of their lists
+   unsigned off[MAX_PEERS + 1];
+   off[0] = 0u;
+#pragma unroll
+   for( int r = 0; r < MAX_PEERS; ++r )
+      off[r + 1] = off[r] + (r < t.n ? s_count[r] : 0u);
+   const unsigned total = off[MAX_PEERS];
+   const unsigned nthreads = gridDim.x * blockDim.x;
+   for( unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total && !s_fail; i += nthreads )
    {
-      if( r == t.rank )
-         continue;
-      const PeerEntry* ent = peerEntries(t, t.box[t.rank], parity, r);
-      const unsigned n = s_count[r];
-      // (the blocks start at different places of the list, so that short lists of several sources keep all blocks busy)
-      for( unsigned i = ((blockIdx.x + 37u * (unsigned)r) % gridDim.x) * blockDim.x + threadIdx.x; i < n; i += nthreads )
+      int r = 0;
+      unsigned o = 0u;
+#pragma unroll
+      for( int q = 1; q < MAX_PEERS; ++q )
       {
-         // the entry may still be on its way: both halves carry the exchange number once they have landed
-         uint4 a = loadV4Volatile(&ent[i].a);
-         uint4 b = loadV4Volatile(&ent[i].b);
+         if( i >= off[q] )
+         {
+            r = q;
+            o = off[q];
+         }
+      }
+      const PeerEntry* ent = peerEntries(t, t.box[t.rank], parity, r) + (i - o);
+      // the entry may still be on its way: both halves carry the exchange number once they have landed
+      uint4 a = loadV4Volatile(&ent->a);
+      uint4 b = loadV4Volatile(&ent->b);
+      if( a.y != epoch || b.z != epoch )
+      {
+         const unsigned long long tstart = globaltimer();
+         do
+         {
+            a = loadV4Volatile(&ent->a);
+            b = loadV4Volatile(&ent->b);
+         } while( (a.y != epoch || b.z != epoch) && globaltimer() - tstart < 5000000000ull );
          if( a.y != epoch || b.z != epoch )
          {
-            const unsigned long long tstart = globaltimer();
-            do
-            {
-               a = loadV4Volatile(&ent[i].a);
-               b = loadV4Volatile(&ent[i].b);
-            } while( (a.y != epoch || b.z != epoch) && globaltimer() - tstart < 5000000000ull );
-            if( a.y != epoch || b.z != epoch )
-            {
-               s_fail = 1;
-               break;
-            }
+            s_fail = 1;
+            break;
          }
-         const int j = (int)a.x;
-         const long long kl = (long long)(((unsigned long long)a.w << 32) | a.z);
-         const long long ku = (long long)(((unsigned long long)b.y << 32) | b.x);
-         atomicMin(&p.cand[2 * (size_t)j], kl);
-         atomicMin(&p.cand[2 * (size_t)j + 1], ku);
-         const bool first = raiseColumnBit(s, j);
-         listChangedColumn(s, j, first);
       }
+      const int j = (int)a.x;
+      const long long kl = (long long)(((unsigned long long)a.w << 32) | a.z);
+      const long long ku = (long long)(((unsigned long long)b.y << 32) | b.x);
+      atomicMin(&p.cand[2 * (size_t)j], kl);
+      atomicMin(&p.cand[2 * (size_t)j + 1], ku);
+      const bool first = raiseColumnBit(s, j);
+      listChangedColumn(s, j, first);
    }
    __syncthreads();
    if( s_fail && threadIdx.x == 0 )
