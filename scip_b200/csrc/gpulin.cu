@@ -242,6 +242,23 @@ static int launchCollect(gpulin* h)
    return GPULIN_OK;
 }
 
+// the exact rules for the rows the filter sweeps handed over; the rows that came with their activities run beside the
+// others (fast_rows_kernel on a side stream: a parallel branch of the graph)
+static int launchExact(gpulin* h)
+{
+   if( h->nfastblocks > 0 )
+   {
+      CU(cudaEventRecord(h->evfork2, h->stream));
+      CU(cudaStreamWaitEvent(h->aux[0], h->evfork2, 0));
+      fast_rows_kernel<<<h->nfastblocks, FAST_THREADS, 0, h->aux[0]>>>(h->p);
+      CU(cudaEventRecord(h->evjoin2, h->aux[0]));
+   }
+   h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
+   if( h->nfastblocks > 0 )
+      CU(cudaStreamWaitEvent(h->stream, h->evjoin2, 0));
+   return GPULIN_OK;
+}
+
 template <int MODE, bool GRAPH>
 static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = true)
 {
@@ -284,19 +301,7 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = 
       for( int i = 0; i < side; ++i )
          CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
       if( h->nexactblocks > 0 )
-      {
-         // the rows that came with their activities run beside the exact rules of the others
-         if( h->nfastblocks > 0 )
-         {
-            CU(cudaEventRecord(h->evfork2, h->stream));
-            CU(cudaStreamWaitEvent(h->aux[0], h->evfork2, 0));
-            fast_rows_kernel<<<h->nfastblocks, FAST_THREADS, 0, h->aux[0]>>>(h->p);
-            CU(cudaEventRecord(h->evjoin2, h->aux[0]));
-         }
-         h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
-         if( h->nfastblocks > 0 )
-            CU(cudaStreamWaitEvent(h->stream, h->evjoin2, 0));
-      }
+         OK(launchExact(h));
       if( collect )
          OK(launchCollect(h));
    }
@@ -1998,9 +2003,7 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    OK((launchRoundKernels<APPLY_LIST, false>(h, true, false, false)));
    h->nexactblocks = keepexact;
    CU(cudaEventRecord(h->evprof[1], h->stream));
-   if( h->nfastblocks > 0 )
-      fast_rows_kernel<<<h->nfastblocks, FAST_THREADS, 0, h->stream>>>(h->p);
-   h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);   // ... which is timed on its own
+   OK(launchExact(h));                                // ... which is timed on its own
    CU(cudaEventRecord(h->evprof[2], h->stream));
    OK(launchCollect(h));                              // (counted with the apply stage)
    OK((launchRoundKernels<APPLY_LIST, false>(h, false, true)));

@@ -1704,6 +1704,13 @@ __device__ __forceinline__ void exactPhase(const DevProblem& p, const int* list0
    }
 
    // ---- medium rows: one warp per row
+   // (Instruction bound, not latency bound: ncu on C4's first round -- 200k rows of ~250 nonzeros, all of which tighten
+   // something -- counts ~2000 warp instructions per row, 45 % issue utilisation at 16 warps per SM, 1.8 long-scoreboard
+   // stalls per issue; most of them are the candidate rules, which a good part of a row's nonzeros reach.  Two variants
+   // were measured and dropped: this loop as its own kernel with the header and the first 128 column words of the NEXT
+   // row and the next 128 of the current row in flight -- 661 us for these rows against ~620 us here; and a candidate
+   // queue carried across the rows of a warp, so that the rules always run with 32 entries -- 881 us for the kernel
+   // against 765 us: the per-row queue is nearly full anyway, and every entry had to fetch its row's state.)
    {
       const int gw = gtid >> 5;
       const int nw = nthreads >> 5;
