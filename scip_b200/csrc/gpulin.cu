@@ -805,10 +805,11 @@ extern "C" int gpulin_create(int device, int64_t nrows, int64_t ncols, int64_t n
       if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->exactkernel, EXACT_THREADS, 0) != cudaSuccess || occ < 1 )
          occ = 1;
       h->nexactblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + EXACT_THREADS - 1) / EXACT_THREADS, (int64_t)h->nsm * occ));
-      // the thread-per-row phase of the exact kernel takes the rows that came with their activities when there are enough of
-      // them: it needs ~36 us whatever their number (up to 32 rows per resident warp), eight lanes per row need ~6.4 us per
-      // trip of 4 rows per warp -- the break-even is at ~22 rows per warp (measured on C3; GPULIN_FASTMIN overrides the
-      // threshold: the tests run the phase on small instances with it)
+      // fast_rows_kernel (a thread per row) takes the rows that came with their activities when there are enough of them:
+      // it needs ~36 us whatever their number (up to 32 rows per resident warp), eight lanes per row in exact_rows_kernel
+      // need ~6.4 us per trip of 4 rows per warp -- the break-even is at ~22 rows per warp (measured on C3;
+      // GPULIN_FASTMIN overrides the threshold: the tests run the kernel on small instances with it).  Launched only if
+      // the thread-per-row class holds a row that can qualify (ROWLEN_INT).
       {
          int occf = 0;
          if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, fast_rows_kernel, FAST_THREADS, 0) != cudaSuccess || occf < 1 )
