@@ -13,7 +13,7 @@ metric  propagation_fixpoint_nnz_per_s = nonzeros of the instance / time to reac
 value   bounds resident in HBM when the timed region starts (device-side reset of the bounds inside it)
 e2e     the same through the C ABI with HOST buffers, as the plugin calls it at a node: H2D of the bounds (2 bits per
         column against resident reference bounds + an explicit list, pinned), fixpoint, D2H of the verdict + the
-        round-ordered change log (12 bytes per change), every step
+        round-ordered change log (one word per change whose new bound is 0 or 1, 16 bytes per other change), every step
 roofline  one FULL ROUND at the fixpoint bounds (filter sweep + exact rules + collect + apply; cold L2): algorithmic bytes
         (nnz*12 + nrows*20 + ncols*17) / its CUDA-event time against the measured HBM copy peak of
         MEASURED_PEAKS.json; the dominant kernel (the filter sweep) alone and the first real round are sub-keys
@@ -268,7 +268,8 @@ class Harness:
             self.h_eub = torch.from_numpy(eub).pin_memory()
             self.nexplicit = len(idx)
             self.h2d_bytes = 4 * len(words) + 20 * len(idx)
-            self.h_chg = torch.empty(self.logcap * 12, dtype=torch.uint8).pin_memory()
+            self.h_chg = torch.empty(self.logcap * 4, dtype=torch.uint8).pin_memory()       # one word per change ...
+            self.h_side = torch.empty(self.logcap * 12, dtype=torch.uint8).pin_memory()     # ... + bounds other than 0 / 1
 
     def step_resident(self):
         self.lp.set_bounds_ptr(self.d_lb0.data_ptr(), self.d_ub0.data_ptr(), on_device=True)
@@ -281,8 +282,8 @@ class Harness:
         else:
             self.lp.set_bounds_packed_ptr(self.h_words.data_ptr())
         res = self.lp.propagate(0)                                            # verdict: 32 bytes, synchronises
-        n = self.lp.changes_packed_ptr(self.h_chg.data_ptr(), self.logcap)
-        self.d2h_bytes = 12 * min(n, self.logcap) + 32
+        n, nx = self.lp.changes_compact_ptr(self.h_chg.data_ptr(), self.logcap, self.h_side.data_ptr(), self.logcap)
+        self.d2h_bytes = 4 * min(n, self.logcap) + 12 * min(nx, self.logcap) + 4 + 32
         return res
 
     def barrier(self):
@@ -452,7 +453,8 @@ def run_ours(args):
                     e2e=dict(value=hz.nnz * K / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=hz.h2d_bytes,
                              d2h_bytes_per_step=hz.d2h_bytes,
                              h2d="bounds as 2 bits per column against resident reference bounds + explicit list (gpulin_set_bounds_packed)",
-                             d2h="verdict + round-ordered change log, 12 bytes per change (gpulin_get_changes_packed)"),
+                             d2h="verdict + round-ordered change log, 4 bytes per change whose new bound is 0 or 1 and 16 per other change "
+                                 "(gpulin_get_changes_compact: what the plugin replays)"),
                     gpu_launches=launches, clocks=clocks.summary(), status_consistent=res["status"] == res2["status"],
                     setup_ms=hz.setup_ms,
                     round_us=[round(float(x) * 1e3, 1) for x in ms], round_nnz=[int(x) for x in rn], round_changes=[int(x) for x in rc],

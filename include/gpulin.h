@@ -181,6 +181,14 @@ int gpulin_get_changes(gpulin_t* h, gpulin_change* out, int64_t maxn, int64_t* n
  *  of an entry follows from its position: the log is round ordered, gpulin_get_round_stats gives the counts per round */
 int gpulin_get_changes_packed(gpulin_t* h, void* out, int64_t maxn, int64_t* n);
 
+/** the same log as ONE 32-bit word per entry, in log (= round) order: column (bits 0-28) | code << 29 | is_upper << 31, where
+ *  code 0 / 1 says the new bound is 0.0 / 1.0 -- what the bound of a binary moves to -- and code 2 that the bound is in the
+ *  side list xout: { position of the entry in the log, low word, high word of the bound } per entry, 12 bytes each, in no
+ *  particular order.  *n = entries produced (as gpulin_get_changes), *nx = side-list entries produced (only min(*nx, maxx)
+ *  are written).  A propagation of a binary program comes back in 4 bytes per change instead of 24; needs ncols < 2^29.
+ *  (The bounds are what SCIPinferVarLbProp/UbProp get, scip_var.c:7589/7705.) */
+int gpulin_get_changes_compact(gpulin_t* h, uint32_t* out, int64_t maxn, int64_t* n, uint32_t* xout, int64_t maxx, int64_t* nx);
+
 /** per-round statistics of the last gpulin_propagate call (up to maxn rounds; any output array may be NULL):
  *  device time [ms] (%globaltimer stamps taken by the kernels), nonzeros swept, bound changes accepted */
 int gpulin_get_round_stats(gpulin_t* h, double* ms, int64_t* nnz, int64_t* nchg, int32_t maxn, int32_t* n);

@@ -106,6 +106,9 @@ struct gpulin
    unsigned*   d_codes = nullptr;   // ... and the staged codes, 2 bits per column
    unsigned*   d_packlog = nullptr; // staging of gpulin_get_changes_packed (12 bytes per entry)
    int64_t     packlogcap = 0;
+   unsigned*   d_clog = nullptr;    // staging of gpulin_get_changes_compact: count | words | explicit entries
+   int64_t     clogcap = 0;
+   unsigned*   h_clogcount = nullptr;  // pinned: number of explicit entries
    cudaStream_t stream = nullptr;
    bool        ownstream = true;
    cudaStream_t aux[2] = {nullptr, nullptr};     // the medium / long sweeps run beside the short sweep
@@ -893,6 +896,9 @@ extern "C" void gpulin_destroy(gpulin_t* h)
    cudaFree(h->d_ref);
    cudaFree(h->d_codes);
    cudaFree(h->d_packlog);
+   cudaFree(h->d_clog);
+   if( h->h_clogcount != nullptr )
+      cudaFreeHost(h->h_clogcount);
    for( int i = 0; i < 2; ++i )
    {
       if( h->aux[i] != nullptr )
@@ -1063,6 +1069,55 @@ extern "C" int gpulin_get_changes_packed(gpulin_t* h, void* out, int64_t maxn, i
    CU(cudaGetLastError());
    CU(cudaMemcpyAsync(out, h->d_packlog, 12 * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
    CU(cudaStreamSynchronize(h->stream));
+   return GPULIN_OK;
+}
+
+extern "C" int gpulin_get_changes_compact(gpulin_t* h, uint32_t* out, int64_t maxn, int64_t* n, uint32_t* xout, int64_t maxx,
+   int64_t* nx)
+{
+   if( h == nullptr || n == nullptr || nx == nullptr || maxn < 0 || maxx < 0 || (maxn > 0 && out == nullptr) || (maxx > 0 && xout == nullptr) )
+      return fail(GPULIN_ERR_ARG, "invalid argument");
+   if( h->ncols >= (1LL << 29) )
+      return fail(GPULIN_ERR_ARG, "the compact change log holds column indices below 2^29");
+   CU(cudaSetDevice(h->device));
+   const int64_t produced = (int64_t)h->h_ctrl->logcount;
+   *n = produced;
+   *nx = 0;
+   const int64_t m = std::min(std::min(produced, h->logcap), maxn);
+   if( m <= 0 )
+      return GPULIN_OK;
+   if( m >= (1LL << 32) )
+      return fail(GPULIN_ERR_ARG, "more than 2^32 log entries");
+   if( m > h->clogcap )
+   {
+      CU(cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_clog);
+      h->d_clog = nullptr;
+      h->clogcap = 0;
+      const int64_t cap = std::max<int64_t>(h->logcap, m);
+      // [ explicit count (16 bytes) | one word per entry | three words per explicit entry ]
+      if( cudaMalloc((void**)&h->d_clog, 16 + 16 * (size_t)cap) != cudaSuccess )
+         return fail(GPULIN_ERR_NOMEM, "cudaMalloc of the compact change log failed");
+      h->clogcap = cap;
+   }
+   if( h->h_clogcount == nullptr )
+      CU(cudaMallocHost((void**)&h->h_clogcount, sizeof(unsigned)));
+   unsigned* d_count = h->d_clog;
+   unsigned* d_words = h->d_clog + 4;
+   unsigned* d_x = d_words + h->clogcap;
+   CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned), h->stream));
+   compact_log_kernel<<<gridFor(h, m), 256, 0, h->stream>>>(h->d_log, m, d_words, d_x, d_count);
+   CU(cudaGetLastError());
+   CU(cudaMemcpyAsync(out, d_words, 4 * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaMemcpyAsync(h->h_clogcount, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+   CU(cudaStreamSynchronize(h->stream));
+   *nx = (int64_t)*h->h_clogcount;
+   const int64_t mx = std::min(*nx, maxx);
+   if( mx > 0 )
+   {
+      CU(cudaMemcpyAsync(xout, d_x, 12 * (size_t)mx, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+   }
    return GPULIN_OK;
 }
 

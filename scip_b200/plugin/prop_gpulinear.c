@@ -89,6 +89,8 @@ struct SCIP_PropData
    SCIP_Real*            refub;              /**<   upload sends 2 bits per column against them (gpulin_set_bounds_packed) */
    uint32_t*             codes;              /**< the 2-bit codes, 16 columns per word */
    gpulin_change*        changes;            /**< change log buffer */
+   uint32_t*             clog;               /**< long logs come back compact (gpulin_get_changes_compact): one word per entry ... */
+   uint32_t*             cside;              /**<   ... and three per entry whose bound is not 0 or 1 */
    int64_t*              rowptr;             /**< host CSR (kept for PROPRESPROP) */
    int32_t*              colidx;
    SCIP_Real*            vals;
@@ -196,6 +198,8 @@ void freeDeviceCopy(
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->colrows, propdata->nnz);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->colpos, propdata->nnz);
    SCIPfreeBlockMemoryArrayNull(scip, &propdata->changes, propdata->logcap);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->clog, propdata->logcap);
+   SCIPfreeBlockMemoryArrayNull(scip, &propdata->cside, 3 * propdata->logcap);
    propdata->ncols = 0;
    propdata->nrows = 0;
    propdata->nnz = 0;
@@ -606,6 +610,8 @@ SCIP_RETCODE buildDeviceCopy(
 
    propdata->logcap = (int64_t)DEFAULT_LOGCAPFAC * ncols + 1024;
    SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->changes, propdata->logcap) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->clog, propdata->logcap) );
+   SCIP_CALL( SCIPallocBlockMemoryArray(scip, &propdata->cside, 3 * propdata->logcap) );
    rc = gpulin_set_change_log(propdata->gpu, propdata->logcap);
    /* (the same log on every device: the devices must take every decision alike, also "the log is full") */
    for( j = 0; j < propdata->npeergpus && rc == GPULIN_OK; ++j )
@@ -747,6 +753,68 @@ SCIP_DECL_PROPEXITSOL(propExitsolGpulinear)
    freeDeviceCopy(scip, propdata);
 
    return SCIP_OKAY;
+}
+
+/** the change log of the last device call into propdata->changes.  A long log (a root propagation fixes hundreds of thousands
+ *  of binaries) comes back compact -- one word per change whose new bound is 0 or 1 instead of 24 bytes, see
+ *  gpulin_get_changes_compact; the round of an entry then follows from its position and the per-round counts -- a short one
+ *  (the call at a node: a handful of changes) as plain records with one copy and one synchronisation.
+ */
+#define COMPACTLOG_MINCHANGES  4096
+#define COMPACTLOG_MAXROUNDS   1024
+static
+int fetchChanges(
+   SCIP_PROPDATA*        propdata,
+   int64_t               nchanges,           /**< accepted changes of the call (gpulin_result) */
+   int64_t*              nlog                /**< entries produced */
+   )
+{
+   int64_t roundchg[COMPACTLOG_MAXROUNDS];
+   int64_t nside;
+   int64_t sum;
+   int64_t e;
+   int32_t nrounds;
+   int rc;
+   int r;
+
+   if( nchanges < COMPACTLOG_MINCHANGES || propdata->ncols >= (1 << 29) )
+      return gpulin_get_changes(propdata->gpu, propdata->changes, propdata->logcap, nlog);
+
+   rc = gpulin_get_round_stats(propdata->gpu, NULL, NULL, roundchg, COMPACTLOG_MAXROUNDS, &nrounds);
+   if( rc != GPULIN_OK )
+      return rc;
+   sum = 0;
+   for( r = 0; r < nrounds; ++r )
+      sum += roundchg[r];
+   rc = gpulin_get_changes_compact(propdata->gpu, propdata->clog, propdata->logcap, nlog, propdata->cside, propdata->logcap, &nside);
+   if( rc != GPULIN_OK )
+      return rc;
+   if( *nlog > propdata->logcap )
+      return GPULIN_OK;                      /* overflow: the caller takes the final bounds instead */
+   if( sum != *nlog || nside > propdata->logcap )
+      return gpulin_get_changes(propdata->gpu, propdata->changes, propdata->logcap, nlog);   /* (more rounds than the statistics hold) */
+
+   e = 0;
+   for( r = 0; r < nrounds; ++r )
+   {
+      int64_t k;
+      for( k = 0; k < roundchg[r]; ++k, ++e )
+      {
+         const uint32_t w = propdata->clog[e];
+         propdata->changes[e].var = (int32_t)(w & 0x1fffffffu);
+         propdata->changes[e].round = r;
+         propdata->changes[e].is_upper = (int32_t)(w >> 31);
+         propdata->changes[e].reserved = 0;
+         propdata->changes[e].newbound = ((w >> 29) & 3u) == 1u ? 1.0 : 0.0;
+      }
+   }
+   for( e = 0; e < nside; ++e )
+   {
+      const uint32_t pos = propdata->cside[3 * e];
+      uint64_t bits = (uint64_t)propdata->cside[3 * e + 1] | ((uint64_t)propdata->cside[3 * e + 2] << 32);
+      memcpy(&propdata->changes[pos].newbound, &bits, sizeof(double));
+   }
+   return GPULIN_OK;
 }
 
 /** order of the replay: by round (the order that makes every change explainable), inside a round by column and bound.
@@ -929,10 +997,10 @@ SCIP_DECL_PROPEXEC(propExecGpulinear)
    }
 
    ntightened = 0;
-   rc = gpulin_get_changes(propdata->gpu, propdata->changes, propdata->logcap, &nlog);
+   rc = fetchChanges(propdata, res.nchanges, &nlog);
    if( rc != GPULIN_OK )
    {
-      SCIPerrorMessage("prop_gpulinear: gpulin_get_changes failed (%d): %s\n", rc, gpulin_last_error());
+      SCIPerrorMessage("prop_gpulinear: reading the change log failed (%d): %s\n", rc, gpulin_last_error());
       return SCIP_ERROR;
    }
    if( nlog <= propdata->logcap )

@@ -74,6 +74,8 @@ _SIGNATURES = {
     "gpulin_set_reference_bounds": (ctypes.c_int, [_P, _P, _P]),
     "gpulin_set_bounds_packed": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P]),
     "gpulin_get_changes_packed": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "gpulin_get_changes_compact": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), _P, ctypes.c_int64,
+                                                  ctypes.POINTER(ctypes.c_int64)]),
     "gpulin_set_rangedrow": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P]),
     "gpulin_get_trace": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "gpulin_get_exchange_stats": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
@@ -237,6 +239,33 @@ class LinearPropagator:
         upper = (rec[:, 0] >> 31).astype(np.int32)
         val = (rec[:, 1].astype(np.uint64) | (rec[:, 2].astype(np.uint64) << np.uint64(32))).view(np.float64)
         return var, upper, val, n.value
+
+    def changes_compact(self, maxn: int):
+        """the change log through gpulin_get_changes_compact (one word per entry + a side list for bounds other than 0 / 1),
+        decoded to (var, is_upper, newbound) arrays + number of entries produced"""
+        words = np.empty(max(maxn, 1), dtype=np.uint32)
+        side = np.empty(3 * max(maxn, 1), dtype=np.uint32)
+        n = ctypes.c_int64(0)
+        nx = ctypes.c_int64(0)
+        _check(self._lib.gpulin_get_changes_compact(self._h, words.ctypes.data, maxn, ctypes.byref(n), side.ctypes.data, maxn,
+                                                    ctypes.byref(nx)))
+        m = min(n.value, maxn)
+        w = words[:m]
+        var = (w & np.uint32(0x1FFFFFFF)).astype(np.int32)
+        upper = (w >> np.uint32(31)).astype(np.int32)
+        code = (w >> np.uint32(29)) & np.uint32(3)
+        val = np.where(code == 1, 1.0, 0.0)
+        rec = side[:3 * min(nx.value, maxn)].reshape(-1, 3)
+        pos = rec[:, 0].astype(np.int64)
+        assert int((code == 2).sum()) == len(pos)
+        val[pos] = (rec[:, 1].astype(np.uint64) | (rec[:, 2].astype(np.uint64) << np.uint64(32))).view(np.float64)
+        return var, upper, val, n.value
+
+    def changes_compact_ptr(self, out_ptr: int, maxn: int, side_ptr: int, maxx: int):
+        n = ctypes.c_int64(0)
+        nx = ctypes.c_int64(0)
+        _check(self._lib.gpulin_get_changes_compact(self._h, out_ptr, maxn, ctypes.byref(n), side_ptr, maxx, ctypes.byref(nx)))
+        return n.value, nx.value
 
     def changes_packed_ptr(self, out_ptr: int, maxn: int) -> int:
         n = ctypes.c_int64(0)

@@ -436,6 +436,24 @@ def test_packed_bounds_and_packed_change_log(gpulin):
         assert key(var, upper, val) == key(log["var"], log["is_upper"], log["newbound"])
 
 
+@pytest.mark.parametrize("gen", ["setcover", "mixedknap"])
+def test_compact_change_log_is_the_change_log(gpulin, gen):
+    """gpulin_get_changes_compact (one word per change whose new bound is 0 or 1, a side list for the others) returns the
+    log of gpulin_get_changes entry by entry, in the same order"""
+    prob = {"setcover": lambda: synth.setcover(60_000, 60_000, 600_000, seed=19),
+            "mixedknap": lambda: synth.mixed_knapsack(1500, 15_000, 300_000, seed=42, dense_range=(1200, 2500))}[gen]()
+    with gpulin.LinearPropagator(prob) as lp:
+        lp.set_change_log(400_000)
+        lp.set_bounds(prob["lb"], prob["ub"])
+        res = lp.propagate()
+        log, nlog = lp.changes(400_000)
+        var, upper, val, ncp = lp.changes_compact(400_000)
+    assert res["status"] == gpulin.FIXPOINT and nlog == ncp == res["nchanges"] > 0
+    assert np.array_equal(var, log["var"]) and np.array_equal(upper, log["is_upper"]) and np.array_equal(val, log["newbound"])
+    other = (log["newbound"] != 0.0) & (log["newbound"] != 1.0)
+    assert (gen == "setcover") == (not other.any())       # binaries: nothing in the side list; general integers: something
+
+
 # ---- ranged-row (gcd) propagation: rangedRowPropagation, cons_linear.c:5715-6696 ------------------------------------------
 
 @pytest.mark.parametrize("name", golden_ranged_names())

@@ -59,6 +59,28 @@ def test_plugin_reaches_the_reference_fixpoint(tmp_path, name):
 
 @needs_driver
 @pytest.mark.gpu
+@pytest.mark.parametrize("gen", ["setcover", "mixedknap"])
+def test_plugin_replays_a_long_change_log(tmp_path, gen):
+    """a root propagation with thousands of changes: the plugin reads the log through gpulin_get_changes_compact (one
+    word per change of a binary, a side list for general bounds) and replays it round by round -- SCIP ends with the
+    bounds of the propagation fixpoint"""
+    from scip_b200 import synth
+    from scip_b200.lpb import write_lpb
+    prob = {"setcover": lambda: synth.setcover(40_000, 40_000, 400_000, seed=53),
+            "mixedknap": lambda: synth.mixed_knapsack(3000, 30_000, 600_000, seed=51, dense_range=(1200, 2500))}[gen]()
+    want = oracle.propagate(prob, boundstreps=1e-9)
+    assert want["status"] == oracle.STATUS_FIXPOINT and want["nchanges"] > 4096
+    lpb = str(tmp_path / "p.lpb")
+    out = str(tmp_path / "o.lpr")
+    write_lpb(lpb, prob)
+    info = run_driver("--lpb", lpb, "--boundstreps", "1e-9", "--out", out)
+    got = oracle.read_lpr(out)
+    assert not got["infeasible"] and info["gpu_prop_calls"] >= 1 and info["gpu_domreds"] > 4096
+    assert_bounds_match(got["lb"] + 0.0, got["ub"] + 0.0, want["lb"] + 0.0, want["ub"] + 0.0, prob["vartype"], what=gen)
+
+
+@needs_driver
+@pytest.mark.gpu
 def test_plugin_in_tree_search_with_conflict_analysis():
     """thousands of EXEC calls with local bounds, backtracking and PROPRESPROP: enigma is solved by propagation +
     branching (the reference build has no LP solver); both runs must prove the same status"""
