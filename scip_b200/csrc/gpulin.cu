@@ -247,9 +247,11 @@ static int launchCollect(gpulin* h)
 
 // the exact rules for the rows the filter sweeps handed over; the rows that came with their activities run beside the
 // others (fast_rows_kernel on a side stream: a parallel branch of the graph)
-static int launchExact(gpulin* h)
+static int launchExact(gpulin* h, bool firstround)
 {
-   if( h->nfastblocks > 0 )
+   const bool fast = firstround && h->nfastblocks > 0;
+   h->p.fastround = fast ? 1 : 0;      // (the kernels take the problem by value: this launch's copy says who takes flist)
+   if( fast )
    {
       CU(cudaEventRecord(h->evfork2, h->stream));
       CU(cudaStreamWaitEvent(h->aux[0], h->evfork2, 0));
@@ -257,13 +259,14 @@ static int launchExact(gpulin* h)
       CU(cudaEventRecord(h->evjoin2, h->aux[0]));
    }
    h->exactkernel<<<h->nexactblocks, EXACT_THREADS, 0, h->stream>>>(h->p);
-   if( h->nfastblocks > 0 )
+   if( fast )
       CU(cudaStreamWaitEvent(h->stream, h->evjoin2, 0));
+   h->p.fastround = 0;
    return GPULIN_OK;
 }
 
 template <int MODE, bool GRAPH>
-static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = true)
+static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = true, bool firstround = false)
 {
    if( sweep )
    {
@@ -304,7 +307,7 @@ static int launchRoundKernels(gpulin* h, bool sweep, bool apply, bool collect = 
       for( int i = 0; i < side; ++i )
          CU(cudaStreamWaitEvent(h->stream, h->evjoin[i], 0));
       if( h->nexactblocks > 0 )
-         OK(launchExact(h));
+         OK(launchExact(h, firstround));
       if( collect )
          OK(launchCollect(h));
    }
@@ -341,14 +344,32 @@ static int buildGraph(gpulin* h)
       kp.kernelParams = args;
       CU(cudaGraphAddKernelNode(&beginNode, h->graph, nullptr, 0, &kp));
    }
-   cudaGraphNode_t afterBegin = beginNode;
+   // the first round in front of the loop: the one round that launches fast_rows_kernel (see DevProblem::fastround); its
+   // apply step sets the condition of the loop like every other
+   std::vector<cudaGraphNode_t> afterFirst;
+   {
+      CU(cudaStreamBeginCaptureToGraph(h->stream, h->graph, &beginNode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+      const int frc = launchRoundKernels<APPLY_LIST, true>(h, true, true, true, true);
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      const cudaGraphNode_t* deps = nullptr;
+      size_t ndeps = 0;
+      cudaError_t ce = cudaStreamGetCaptureInfo(h->stream, &st, nullptr, nullptr, &deps, &ndeps);
+      if( ce == cudaSuccess )
+         afterFirst.assign(deps, deps + ndeps);
+      cudaGraph_t captured1 = nullptr;
+      CU(cudaStreamEndCapture(h->stream, &captured1));
+      OK(frc);
+      CU(ce);
+      if( afterFirst.empty() )
+         return fail(GPULIN_ERR_CUDA, "the capture of the first round left no node to continue from");
+   }
    cudaGraphNodeParams cp = {};
    cp.type = cudaGraphNodeTypeConditional;
    cp.conditional.handle = h->handle;
    cp.conditional.type = cudaGraphCondTypeWhile;
    cp.conditional.size = 1;
    cudaGraphNode_t whileNode;
-   CU(cudaGraphAddNode(&whileNode, h->graph, &afterBegin, 1, &cp));
+   CU(cudaGraphAddNode(&whileNode, h->graph, afterFirst.data(), afterFirst.size(), &cp));
    cudaGraph_t body = cp.conditional.phGraph_out[0];
 
    CU(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
@@ -1306,9 +1327,9 @@ extern "C" int gpulin_propagate_async(gpulin_t* h, int maxrounds)
    else
    {
       begin_kernel<<<1, 1, 0, h->stream>>>(h->p.ctrl);
-      for( ;; )
+      for( bool first = true; ; first = false )
       {
-         OK((launchRoundKernels<APPLY_LIST, false>(h, true, true)));
+         OK((launchRoundKernels<APPLY_LIST, false>(h, true, true, true, first)));
          int cont = 0;
          CU(cudaMemcpyAsync(&h->h_ctrl->cont, &h->p.ctrl->cont, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
          CU(cudaStreamSynchronize(h->stream));
@@ -1918,7 +1939,10 @@ extern "C" int gpulin_get_call_stats(gpulin_t* h, int64_t* stats, int32_t nstats
       if( dense < 0 )
          dense = 0;
       // begin; per dense round: sweeps, exact, collect, [merge with peers], apply, sparse rounds
-      launches = (h->lastresumed ? 1 : 0) + 1 + dense * (nkinds + 3 + (h->nfastblocks > 0 ? 1 : 0) + (h->npeers > 1 ? 1 : 0) + (h->nsparseblocks > 0 ? 1 : 0));
+      // (the graph runs its first round unconditionally; fast_rows_kernel is part of that round only)
+      const int64_t looprounds = std::max<int64_t>(dense, 1);
+      launches = (h->lastresumed ? 1 : 0) + 1 + (h->nfastblocks > 0 ? 1 : 0)
+         + looprounds * (nkinds + 3 + (h->npeers > 1 ? 1 : 0) + (h->nsparseblocks > 0 ? 1 : 0));
    }
    const int64_t v[6] = {launches, dense, sparse, h->lastsmall ? 1 : 0, h->lastresumed ? 1 : 0, (int64_t)c->nfastrows};
    for( int i = 0; i < nstats && i < 6; ++i )
@@ -2059,7 +2083,7 @@ extern "C" int gpulin_profile_round(gpulin_t* h, double* sweep_ms, double* exact
    OK((launchRoundKernels<APPLY_LIST, false>(h, true, false, false)));
    h->nexactblocks = keepexact;
    CU(cudaEventRecord(h->evprof[1], h->stream));
-   OK(launchExact(h));                                // ... which is timed on its own
+   OK(launchExact(h, false));                         // ... which is timed on its own (as in the loop body)
    CU(cudaEventRecord(h->evprof[2], h->stream));
    OK(launchCollect(h));                              // (counted with the apply stage)
    OK((launchRoundKernels<APPLY_LIST, false>(h, false, true)));

@@ -167,7 +167,9 @@ struct DevProblem
    int                 st0, st1;
    int                 nranks, rank;
    unsigned            markall_min; // an apply step with at least this many changed columns marks ALL rows (see apply_kernel)
-   unsigned            fastmin;     // exact_rows_kernel: the rows of flist take the thread-per-row phase if there are more than this
+   unsigned            fastmin;     // the rows of flist are finished by fast_rows_kernel if there are more than this ...
+   int                 fastround;   // ... in a round that launches it: the first round of a call (the one round with work for it;
+                                    // in the later rounds of the loop its empty launch would cost 3 - 5 us each)
    RangedRows          rr;          // ranged-row propagation (gpulin_set_rangedrow); rr.n == 0: off
    Num                 num;
 };
@@ -2026,7 +2028,7 @@ __global__ void __launch_bounds__(EXACT_THREADS, MINB) exact_rows_kernel(const D
    // (the rows of flist -- the short rows that came with their activities -- are finished by fast_rows_kernel when there are
    // enough of them; otherwise they simply join the short rows of xlist and their activities are computed like everybody
    // else's: a few rows are finished sooner by eight lanes each, in one trip, than by a loop over their nonzeros)
-   const unsigned nfast = p.ctrl->nexact[3] > p.fastmin ? 0u : p.ctrl->nexact[3];
+   const unsigned nfast = (p.fastround != 0 && p.ctrl->nexact[3] > p.fastmin) ? 0u : p.ctrl->nexact[3];
    if( (n0 | n1 | n2 | nfast) == 0u )
       return;
    exactPhase<false>(p, p.xlist, n0, p.xlist + p.nsell, n1, p.xlist + p.nsx, n2, s_acc, s_queue, EXACT_THREADS, p.flist, nfast);
